@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- BiGCN training throughput (trees/s) on B200, the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path over one batch: graph prep + forward + nll_loss + backward
++ Adam on a Twitter16-shaped synthetic batch of 128 reply trees per GPU (BASELINE.json
+configs[1]; K = 5000 bag-of-words, 4 classes, DropEdge 0.2/0.2, train mode, fp32).
+`value` times the steps with the batches resident in HBM (three batches in rotation, each
+~600 MB of features >> the 126 MB L2); `e2e` times the same steps fed from pinned HOST
+buffers (H2D of every input inside the timed region, loss read back).  `roofline` is the
+dominant kernel (the X stream) timed alone with CUDA events; `cpu_baseline` is the oracle's
+restatement of the reference module -- including its Python max()/mask loops, which is what
+the reference executes -- on this host's cores, on a bounded sample of the same workload.
+Multi-GPU: trees are sharded per rank (weak scaling, 128 trees per GPU), one NCCL all-reduce of
+the flat 5.16 MB gradient per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPE = "twitter16"
+TREES_PER_GPU = 128
+K_FEATS, N_CLASSES = 5000, 4
+N_ROTATE = 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="bigcn_b200", choices=["bigcn_b200", "reference"])
+    ap.add_argument("--gemm-mode", default="fp32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--cpu-sample-trees", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also time propagate/readout-size kernels at large N")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_run(steps, warmup, sample_trees, seed=0):
+    """The reference's own CPU implementation of the path (oracle restatement with the
+    reference's Python loops), train mode, fwd + nll_loss + bwd + Adam, all host threads."""
+    import torch
+    from oracle import bigcn_oracle
+    from bigcn_b200.data import make_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    b = make_batch(SHAPE, sample_trees, seed=seed, train=True)
+    model = bigcn_oracle.BiGCN(K_FEATS, 64, 64, num_classes=N_CLASSES, reference_loops=True).train()
+    opt = bigcn_oracle.make_optimizer(model)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = model(b)
+        loss = torch.nn.functional.nll_loss(out, b.y)
+        opt.zero_grad()
+        loss.backward()
+        float(loss.item())
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": sample_trees / med, "unit": "trees/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_trees} {SHAPE}-shaped trees ({int(b.x.shape[0])} nodes), {steps} timed steps "
+                      f"after {warmup} warm-up, median; oracle restatement incl. the reference's Python loops",
+            "ms_per_step": med * 1e3, "nodes": int(b.x.shape[0])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    r = cpu_reference_run(steps, warm, args.cpu_sample_trees)
+    line = {"impl": "reference", "metric": "BiGCN train trees/sec", "value": r["value"], "unit": "trees/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic",
+            "config": {"workload": f"{SHAPE}-shaped BiGCN training step (fwd+nll+bwd+Adam), K={K_FEATS}, C={N_CLASSES}, "
+                                   f"DropEdge 0.2/0.2; CPU arm runs a bounded sample of {args.cpu_sample_trees} trees per step",
+                       "trees_per_step": args.cpu_sample_trees},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def time_kernel(fn, iters, torch):
+    """CUDA-event time of `iters` back-to-back launches on the current stream (ms per launch)."""
+    for _ in range(3):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_ours(args):
+    import torch
+    import bigcn_b200
+    from bigcn_b200 import _lib as L, ops
+    from bigcn_b200.data import make_batch, Batch
+    from bigcn_b200.trainer import launches_per_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    L.require_device()
+
+    # ---- data: N_ROTATE distinct batches per rank, pinned on the host and resident in HBM
+    host = [make_batch(SHAPE, TREES_PER_GPU, seed=1000 * rank + i, train=True).pin_memory() for i in range(N_ROTATE)]
+    resident = [Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys}) for b in host]
+    nodes = [int(b.x.shape[0]) for b in host]
+    h2d_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in Batch._tensor_keys)
+
+    torch.manual_seed(0)
+    model = bigcn_b200.BiGCN(K_FEATS, 64, 64, dev, num_classes=N_CLASSES, gemm_mode=args.gemm_mode,
+                             validate="off").to(dev).train()
+    tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world)
+    b_global = TREES_PER_GPU * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ------------------------------------------------------
+    for i in range(args.warmup):
+        tr.step(resident[i % N_ROTATE], b_global=b_global)
+    tr.check_inputs()
+    barrier()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for i in range(args.steps):
+            loss = tr.step(resident[i % N_ROTATE], b_global=b_global)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = TREES_PER_GPU * world * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end to end: host buffers in, loss out ---------------------------------------
+    stage = [Batch(**{k: torch.empty_like(getattr(b, k), device=dev) for k in Batch._tensor_keys}) for b in host[:2]]
+
+    def e2e_step(i):
+        src, dst = host[i % N_ROTATE], stage[i % 2]
+        for k in Batch._tensor_keys:
+            s, d = getattr(src, k), getattr(dst, k)
+            if d.shape != s.shape:
+                d = torch.empty_like(s, device=dev)
+                setattr(dst, k, d)
+            d.copy_(s, non_blocking=True)
+        l = tr.step(dst, b_global=b_global)
+        return float(l.item())           # device -> host read of the step's result
+
+    for i in range(max(1, min(args.warmup, 3))):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 12))
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    g1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), 0.0))
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_value = TREES_PER_GPU * world * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernels (rank 0, timed alone, inputs >> L2) ---------
+    hbm_peak, peak_src = peaks()
+    import ctypes as C
+    lib = L.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    n0 = nodes[0]
+    wt = torch.randn(K_FEATS, 128, device=dev) * 0.02
+    ys = [torch.empty(n, 128, device=dev) for n in nodes]
+
+    def xw_fn(i):
+        j = i % N_ROTATE
+        L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, wt.data_ptr(), 128, ys[j].data_ptr(),
+                             128, L.GEMM_MODE[args.gemm_mode], st))
+    xw_ms = time_kernel(xw_fn, 12, torch)
+    mean_nodes = sum(nodes[i % N_ROTATE] for i in range(12)) / 12
+    xw_bytes = mean_nodes * K_FEATS * 4 + K_FEATS * 128 * 4 + mean_nodes * 128 * 4
+    xw_gbs = xw_bytes / (xw_ms * 1e-3) / 1e9
+    roof = {"kernel": "k_xw_scan<128> (X * [W1_td;W1_bu]^T, conv1 lin of both directions in one pass over X)",
+            "bound": "hbm", "achieved": xw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xw_gbs / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "ms": xw_ms,
+            "algorithmic_bytes": xw_bytes, "frac_of_8TBs_nominal": xw_gbs / 8000.0}
+    others = {}
+    if args.kernels:
+        others = kernel_microbench(torch, L, ops, dev, hbm_peak)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_run(1, 1, args.cpu_sample_trees)
+
+    line = {"metric": "BiGCN train trees/sec", "value": value, "unit": "trees/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic",
+            "config": {"workload": f"{SHAPE}-shaped BiGCN training step (graph prep+fwd+nll+bwd+Adam), "
+                                   f"{TREES_PER_GPU} trees/GPU, K={K_FEATS}, C={N_CLASSES}, DropEdge 0.2/0.2, dropout 0.5",
+                       "trees_per_gpu": TREES_PER_GPU, "nodes_per_batch": nodes, "gemm_mode": args.gemm_mode,
+                       "l2": f"{N_ROTATE} batches in rotation, {nodes[0] * K_FEATS * 4 / 1e6:.0f} MB of features each (> 126 MB L2)",
+                       "parallelism": f"dp{world} (trees sharded, one NCCL all-reduce of the flat gradient)" if world > 1 else "single GPU"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps},
+            "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True),
+            "roofline": roof, "final_loss": final_loss}
+    if others:
+        line["roofline_others"] = others
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def kernel_microbench(torch, L, ops, dev, hbm_peak):
+    """propagate (both CSR orientations) on a forest far larger than L2."""
+    from bigcn_b200.data import make_device_forest
+    out = {}
+    n_trees, per = 16384, 256
+    n = n_trees * per
+    f = make_device_forest(n_trees, per, dev, seed=3)
+    graphs, node_ptr, flags = ops.graph_prep([f.edge_index, f.BU_edge_index], n, f.batch, n_trees, rowsum=False)
+    e = int(f.edge_index.shape[1])
+    hs = [torch.randn(n, 64, device=dev) for _ in range(2)]
+    outb = torch.empty(n, 64, device=dev)
+    lib = L.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    bias = torch.zeros(64, device=dev)
+    for name, g, tr in (("propagate_td_parent_gather", graphs[0], False), ("propagate_bu_child_segment_sum", graphs[1], False)):
+        ptr, idx = g["in_ptr"], g["in_idx"]
+
+        def fn(i, ptr=ptr, idx=idx, g=g):
+            L.check(lib.bigcn_propagate(ptr.data_ptr(), idx.data_ptr(), g["dis"].data_ptr(), n, hs[i % 2].data_ptr(), 64,
+                                        bias.data_ptr(), 1, outb.data_ptr(), 64, st))
+        ms = time_kernel(fn, 10, torch)
+        # N*(2*256 + 8) + 4E + 260 bytes (each source row counted once)
+        byt = n * (2 * 256 + 8) + 4 * e + 260
+        gbs = byt / (ms * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                     "ms": ms, "nodes": n, "edges": e}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

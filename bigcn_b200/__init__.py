@@ -1,0 +1,17 @@
+"""bigcn_b200 -- B200-native (sm_100a) BiGCN hot path behind the reference's module API.
+
+    from bigcn_b200 import BiGCN, Net, TDrumorGCN, BUrumorGCN, GCNConv
+
+The CUDA library (bigcn_b200/libbigcn_b200.so, C-ABI in include/bigcn_b200.h) is the
+product; importing this package without it raises, and no op has a CPU fallback.
+"""
+from ._lib import BigcnError, LIB_PATH, lib  # noqa: F401
+
+lib()  # fail loudly at import time if the CUDA library has not been built
+
+from .nn import GCNConv, TDrumorGCN, BUrumorGCN, BiGCN, Net  # noqa: E402,F401
+from .trainer import FusedTrainer  # noqa: E402,F401
+from . import data, ops  # noqa: E402,F401
+
+__all__ = ["GCNConv", "TDrumorGCN", "BUrumorGCN", "BiGCN", "Net", "FusedTrainer", "BigcnError",
+           "data", "ops"]

@@ -1,0 +1,473 @@
+// C-ABI orchestration: the two-direction feature path (forward / backward), GCNConv on its
+// own, and the small exported helpers.  Every function only enqueues kernels on the caller's
+// stream; the workspace carved here carries what backward needs.
+#include <stdarg.h>
+
+#include "kernels.cuh"
+
+namespace bigcn {
+
+// ---- error / device helpers ---------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int xw_dispatch(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y,
+                int64_t ldy, int mode, cudaStream_t st) {
+  BIGCN_CHECK_ARG(n_out == 64 || n_out == 128, "xw: n_out must be 64 or 128");
+  if (mode == BIGCN_GEMM_FP32) return xw_fp32(x, N, K, wt, n_out, y, ldy, st);
+  BIGCN_CHECK_ARG(mode == BIGCN_GEMM_TF32 || mode == BIGCN_GEMM_TF32X3, "xw: unknown gemm_mode %d", mode);
+  return xw_tc(x, N, K, wt, n_out, y, ldy, mode, st);
+}
+
+// ---- workspace of the feature path -----------------------------------------------
+struct FeatWs {
+  bigcn_graph_t g[2];       // [0] = TD, [1] = BU
+  int32_t* node_ptr;
+  float* w1T;               // [K][128]  (TD cols 0..63, BU cols 64..127)
+  float* w2aT[2];           // [64][64]
+  float* w2bT[2];           // [K][64]
+  int32_t* rnz_cnt; int32_t* rnz_col; float* rnz_val;
+  float* P[2];              // [B][64]
+  float* xw;                // [N][128]      (backward: T2[0], T2[1] as two [N][64] halves)
+  float* h1[2];             // [N][64]
+  float* a1[2];             // [N][64]
+  float* z[2];              // [N][64]       (backward: G2 then G1)
+  float* h2[2];             // [N][64]       (backward: T1cat [N][128] once G2 is formed)
+  float* cs_part[2];        // [chunks][64]  column-sum partials
+  float* op_part[2];        // [chunks][4096]
+  float* dw_part;           // dW1 slab partials
+  float* dP[2];             // [B][64]
+  void* prep_ws; size_t prep_bytes;
+  size_t total;
+};
+
+static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
+  FeatWs w{};
+  Carver c(ws, bytes);
+  const int64_t N = dm->N, B = dm->B, K = dm->K;
+  const int64_t E[2] = {dm->E_td, dm->E_bu};
+  for (int d = 0; d < 2; ++d) {
+    w.g[d].in_ptr = c.take<int32_t>(N + 1);
+    w.g[d].out_ptr = c.take<int32_t>(N + 1);
+    w.g[d].in_idx = c.take<int32_t>(E[d] > 0 ? E[d] : 1);
+    w.g[d].out_idx = c.take<int32_t>(E[d] > 0 ? E[d] : 1);
+    w.g[d].deg = c.take<int32_t>(N > 0 ? N : 1);
+    w.g[d].dis = c.take<float>(N > 0 ? N : 1);
+    w.g[d].rowsum = nullptr;
+  }
+  w.node_ptr = c.take<int32_t>(B + 1);
+  w.w1T = c.take<float>((size_t)K * 128);
+  for (int d = 0; d < 2; ++d) {
+    w.w2aT[d] = c.take<float>(H * H);
+    w.w2bT[d] = c.take<float>((size_t)K * H);
+  }
+  w.rnz_cnt = c.take<int32_t>(B > 0 ? B : 1);
+  w.rnz_col = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
+  w.rnz_val = c.take<float>((size_t)(B > 0 ? B : 1) * K);
+  const size_t nh = (size_t)(N > 0 ? N : 1) * H;
+  for (int d = 0; d < 2; ++d) w.P[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
+  w.xw = c.take<float>(2 * nh);
+  for (int d = 0; d < 2; ++d) w.h1[d] = c.take<float>(nh);
+  for (int d = 0; d < 2; ++d) w.a1[d] = c.take<float>(nh);
+  w.z[0] = c.take<float>(2 * nh);
+  w.z[1] = w.z[0] + nh;
+  w.h2[0] = c.take<float>(2 * nh);
+  w.h2[1] = w.h2[0] + nh;
+  const int csn = cs_chunks(N) > bm_chunks(N) ? cs_chunks(N) : bm_chunks(N);
+  for (int d = 0; d < 2; ++d) w.cs_part[d] = c.take<float>((size_t)csn * H);
+  for (int d = 0; d < 2; ++d) w.op_part[d] = c.take<float>((size_t)op_chunks(N) * H * H);
+  w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
+  for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
+  const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
+  w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
+  w.prep_ws = c.take<char>(w.prep_bytes);
+  w.total = align_up(c.off, 256);
+  return w;
+}
+
+// active directions: order TD (0), BU (1); feat base: BU -> 0, TD -> 128 (cat order of :128)
+struct Dirs {
+  int n;
+  int id[2];
+};
+static Dirs active_dirs(int mask) {
+  Dirs r{0, {0, 0}};
+  if (mask & BIGCN_DIR_TD) r.id[r.n++] = 0;
+  if (mask & BIGCN_DIR_BU) r.id[r.n++] = 1;
+  return r;
+}
+static const float* dir_w1(const bigcn_params_t* p, int d) { return d == 0 ? p->td_w1 : p->bu_w1; }
+static const float* dir_b1(const bigcn_params_t* p, int d) { return d == 0 ? p->td_b1 : p->bu_b1; }
+static const float* dir_w2(const bigcn_params_t* p, int d) { return d == 0 ? p->td_w2 : p->bu_w2; }
+static const float* dir_b2(const bigcn_params_t* p, int d) { return d == 0 ? p->td_b2 : p->bu_b2; }
+static float* gdir_w1(const bigcn_params_t* p, int d) { return d == 0 ? p->td_w1 : p->bu_w1; }
+static float* gdir_b1(const bigcn_params_t* p, int d) { return d == 0 ? p->td_b1 : p->bu_b1; }
+static float* gdir_w2(const bigcn_params_t* p, int d) { return d == 0 ? p->td_w2 : p->bu_w2; }
+static float* gdir_b2(const bigcn_params_t* p, int d) { return d == 0 ? p->td_b2 : p->bu_b2; }
+static int feat_base(int d) { return d == 0 ? 2 * H : 0; }
+
+static int check_common(const bigcn_dims_t* dm, const bigcn_opts_t* o, const char* who) {
+  BIGCN_CHECK_ARG(dm && o, "%s: NULL dims/opts", who);
+  BIGCN_CHECK_ARG(dm->N >= 0 && dm->B >= 0 && dm->K > 0, "%s: bad dims", who);
+  BIGCN_CHECK_ARG(dm->N < (1ll << 31) - 1 && dm->E_td < (1ll << 31) - 1 && dm->E_bu < (1ll << 31) - 1,
+                  "%s: N/E exceed int32", who);
+  BIGCN_CHECK_ARG((o->dir_mask & 3) != 0, "%s: dir_mask selects no direction", who);
+  BIGCN_CHECK_ARG(o->p_drop >= 0.f && o->p_drop < 1.f, "%s: p_drop must be in [0,1)", who);
+  return 0;
+}
+
+int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_params_t* pr,
+                     const bigcn_opts_t* o, float* feat, int32_t* flags, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  if (int rc = check_common(dm, o, "features_forward")) return rc;
+  FeatWs w = carve_features(dm, ws, ws_bytes);
+  BIGCN_CHECK_ARG(ws != nullptr && ws_bytes >= w.total, "features_forward: workspace too small (%zu < %zu)",
+                  ws_bytes, w.total);
+  const int64_t N = dm->N, B = dm->B, K = dm->K;
+  const Dirs dirs = active_dirs(o->dir_mask);
+  // 1. structure of both directions, node_ptr
+  {
+    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
+    const int64_t E[2] = {dm->E_td, dm->E_bu};
+    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
+                                 w.prep_bytes, st))
+      return rc;
+  }
+  // 2. weights in the layouts the kernels stream
+  const int n_out = dirs.n == 2 ? 128 : 64;
+  for (int q = 0; q < dirs.n; ++q) {
+    const int d = dirs.id[q];
+    if (int rc = transpose_weight(dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H, st)) return rc;
+    if (int rc = transpose_weight(dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0, st)) return rc;
+    if (int rc = transpose_weight(dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0, st)) return rc;
+  }
+  // 3. X W1^T for all active directions in one pass over X
+  if (int rc = xw_dispatch(bt->x, N, K, w.w1T, n_out, w.xw, n_out, o->gemm_mode, st)) return rc;
+  // 4. root columns (and, without dropout, the per-tree projection)
+  {
+    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags};
+    if (int rc = root_nz_launch(a, st)) return rc;
+  }
+  const bool dropping = o->training && o->p_drop > 0.f;
+  if (!dropping) {
+    RootProjArgs a{};
+    a.cnt = w.rnz_cnt; a.col = w.rnz_col; a.val = w.rnz_val; a.B = B; a.K = K;
+    for (int q = 0; q < dirs.n; ++q) {
+      a.w2bT[q] = w.w2bT[dirs.id[q]];
+      a.P[q] = w.P[dirs.id[q]];
+    }
+    if (int rc = root_proj_launch(a, dirs.n, st)) return rc;
+  }
+  // 5. conv1 propagate + relu/dropout + conv2 lin
+  {
+    MixArgs a{};
+    a.N = N; a.K = K; a.ldxw = n_out; a.node_id_base = bt->node_id_base; a.batch = bt->batch;
+    a.rnz_cnt = w.rnz_cnt; a.rnz_col = w.rnz_col; a.rnz_val = w.rnz_val;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      MixDir& m = a.d[q];
+      m.ptr = w.g[d].in_ptr; m.idx = w.g[d].in_idx; m.dis = w.g[d].dis;
+      m.xw = w.xw + q * H; m.b1 = dir_b1(pr, d);
+      m.w2aT = w.w2aT[d]; m.w2bT = w.w2bT[d]; m.P = w.P[d];
+      m.h1 = w.h1[d]; m.a1 = w.a1[d]; m.z = w.z[d];
+      m.drop = make_drop(o, d);
+    }
+    if (int rc = prop1_mix_launch(a, dirs.n, st)) return rc;
+  }
+  // 6. conv2 propagate + bias + relu
+  {
+    PropArgs a{};
+    a.N = N; a.relu = 1;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.d[q] = PropDir{w.g[d].in_ptr, w.g[d].in_idx, w.g[d].dis, w.z[d], dir_b2(pr, d), w.h2[d], H, H};
+    }
+    if (int rc = propagate_launch(a, dirs.n, st)) return rc;
+  }
+  // 7. readout
+  {
+    if (dirs.n < 2) cudaMemsetAsync(feat, 0, (size_t)B * 4 * H * sizeof(float), st);
+    ReadoutArgs a{};
+    a.ndir = dirs.n; a.node_ptr = w.node_ptr; a.rootindex = bt->rootindex; a.feat = feat;
+    a.N = N; a.B = B; a.flags = flags;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.h2[q] = w.h2[d]; a.h1[q] = w.h1[d]; a.feat_base[q] = feat_base(d);
+    }
+    if (int rc = readout_launch(a, st)) return rc;
+  }
+  return 0;
+}
+
+int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_params_t* pr,
+                      const bigcn_opts_t* o, const float* grad_feat, const bigcn_params_t* gr,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (int rc = check_common(dm, o, "features_backward")) return rc;
+  FeatWs w = carve_features(dm, ws, ws_bytes);
+  BIGCN_CHECK_ARG(ws != nullptr && ws_bytes >= w.total, "features_backward: workspace too small");
+  const int64_t N = dm->N, B = dm->B, K = dm->K;
+  const Dirs dirs = active_dirs(o->dir_mask);
+  const int n_out = dirs.n == 2 ? 128 : 64;
+  const bool dropping = o->training && o->p_drop > 0.f;
+  const size_t nh = (size_t)(N > 0 ? N : 1) * H;
+  float* g2[2] = {w.z[0], w.z[1]};       // Z is dead after forward
+  float* t2[2] = {w.xw, w.xw + nh};      // XW is dead after forward
+  float* g1[2] = {w.z[0], w.z[1]};       // G2 is dead once T2 exists
+  float* t1cat = w.h2[0];                // H2 is dead once G2 exists
+  // 1. G2 = grad through mean and relu; db2
+  {
+    G2Args a{};
+    a.grad_feat = grad_feat; a.batch = bt->batch; a.node_ptr = w.node_ptr; a.N = N;
+    ColsumArgs c{};
+    c.nchunk = N > 0 ? cs_chunks(N) : 0;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.h2[q] = w.h2[d]; a.g2[q] = g2[d]; a.part[q] = w.cs_part[d]; a.feat_base[q] = feat_base(d);
+      c.part[q] = w.cs_part[d]; c.out[q] = gdir_b2(gr, d);
+    }
+    if (int rc = g2_launch(a, dirs.n, st)) return rc;
+    if (int rc = colsum_reduce_launch(c, dirs.n, st)) return rc;
+  }
+  // 2. T2 = A-hat^T G2
+  {
+    PropArgs a{};
+    a.N = N; a.relu = 0;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.d[q] = PropDir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, g2[d], nullptr, t2[d], H, H};
+    }
+    if (int rc = propagate_launch(a, dirs.n, st)) return rc;
+  }
+  // 3. dW2a = T2^T A1
+  {
+    OuterArgs a{};
+    OuterReduceArgs r{};
+    a.N = N; r.ld = H + K; r.nchunk = N > 0 ? op_chunks(N) : 0;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.u[q] = t2[d]; a.v[q] = w.a1[d]; a.part[q] = w.op_part[d];
+      r.part[q] = w.op_part[d]; r.dst[q] = gdir_w2(gr, d);
+    }
+    if (int rc = outer64_launch(a, r, dirs.n, st)) return rc;
+  }
+  // 4. dW2b (root part of conv2.lin)
+  {
+    if (!dropping) {
+      SegSumArgs s{};
+      s.node_ptr = w.node_ptr;
+      for (int q = 0; q < dirs.n; ++q) {
+        s.t[q] = t2[dirs.id[q]];
+        s.out[q] = w.dP[dirs.id[q]];
+      }
+      if (int rc = segsum_launch(s, B, dirs.n, st)) return rc;
+    }
+    Dw2bArgs a{};
+    a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr;
+    a.N = N; a.B = B; a.K = K; a.ld = H + K; a.node_id_base = bt->node_id_base;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), make_drop(o, d)};
+    }
+    if (int rc = dw2b_launch(a, dirs.n, st)) return rc;
+  }
+  // 5. G1 = (T2 W2a) * mask * [H1 > 0]; db1
+  {
+    BwdMixArgs a{};
+    a.N = N; a.ldw2 = H + K; a.node_id_base = bt->node_id_base;
+    ColsumArgs c{};
+    c.nchunk = N > 0 ? bm_chunks(N) : 0;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.d[q] = BwdMixDir{t2[d], w.h1[d], dir_w2(pr, d), g1[d], w.cs_part[d], make_drop(o, d)};
+      c.part[q] = w.cs_part[d]; c.out[q] = gdir_b1(gr, d);
+    }
+    if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;
+    if (int rc = colsum_reduce_launch(c, dirs.n, st)) return rc;
+  }
+  // 6. T1 = A-hat^T G1, both directions side by side in one [N][n_out] matrix
+  {
+    PropArgs a{};
+    a.N = N; a.relu = 0;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      a.d[q] = PropDir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, g1[d], nullptr, t1cat + q * H, H, n_out};
+    }
+    if (int rc = propagate_launch(a, dirs.n, st)) return rc;
+  }
+  // 7. dW1 = T1^T X, one more pass over X
+  {
+    float* da = gdir_w1(gr, dirs.id[0]);
+    float* db = dirs.n == 2 ? gdir_w1(gr, dirs.id[1]) : nullptr;
+    if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
+  }
+  return 0;
+}
+
+// ---- GCNConv on its own ------------------------------------------------------------
+struct ConvWs {
+  bigcn_graph_t g;
+  float* wT;      // [K][64]
+  float* xw;      // [N][64]  (backward: T)
+  float* cs_part;
+  float* dw_part;
+  void* prep_ws; size_t prep_bytes;
+  size_t total;
+};
+static ConvWs carve_conv(int64_t N, int64_t E, int64_t K, void* ws, size_t bytes) {
+  ConvWs w{};
+  Carver c(ws, bytes);
+  w.g.in_ptr = c.take<int32_t>(N + 1);
+  w.g.out_ptr = c.take<int32_t>(N + 1);
+  w.g.in_idx = c.take<int32_t>(E > 0 ? E : 1);
+  w.g.out_idx = c.take<int32_t>(E > 0 ? E : 1);
+  w.g.deg = c.take<int32_t>(N > 0 ? N : 1);
+  w.g.dis = c.take<float>(N > 0 ? N : 1);
+  w.g.rowsum = nullptr;
+  w.wT = c.take<float>((size_t)K * H);
+  w.xw = c.take<float>((size_t)(N > 0 ? N : 1) * H);
+  w.cs_part = c.take<float>((size_t)cs_chunks(N) * H);
+  w.dw_part = c.take<float>(dw_partial_floats(N, K, 64));
+  w.prep_bytes = graph_prep_ws_bytes(N, E, 1);
+  w.prep_ws = c.take<char>(w.prep_bytes);
+  w.total = align_up(c.off, 256);
+  return w;
+}
+
+// column sums of a [N][64] matrix: partials per CS chunk, then ordered reduce
+__global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ g, int64_t N,
+                                                     float* __restrict__ part) {
+  __shared__ float red[4][H];
+  const int gq = threadIdx.x >> 6, f = threadIdx.x & 63;
+  const int64_t base = (int64_t)blockIdx.x * 256;
+  const int64_t end = min(N, base + 256);
+  float acc = 0.f;
+  for (int64_t i = base + gq; i < end; i += 4) acc += g[i * H + f];
+  red[gq][f] = acc;
+  __syncthreads();
+  if (gq == 0) part[(int64_t)blockIdx.x * H + f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
+}
+
+}  // namespace bigcn
+
+using namespace bigcn;
+
+extern "C" const char* bigcn_last_error(void) { return g_err; }
+extern "C" int bigcn_version(void) { return 100; }
+extern "C" int bigcn_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int bigcn_xw(const float* x, int64_t N, int64_t K, const float* wt, int32_t n_out, float* y,
+                        int64_t ldy, int32_t gemm_mode, bigcn_stream_t stream) {
+  return xw_dispatch(x, N, K, wt, n_out, y, ldy, gemm_mode, (cudaStream_t)stream);
+}
+
+extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N,
+                               const float* h, int64_t ldh, const float* bias, int32_t relu, float* out,
+                               int64_t ldo, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG((ldh % 2 == 0) && (ldo % 2 == 0), "propagate: row pitches must be even");
+  PropArgs a{};
+  a.N = N; a.relu = relu;
+  a.d[0] = PropDir{ptr, idx, dis, h, bias, out, ldh, ldo};
+  return propagate_launch(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" int bigcn_dropout_mask(uint64_t seed, int32_t stream_id, int64_t node_id_base, int64_t N,
+                                  int64_t n_cols, float p, uint8_t* keep, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(p >= 0.f && p < 1.f, "dropout_mask: p must be in [0,1)");
+  bigcn_opts_t o{};
+  o.training = 1; o.p_drop = p; o.seed = seed;
+  DropSpec ds = make_drop(&o, stream_id);
+  return dropout_mask_launch(ds, node_id_base, N, n_cols, keep, (cudaStream_t)stream);
+}
+
+extern "C" size_t bigcn_features_workspace_bytes(const bigcn_dims_t* dims) {
+  if (!dims) return 0;
+  return carve_features(dims, nullptr, 0).total;
+}
+
+extern "C" int bigcn_features_forward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
+                                      const bigcn_params_t* params, const bigcn_opts_t* opts,
+                                      float* feat, int32_t* flags, void* workspace,
+                                      size_t workspace_bytes, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(batch && params && feat && flags, "features_forward: NULL argument");
+  return features_forward(dims, batch, params, opts, feat, flags, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int bigcn_features_backward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
+                                       const bigcn_params_t* params, const bigcn_opts_t* opts,
+                                       const float* grad_feat, const bigcn_params_t* grads,
+                                       void* workspace, size_t workspace_bytes,
+                                       bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(batch && params && grad_feat && grads, "features_backward: NULL argument");
+  return features_backward(dims, batch, params, opts, grad_feat, grads, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+extern "C" size_t bigcn_gcnconv_workspace_bytes(int64_t N, int64_t E, int64_t K) {
+  return carve_conv(N, E, K, nullptr, 0).total;
+}
+
+extern "C" int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const int64_t* edge_index,
+                                     int64_t E, const float* w, const float* bias, int32_t deg_by,
+                                     int32_t gemm_mode, float* out, int32_t* flags, void* workspace,
+                                     size_t workspace_bytes, bigcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BIGCN_CHECK_ARG(N >= 0 && K > 0 && E >= 0, "gcnconv_forward: bad dims");
+  ConvWs cw = carve_conv(N, E, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= cw.total, "gcnconv_forward: workspace too small");
+  const int64_t* ei[1] = {edge_index};
+  const int64_t Es[1] = {E};
+  if (int rc = graph_prep_impl(1, ei, Es, N, nullptr, 0, deg_by, &cw.g, nullptr, flags, cw.prep_ws,
+                               cw.prep_bytes, st))
+    return rc;
+  if (int rc = transpose_weight(w, K, 0, K, cw.wT, H, 0, st)) return rc;
+  if (int rc = xw_dispatch(x, N, K, cw.wT, H, cw.xw, H, gemm_mode, st)) return rc;
+  PropArgs a{};
+  a.N = N; a.relu = 0;
+  a.d[0] = PropDir{cw.g.in_ptr, cw.g.in_idx, cw.g.dis, cw.xw, bias, out, H, H};
+  return propagate_launch(a, 1, st);
+}
+
+extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int64_t E,
+                                      const float* grad_out, float* dw, float* db, void* workspace,
+                                      size_t workspace_bytes, bigcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvWs cw = carve_conv(N, E, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= cw.total, "gcnconv_backward: workspace too small");
+  // db = column sums of grad_out
+  const int nchunk = N > 0 ? cs_chunks(N) : 0;
+  if (N > 0) {
+    k_colsum_part<<<nchunk, 256, 0, st>>>(grad_out, N, cw.cs_part);
+    BIGCN_CHECK_LAUNCH("k_colsum_part");
+  }
+  ColsumArgs c{};
+  c.nchunk = nchunk; c.part[0] = cw.cs_part; c.out[0] = db;
+  if (int rc = colsum_reduce_launch(c, 1, st)) return rc;
+  // T = A-hat^T grad_out
+  PropArgs a{};
+  a.N = N; a.relu = 0;
+  a.d[0] = PropDir{cw.g.out_ptr, cw.g.out_idx, cw.g.dis, grad_out, nullptr, cw.xw, H, H};
+  if (int rc = propagate_launch(a, 1, st)) return rc;
+  // dw = T^T x
+  return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);
+}

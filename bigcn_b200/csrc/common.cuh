@@ -1,0 +1,125 @@
+// Shared device helpers for libbigcn_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bigcn_b200.h"
+
+#define H BIGCN_H
+#define FULL_MASK 0xffffffffu
+
+namespace bigcn {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+#define BIGCN_CHECK_ARG(cond, ...)          \
+  do {                                      \
+    if (!(cond)) {                          \
+      bigcn::set_error(__VA_ARGS__);        \
+      return 1;                             \
+    }                                       \
+  } while (0)
+
+#define BIGCN_CHECK_LAUNCH(name)                                                        \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) {                                                           \
+      bigcn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));         \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace (256 B aligned slices).
+struct Carver {
+  char* base;
+  size_t off = 0;
+  size_t cap;
+  Carver(void* p, size_t bytes) : base(reinterpret_cast<char*>(p)), cap(bytes) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+    off += n * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// ---------------------------------------------------------------- device side
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al. SC'11); spec mirrored by oracle/gcn_oracle.py.
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// Dropout spec: keep[node, col] = philox(ctr=(col>>2, node_lo, node_hi, stream), key=seed)[col&3] >= thresh
+struct DropSpec {
+  uint32_t k0, k1;     // seed
+  uint32_t thresh;     // round(p * 2^32)
+  uint32_t stream;     // 0 TD, 1 BU
+  float scale;         // 1/(1-p)
+  int32_t on;          // training
+};
+__device__ __forceinline__ Philox4 drop_block(const DropSpec& d, int64_t node, uint32_t col_block) {
+  return philox4x32_10(col_block, (uint32_t)(node & 0xffffffffll), (uint32_t)((uint64_t)node >> 32),
+                       d.stream, d.k0, d.k1);
+}
+__device__ __forceinline__ uint32_t philox_elem(const Philox4& r, int e) {
+  return e == 0 ? r.x : (e == 1 ? r.y : (e == 2 ? r.z : r.w));
+}
+
+static inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  double r = t + 0.5;
+  // round-half-even to mirror Python round()
+  double f = (double)(uint64_t)r;
+  if (r == f && ((uint64_t)f & 1ull) && (t - (double)(uint64_t)t) == 0.5) f -= 1.0;
+  if (f < 0) f = 0;
+  if (f > 4294967295.0) f = 4294967295.0;
+  return (uint32_t)f;
+}
+static inline DropSpec make_drop(const bigcn_opts_t* o, int stream_id) {
+  DropSpec d;
+  d.k0 = (uint32_t)(o->seed & 0xffffffffull);
+  d.k1 = (uint32_t)(o->seed >> 32);
+  d.thresh = drop_threshold(o->p_drop);
+  d.stream = (uint32_t)stream_id;
+  d.scale = 1.0f / (1.0f - o->p_drop);
+  d.on = o->training && o->p_drop > 0.f;
+  return d;
+}
+
+}  // namespace bigcn

@@ -1,0 +1,185 @@
+// Head (fc + log_softmax), nll loss and Adam: the small fp32 pieces around the path.
+// Replaces BiGCN_Twitter.py:129-130 (fc, log_softmax), :184 (F.nll_loss) and the
+// torch.optim.Adam step configured at :146-153.
+#include "common.cuh"
+
+namespace bigcn {
+
+constexpr int FEAT = 4 * H;  // 256 = (out_feats + hid_feats) * 2
+
+// warp per tree; lane c holds logit c (C <= 32)
+__global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ feat, int64_t B, int C,
+                                                  const float* __restrict__ W,
+                                                  const float* __restrict__ bias,
+                                                  float* __restrict__ logp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float fv[FEAT / 32];
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) fv[j] = feat[b * FEAT + j * 32 + lane];
+  float mine = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    float p = 0.f;
+#pragma unroll
+    for (int j = 0; j < FEAT / 32; ++j) p = fmaf(fv[j], W[c * FEAT + j * 32 + lane], p);
+    p = warp_sum(p) + bias[c];
+    if (lane == c) mine = p;
+  }
+  float m = mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+  const float ex = lane < C ? expf(mine - m) : 0.f;
+  const float se = warp_sum(ex);
+  if (lane < C) logp[b * C + lane] = (mine - m) - logf(se);
+}
+
+// grad_feat[b][f] = sum_c dl[b][c] W[c][f],  dl = g - exp(logp) * sum_c g  (log_softmax backward)
+__global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__ g,
+                                                       const float* __restrict__ logp, int64_t B,
+                                                       int C, const float* __restrict__ W,
+                                                       float* __restrict__ gfeat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float gv = lane < C ? g[b * C + lane] : 0.f;
+  const float sg = warp_sum(gv);
+  const float dl = lane < C ? gv - expf(logp[b * C + lane]) * sg : 0.f;
+  float out[FEAT / 32];
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) out[j] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = __shfl_sync(FULL_MASK, dl, c);
+#pragma unroll
+    for (int j = 0; j < FEAT / 32; ++j) out[j] = fmaf(d, W[c * FEAT + j * 32 + lane], out[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
+}
+
+// thread per (c, f) [+ bias column f == 256]; trees in order
+__global__ void k_head_bwd_w(const float* __restrict__ g, const float* __restrict__ logp,
+                             const float* __restrict__ feat, int64_t B, int C,
+                             float* __restrict__ dW, float* __restrict__ db) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * (FEAT + 1)) return;
+  const int c = idx / (FEAT + 1), f = idx % (FEAT + 1);
+  float acc = 0.f;
+  for (int64_t b = 0; b < B; ++b) {
+    float sg = 0.f;
+    for (int q = 0; q < C; ++q) sg += g[b * C + q];
+    const float dl = g[b * C + c] - expf(logp[b * C + c]) * sg;
+    acc = fmaf(dl, f < FEAT ? feat[b * FEAT + f] : 1.f, acc);
+  }
+  if (f < FEAT) dW[c * FEAT + f] = acc;
+  else db[c] = acc;
+}
+
+// loss = -(1/Bg) sum_b logp[b][y_b]; grad[b][c] = -(1/Bg) [c == y_b]   (single CTA, trees in order)
+__global__ void __launch_bounds__(256) k_nll(const float* __restrict__ logp,
+                                             const int64_t* __restrict__ y, int64_t B, int C,
+                                             float inv_bg, float* loss, float* grad) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += 256) {
+    const int64_t t = y[b];
+    if (t >= 0 && t < C) acc -= logp[b * C + t];
+    if (grad)
+      for (int c = 0; c < C; ++c) grad[b * C + c] = (c == t) ? -inv_bg : 0.f;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss) *loss = red[0] * inv_bg;
+}
+
+// torch.optim.Adam, single-tensor form (coupled L2 weight decay, no amsgrad)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, int64_t n, const int64_t* __restrict__ seg_end,
+                       const float* __restrict__ seg_lr, int n_seg, double beta1d, double beta2d,
+                       float eps, float wd, float gscale, const int64_t* step_count) {
+  const double step = (double)(*step_count + 1);
+  const float bc1 = (float)(1.0 - pow(beta1d, step));
+  const float bc2s = (float)sqrt(1.0 - pow(beta2d, step));
+  const float beta2 = (float)beta2d;
+  const float omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float lr = seg_lr[n_seg - 1];
+    for (int s = 0; s < n_seg; ++s)
+      if (i < seg_end[s]) {
+        lr = seg_lr[s];
+        break;
+      }
+    const float pv = p[i];
+    const float gr = fmaf(wd, pv, g[i] * gscale);
+    const float mi = m[i] + (gr - m[i]) * omb1;
+    const float vi = v[i] * beta2 + omb2 * (gr * gr);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    p[i] = pv - (lr / bc1) * (mi / denom);
+  }
+}
+__global__ void k_step_inc(int64_t* step_count) { *step_count += 1; }
+
+}  // namespace bigcn
+
+using namespace bigcn;
+
+extern "C" int bigcn_head_forward(const float* feat, int64_t B, int64_t C, const float* fc_w,
+                                  const float* fc_b, float* logp, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(C >= 1 && C <= 32, "head_forward: C must be in [1,32]");
+  if (B == 0) return 0;
+  k_head_fwd<<<(int)ceil_div(B, 8), 256, 0, (cudaStream_t)stream>>>(feat, B, (int)C, fc_w, fc_b, logp);
+  BIGCN_CHECK_LAUNCH("k_head_fwd");
+  return 0;
+}
+
+extern "C" int bigcn_head_backward(const float* grad_logp, const float* logp, const float* feat,
+                                   int64_t B, int64_t C, const float* fc_w, float* grad_feat,
+                                   float* d_fc_w, float* d_fc_b, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(C >= 1 && C <= 32, "head_backward: C must be in [1,32]");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0 && grad_feat) {
+    k_head_bwd_feat<<<(int)ceil_div(B, 8), 256, 0, st>>>(grad_logp, logp, B, (int)C, fc_w, grad_feat);
+    BIGCN_CHECK_LAUNCH("k_head_bwd_feat");
+  }
+  if (d_fc_w) {
+    const int tot = (int)C * (FEAT + 1);
+    k_head_bwd_w<<<(tot + 127) / 128, 128, 0, st>>>(grad_logp, logp, feat, B, (int)C, d_fc_w, d_fc_b);
+    BIGCN_CHECK_LAUNCH("k_head_bwd_w");
+  }
+  return 0;
+}
+
+extern "C" int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C,
+                              int64_t B_global, float* loss, float* grad_logp,
+                              bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(B_global > 0, "nll_loss: B_global must be positive");
+  k_nll<<<1, 256, 0, (cudaStream_t)stream>>>(logp, y, B, (int)C, 1.0f / (float)B_global, loss, grad_logp);
+  BIGCN_CHECK_LAUNCH("k_nll");
+  return 0;
+}
+
+extern "C" int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                               int64_t n, const int64_t* seg_end, const float* seg_lr, int32_t n_seg,
+                               double beta1, double beta2, double eps, double weight_decay,
+                               double grad_scale, int64_t* step_count, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(n_seg >= 1, "adam_step: need at least one lr segment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    int blocks = (int)ceil_div(n, 256);
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    k_adam<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, seg_end, seg_lr, n_seg, beta1,
+                                   beta2, (float)eps, (float)weight_decay, (float)grad_scale, step_count);
+    BIGCN_CHECK_LAUNCH("k_adam");
+  }
+  k_step_inc<<<1, 1, 0, st>>>(step_count);
+  BIGCN_CHECK_LAUNCH("k_step_inc");
+  return 0;
+}

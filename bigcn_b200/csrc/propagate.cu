@@ -1,0 +1,590 @@
+// Propagate, conv2 input mix, readout and their backward kernels.
+//
+// Replaces, per direction (BiGCN_Twitter.py:26-67 / 77-114):
+//   MessagePassing.propagate + bias [torch_geometric]        -> k_propagate / k_prop1_mix
+//   root-extend loops, cat, relu, dropout (:45-54)             -> k_root_nz, k_root_proj, k_prop1_mix
+//   conv2.lin on the [h1 | root_extend] tensor (:56)           -> k_prop1_mix (never materialises N x 5064)
+//   second root-extend + scatter_mean (:58-65)                 -> k_readout
+// All kernels are warp-per-row over 64-wide fp32 rows (float2 per lane, 256 B coalesced),
+// gather through the int32 CSR built by graph_prep, sum in COO' order with separate
+// multiply and add (bit-identical to the CPU index_add_ order), and use no atomics.
+#include "kernels.cuh"
+
+namespace bigcn {
+
+// ---------------------------------------------------------------- A-hat row gather
+// acc = sum_{e in row} (dis[src]*dis[i]) * h[src]  (edge order)  + (dis[i]*dis[i]) * h[i]
+__device__ __forceinline__ float2 gather_row(const int32_t* __restrict__ ptr,
+                                             const int32_t* __restrict__ idx,
+                                             const float* __restrict__ dis,
+                                             const float* __restrict__ h, int64_t ldh, int64_t i,
+                                             int lane) {
+  const int s = ptr[i], e = ptr[i + 1];
+  const float di = dis[i];
+  float2 acc = make_float2(0.f, 0.f);
+  for (int b = s; b < e; b += 32) {
+    const int n = min(32, e - b);
+    int j = 0;
+    float dj = 0.f;
+    if (lane < n) {
+      j = idx[b + lane];
+      dj = dis[j];
+    }
+    int l = 0;
+    for (; l + 4 <= n; l += 4) {
+      float2 hv[4];
+      float w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jj = __shfl_sync(FULL_MASK, j, l + q);
+        w[q] = __fmul_rn(__shfl_sync(FULL_MASK, dj, l + q), di);
+        hv[q] = *reinterpret_cast<const float2*>(h + (int64_t)jj * ldh + 2 * lane);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(w[q], hv[q].x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(w[q], hv[q].y));
+      }
+    }
+    for (; l < n; ++l) {
+      const int jj = __shfl_sync(FULL_MASK, j, l);
+      const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l), di);
+      const float2 hv = *reinterpret_cast<const float2*>(h + (int64_t)jj * ldh + 2 * lane);
+      acc.x = __fadd_rn(acc.x, __fmul_rn(w, hv.x));
+      acc.y = __fadd_rn(acc.y, __fmul_rn(w, hv.y));
+    }
+  }
+  const float ws = __fmul_rn(di, di);
+  const float2 hs = *reinterpret_cast<const float2*>(h + i * ldh + 2 * lane);
+  acc.x = __fadd_rn(acc.x, __fmul_rn(ws, hs.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(ws, hs.y));
+  return acc;
+}
+
+
+__global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
+  const PropDir& p = a.d[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float2 b = make_float2(0.f, 0.f);
+  if (p.bias) b = *reinterpret_cast<const float2*>(p.bias + 2 * lane);
+  for (int64_t i = warp0; i < a.N; i += nwarp) {
+    float2 acc = gather_row(p.ptr, p.idx, p.dis, p.h, p.ldh, i, lane);
+    if (p.bias) {
+      acc.x = __fadd_rn(acc.x, b.x);
+      acc.y = __fadd_rn(acc.y, b.y);
+    }
+    if (a.relu) {
+      acc.x = fmaxf(acc.x, 0.f);
+      acc.y = fmaxf(acc.y, 0.f);
+    }
+    *reinterpret_cast<float2*>(p.out + i * p.ldo + 2 * lane) = acc;
+  }
+}
+
+static int row_blocks(int64_t N) {
+  int64_t blocks = ceil_div(N, 8);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int propagate_launch(const PropArgs& a, int ndir, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  k_propagate<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_propagate");
+  return 0;
+}
+
+// ---------------------------------------------------------------- root non-zeros
+// Per tree: the columns k with relu(x[root,k]) > 0, ascending, and their values.
+// (root_extend of BiGCN_Twitter.py:45-50 is x1[rootindex[batch]]: only these columns
+// can contribute to conv2 after the relu of :53.)
+__global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= a.B) return;
+  const int64_t r = a.rootindex[b];
+  if (r < 0 || r >= a.N) {
+    if (lane == 0) {
+      atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+      a.cnt[b] = 0;
+    }
+    return;
+  }
+  const float* xr = a.x + r * a.K;
+  int base = 0;
+  for (int64_t k0 = 0; k0 < a.K; k0 += 32) {
+    const int64_t k = k0 + lane;
+    const float v = k < a.K ? xr[k] : 0.f;
+    const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
+    if (v > 0.f) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      a.col[b * a.K + pos] = (int32_t)k;
+      a.val[b * a.K + pos] = v;
+    }
+    base += __popc(m);
+  }
+  if (lane == 0) a.cnt[b] = base;
+}
+
+// eval mode: P[d][b][:] = relu(x_root[b]) * W2b_d^T, once per tree
+__global__ void __launch_bounds__(256) k_root_proj(RootProjArgs a) {
+  const int d = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= a.B) return;
+  const int n = a.cnt[b];
+  float2 acc = make_float2(0.f, 0.f);
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int t = t0 + lane;
+    int k = 0;
+    float v = 0.f;
+    if (t < n) {
+      k = a.col[b * a.K + t];
+      v = a.val[b * a.K + t];
+    }
+    const int m = min(32, n - t0);
+    for (int l = 0; l < m; ++l) {
+      const int kk = __shfl_sync(FULL_MASK, k, l);
+      const float vv = __shfl_sync(FULL_MASK, v, l);
+      const float2 w = *reinterpret_cast<const float2*>(a.w2bT[d] + (int64_t)kk * H + 2 * lane);
+      acc.x = fmaf(vv, w.x, acc.x);
+      acc.y = fmaf(vv, w.y, acc.y);
+    }
+  }
+  *reinterpret_cast<float2*>(a.P[d] + b * H + 2 * lane) = acc;
+}
+
+// ---------------------------------------------------------------- conv1 propagate + conv2 input
+// Per node i and direction d:
+//   h1 = A-hat (XW1)[i] + b1                      (:42)    -> H1 (pre-relu, kept for :44 and backward)
+//   a1 = dropout(relu(h1))                        (:53-54) -> A1 (kept for dW2a)
+//   z  = a1 W2a^T + dropout(relu(x_root[b_i])) W2b^T   (:51-56, the lin of conv2 on the cat)
+// The root part touches only the non-zero root columns (k_root_nz); one Philox block per
+// lane decides which of them survive for this node.
+
+__device__ __forceinline__ void drop_pair(const DropSpec& ds, int64_t node, int lane, float2& a) {
+  // lane holds columns 2*lane, 2*lane+1 -> Philox block lane>>1, elements (lane&1)*2 + {0,1}
+  const Philox4 r = drop_block(ds, node, (uint32_t)(lane >> 1));
+  const uint32_t r0 = (lane & 1) ? r.z : r.x;
+  const uint32_t r1 = (lane & 1) ? r.w : r.y;
+  a.x = r0 >= ds.thresh ? __fmul_rn(a.x, ds.scale) : 0.f;
+  a.y = r1 >= ds.thresh ? __fmul_rn(a.y, ds.scale) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
+  __shared__ float sW[H * H];
+  const MixDir& p = a.d[blockIdx.y];
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2aT[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float2 b1 = *reinterpret_cast<const float2*>(p.b1 + 2 * lane);
+  for (int64_t i = warp0; i < a.N; i += nwarp) {
+    float2 h1 = gather_row(p.ptr, p.idx, p.dis, p.xw, a.ldxw, i, lane);
+    h1.x = __fadd_rn(h1.x, b1.x);
+    h1.y = __fadd_rn(h1.y, b1.y);
+    *reinterpret_cast<float2*>(p.h1 + i * H + 2 * lane) = h1;
+    float2 av = make_float2(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f));
+    const int64_t node = a.node_id_base + i;
+    if (p.drop.on) drop_pair(p.drop, node, lane, av);
+    *reinterpret_cast<float2*>(p.a1 + i * H + 2 * lane) = av;
+    float2 z = make_float2(0.f, 0.f);
+#pragma unroll 16
+    for (int k = 0; k < H; ++k) {
+      const float s = __shfl_sync(FULL_MASK, (k & 1) ? av.y : av.x, k >> 1);
+      const float2 w = *reinterpret_cast<const float2*>(sW + k * H + 2 * lane);
+      z.x = fmaf(s, w.x, z.x);
+      z.y = fmaf(s, w.y, z.y);
+    }
+    const int64_t b = a.batch[i];
+    if (p.drop.on) {
+      const int n = a.rnz_cnt[b];
+      float2 racc = make_float2(0.f, 0.f);
+      for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        int k = 0;
+        float v = 0.f;
+        bool keep = false;
+        if (t < n) {
+          k = a.rnz_col[b * a.K + t];
+          v = a.rnz_val[b * a.K + t];
+          const uint32_t c = (uint32_t)(H + k);
+          const Philox4 r = drop_block(p.drop, node, c >> 2);
+          keep = philox_elem(r, c & 3) >= p.drop.thresh;
+        }
+        unsigned m = __ballot_sync(FULL_MASK, keep);
+        while (m) {
+          const int sl = __ffs(m) - 1;
+          m &= m - 1;
+          const int kk = __shfl_sync(FULL_MASK, k, sl);
+          const float vv = __shfl_sync(FULL_MASK, v, sl);
+          const float2 w = *reinterpret_cast<const float2*>(p.w2bT + (int64_t)kk * H + 2 * lane);
+          racc.x = fmaf(vv, w.x, racc.x);
+          racc.y = fmaf(vv, w.y, racc.y);
+        }
+      }
+      z.x = fmaf(p.drop.scale, racc.x, z.x);
+      z.y = fmaf(p.drop.scale, racc.y, z.y);
+    } else {
+      const float2 pv = *reinterpret_cast<const float2*>(p.P + b * H + 2 * lane);
+      z.x += pv.x;
+      z.y += pv.y;
+    }
+    *reinterpret_cast<float2*>(p.z + i * H + 2 * lane) = z;
+  }
+}
+
+// ---------------------------------------------------------------- readout
+// feat[b, base_d + f]      = mean_{i in tree b} H2_d[i, f]           (scatter_mean, :65)
+// feat[b, base_d + 64 + f] = H1_d[rootindex[b], f]                   (:58-63; the mean of n_b
+//                            identical rows, taken as the row itself)
+// CTA per tree: 4 row-lanes x 64 features per direction, fixed-order combine.
+__global__ void __launch_bounds__(512) k_readout(ReadoutArgs a) {
+  __shared__ float part[2][4][H];
+  const int64_t b = blockIdx.x;
+  const int d = threadIdx.x >> 8, g = (threadIdx.x >> 6) & 3, f = threadIdx.x & 63;
+  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+  float acc = 0.f;
+  if (d < a.ndir) {
+    const float* h2 = a.h2[d];
+    int i = s + g;
+    for (; i + 12 < e; i += 16) {
+      const float v0 = h2[(int64_t)i * H + f], v1 = h2[(int64_t)(i + 4) * H + f];
+      const float v2 = h2[(int64_t)(i + 8) * H + f], v3 = h2[(int64_t)(i + 12) * H + f];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; i < e; i += 4) acc += h2[(int64_t)i * H + f];
+    part[d][g][f] = acc;
+  }
+  __syncthreads();
+  if (d < a.ndir && g == 0) {
+    const float sum = ((part[d][0][f] + part[d][1][f]) + part[d][2][f]) + part[d][3][f];
+    const int n = e - s;
+    float* fr = a.feat + b * 4 * H + a.feat_base[d];
+    fr[f] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
+    float rv = 0.f;
+    if (n > 0) {
+      const int64_t r = a.rootindex[b];
+      if (r >= 0 && r < a.N) rv = a.h1[d][r * H + f];
+      else if (f == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+    }
+    fr[H + f] = rv;
+  }
+}
+
+// ---------------------------------------------------------------- backward pieces
+// G2[d][i][f] = grad_feat[b_i][base_d + f] / n_b * [H2 > 0]; partial column sums for db2
+__global__ void __launch_bounds__(256) k_g2(G2Args a) {
+  __shared__ float red[4][H];
+  const int d = blockIdx.y;
+  const int g = threadIdx.x >> 6, f = threadIdx.x & 63;
+  const int64_t base = (int64_t)blockIdx.x * CS_ROWS;
+  const int64_t end = min(a.N, base + CS_ROWS);
+  float acc = 0.f;
+  for (int64_t i = base + g; i < end; i += 4) {
+    const int64_t b = a.batch[i];
+    const int n = a.node_ptr[b + 1] - a.node_ptr[b];
+    float gv = __fdiv_rn(a.grad_feat[b * 4 * H + a.feat_base[d] + f], (float)(n > 0 ? n : 1));
+    gv = a.h2[d][i * H + f] > 0.f ? gv : 0.f;
+    a.g2[d][i * H + f] = gv;
+    acc += gv;
+  }
+  red[g][f] = acc;
+  __syncthreads();
+  if (g == 0) a.part[d][(int64_t)blockIdx.x * H + f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
+}
+
+// out[f] = sum_chunk part[chunk][f], chunks in order
+__global__ void k_colsum_reduce(ColsumArgs a) {
+  const int j = blockIdx.x;
+  const int f = threadIdx.x;
+  float s = 0.f;
+  for (int c = 0; c < a.nchunk; ++c) s += a.part[j][(int64_t)c * H + f];
+  a.out[j][f] = s;
+}
+
+// G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1
+__global__ void __launch_bounds__(256) k_bwd_mix(BwdMixArgs a) {
+  __shared__ float sW[H * H];
+  __shared__ float red[8][H];
+  const BwdMixDir& p = a.d[blockIdx.y];
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2[(int64_t)(i >> 6) * a.ldw2 + (i & 63)];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * BM_ROWS + w * 16;
+  float2 cs = make_float2(0.f, 0.f);
+  for (int r = 0; r < 16; ++r) {
+    const int64_t i = base + r;
+    if (i >= a.N) break;
+    const float2 t = *reinterpret_cast<const float2*>(p.t2 + i * H + 2 * lane);
+    float2 g = make_float2(0.f, 0.f);
+#pragma unroll 16
+    for (int o = 0; o < H; ++o) {
+      const float s = __shfl_sync(FULL_MASK, (o & 1) ? t.y : t.x, o >> 1);
+      const float2 wv = *reinterpret_cast<const float2*>(sW + o * H + 2 * lane);
+      g.x = fmaf(s, wv.x, g.x);
+      g.y = fmaf(s, wv.y, g.y);
+    }
+    if (p.drop.on) drop_pair(p.drop, a.node_id_base + i, lane, g);
+    const float2 h = *reinterpret_cast<const float2*>(p.h1 + i * H + 2 * lane);
+    g.x = h.x > 0.f ? g.x : 0.f;
+    g.y = h.y > 0.f ? g.y : 0.f;
+    *reinterpret_cast<float2*>(p.g1 + i * H + 2 * lane) = g;
+    cs.x += g.x;
+    cs.y += g.y;
+  }
+  red[w][2 * lane] = cs.x;
+  red[w][2 * lane + 1] = cs.y;
+  __syncthreads();
+  if (threadIdx.x < H) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x];
+    p.part[(int64_t)blockIdx.x * H + threadIdx.x] = s;
+  }
+}
+
+// C[o][k] = sum_i U[i][o] * V[i][k]  (64 x 64), rows chunked; partial[chunk][64*64]
+__global__ void __launch_bounds__(256) k_outer64(OuterArgs a) {
+  __shared__ __align__(16) float sU[64][H];
+  __shared__ __align__(16) float sV[64][H];
+  const int d = blockIdx.y;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int64_t base = (int64_t)blockIdx.x * OP_ROWS;
+  const int64_t end = min(a.N, base + OP_ROWS);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t r0 = base; r0 < end; r0 += 64) {
+    const int nr = (int)min((int64_t)64, end - r0);
+    for (int i = threadIdx.x; i < 64 * H / 4; i += 256) {
+      const int r = i >> 4, c4 = i & 15;
+      float4 uv = make_float4(0.f, 0.f, 0.f, 0.f), vv = uv;
+      if (r < nr) {
+        uv = *reinterpret_cast<const float4*>(a.u[d] + (r0 + r) * H + c4 * 4);
+        vv = *reinterpret_cast<const float4*>(a.v[d] + (r0 + r) * H + c4 * 4);
+      }
+      *reinterpret_cast<float4*>(&sU[r][c4 * 4]) = uv;
+      *reinterpret_cast<float4*>(&sV[r][c4 * 4]) = vv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) {
+      const float4 u4 = *reinterpret_cast<const float4*>(&sU[r][ty * 4]);
+      const float4 v4 = *reinterpret_cast<const float4*>(&sV[r][tx * 4]);
+      const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = a.part[d] + (int64_t)blockIdx.x * H * H;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(out + (ty * 4 + i) * H + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+// dst[o*ld + k] = sum_chunk part[chunk][o*64 + k]
+__global__ void k_outer_reduce(OuterReduceArgs a) {
+  const int d = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 0..4095
+  float s = 0.f;
+  for (int c = 0; c < a.nchunk; ++c) s += a.part[d][(int64_t)c * H * H + idx];
+  a.dst[d][(int64_t)(idx >> 6) * a.ld + (idx & 63)] = s;
+}
+
+// per-tree segment sum: dP[d][b][f] = sum_{i in b} T2_d[i][f]   (eval-mode dW2b)
+__global__ void __launch_bounds__(256) k_segsum(SegSumArgs a) {
+  __shared__ float part[4][H];
+  const int d = blockIdx.y;
+  const int64_t b = blockIdx.x;
+  const int g = threadIdx.x >> 6, f = threadIdx.x & 63;
+  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+  float acc = 0.f;
+  for (int i = s + g; i < e; i += 4) acc += a.t[d][(int64_t)i * H + f];
+  part[g][f] = acc;
+  __syncthreads();
+  if (g == 0) a.out[d][b * H + f] = ((part[0][f] + part[1][f]) + part[2][f]) + part[3][f];
+}
+
+// dW2[o][64 + k] for one column k per CTA (4 warps):
+//   train: scale * sum_b relu(x_root_b[k]) * sum_{i in b} keep(i, 64+k) * T2[i][o]
+//   eval : sum_b relu(x_root_b[k]) * dP[b][o]
+// Trees ascending, rows ascending inside a warp's strip, warps combined in order.
+__global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
+  __shared__ float red[4][H];
+  __shared__ int s_hit_b[128];
+  __shared__ float s_hit_v[128];
+  __shared__ int s_nhit;
+  const Dw2bDir& p = a.d[blockIdx.y];
+  const int64_t k = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float2 acc = make_float2(0.f, 0.f);
+  const uint32_t c = (uint32_t)(H + k);
+  for (int64_t b0 = 0; b0 < a.B; b0 += 128) {
+    // ordered hit list of this group of 128 trees (warp 0 compacts in tree order)
+    __syncthreads();
+    if (w == 0) {
+      int n = 0;
+      for (int q = 0; q < 4; ++q) {
+        const int64_t b = b0 + q * 32 + lane;
+        float v = 0.f;
+        if (b < a.B) {
+          const int64_t r = a.rootindex[b];
+          if (r >= 0 && r < a.N) v = a.x[r * a.K + k];
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
+        if (v > 0.f) {
+          const int pos = n + __popc(m & ((1u << lane) - 1u));
+          s_hit_b[pos] = (int)b;
+          s_hit_v[pos] = v;
+        }
+        n += __popc(m);
+      }
+      if (lane == 0) s_nhit = n;
+    }
+    __syncthreads();
+    const int nhit = s_nhit;
+    for (int hI = 0; hI < nhit; ++hI) {
+      const int b = s_hit_b[hI];
+      const float v = s_hit_v[hI];
+      if (p.drop.on) {
+        const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+        float2 sub = make_float2(0.f, 0.f);
+        for (int i0 = s + w * 32; i0 < e; i0 += 128) {
+          const int i = i0 + lane;
+          bool keep = false;
+          if (i < e) {
+            const Philox4 r = drop_block(p.drop, a.node_id_base + i, c >> 2);
+            keep = philox_elem(r, c & 3) >= p.drop.thresh;
+          }
+          unsigned m = __ballot_sync(FULL_MASK, keep);
+          while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float2 t = *reinterpret_cast<const float2*>(p.t2 + (int64_t)(i0 + sl) * H + 2 * lane);
+            sub.x += t.x;
+            sub.y += t.y;
+          }
+        }
+        acc.x = fmaf(v, sub.x, acc.x);
+        acc.y = fmaf(v, sub.y, acc.y);
+      } else if (w == 0) {
+        const float2 t = *reinterpret_cast<const float2*>(p.dP + (int64_t)b * H + 2 * lane);
+        acc.x = fmaf(v, t.x, acc.x);
+        acc.y = fmaf(v, t.y, acc.y);
+      }
+    }
+  }
+  red[w][2 * lane] = acc.x;
+  red[w][2 * lane + 1] = acc.y;
+  __syncthreads();
+  if (threadIdx.x < H) {
+    const float s = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+    p.dw2[(int64_t)threadIdx.x * a.ld + H + k] = p.drop.on ? s * p.drop.scale : s;
+  }
+}
+
+// ---------------------------------------------------------------- dropout mask materialisation (tests)
+__global__ void k_dropout_mask(DropSpec ds, int64_t node_id_base, int64_t N, int64_t n_cols,
+                               uint8_t* keep) {
+  const int64_t nblk = (n_cols + 3) / 4;
+  const int64_t tot = N * nblk;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / nblk, blk = t % nblk;
+    const Philox4 r = drop_block(ds, node_id_base + i, (uint32_t)blk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t c = blk * 4 + e;
+      if (c < n_cols) keep[i * n_cols + c] = philox_elem(r, e) >= ds.thresh ? 1 : 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host-side launchers
+int root_nz_launch(const RootNzArgs& a, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  k_root_nz<<<(int)ceil_div(a.B, 8), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_root_nz");
+  return 0;
+}
+int root_proj_launch(const RootProjArgs& a, int ndir, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  k_root_proj<<<dim3((int)ceil_div(a.B, 8), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_root_proj");
+  return 0;
+}
+int prop1_mix_launch(const MixArgs& a, int ndir, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  k_prop1_mix<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_prop1_mix");
+  return 0;
+}
+int readout_launch(const ReadoutArgs& a, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  k_readout<<<(int)a.B, 512, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_readout");
+  return 0;
+}
+int cs_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, CS_ROWS); }
+int bm_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, BM_ROWS); }
+int op_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, OP_ROWS); }
+
+int g2_launch(const G2Args& a, int ndir, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  k_g2<<<dim3(cs_chunks(a.N), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_g2");
+  return 0;
+}
+int colsum_reduce_launch(const ColsumArgs& a, int njobs, cudaStream_t st) {
+  k_colsum_reduce<<<njobs, H, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_colsum_reduce");
+  return 0;
+}
+int bwd_mix_launch(const BwdMixArgs& a, int ndir, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  k_bwd_mix<<<dim3(bm_chunks(a.N), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_bwd_mix");
+  return 0;
+}
+int outer64_launch(const OuterArgs& a, const OuterReduceArgs& r, int ndir, cudaStream_t st) {
+  if (a.N > 0) {
+    k_outer64<<<dim3(op_chunks(a.N), ndir), 256, 0, st>>>(a);
+    BIGCN_CHECK_LAUNCH("k_outer64");
+  }
+  k_outer_reduce<<<dim3(H * H / 256, ndir), 256, 0, st>>>(r);
+  BIGCN_CHECK_LAUNCH("k_outer_reduce");
+  return 0;
+}
+int segsum_launch(const SegSumArgs& a, int64_t B, int ndir, cudaStream_t st) {
+  if (B == 0) return 0;
+  k_segsum<<<dim3((int)B, ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_segsum");
+  return 0;
+}
+int dw2b_launch(const Dw2bArgs& a, int ndir, cudaStream_t st) {
+  if (a.K == 0) return 0;
+  k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_dw2b");
+  return 0;
+}
+int dropout_mask_launch(const DropSpec& ds, int64_t base, int64_t N, int64_t n_cols, uint8_t* keep,
+                        cudaStream_t st) {
+  if (N == 0 || n_cols == 0) return 0;
+  k_dropout_mask<<<num_sms() * 4, 256, 0, st>>>(ds, base, N, n_cols, keep);
+  BIGCN_CHECK_LAUNCH("k_dropout_mask");
+  return 0;
+}
+
+}  // namespace bigcn

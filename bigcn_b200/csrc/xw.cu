@@ -1,0 +1,321 @@
+// X * W^T and its weight-gradient X^T * T, exact-fp32 streaming path.
+//
+// Replaces GCNConv.lin (cuBLAS SGEMM) at BiGCN_Twitter.py:42,92 and the autograd
+// transpose of it (dW1 = T1^T X).  X is the 5000-wide
+// bag-of-words matrix (~99.7 % zeros, small integer counts): both kernels are pure
+// HBM streams over X -- every 32 B sector of X is read exactly once -- that do
+// FFMA work only for the non-zero entries they meet, in a fixed order (no atomics),
+// so results are exact fp32 sums and bit-reproducible.  Dense inputs stay correct
+// (every entry then takes the FFMA branch); the tcgen05 kind::tf32 GEMM in
+// gemm_tc.cu is the path for those.
+#include "common.cuh"
+
+namespace bigcn {
+
+// ------------------------------------------------------------------ y = x * wt
+// warp per row; lane loads float4 strips of the row (512 B per warp-load, XW_U loads
+// in flight), ballots the non-zeros and accumulates val * wt[k, :] (n_out floats,
+// L1/L2 resident) into n_out/32 registers per lane.
+constexpr int XW_U = 8;
+
+template <int NOUT, bool VEC4>
+__global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, int64_t N, int64_t K,
+                                                 const float* __restrict__ wt,
+                                                 float* __restrict__ y, int64_t ldy) {
+  constexpr int V = NOUT / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < N; row += nwarp) {
+    const float* xr = x + row * K;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int64_t k0 = 0; k0 < K; k0 += 128 * XW_U) {
+      float4 v[XW_U];
+#pragma unroll
+      for (int u = 0; u < XW_U; ++u) {
+        const int64_t kk = k0 + u * 128 + lane * 4;
+        if (VEC4) {
+          v[u] = kk < K ? ldg_stream_f4(xr + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          v[u].x = kk + 0 < K ? __ldg(xr + kk + 0) : 0.f;
+          v[u].y = kk + 1 < K ? __ldg(xr + kk + 1) : 0.f;
+          v[u].z = kk + 2 < K ? __ldg(xr + kk + 2) : 0.f;
+          v[u].w = kk + 3 < K ? __ldg(xr + kk + 3) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < XW_U; ++u) {
+        const bool any = (v[u].x != 0.f) | (v[u].y != 0.f) | (v[u].z != 0.f) | (v[u].w != 0.f);
+        if (__ballot_sync(FULL_MASK, any) == 0u) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float comp = c == 0 ? v[u].x : (c == 1 ? v[u].y : (c == 2 ? v[u].z : v[u].w));
+          unsigned m = __ballot_sync(FULL_MASK, comp != 0.f);
+          while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float val = __shfl_sync(FULL_MASK, comp, sl);
+            const int64_t k = k0 + u * 128 + sl * 4 + c;
+            const float* wr = wt + k * NOUT + lane * V;
+            if (V == 4) {
+              const float4 w = *reinterpret_cast<const float4*>(wr);
+              acc[0] = fmaf(val, w.x, acc[0]);
+              acc[1] = fmaf(val, w.y, acc[1]);
+              acc[2] = fmaf(val, w.z, acc[2]);
+              acc[3] = fmaf(val, w.w, acc[3]);
+            } else {
+              const float2 w = *reinterpret_cast<const float2*>(wr);
+              acc[0] = fmaf(val, w.x, acc[0]);
+              acc[1] = fmaf(val, w.y, acc[1]);
+            }
+          }
+        }
+      }
+    }
+    float* yr = y + row * ldy + lane * V;
+    if (V == 4)
+      *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+      *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+  }
+}
+
+int xw_fp32(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
+            cudaStream_t st) {
+  if (N == 0) return 0;
+  const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int blocks = (int)ceil_div(N, 8);
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (n_out == 128) {
+    if (vec4) k_xw_scan<128, true><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
+    else k_xw_scan<128, false><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
+  } else {
+    if (vec4) k_xw_scan<64, true><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
+    else k_xw_scan<64, false><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
+  }
+  BIGCN_CHECK_LAUNCH("k_xw_scan");
+  return 0;
+}
+
+// ------------------------------------------------------------ weight transposes
+// wt[k*ldwt + col0 + o] = w[o*ldw + k0 + k], o < 64  (32 x 64 tiles through smem)
+__global__ void k_transpose_w(const float* __restrict__ w, int64_t ldw, int64_t k0, int64_t K,
+                              float* __restrict__ wt, int64_t ldwt, int64_t col0) {
+  __shared__ float t[64][33];
+  const int64_t kb = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: ty 0..7
+  for (int o = ty; o < 64; o += 8) {
+    const int64_t k = kb + tx;
+    t[o][tx] = k < K ? w[o * ldw + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  for (int kk = ty; kk < 32; kk += 8) {
+    const int64_t k = kb + kk;
+    if (k < K) {
+      wt[k * ldwt + col0 + tx] = t[tx][kk];
+      wt[k * ldwt + col0 + 32 + tx] = t[tx + 32][kk];
+    }
+  }
+}
+
+int transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K, float* wt, int64_t ldwt,
+                     int64_t col0, cudaStream_t st) {
+  if (K == 0) return 0;
+  k_transpose_w<<<(int)ceil_div(K, 32), 256, 0, st>>>(w, ldw, k0, K, wt, ldwt, col0);
+  BIGCN_CHECK_LAUNCH("k_transpose_w");
+  return 0;
+}
+
+// ------------------------------------------------------- gT[k, :] = sum_i x[i,k] * t[i, :]
+// CTA = 8 warps x 8 columns = one 64-column slab of X, one chunk of rows.  A warp owns its
+// 8 columns (one 32 B sector per row) and their NOUT accumulators in shared memory, so no
+// two warps ever add into the same address and each column's contributions arrive in
+// ascending row order.  Lanes (2j, 2j+1) read the sector of row r0+j: 16 rows per load,
+// DW_U loads in flight.  Row chunks produce partial[chunk][K][NOUT]; k_dw_reduce sums the
+// chunks in order and writes PyG's [out, in] layout.
+constexpr int DW_U = 8;
+constexpr int DW_COLS = 64;
+
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_dw_slab(const float* __restrict__ x, int64_t N, int64_t K,
+                                                 const float* __restrict__ t, int64_t ldt,
+                                                 float* __restrict__ partial, int rows_per_chunk) {
+  constexpr int V = NOUT / 32;
+  extern __shared__ float acc_s[];  // [64][NOUT]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * DW_COLS + w * 8;  // first column of this warp
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r_end = min(N, r_begin + rows_per_chunk);
+  float* acc = acc_s + (size_t)w * 8 * NOUT;
+  for (int i = lane; i < 8 * NOUT; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const int sub = lane & 1;       // which half of the sector
+  const int rl = lane >> 1;       // row within the 16-row group
+  const int64_t col = c0 + sub * 4;
+  const bool col_ok = col < K;    // K % 4 == 0 -> whole float4 valid
+  if (c0 < K) {
+    for (int64_t rb = r_begin; rb < r_end; rb += 16 * DW_U) {
+      float4 v[DW_U];
+#pragma unroll
+      for (int u = 0; u < DW_U; ++u) {
+        const int64_t r = rb + u * 16 + rl;
+        v[u] = (col_ok && r < r_end) ? ldg_stream_f4(x + r * K + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < DW_U; ++u) {
+        const bool any = (v[u].x != 0.f) | (v[u].y != 0.f) | (v[u].z != 0.f) | (v[u].w != 0.f);
+        if (__ballot_sync(FULL_MASK, any) == 0u) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float comp = c == 0 ? v[u].x : (c == 1 ? v[u].y : (c == 2 ? v[u].z : v[u].w));
+          unsigned m = __ballot_sync(FULL_MASK, comp != 0.f);
+          while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float val = __shfl_sync(FULL_MASK, comp, sl);
+            const int64_t r = rb + u * 16 + (sl >> 1);
+            const int cl = (sl & 1) * 4 + c;
+            const float* tr = t + r * ldt + lane * V;
+            float* a = acc + cl * NOUT + lane * V;
+            if (V == 4) {
+              const float4 tv = *reinterpret_cast<const float4*>(tr);
+              float4 av = *reinterpret_cast<float4*>(a);
+              av.x = fmaf(val, tv.x, av.x);
+              av.y = fmaf(val, tv.y, av.y);
+              av.z = fmaf(val, tv.z, av.z);
+              av.w = fmaf(val, tv.w, av.w);
+              *reinterpret_cast<float4*>(a) = av;
+            } else {
+              const float2 tv = *reinterpret_cast<const float2*>(tr);
+              float2 av = *reinterpret_cast<float2*>(a);
+              av.x = fmaf(val, tv.x, av.x);
+              av.y = fmaf(val, tv.y, av.y);
+              *reinterpret_cast<float2*>(a) = av;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  float* out = partial + ((size_t)blockIdx.y * K) * NOUT;
+  for (int cl = 0; cl < 8; ++cl) {
+    const int64_t k = c0 + cl;
+    if (k < K) {
+      for (int j = lane; j < NOUT; j += 32) out[k * NOUT + j] = acc[cl * NOUT + j];
+    }
+  }
+}
+
+// scalar fallback for K % 4 != 0 or unaligned x: thread per (k, o) pair, rows in order
+template <int NOUT>
+__global__ void k_dw_naive(const float* __restrict__ x, int64_t N, int64_t K,
+                           const float* __restrict__ t, int64_t ldt, float* __restrict__ partial) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * NOUT) return;
+  const int64_t k = idx / NOUT;
+  const int o = (int)(idx % NOUT);
+  float acc = 0.f;
+  for (int64_t i = 0; i < N; ++i) {
+    const float xv = x[i * K + k];
+    if (xv != 0.f) acc = fmaf(xv, t[i * ldt + o], acc);
+  }
+  partial[k * NOUT + o] = acc;
+}
+
+// dw[o*ldw + k0 + k] = sum_chunk partial[chunk][k][col0 + o]   (o < 64), chunks in order
+__global__ void k_dw_reduce(const float* __restrict__ partial, int nchunk, int64_t K, int nout,
+                            int col0, float* __restrict__ dw, int64_t ldw, int64_t k0) {
+  __shared__ float tile[32][65];
+  const int64_t kb = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 4 x 64
+  for (int kk = ty; kk < 32; kk += 4) {
+    const int64_t k = kb + kk;
+    float s = 0.f;
+    if (k < K)
+      for (int c = 0; c < nchunk; ++c) s += partial[((size_t)c * K + k) * nout + col0 + tx];
+    tile[kk][tx] = s;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 8 x 32
+  for (int o = ly; o < 64; o += 8) {
+    const int64_t k = kb + lx;
+    if (k < K) dw[o * ldw + k0 + k] = tile[lx][o];
+  }
+}
+
+struct DwPlan {
+  int nchunk;
+  int rows_per_chunk;
+  bool fast;
+};
+DwPlan dw_plan(int64_t N, int64_t K, const float* x) {
+  DwPlan p;
+  p.fast = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (!p.fast) {
+    p.nchunk = 1;
+    p.rows_per_chunk = (int)N;
+    return p;
+  }
+  const int64_t slabs = ceil_div(K, DW_COLS);
+  int64_t want = ceil_div((int64_t)num_sms() * 4, slabs);
+  const int64_t max_chunks = ceil_div(N, 16 * DW_U);  // at least one full load group per chunk
+  if (want > max_chunks) want = max_chunks;
+  if (want < 1) want = 1;
+  int64_t rpc = ceil_div(N, want);
+  rpc = ceil_div(rpc, 16) * 16;
+  p.rows_per_chunk = (int)rpc;
+  p.nchunk = (int)ceil_div(N, rpc);
+  return p;
+}
+size_t dw_partial_floats(int64_t N, int64_t K, int n_out) {
+  // upper bound independent of the pointer alignment
+  const int64_t slabs = ceil_div(K, DW_COLS);
+  int64_t want = ceil_div((int64_t)num_sms() * 4, slabs > 0 ? slabs : 1);
+  if (want < 1) want = 1;
+  return (size_t)(want + 1) * (size_t)K * (size_t)n_out;
+}
+
+// grad of x*wt wrt the weights: writes dw_a (cols [0,64) of t) and, if n_out == 128, dw_b (cols [64,128))
+int dw_fp32(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int n_out,
+            float* partial, float* dw_a, int64_t ldw_a, int64_t k0_a, float* dw_b, int64_t ldw_b,
+            int64_t k0_b, cudaStream_t st) {
+  if (K == 0) return 0;
+  const DwPlan p = dw_plan(N, K, x);
+  if (N == 0) {
+    cudaMemsetAsync(partial, 0, (size_t)K * n_out * sizeof(float), st);
+  } else if (p.fast) {
+    dim3 grid((unsigned)ceil_div(K, DW_COLS), (unsigned)p.nchunk);
+    const size_t smem = (size_t)DW_COLS * n_out * sizeof(float);
+    if (n_out == 128) {
+      k_dw_slab<128><<<grid, 256, smem, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+    } else {
+      k_dw_slab<64><<<grid, 256, smem, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+    }
+    BIGCN_CHECK_LAUNCH("k_dw_slab");
+  } else {
+    const int64_t tot = K * n_out;
+    if (n_out == 128) k_dw_naive<128><<<(int)ceil_div(tot, 256), 256, 0, st>>>(x, N, K, t, ldt, partial);
+    else k_dw_naive<64><<<(int)ceil_div(tot, 256), 256, 0, st>>>(x, N, K, t, ldt, partial);
+    BIGCN_CHECK_LAUNCH("k_dw_naive");
+  }
+  const int nchunk = N == 0 ? 1 : p.nchunk;
+  k_dw_reduce<<<(int)ceil_div(K, 32), 256, 0, st>>>(partial, nchunk, K, n_out, 0, dw_a, ldw_a, k0_a);
+  BIGCN_CHECK_LAUNCH("k_dw_reduce");
+  if (n_out == 128 && dw_b != nullptr) {
+    k_dw_reduce<<<(int)ceil_div(K, 32), 256, 0, st>>>(partial, nchunk, K, n_out, 64, dw_b, ldw_b, k0_b);
+    BIGCN_CHECK_LAUNCH("k_dw_reduce");
+  }
+  return 0;
+}
+
+}  // namespace bigcn
+
+extern "C" int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K, float* wt,
+                                      int64_t ldwt, int64_t col0, bigcn_stream_t stream) {
+  return bigcn::transpose_weight(w, ldw, k0, K, wt, ldwt, col0, reinterpret_cast<cudaStream_t>(stream));
+}

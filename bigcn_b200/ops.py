@@ -1,0 +1,283 @@
+"""Host-side wrappers over the C-ABI: torch supplies device memory, streams and
+autograd plumbing; every arithmetic step runs in libbigcn_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import H, Dims, BatchPtrs, Params, Graph, Opts, check, lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.BigcnError("bigcn_b200 ops take CUDA tensors only (no CPU fallback)")
+
+
+def _i64(t):
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------- graph prep
+def graph_prep(edge_indexes, num_nodes, batch=None, num_graphs=0, deg_by="target", rowsum=True):
+    """gcn_norm structure for 1 or 2 edge lists.  Returns (graphs, node_ptr, flags) where each
+    graph is a dict of device tensors (see include/bigcn_b200.h: bigcn_graph_t)."""
+    L.require_device()
+    eis = [_i64(e) for e in edge_indexes]
+    _need_cuda(*eis)
+    dev = eis[0].device
+    n = int(num_nodes)
+    nd = len(eis)
+    graphs, structs = [], (Graph * nd)()
+    for d, ei in enumerate(eis):
+        e = int(ei.shape[1])
+        g = dict(in_ptr=torch.empty(n + 1, dtype=torch.int32, device=dev),
+                 in_idx=torch.empty(max(e, 1), dtype=torch.int32, device=dev),
+                 out_ptr=torch.empty(n + 1, dtype=torch.int32, device=dev),
+                 out_idx=torch.empty(max(e, 1), dtype=torch.int32, device=dev),
+                 deg=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
+                 dis=torch.empty(max(n, 1), dtype=torch.float32, device=dev),
+                 rowsum=torch.empty(max(n, 1), dtype=torch.float32, device=dev) if rowsum else None)
+        for k, v in g.items():
+            setattr(structs[d], k, _p(v))
+        g["E"] = e
+        graphs.append(g)
+    node_ptr = None
+    if batch is not None:
+        batch = _i64(batch)
+        node_ptr = torch.empty(int(num_graphs) + 1, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    emax = max(int(e.shape[1]) for e in eis)
+    ws_bytes = lib().bigcn_graph_prep_workspace_bytes(n, emax, nd)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ei_ptrs = (C.c_void_p * nd)(*[e.data_ptr() for e in eis])
+    e_arr = (C.c_int64 * nd)(*[int(e.shape[1]) for e in eis])
+    check(lib().bigcn_graph_prep(nd, ei_ptrs, e_arr, n, _p(batch), int(num_graphs), L.DEG_BY[deg_by],
+                                 structs, _p(node_ptr), _p(flags), _p(ws), ws_bytes, _stream()),
+          "graph_prep")
+    for g in graphs:
+        g["_keep"] = (ws,)
+    return graphs, node_ptr, flags
+
+
+def transpose_weight(w, k0, k, wt, col0):
+    check(lib().bigcn_transpose_weight(_p(w), w.stride(0), k0, k, _p(wt), wt.stride(0), col0, _stream()),
+          "transpose_weight")
+
+
+def xw(x, weights, gemm_mode="fp32"):
+    """y[N, 64*len(weights)] = x @ cat(weights).T with one pass over x (weights: [64,K] each)."""
+    L.require_device()
+    x = _f32(x)
+    _need_cuda(x, *weights)
+    n, k = x.shape
+    n_out = H * len(weights)
+    wt = torch.empty(k, n_out, dtype=torch.float32, device=x.device)
+    for q, w in enumerate(weights):
+        transpose_weight(_f32(w), 0, k, wt, q * H)
+    y = torch.empty(n, n_out, dtype=torch.float32, device=x.device)
+    check(lib().bigcn_xw(_p(x), n, k, _p(wt), n_out, _p(y), n_out, L.GEMM_MODE[gemm_mode], _stream()), "xw")
+    return y
+
+
+def propagate(graph, h, bias=None, relu=False, transpose=False):
+    """out = A-hat h (+bias)(relu), or A-hat^T h with transpose=True."""
+    L.require_device()
+    h = _f32(h)
+    n = h.shape[0]
+    out = torch.empty(n, H, dtype=torch.float32, device=h.device)
+    ptr, idx = (graph["out_ptr"], graph["out_idx"]) if transpose else (graph["in_ptr"], graph["in_idx"])
+    check(lib().bigcn_propagate(_p(ptr), _p(idx), _p(graph["dis"]), n, _p(h), h.stride(0), _p(bias),
+                                int(relu), _p(out), H, _stream()), "propagate")
+    return out
+
+
+def dropout_mask(seed, stream_id, node_id_base, n, n_cols, p, device):
+    L.require_device()
+    keep = torch.empty(n, n_cols, dtype=torch.uint8, device=device)
+    check(lib().bigcn_dropout_mask(seed, stream_id, node_id_base, n, n_cols, p, _p(keep), _stream()),
+          "dropout_mask")
+    return keep
+
+
+def raise_on_flags(flags: torch.Tensor):
+    """Host read of the device-side violation word (synchronises the stream)."""
+    v = int(flags.item())
+    if v == 0:
+        return
+    msgs = []
+    if v & L.FLAG_EDGE_RANGE:
+        msgs.append("an edge endpoint is outside [0, N)")
+    if v & L.FLAG_BATCH_ORDER:
+        msgs.append("data.batch is not sorted ascending within [0, B)")
+    if v & L.FLAG_ROOT_RANGE:
+        msgs.append("data.rootindex has an entry outside [0, N)")
+    raise IndexError("bigcn_b200: invalid graph input: " + "; ".join(msgs))
+
+
+# ----------------------------------------------------------------------------- GCNConv
+class GCNConvFunction(torch.autograd.Function):
+    """conv(x, edge_index) -> [N,64]; gradients for weight and bias (x is treated as data)."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, weight, bias, deg_by, gemm_mode):
+        L.require_device()
+        x, weight, bias = _f32(x), _f32(weight), _f32(bias)
+        ei = _i64(edge_index)
+        _need_cuda(x, ei, weight, bias)
+        n, k = x.shape
+        e = int(ei.shape[1])
+        if weight.shape != (H, k):
+            raise L.BigcnError(f"GCNConv: out_channels must be {H} and weight [64,{k}], got {tuple(weight.shape)}")
+        ws_bytes = lib().bigcn_gcnconv_workspace_bytes(n, e, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        out = torch.empty(n, H, dtype=torch.float32, device=x.device)
+        check(lib().bigcn_gcnconv_forward(_p(x), n, k, _p(ei), e, _p(weight), _p(bias), L.DEG_BY[deg_by],
+                                          L.GEMM_MODE[gemm_mode], _p(out), _p(flags), _p(ws), ws_bytes,
+                                          _stream()), "gcnconv_forward")
+        ctx.save_for_backward(x, ws)
+        ctx.dims = (n, k, e)
+        ctx.flags = flags
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, ws = ctx.saved_tensors
+        n, k, e = ctx.dims
+        g = _f32(grad_out)
+        dw = torch.empty(H, k, dtype=torch.float32, device=x.device)
+        db = torch.empty(H, dtype=torch.float32, device=x.device)
+        check(lib().bigcn_gcnconv_backward(_p(x), n, k, e, _p(g), _p(dw), _p(db), _p(ws), ws.numel(),
+                                           _stream()), "gcnconv_backward")
+        return None, None, dw, db, None, None
+
+
+# ----------------------------------------------------------------------------- feature path
+_PNAMES = ("td_w1", "td_b1", "td_w2", "td_b2", "bu_w1", "bu_b1", "bu_w2", "bu_b2")
+
+
+def _make_structs(x, ei, bu_ei, batch, rootindex, params, num_classes, node_id_base):
+    n, k = x.shape
+    dims = Dims(N=n, B=int(rootindex.numel()), K=k, C=num_classes, E_td=int(ei.shape[1]),
+                E_bu=int(bu_ei.shape[1]))
+    bt = BatchPtrs(x=_p(x), edge_index=_p(ei), bu_edge_index=_p(bu_ei), batch=_p(batch),
+                   rootindex=_p(rootindex), node_id_base=int(node_id_base))
+    pr = Params()
+    for name, t in zip(_PNAMES, params):
+        setattr(pr, name, _p(t))
+    return dims, bt, pr
+
+
+class FeaturesFunction(torch.autograd.Function):
+    """TDrumorGCN / BUrumorGCN forward for the directions in dir_mask -> feat [B,256]
+    laid out [BU mean | BU root | TD mean | TD root] (cat order of BiGCN_Twitter.py:128)."""
+
+    @staticmethod
+    def forward(ctx, x, ei, bu_ei, batch, rootindex, opts, *params):
+        L.require_device()
+        x = _f32(x)
+        ei, bu_ei, batch, rootindex = _i64(ei), _i64(bu_ei), _i64(batch), _i64(rootindex)
+        params = tuple(None if p is None else _f32(p) for p in params)
+        _need_cuda(x, ei, bu_ei, batch, rootindex, *params)
+        k = x.shape[1]
+        for name, p in zip(_PNAMES, params):
+            if p is None:
+                continue
+            want = {"w1": (H, k), "b1": (H,), "w2": (H, H + k), "b2": (H,)}[name[3:]]
+            if tuple(p.shape) != want:
+                raise L.BigcnError(f"{name}: expected shape {want} (hid_feats = out_feats = 64), got {tuple(p.shape)}")
+        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, opts["node_id_base"])
+        o = Opts(training=int(opts["training"]), p_drop=float(opts["p"]), seed=int(opts["seed"]),
+                 deg_by=L.DEG_BY[opts["deg_by"]], gemm_mode=L.GEMM_MODE[opts["gemm_mode"]],
+                 dir_mask=int(opts["dir_mask"]))
+        ws_bytes = lib().bigcn_features_workspace_bytes(C.byref(dims))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        flags = opts.get("flags")
+        if flags is None:
+            flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        feat = torch.empty(dims.B, 4 * H, dtype=torch.float32, device=x.device)
+        check(lib().bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(pr), C.byref(o), _p(feat),
+                                           _p(flags), _p(ws), ws_bytes, _stream()), "features_forward")
+        ctx.save_for_backward(x, ei, bu_ei, batch, rootindex, ws, *[p for p in params if p is not None])
+        ctx.present = [p is not None for p in params]
+        ctx.o = o
+        ctx.node_id_base = opts["node_id_base"]
+        ctx.flags = flags
+        return feat
+
+    @staticmethod
+    def backward(ctx, grad_feat):
+        saved = ctx.saved_tensors
+        x, ei, bu_ei, batch, rootindex, ws = saved[:6]
+        it = iter(saved[6:])
+        params = tuple(next(it) if pres else None for pres in ctx.present)
+        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, ctx.node_id_base)
+        grads = tuple(None if p is None else torch.empty_like(p) for p in params)
+        gs = Params()
+        for name, t in zip(_PNAMES, grads):
+            setattr(gs, name, _p(t))
+        g = _f32(grad_feat)
+        check(lib().bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(pr), C.byref(ctx.o), _p(g),
+                                            C.byref(gs), _p(ws), ws.numel(), _stream()),
+              "features_backward")
+        return (None, None, None, None, None, None) + grads
+
+
+class HeadFunction(torch.autograd.Function):
+    """log_softmax(feat @ fc_w.T + fc_b) (BiGCN_Twitter.py:129-130)."""
+
+    @staticmethod
+    def forward(ctx, feat, fc_w, fc_b):
+        L.require_device()
+        feat, fc_w, fc_b = _f32(feat), _f32(fc_w), _f32(fc_b)
+        b, c = feat.shape[0], fc_w.shape[0]
+        if fc_w.shape[1] != 4 * H or feat.shape[1] != 4 * H:
+            raise L.BigcnError("head: fc.weight must be [C,256]")
+        logp = torch.empty(b, c, dtype=torch.float32, device=feat.device)
+        check(lib().bigcn_head_forward(_p(feat), b, c, _p(fc_w), _p(fc_b), _p(logp), _stream()), "head_forward")
+        ctx.save_for_backward(feat, fc_w, logp)
+        return logp
+
+    @staticmethod
+    def backward(ctx, grad_logp):
+        feat, fc_w, logp = ctx.saved_tensors
+        b, c = logp.shape
+        g = _f32(grad_logp)
+        gfeat = torch.empty_like(feat)
+        dw = torch.empty_like(fc_w)
+        db = torch.empty(c, dtype=torch.float32, device=feat.device)
+        check(lib().bigcn_head_backward(_p(g), _p(logp), _p(feat), b, c, _p(fc_w), _p(gfeat), _p(dw), _p(db),
+                                        _stream()), "head_backward")
+        return gfeat, dw, db
+
+
+# ----------------------------------------------------------------------------- loss / optimiser
+def nll_loss(logp, y, b_global=None, want_grad=False):
+    """F.nll_loss(logp, y) with mean over b_global trees (BiGCN_Twitter.py:184)."""
+    L.require_device()
+    b, c = logp.shape
+    y = _i64(y)
+    loss = torch.empty(1, dtype=torch.float32, device=logp.device)
+    grad = torch.empty_like(logp) if want_grad else None
+    check(lib().bigcn_nll_loss(_p(logp), _p(y), b, c, int(b_global or b), _p(loss), _p(grad), _stream()),
+          "nll_loss")
+    return (loss, grad) if want_grad else loss

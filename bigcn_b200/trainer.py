@@ -1,0 +1,142 @@
+"""The training step around the path (BiGCN_Twitter.py:146-153 optimizer, :183-189 step).
+
+``FusedTrainer`` keeps the ten parameter tensors as views of ONE flat fp32 buffer (and one
+flat gradient buffer), so a step is: features forward -> head -> nll -> head backward ->
+features backward written straight into the flat gradient -> (data-parallel: one NCCL
+all-reduce of that 5 MB buffer) -> one fused Adam kernel with the reference's three lr
+groups (BU convs at lr/5).  Nothing in a step synchronises the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import H, Opts, Params, check, lib
+from .ops import _make_structs, _p, _stream, _i64, _f32, raise_on_flags
+
+_ORDER = ("TDrumorGCN.conv1.lin.weight", "TDrumorGCN.conv1.bias", "TDrumorGCN.conv2.lin.weight",
+          "TDrumorGCN.conv2.bias", "fc.weight", "fc.bias",
+          "BUrumorGCN.conv1.lin.weight", "BUrumorGCN.conv1.bias", "BUrumorGCN.conv2.lin.weight",
+          "BUrumorGCN.conv2.bias")
+_STRUCT = {"TDrumorGCN.conv1.lin.weight": "td_w1", "TDrumorGCN.conv1.bias": "td_b1",
+           "TDrumorGCN.conv2.lin.weight": "td_w2", "TDrumorGCN.conv2.bias": "td_b2",
+           "BUrumorGCN.conv1.lin.weight": "bu_w1", "BUrumorGCN.conv1.bias": "bu_b1",
+           "BUrumorGCN.conv2.lin.weight": "bu_w2", "BUrumorGCN.conv2.bias": "bu_b2",
+           "fc.weight": "fc_w", "fc.bias": "fc_b"}
+
+
+class FusedTrainer:
+    """Adam(lr, weight_decay) with BU conv1/conv2 at lr/5 over a flat parameter buffer."""
+
+    def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 process_group=None, world_size=1, validate=False):
+        L.require_device()
+        self.model = model
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg, self.world = process_group, world_size
+        self.validate = validate
+        named = dict(model.named_parameters())
+        dev = named[_ORDER[0]].device
+        if dev.type != "cuda":
+            raise L.BigcnError("FusedTrainer needs the model on a CUDA device")
+        sizes = [named[n].numel() for n in _ORDER]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + (s + 3) // 4 * 4)   # keep every tensor 16 B aligned
+        self.n = offs[-1]
+        self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.views, self.gviews = {}, {}
+        with torch.no_grad():
+            for name, o, s in zip(_ORDER, offs, sizes):
+                p = named[name]
+                v = self.flat[o:o + s].view(p.shape)
+                v.copy_(p)
+                p.data = v                         # the module now reads the flat buffer
+                self.views[name] = v
+                self.gviews[name] = self.grad[o:o + s].view(p.shape)
+        # lr groups: [TD convs + fc] at lr, [BU convs] at lr/5  (BiGCN_Twitter.py:146-153)
+        split = offs[6]
+        self.seg_end = torch.tensor([split, self.n], dtype=torch.int64, device=dev)
+        self.seg_lr = torch.tensor([lr, lr / 5], dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pr, self._gr = Params(), Params()
+        for name in _ORDER:
+            setattr(self._pr, _STRUCT[name], _p(self.views[name]))
+            setattr(self._gr, _STRUCT[name], _p(self.gviews[name]))
+        self._ws = None
+        self._calls = 0
+        self.launches_per_step = None
+
+    # -------------------------------------------------------------------------------
+    def _workspace(self, dims, dev):
+        need = lib().bigcn_features_workspace_bytes(C.byref(dims))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def step(self, data, b_global=None, node_id_base=0, seed=None):
+        """One optimisation step on a device-resident batch; returns the loss (device scalar)."""
+        m = self.model
+        x = _f32(data.x)
+        ei, bu, batch, root = _i64(data.edge_index), _i64(data.BU_edge_index), _i64(data.batch), \
+            _i64(data.rootindex)
+        y = _i64(data.y)
+        td = m.TDrumorGCN
+        c = m.fc.weight.shape[0]
+        dims, bt, _ = _make_structs(x, ei, bu, batch, root, (None,) * 8, c, node_id_base)
+        if seed is None:
+            seed = (td.seed + self._calls) & ((1 << 64) - 1)
+        self._calls += 1
+        o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(seed), deg_by=L.DEG_BY[td.deg_by],
+                 gemm_mode=L.GEMM_MODE[td.gemm_mode], dir_mask=L.DIR_TD | L.DIR_BU)
+        ws = self._workspace(dims, x.device)
+        b = dims.B
+        dev = x.device
+        feat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
+        logp = torch.empty(b, c, dtype=torch.float32, device=dev)
+        glogp = torch.empty(b, c, dtype=torch.float32, device=dev)
+        gfeat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        st = _stream()
+        l = lib()
+        check(l.bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(feat),
+                                       _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
+        check(l.bigcn_head_forward(_p(feat), b, c, self._pr.fc_w, self._pr.fc_b, _p(logp), st), "head_forward")
+        check(l.bigcn_nll_loss(_p(logp), _p(y), b, c, int(b_global or b), _p(loss), _p(glogp), st), "nll_loss")
+        check(l.bigcn_head_backward(_p(glogp), _p(logp), _p(feat), b, c, self._pr.fc_w, _p(gfeat),
+                                    self._gr.fc_w, self._gr.fc_b, st), "head_backward")
+        check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                        C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        check(l.bigcn_adam_step(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
+                                _p(self.seg_end), _p(self.seg_lr), 2, self.betas[0], self.betas[1], self.eps,
+                                self.wd, 1.0, _p(self.step_count), st), "adam_step")
+        self.last_logp = logp
+        if self.validate:
+            raise_on_flags(self.flags)
+        return loss
+
+    def check_inputs(self):
+        raise_on_flags(self.flags)
+
+
+def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True) -> int:
+    """How many kernels of this library one FusedTrainer.step enqueues (for bench.py's
+    gpu_launches claim); mirrors the launch sequence in csrc/api.cu + graph_prep.cu."""
+    bits = 1
+    while (1 << bits) <= n_nodes:
+        bits += 1
+    passes = (bits + 7) // 8
+    prep = 1 + 2 + 3 * passes + 1            # count, scan x2, radix passes, deg  (memset not counted)
+    fwd = prep + 3 * n_dirs + 1 + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
+    head = 1 + 1 + 2                           # head fwd, nll, head bwd x2
+    bwd = 2 + 1 + 2 + (0 if training else 1) + 1 + 2 + 1 + 1 + n_dirs   # g2+colsum, propT, outer x2, [segsum], dw2b, bwdmix+colsum, propT, dw slab, dw reduce x dirs
+    adam = 2
+    return fwd + head + bwd + adam

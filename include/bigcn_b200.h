@@ -1,0 +1,207 @@
+/*
+ * bigcn_b200 -- C-ABI of the B200-native BiGCN hot path (libbigcn_b200.so).
+ *
+ * Every entry point takes plain DEVICE pointers, sizes and a CUDA stream
+ * (passed as void*, i.e. cudaStream_t).  Nothing here depends on torch.
+ * Buffers are borrowed: the caller allocates inputs, outputs and workspaces
+ * (sizes come from the *_bytes queries) and keeps them alive until the stream
+ * has drained.  No entry point synchronises the host, allocates device memory
+ * or touches any stream but the one given, so all of them can be captured in a
+ * CUDA graph.  Return value: 0 = ok, non-zero = error (bigcn_last_error()).
+ * Data-dependent input violations (edge endpoint >= N, unsorted batch, root
+ * outside its tree) never produce a silent wrong answer: they raise bits in the
+ * caller's device-side `flags` word, which the host reads at its next sync.
+ *
+ * The reference (cwkd/BiGCN, /root/reference) has no FFI: its hot path is the
+ * nn.Module code of model/Twitter/BiGCN_Twitter.py:19-131 calling
+ * torch_geometric.nn.GCNConv and torch_scatter.scatter_mean.  Each function
+ * below cites the reference lines (and the library routine behind them) that
+ * it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions: fp32 row-major; hid_feats == out_feats == 64 (the reference's
+ * only configuration, BiGCN_Twitter.py:140-144); int64 index inputs exactly as
+ * PyG hands them over, narrowed to int32 on the device (N, E < 2^31).
+ */
+#ifndef BIGCN_B200_H
+#define BIGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIGCN_H 64 /* hid_feats == out_feats */
+
+/* flags word bits (device int32, OR-ed by kernels) */
+#define BIGCN_FLAG_EDGE_RANGE 1   /* an edge endpoint is < 0 or >= N            */
+#define BIGCN_FLAG_BATCH_ORDER 2  /* batch[] not sorted ascending / out of [0,B) */
+#define BIGCN_FLAG_ROOT_RANGE 4   /* rootindex[b] outside [0,N)                 */
+
+/* degree convention of gcn_norm: PyG 2.x sums at the target (col); the
+ * readme-pinned 1.3.2 summed at the source (row). */
+#define BIGCN_DEG_BY_TARGET 0
+#define BIGCN_DEG_BY_SOURCE 1
+
+/* X*W arithmetic: exact fp32 FFMA scan, or tcgen05 kind::tf32 with 1 / 3 passes */
+#define BIGCN_GEMM_FP32 0
+#define BIGCN_GEMM_TF32 1
+#define BIGCN_GEMM_TF32X3 2
+
+/* direction bits */
+#define BIGCN_DIR_TD 1
+#define BIGCN_DIR_BU 2
+
+typedef void* bigcn_stream_t; /* cudaStream_t */
+
+typedef struct bigcn_dims {
+  int64_t N;    /* nodes in the batch                    */
+  int64_t B;    /* trees in the batch (rootindex.numel())*/
+  int64_t K;    /* in_feats                              */
+  int64_t C;    /* classes of the head (4 / 2)           */
+  int64_t E_td; /* columns of data.edge_index            */
+  int64_t E_bu; /* columns of data.BU_edge_index         */
+} bigcn_dims_t;
+
+/* The five attributes forward(data) reads (BiGCN_Twitter.py:27,45-47,78). */
+typedef struct bigcn_batch {
+  const float* x;               /* [N,K]    data.x                       */
+  const int64_t* edge_index;    /* [2,E_td] data.edge_index  [parent;child] */
+  const int64_t* bu_edge_index; /* [2,E_bu] data.BU_edge_index [child;parent] */
+  const int64_t* batch;         /* [N]      data.batch (sorted)          */
+  const int64_t* rootindex;     /* [B]      data.rootindex (global ids)  */
+  int64_t node_id_base;         /* global id of local node 0: dropout masks are keyed on
+                                   global ids so they do not depend on the world size */
+} bigcn_batch_t;
+
+/* Parameters in PyG-2.x state_dict layout:
+ *   <dir>.conv1.lin.weight [64,K], <dir>.conv1.bias [64],
+ *   <dir>.conv2.lin.weight [64,64+K], <dir>.conv2.bias [64], fc.weight [C,256], fc.bias [C].
+ * The same struct with non-const meaning is used for gradients. */
+typedef struct bigcn_params {
+  float* td_w1; float* td_b1; float* td_w2; float* td_b2;
+  float* bu_w1; float* bu_b1; float* bu_w2; float* bu_b2;
+  float* fc_w;  float* fc_b;
+} bigcn_params_t;
+
+/* Normalised structure of one direction, emitted instead of PyG's COO' list. */
+typedef struct bigcn_graph {
+  int32_t* in_ptr;  /* [N+1] CSR by target                                  */
+  int32_t* in_idx;  /* [E]   sources of in-edges, edge-list (COO') order    */
+  int32_t* out_ptr; /* [N+1] CSR by source (A-hat^T, used by backward)      */
+  int32_t* out_idx; /* [E]   targets of out-edges, edge-list order          */
+  int32_t* deg;     /* [N]   degree incl. the unit self-loop                */
+  float* dis;       /* [N]   deg^-1/2 = 1.0f / sqrtf(deg), IEEE             */
+  float* rowsum;    /* [N]   sum_j A-hat[i,j] in COO' order, or NULL        */
+} bigcn_graph_t;
+
+typedef struct bigcn_opts {
+  int32_t training;   /* module.training: dropout on/off (BiGCN_Twitter.py:54)      */
+  float p_drop;       /* F.dropout default 0.5                                      */
+  uint64_t seed;      /* Philox key                                                 */
+  int32_t deg_by;     /* BIGCN_DEG_BY_*                                             */
+  int32_t gemm_mode;  /* BIGCN_GEMM_*                                               */
+  int32_t dir_mask;   /* BIGCN_DIR_TD | BIGCN_DIR_BU                                */
+} bigcn_opts_t;
+
+const char* bigcn_last_error(void);
+int bigcn_version(void);
+/* 1 if the library carries sm_100a code and the current device is cc 10.x */
+int bigcn_device_ok(void);
+
+/* ---- graph prep ---------------------------------------------------------
+ * Replaces gcn_norm / add_remaining_self_loops [torch_geometric], reached 4x
+ * per forward from conv1/conv2 (BiGCN_Twitter.py:42,56,92,105), and the
+ * Python max(data.batch) (:47) -- B is an argument, node_ptr comes from the
+ * sorted batch vector.  Bit-exact vs oracle.gcn_oracle.graph_prep.
+ * n_dirs = 1 or 2; edge_index[d] is [2,E[d]] int64; graphs[d] receives the
+ * structure.  batch/node_ptr may be NULL (GCNConv called on its own). */
+size_t bigcn_graph_prep_workspace_bytes(int64_t N, int64_t E_max, int32_t n_dirs);
+int bigcn_graph_prep(int32_t n_dirs, const int64_t* const* edge_index, const int64_t* E,
+                     int64_t N, const int64_t* batch, int64_t B, int32_t deg_by,
+                     const bigcn_graph_t* graphs, int32_t* node_ptr /*[B+1] or NULL*/,
+                     int32_t* flags, void* workspace, size_t workspace_bytes,
+                     bigcn_stream_t stream);
+
+/* ---- X * W^T ------------------------------------------------------------
+ * Replaces GCNConv.lin (cuBLAS SGEMM) at BiGCN_Twitter.py:42,92.
+ * y[N,n_out] = x[N,K] * wt[K,n_out]  (wt = transposed, concatenated weights;
+ * n_out = 64 or 128 so TD and BU share one pass over x).  ldy = row pitch of y. */
+int bigcn_xw(const float* x, int64_t N, int64_t K, const float* wt, int32_t n_out,
+             float* y, int64_t ldy, int32_t gemm_mode, bigcn_stream_t stream);
+/* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
+int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
+                           float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);
+
+/* ---- propagate ----------------------------------------------------------
+ * Replaces MessagePassing.propagate + bias [torch_geometric] (index_select,
+ * broadcast mul, atomic scatter_add) inside every GCNConv call.
+ * out[i] = sum_{e in ptr[i]..ptr[i+1]} (dis[idx[e]]*dis[i]) * h[idx[e]]
+ *          + (dis[i]*dis[i]) * h[i]  (+ bias) (relu)
+ * summed in COO' order, no atomics, deterministic.  Pass in_ptr/in_idx for
+ * A-hat, out_ptr/out_idx for A-hat^T (backward). */
+int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N,
+                    const float* h, int64_t ldh, const float* bias /*or NULL*/, int32_t relu,
+                    float* out, int64_t ldo, bigcn_stream_t stream);
+
+/* ---- dropout mask spec (tests) -----------------------------------------
+ * keep[i,c] (uint8) for c < n_cols of the concatenated [h1|root_extend] tensor
+ * (BiGCN_Twitter.py:51-54); stream = 0 (TD) / 1 (BU). */
+int bigcn_dropout_mask(uint64_t seed, int32_t stream_id, int64_t node_id_base, int64_t N,
+                       int64_t n_cols, float p, uint8_t* keep, bigcn_stream_t stream);
+
+/* ---- GCNConv on its own -------------------------------------------------
+ * conv(x, edge_index) as called at explain_PHEME.py:95,132.  w is [64,K]
+ * (lin.weight), bias [64]; out [N,64].  Backward returns dw, db (x is an input of the
+ * path and carries no gradient). */
+size_t bigcn_gcnconv_workspace_bytes(int64_t N, int64_t E, int64_t K);
+int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const int64_t* edge_index,
+                          int64_t E, const float* w, const float* bias, int32_t deg_by,
+                          int32_t gemm_mode, float* out, int32_t* flags, void* workspace,
+                          size_t workspace_bytes, bigcn_stream_t stream);
+int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int64_t E,
+                           const float* grad_out /*[N,64]*/, float* dw /*[64,K]*/, float* db /*[64]*/,
+                           void* workspace /* the forward's */, size_t workspace_bytes,
+                           bigcn_stream_t stream);
+
+/* ---- the two-direction feature path ------------------------------------
+ * Replaces TDrumorGCN.forward / BUrumorGCN.forward (BiGCN_Twitter.py:26-67,
+ * 77-114): conv1, root-extend, relu, dropout, conv2, relu, root-extend,
+ * scatter_mean.  feat[B,256] = [BU mean(H2) | BU H1[root] | TD mean(H2) | TD H1[root]]
+ * (the cat order of :128).  The workspace carries what backward needs. */
+size_t bigcn_features_workspace_bytes(const bigcn_dims_t* dims);
+int bigcn_features_forward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
+                           const bigcn_params_t* params, const bigcn_opts_t* opts,
+                           float* feat /*[B,256]*/, int32_t* flags, void* workspace,
+                           size_t workspace_bytes, bigcn_stream_t stream);
+/* grad_feat[B,256] -> gradients of the eight conv tensors (fc_* untouched).
+ * The gradient through the second root-extend is dropped, as copy.copy does at :44. */
+int bigcn_features_backward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
+                            const bigcn_params_t* params, const bigcn_opts_t* opts,
+                            const float* grad_feat, const bigcn_params_t* grads,
+                            void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+
+/* ---- head ---------------------------------------------------------------
+ * Replaces fc + log_softmax (BiGCN_Twitter.py:129-130). */
+int bigcn_head_forward(const float* feat, int64_t B, int64_t C, const float* fc_w,
+                       const float* fc_b, float* logp /*[B,C]*/, bigcn_stream_t stream);
+int bigcn_head_backward(const float* grad_logp, const float* logp, const float* feat, int64_t B,
+                        int64_t C, const float* fc_w, float* grad_feat /*[B,256]*/,
+                        float* d_fc_w, float* d_fc_b, bigcn_stream_t stream);
+
+/* ---- loss and optimiser (the step around the path, :184-189, :146-153) --
+ * loss = -(1/B_global) sum_b logp[b,y[b]] (F.nll_loss, mean); grad_logp = dloss/dlogp. */
+int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
+                   float* loss /*[1]*/, float* grad_logp /*[B,C] or NULL*/, bigcn_stream_t stream);
+/* torch.optim.Adam (coupled L2) over one flat buffer; lr_of_segment: n_seg pairs
+ * (end_offset, lr) on the DEVICE; step_count: device int64, incremented here. */
+int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    int64_t n, const int64_t* seg_end, const float* seg_lr, int32_t n_seg,
+                    double beta1, double beta2, double eps, double weight_decay,
+                    double grad_scale, int64_t* step_count, bigcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGCN_B200_H */

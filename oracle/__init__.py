@@ -1,0 +1,25 @@
+"""CPU oracle for the BiGCN hot path -- TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the arithmetic of the reference's hot path lives in two
+third-party wheels that are NOT vendored under /root/reference and are NOT
+installable in this image (no network): ``torch_geometric`` (GCNConv /
+gcn_norm / add_remaining_self_loops) and ``torch_scatter`` (scatter_mean).
+The reference ships no test, golden vector or logged output for this path
+(SURVEY.md section 4 / 8c).  This package therefore *restates* the published
+algorithm of those libraries (PyG 2.x semantics, degree-by-target; the
+readme-pinned 1.3.2 degree-by-source convention is kept behind a switch) and
+anchors it on the reference's own call sites:
+
+  model/Twitter/BiGCN_Twitter.py:19-131   (TDrumorGCN / BUrumorGCN / BiGCN)
+  model/Weibo/BiGCN_Weibo.py:16-89        (same maths, class Net, 2 classes)
+  Process/dataset.py:64-99                (input contract, DropEdge)
+
+The only pin available is the hand-checkable 5-node known-answer vector of
+SURVEY.md section 8c (tests/golden/kat_tree5.json) plus torch's own CPU ops
+(Linear, relu, log_softmax, nll_loss, pow(-0.5)) which are used directly.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package.  The
+product (``bigcn_b200``) never does; it fails loudly if its CUDA library is
+missing.
+"""

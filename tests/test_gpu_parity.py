@@ -1,0 +1,415 @@
+"""GPU parity tests: the CUDA path (through the C-ABI in libbigcn_b200.so) against the CPU
+oracle on the same seeded inputs.  Bars: graph prep / propagate / dropout mask bit-exact;
+fp32 log-probs max|d| <= 1e-5 * max|ref| (BASELINE.json north_star); gradients
+max|d| <= 1e-4 * max|ref| per tensor."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigcn_oracle, gcn_oracle
+from bigcn_b200.data import Data, Batch, collate, make_batch, make_tree, drop_edge
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LOGP_TOL = 1e-5      # north_star: fp32 logits within 1e-5 relative
+GRAD_TOL = 1e-4
+
+
+def unhex(lst):
+    return np.array([float.fromhex(v) for v in lst], dtype=np.float32)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def rel_err(got, want):
+    want = want.detach().cpu().double()
+    got = got.detach().cpu().double()
+    scale = max(float(want.abs().max()), 1e-30)
+    return float((got - want).abs().max()) / scale
+
+
+def clone_batch(b, dev):
+    return Batch(x=b.x.to(dev), edge_index=b.edge_index.to(dev), BU_edge_index=b.BU_edge_index.to(dev),
+                 batch=b.batch.to(dev), rootindex=b.rootindex.to(dev), y=b.y.to(dev))
+
+
+def edge_cases():
+    """The shapes the reference's data actually produces."""
+    rng = np.random.default_rng(42)
+    K = 40
+    cases = {}
+    cases["twitter_train_dropedge"] = make_batch("twitter15", 5, seed=1, train=True, in_feats=K)
+    cases["twitter_eval"] = make_batch("twitter16", 4, seed=2, train=False, in_feats=K)
+    cases["pheme_singletons"] = make_batch("pheme", 24, seed=3, train=True, in_feats=K)
+    cases["single_tree"] = make_batch("twitter15", 1, seed=4, train=False, in_feats=K)
+    # all single-node trees: E = 0
+    cases["no_edges"] = collate([make_tree("pheme", 1, rng, in_feats=K) for _ in range(3)])
+    # star with a very high-degree root + deep chain
+    n = 700
+    star = make_tree("twitter15", n, rng, in_feats=K)
+    ei = np.stack([np.zeros(n - 1, np.int64), np.arange(1, n)])
+    star.edge_index = torch.from_numpy(ei); star.BU_edge_index = torch.from_numpy(ei[::-1].copy())
+    star.rootindex = torch.tensor([0])
+    chain = make_tree("twitter15", 90, rng, in_feats=K)
+    ce = np.stack([np.arange(0, 89), np.arange(1, 90)])
+    chain.edge_index = torch.from_numpy(ce); chain.BU_edge_index = torch.from_numpy(ce[::-1].copy())
+    chain.rootindex = torch.tensor([0])
+    cases["star_and_chain"] = collate([star, chain])
+    # general graph: shuffled edge order, duplicates, self-loops, multi-parent
+    g = make_tree("twitter15", 80, rng, in_feats=K)
+    e = g.edge_index.numpy()
+    extra = rng.integers(0, 80, (2, 40))
+    loops = np.stack([np.arange(0, 80, 9), np.arange(0, 80, 9)])
+    e = np.concatenate([e, extra, loops, e[:, :10]], 1)
+    e = e[:, rng.permutation(e.shape[1])]
+    g.edge_index = torch.from_numpy(e.copy())
+    g.BU_edge_index = torch.from_numpy(e[::-1][:, rng.permutation(e.shape[1])].copy())
+    cases["general_graph"] = collate([g, make_tree("twitter15", 60, rng, in_feats=K)])
+    return K, cases
+
+
+# ------------------------------------------------------------------------------- graph prep
+def check_graph_prep(b, dev, deg_by="target"):
+    from bigcn_b200 import ops
+    n, nb = b.x.shape[0], int(b.rootindex.numel())
+    graphs, node_ptr, flags = ops.graph_prep([b.edge_index.to(dev), b.BU_edge_index.to(dev)], n,
+                                             b.batch.to(dev), nb, deg_by)
+    assert int(flags.item()) == 0
+    for g, ei in zip(graphs, (b.edge_index, b.BU_edge_index)):
+        want = gcn_oracle.graph_prep(ei.numpy(), n, b.batch.numpy(), nb, deg_by)
+        ne = want["n_edges"]
+        assert g["in_ptr"].cpu().numpy().tolist() == want["in_ptr"].tolist()
+        assert g["out_ptr"].cpu().numpy().tolist() == want["out_ptr"].tolist()
+        assert g["in_idx"].cpu().numpy()[:ne].tolist() == want["in_idx"].tolist()
+        assert g["out_idx"].cpu().numpy()[:ne].tolist() == want["out_idx"].tolist()
+        if n:
+            assert g["deg"].cpu().numpy()[:n].tolist() == want["deg"].tolist()
+            assert (bits(g["dis"].cpu().numpy()[:n]) == bits(want["dis"])).all()
+            assert (bits(g["rowsum"].cpu().numpy()[:n]) == bits(want["rowsum"])).all()
+        assert node_ptr.cpu().numpy().tolist() == want["node_ptr"].tolist()
+
+
+def test_graph_prep_bit_exact_edge_cases(dev):
+    _, cases = edge_cases()
+    for name, b in cases.items():
+        for deg_by in ("target", "source"):
+            check_graph_prep(b, dev, deg_by)
+
+
+def test_graph_prep_kat_tree5(dev):
+    from bigcn_b200 import ops
+    kat = json.load(open(os.path.join(GOLD, "kat_tree5.json")))
+    ei = torch.tensor([[0, 0, 1, 1], [1, 2, 3, 4]], device=dev)
+    for deg_by in ("target", "source"):
+        graphs, node_ptr, _ = ops.graph_prep([ei, ei.flip(0).contiguous()], 5,
+                                             torch.zeros(5, dtype=torch.int64, device=dev), 1, deg_by)
+        for g, name in zip(graphs, ("TD", "BU")):
+            k = kat[f"{name}_{deg_by}"]
+            assert g["deg"].cpu().tolist() == k["deg"]
+            assert [float(v).hex() for v in g["dis"].cpu()] == k["dis"]
+            assert [float(v).hex() for v in g["rowsum"].cpu()] == k["rowsum"]
+            assert g["in_ptr"].cpu().tolist() == k["in_ptr"] and g["in_idx"].cpu().tolist()[:4] == k["in_idx"]
+            assert g["out_ptr"].cpu().tolist() == k["out_ptr"] and g["out_idx"].cpu().tolist()[:4] == k["out_idx"]
+        assert node_ptr.cpu().tolist() == [0, 5]
+
+
+def test_graph_prep_full_size_batch_and_large_n(dev):
+    """BASELINE config sizes: a 128-tree Twitter15-shaped batch (3 radix passes are not needed,
+    N < 65536) and a 300k-node forest (3 passes, multi-block scan)."""
+    b = make_batch("twitter15", 128, seed=0, train=True, in_feats=8)
+    check_graph_prep(b, dev)
+    from bigcn_b200 import ops
+    from bigcn_b200.data import make_device_forest
+    f = make_device_forest(3000, 100, dev, seed=1)
+    n = 300000
+    graphs, node_ptr, flags = ops.graph_prep([f.edge_index, f.BU_edge_index], n, f.batch, 3000)
+    assert int(flags.item()) == 0
+    want = gcn_oracle.graph_prep(f.edge_index.cpu().numpy(), n, f.batch.cpu().numpy(), 3000)
+    g = graphs[0]
+    assert torch.equal(g["in_ptr"].cpu(), torch.from_numpy(want["in_ptr"]))
+    assert torch.equal(g["in_idx"].cpu()[:want["n_edges"]], torch.from_numpy(want["in_idx"]))
+    assert torch.equal(g["out_idx"].cpu()[:want["n_edges"]], torch.from_numpy(want["out_idx"]))
+    assert (bits(g["dis"].cpu().numpy()) == bits(want["dis"])).all()
+    # size-independent property: the BU structure is the transpose of the TD structure
+    assert torch.equal(graphs[1]["in_ptr"], g["out_ptr"]) and torch.equal(graphs[1]["out_ptr"], g["in_ptr"])
+    assert torch.equal(node_ptr.cpu(), torch.arange(0, n + 1, 100, dtype=torch.int32))
+
+
+def test_invalid_inputs_raise_flags(dev):
+    import bigcn_b200
+    from bigcn_b200 import ops
+    ei = torch.tensor([[0, 1, 7], [1, 2, 0]], device=dev)
+    _, _, flags = ops.graph_prep([ei], 3, torch.tensor([0, 1, 0], device=dev), 2)
+    v = int(flags.item())
+    assert v & 1 and v & 2
+    with pytest.raises(IndexError):
+        ops.raise_on_flags(flags)
+    b = make_batch("twitter15", 2, seed=0, train=False, in_feats=16)
+    b.rootindex = torch.tensor([0, 10 ** 6])
+    m = bigcn_b200.BiGCN(16, 64, 64, dev, validate="sync").to(dev).eval()
+    with pytest.raises(IndexError):
+        m(clone_batch(b, dev))
+
+
+# ------------------------------------------------------------------------------- dropout mask
+def test_dropout_mask_matches_philox_spec(dev):
+    from bigcn_b200 import ops
+    for seed, stream, base, n, cols, p in ((0, 0, 0, 37, 64 + 40, 0.5), (2 ** 40 + 12345, 1, 2 ** 33 + 5, 19, 131, 0.5),
+                                           (99, 1, 7, 50, 70, 0.25)):
+        got = ops.dropout_mask(seed, stream, base, n, cols, p, dev).cpu().numpy().astype(bool)
+        want = gcn_oracle.dropout_keep_mask(seed, stream, base + np.arange(n), cols, p)
+        assert (got == want).all()
+
+
+# ------------------------------------------------------------------------------- X W and propagate
+def test_xw_matches_fp32_reference(dev):
+    from bigcn_b200 import ops
+    torch.manual_seed(0)
+    b = make_batch("twitter15", 6, seed=9, train=False)           # K = 5000 BoW
+    w_td, w_bu = torch.randn(64, 5000) * 0.02, torch.randn(64, 5000) * 0.02
+    want = b.x.double() @ torch.cat([w_td, w_bu]).double().t()
+    got = ops.xw(b.x.to(dev), [w_td.to(dev), w_bu.to(dev)])
+    assert rel_err(got, want) < 2e-6
+    got1 = ops.xw(b.x.to(dev), [w_bu.to(dev)])
+    assert rel_err(got1, want[:, 64:]) < 2e-6
+    # dense signed features, K not a multiple of 4 (scalar path), empty input
+    x = torch.tanh(torch.randn(300, 771))
+    w = torch.randn(64, 771) * 0.05
+    assert rel_err(ops.xw(x.to(dev), [w.to(dev)]), x.double() @ w.double().t()) < 2e-6
+    assert ops.xw(torch.zeros(0, 64, device=dev), [torch.zeros(64, 64, device=dev)]).shape == (0, 64)
+
+
+def test_propagate_bit_exact_and_transpose(dev):
+    from bigcn_b200 import ops
+    _, cases = edge_cases()
+    torch.manual_seed(1)
+    for name, b in cases.items():
+        n = b.x.shape[0]
+        for ei in (b.edge_index, b.BU_edge_index):
+            graphs, _, _ = ops.graph_prep([ei.to(dev)], n)
+            h = torch.randn(n, 64)
+            bias = torch.randn(64)
+            e2, w = gcn_oracle.gcn_norm(ei, n)
+            want = gcn_oracle.propagate_sum(h, e2, w) + bias
+            got = ops.propagate(graphs[0], h.to(dev), bias.to(dev)).cpu()
+            assert (bits(got.numpy()) == bits(want.numpy())).all(), name
+            # A-hat^T: linearity / adjoint property  <A h, g> == <h, A^T g>
+            gq = torch.randn(n, 64)
+            at_g = ops.propagate(graphs[0], gq.to(dev), transpose=True).cpu().double()
+            a_h = gcn_oracle.propagate_sum(h.double(), e2, w.double())
+            lhs, rhs = float((a_h * gq.double()).sum()), float((h.double() * at_g).sum())
+            assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+            relu = ops.propagate(graphs[0], h.to(dev), bias.to(dev), relu=True).cpu()
+            assert torch.equal(relu, torch.relu(got))
+
+
+def test_gcnconv_forward_backward(dev):
+    import bigcn_b200
+    torch.manual_seed(2)
+    K, cases = edge_cases()
+    for name in ("twitter_train_dropedge", "general_graph", "no_edges"):
+        b = cases[name]
+        ref = gcn_oracle.GCNConv(K, 64)
+        with torch.no_grad():
+            ref.bias.uniform_(-0.1, 0.1)
+        conv = bigcn_b200.GCNConv(K, 64).to(dev)
+        conv.load_state_dict(ref.state_dict())
+        want = ref(b.x, b.BU_edge_index)
+        got = conv(b.x.to(dev), b.BU_edge_index.to(dev))
+        assert rel_err(got, want) < LOGP_TOL
+        g = torch.randn_like(want)
+        want.backward(g)
+        got.backward(g.to(dev))
+        assert rel_err(conv.lin.weight.grad, ref.lin.weight.grad) < GRAD_TOL
+        assert rel_err(conv.bias.grad, ref.bias.grad) < GRAD_TOL
+
+
+# ------------------------------------------------------------------------------- the model
+def make_pair(K, C, dev, deg_by="target", seed=0):
+    import bigcn_b200
+    torch.manual_seed(seed)
+    ref = bigcn_oracle.BiGCN(K, 64, 64, num_classes=C, deg_by=deg_by)
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    m = bigcn_b200.BiGCN(K, 64, 64, dev, num_classes=C, deg_by=deg_by).to(dev)
+    m.load_state_dict(ref.state_dict())
+    return ref, m
+
+
+def masks_for(m, b, K):
+    n = b.x.shape[0]
+    seed = m.TDrumorGCN.last_seed
+    ktd = torch.from_numpy(gcn_oracle.dropout_keep_mask(seed, 0, np.arange(n), 64 + K, 0.5))
+    kbu = torch.from_numpy(gcn_oracle.dropout_keep_mask(seed, 1, np.arange(n), 64 + K, 0.5))
+    return ktd, kbu
+
+
+def compare_grads(m, ref, tol=GRAD_TOL):
+    worst = 0.0
+    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, name
+        e = rel_err(p.grad, q.grad if q.grad is not None else torch.zeros_like(q))
+        assert e < tol, f"{name}: grad rel err {e:.3e}"
+        worst = max(worst, e)
+    return worst
+
+
+def test_golden_small_batch(dev):
+    import bigcn_b200
+    gold = json.load(open(os.path.join(GOLD, "bigcn_small.json")))
+    b = Batch(x=torch.from_numpy(unhex(gold["x"]).reshape(gold["N"], gold["K"])),
+              edge_index=torch.tensor(gold["edge_index"]).reshape(2, -1),
+              BU_edge_index=torch.tensor(gold["BU_edge_index"]).reshape(2, -1),
+              batch=torch.tensor(gold["batch"]), rootindex=torch.tensor(gold["rootindex"]),
+              y=torch.tensor(gold["y"]))
+    m = bigcn_b200.BiGCN(gold["K"], 64, 64, dev, num_classes=gold["C"]).to(dev).eval()
+    m.load_state_dict({k: torch.from_numpy(unhex(v["data"]).reshape(v["shape"])) for k, v in gold["state"].items()})
+    got = m(b.to(dev))
+    m.check_inputs()
+    want = torch.from_numpy(unhex(gold["logp"]).reshape(-1, gold["C"]))
+    assert rel_err(got, want) < LOGP_TOL
+    check_graph_prep(Batch(x=b.x.cpu(), edge_index=b.edge_index.cpu(), BU_edge_index=b.BU_edge_index.cpu(),
+                           batch=b.batch.cpu(), rootindex=b.rootindex.cpu()), dev)
+
+
+@pytest.mark.parametrize("deg_by", ["target", "source"])
+def test_eval_logits_and_grads_edge_cases(dev, deg_by):
+    K, cases = edge_cases()
+    for i, (name, b) in enumerate(cases.items()):
+        ref, m = make_pair(K, 4 if i % 2 == 0 else 2, dev, deg_by, seed=i)
+        ref.eval(); m.eval()
+        want = ref(b)
+        got = m(clone_batch(b, dev))
+        m.check_inputs()
+        assert got.shape == want.shape
+        e = rel_err(got, want)
+        assert e < LOGP_TOL, f"{name}: {e:.3e}"
+        assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+        g = torch.randn_like(want)
+        want.backward(g)
+        got.backward(g.to(dev))
+        compare_grads(m, ref)
+
+
+def test_train_mode_with_injected_philox_mask(dev):
+    """Train-mode parity: the kernel's Philox mask (spec in oracle/gcn_oracle.py) is injected
+    into the oracle, then log-probs and all ten gradients must agree."""
+    K, cases = edge_cases()
+    for i, name in enumerate(("twitter_train_dropedge", "pheme_singletons", "star_and_chain", "general_graph")):
+        b = cases[name]
+        ref, m = make_pair(K, 4, dev, seed=10 + i)
+        ref.train(); m.train()
+        got = m(clone_batch(b, dev))
+        ktd, kbu = masks_for(m, b, K)
+        want = ref(b, keep_td=ktd, keep_bu=kbu)
+        e = rel_err(got, want)
+        assert e < LOGP_TOL, f"{name}: {e:.3e}"
+        y = b.y
+        torch.nn.functional.nll_loss(want, y).backward()
+        torch.nn.functional.nll_loss(got, y.to(dev)).backward()
+        compare_grads(m, ref)
+
+
+def test_twitter_shaped_bow_batch_k5000(dev):
+    """BASELINE configs[0] shape at reduced tree count: K=5000 BoW, C=4, DropEdge 0.2/0.2, train mode."""
+    b = make_batch("twitter15", 12, seed=0, train=True)
+    ref, m = make_pair(5000, 4, dev, seed=3)
+    ref.train(); m.train()
+    got = m(clone_batch(b, dev))
+    ktd, kbu = masks_for(m, b, 5000)
+    want = ref(b, keep_td=ktd, keep_bu=kbu)
+    assert rel_err(got, want) < LOGP_TOL
+    assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+    torch.nn.functional.nll_loss(want, b.y).backward()
+    torch.nn.functional.nll_loss(got, b.y.to(dev)).backward()
+    compare_grads(m, ref)
+    # second call draws a different mask; eval is deterministic and mask-free
+    got2 = m(clone_batch(b, dev))
+    assert not torch.equal(got2, got)
+    m.eval(); ref.eval()
+    assert rel_err(m(clone_batch(b, dev)), ref(b)) < LOGP_TOL
+
+
+def test_weibo_and_pheme_shapes(dev):
+    # Weibo: C=2, no DropEdge, reference batch 16, heavy-tailed sizes (capped for oracle time)
+    sizes = np.array([10, 2500, 37, 800, 12, 90, 300, 55, 1200, 20, 64, 33, 410, 77, 150, 18])
+    b = make_batch("weibo", 16, seed=5, train=True, in_feats=200, sizes=sizes)
+    assert torch.equal(b.BU_edge_index, b.edge_index.flip(0))
+    ref, m = make_pair(200, 2, dev, seed=4)
+    ref.eval(); m.eval()
+    assert rel_err(m(clone_batch(b, dev)), ref(b)) < LOGP_TOL
+    # PHEME: K=768 dense signed features, B=24, 21 % single-node trees
+    b = make_batch("pheme", 24, seed=6, train=True)
+    ref, m = make_pair(768, 4, dev, seed=5)
+    ref.train(); m.train()
+    got = m(clone_batch(b, dev))
+    ktd, kbu = masks_for(m, b, 768)
+    want = ref(b, keep_td=ktd, keep_bu=kbu)
+    assert rel_err(got, want) < LOGP_TOL
+    torch.nn.functional.nll_loss(want, b.y).backward()
+    torch.nn.functional.nll_loss(got, b.y.to(dev)).backward()
+    compare_grads(m, ref)
+
+
+def test_single_direction_modules(dev):
+    import bigcn_b200
+    K, cases = edge_cases()
+    b = cases["twitter_train_dropedge"]
+    for cls_ref, cls in ((bigcn_oracle.TDrumorGCN, bigcn_b200.TDrumorGCN), (bigcn_oracle.BUrumorGCN, bigcn_b200.BUrumorGCN)):
+        torch.manual_seed(7)
+        ref = cls_ref(K, 64, 64).eval()
+        m = cls(K, 64, 64, dev).to(dev).eval()
+        m.load_state_dict(ref.state_dict())
+        want = ref(b)
+        got = m(clone_batch(b, dev))
+        assert got.shape == (want.shape[0], 128)
+        assert rel_err(got, want) < LOGP_TOL
+        g = torch.randn_like(want)
+        want.backward(g); got.backward(g.to(dev))
+        compare_grads(m, ref)
+
+
+def test_determinism_run_to_run(dev):
+    b = make_batch("twitter15", 10, seed=8, train=True, in_feats=300)
+    _, m = make_pair(300, 4, dev, seed=6)
+    m.train()
+    outs, grads = [], []
+    for _ in range(2):
+        m.TDrumorGCN._calls = 0
+        m.zero_grad(set_to_none=True)
+        o = m(clone_batch(b, dev))
+        torch.nn.functional.nll_loss(o, b.y.to(dev)).backward()
+        outs.append(o.detach().clone())
+        grads.append([p.grad.clone() for p in m.parameters()])
+    assert torch.equal(outs[0], outs[1])
+    for a, c in zip(*grads):
+        assert torch.equal(a, c)
+
+
+def test_fused_trainer_matches_reference_adam(dev):
+    """Three steps of FusedTrainer (flat buffer, fused Adam, BU convs at lr/5) against
+    torch.optim.Adam on the oracle, eval-mode forward so no mask is involved."""
+    import bigcn_b200
+    K = 48
+    ref, m = make_pair(K, 4, dev, seed=9)
+    ref.eval(); m.eval()
+    opt = bigcn_oracle.make_optimizer(ref, lr=5e-4, weight_decay=1e-4)
+    tr = bigcn_b200.FusedTrainer(m, lr=5e-4, weight_decay=1e-4)
+    for step in range(3):
+        b = make_batch("twitter15", 6, seed=20 + step, train=True, in_feats=K)
+        loss_ref = torch.nn.functional.nll_loss(ref(b), b.y)
+        opt.zero_grad(); loss_ref.backward(); opt.step()
+        loss = tr.step(clone_batch(b, dev))
+        tr.check_inputs()
+        assert abs(float(loss.item()) - float(loss_ref)) < 1e-5 * max(1.0, abs(float(loss_ref)))
+    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert rel_err(p, q) < 2e-5, name
+    assert int(tr.step_count.item()) == 3
