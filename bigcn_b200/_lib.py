@@ -77,8 +77,9 @@ _SIGS = {
                                           C.POINTER(Opts), c_ptr, C.POINTER(Params), c_ptr, C.c_size_t,
                                           c_ptr]),
     "bigcn_head_forward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "bigcn_head_backward_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64]),
     "bigcn_head_backward": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr,
-                                      c_ptr, c_ptr]),
+                                      c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_nll_loss": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_adam_step": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int32,
                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr,

@@ -52,6 +52,11 @@ struct FeatWs {
   float* op_part[2];        // [chunks][4096]
   float* dw_part;           // dW1 slab partials
   float* dP[2];             // [B][64]
+  int32_t* slot;            // [B][K] slot of column k in tree b's root list, or -1
+  int32_t* overflow;        // [1] some root row has more than DW2B_CAP positive columns
+  float* pos[2];            // [B][64] #{i in tree : H2[i][f] > 0}
+  float* gs[2];             // [B][64] grad_feat / n_b
+  float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
   void* prep_ws; size_t prep_bytes;
   size_t total;
 };
@@ -88,11 +93,17 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   w.z[1] = w.z[0] + nh;
   w.h2[0] = c.take<float>(2 * nh);
   w.h2[1] = w.h2[0] + nh;
-  const int csn = cs_chunks(N) > bm_chunks(N) ? cs_chunks(N) : bm_chunks(N);
+  int csn = cs_chunks(N) > bm_chunks(N) ? cs_chunks(N) : bm_chunks(N);
+  if (cs_chunks(B) > csn) csn = cs_chunks(B);
   for (int d = 0; d < 2; ++d) w.cs_part[d] = c.take<float>((size_t)csn * H);
   for (int d = 0; d < 2; ++d) w.op_part[d] = c.take<float>((size_t)op_chunks(N) * H * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
   for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
+  w.slot = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
+  w.overflow = c.take<int32_t>(1);
+  for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
+  for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
+  for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
   const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
   w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
   w.prep_ws = c.take<char>(w.prep_bytes);
@@ -160,7 +171,8 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   if (int rc = xw_dispatch(bt->x, N, K, w.w1T, n_out, w.xw, n_out, o->gemm_mode, st)) return rc;
   // 4. root columns (and, without dropout, the per-tree projection)
   {
-    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags};
+    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
+                 w.slot, w.overflow, DW2B_CAP};
     if (int rc = root_nz_launch(a, st)) return rc;
   }
   const bool dropping = o->training && o->p_drop > 0.f;
@@ -207,7 +219,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     a.N = N; a.B = B; a.flags = flags;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.h2[q] = w.h2[d]; a.h1[q] = w.h1[d]; a.feat_base[q] = feat_base(d);
+      a.h2[q] = w.h2[d]; a.h1[q] = w.h1[d]; a.pos[q] = w.pos[d]; a.feat_base[q] = feat_base(d);
     }
     if (int rc = readout_launch(a, st)) return rc;
   }
@@ -225,33 +237,32 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   const int n_out = dirs.n == 2 ? 128 : 64;
   const bool dropping = o->training && o->p_drop > 0.f;
   const size_t nh = (size_t)(N > 0 ? N : 1) * H;
-  float* g2[2] = {w.z[0], w.z[1]};       // Z is dead after forward
   float* t2[2] = {w.xw, w.xw + nh};      // XW is dead after forward
-  float* g1[2] = {w.z[0], w.z[1]};       // G2 is dead once T2 exists
-  float* t1cat = w.h2[0];                // H2 is dead once G2 exists
-  // 1. G2 = grad through mean and relu; db2
+  float* g1[2] = {w.z[0], w.z[1]};       // Z is dead after forward
+  float* t1cat = w.h2[0];                // H2 is dead once T2 exists
+  // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
-    G2Args a{};
-    a.grad_feat = grad_feat; a.batch = bt->batch; a.node_ptr = w.node_ptr; a.N = N;
+    GScaleArgs a{};
+    a.grad_feat = grad_feat; a.node_ptr = w.node_ptr; a.B = B;
     ColsumArgs c{};
-    c.nchunk = N > 0 ? cs_chunks(N) : 0;
+    c.nchunk = B > 0 ? cs_chunks(B) : 0;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.h2[q] = w.h2[d]; a.g2[q] = g2[d]; a.part[q] = w.cs_part[d]; a.feat_base[q] = feat_base(d);
+      a.pos[q] = w.pos[d]; a.gs[q] = w.gs[d]; a.part[q] = w.cs_part[d]; a.feat_base[q] = feat_base(d);
       c.part[q] = w.cs_part[d]; c.out[q] = gdir_b2(gr, d);
     }
-    if (int rc = g2_launch(a, dirs.n, st)) return rc;
+    if (int rc = gscale_launch(a, dirs.n, st)) return rc;
     if (int rc = colsum_reduce_launch(c, dirs.n, st)) return rc;
   }
-  // 2. T2 = A-hat^T G2
+  // 2. T2 = A-hat^T G2 with G2 = [H2 > 0] * gs[batch] formed inside the gather
   {
-    PropArgs a{};
-    a.N = N; a.relu = 0;
+    PropG2Args a{};
+    a.N = N; a.batch = bt->batch;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = PropDir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, g2[d], nullptr, t2[d], H, H};
+      a.d[q] = PropG2Dir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, w.h2[d], w.gs[d], t2[d]};
     }
-    if (int rc = propagate_launch(a, dirs.n, st)) return rc;
+    if (int rc = propagate_g2_launch(a, dirs.n, st)) return rc;
   }
   // 3. dW2a = T2^T A1
   {
@@ -277,13 +288,15 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       if (int rc = segsum_launch(s, B, dirs.n, st)) return rc;
     }
     Dw2bArgs a{};
-    a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr;
+    a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr; a.batch = bt->batch;
+    a.rnz_cnt = w.rnz_cnt; a.rnz_col = w.rnz_col; a.rnz_val = w.rnz_val; a.slot = w.slot;
+    a.overflow = w.overflow;
     a.N = N; a.B = B; a.K = K; a.ld = H + K; a.node_id_base = bt->node_id_base;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), make_drop(o, d)};
+      a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d)};
     }
-    if (int rc = dw2b_launch(a, dirs.n, st)) return rc;
+    if (int rc = dw2b_launch(a, dirs.n, dropping, st)) return rc;
   }
   // 5. G1 = (T2 W2a) * mask * [H1 > 0]; db1
   {

@@ -38,13 +38,16 @@ __global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ feat
 __global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__ g,
                                                        const float* __restrict__ logp, int64_t B,
                                                        int C, const float* __restrict__ W,
-                                                       float* __restrict__ gfeat) {
+                                                       float* __restrict__ gfeat,
+                                                       float* __restrict__ dl_out) {
   const int lane = threadIdx.x & 31;
   const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
   const float gv = lane < C ? g[b * C + lane] : 0.f;
   const float sg = warp_sum(gv);
   const float dl = lane < C ? gv - expf(logp[b * C + lane]) * sg : 0.f;
+  if (lane < C) dl_out[b * C + lane] = dl;
+  if (gfeat == nullptr) return;
   float out[FEAT / 32];
 #pragma unroll
   for (int j = 0; j < FEAT / 32; ++j) out[j] = 0.f;
@@ -57,20 +60,26 @@ __global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__
   for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
 }
 
-// thread per (c, f) [+ bias column f == 256]; trees in order
-__global__ void k_head_bwd_w(const float* __restrict__ g, const float* __restrict__ logp,
-                             const float* __restrict__ feat, int64_t B, int C,
-                             float* __restrict__ dW, float* __restrict__ db) {
+// dW[c][f] = sum_b dl[b][c] feat[b][f] (+ bias column f == 256): thread per (c, f), a chunk
+// of HB_TREES trees per blockIdx.y, trees in order; chunks are summed in order by k_head_bwd_red.
+constexpr int HB_TREES = 256;
+__global__ void k_head_bwd_w(const float* __restrict__ dl, const float* __restrict__ feat, int64_t B,
+                             int C, float* __restrict__ part) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * (FEAT + 1)) return;
+  const int c = idx / (FEAT + 1), f = idx % (FEAT + 1);
+  const int64_t b0 = (int64_t)blockIdx.y * HB_TREES, b1 = min(B, b0 + HB_TREES);
+  float acc = 0.f;
+  for (int64_t b = b0; b < b1; ++b) acc = fmaf(dl[b * C + c], f < FEAT ? feat[b * FEAT + f] : 1.f, acc);
+  part[(size_t)blockIdx.y * C * (FEAT + 1) + idx] = acc;
+}
+__global__ void k_head_bwd_red(const float* __restrict__ part, int nchunk, int C,
+                               float* __restrict__ dW, float* __restrict__ db) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * (FEAT + 1)) return;
   const int c = idx / (FEAT + 1), f = idx % (FEAT + 1);
   float acc = 0.f;
-  for (int64_t b = 0; b < B; ++b) {
-    float sg = 0.f;
-    for (int q = 0; q < C; ++q) sg += g[b * C + q];
-    const float dl = g[b * C + c] - expf(logp[b * C + c]) * sg;
-    acc = fmaf(dl, f < FEAT ? feat[b * FEAT + f] : 1.f, acc);
-  }
+  for (int q = 0; q < nchunk; ++q) acc += part[(size_t)q * C * (FEAT + 1) + idx];
   if (f < FEAT) dW[c * FEAT + f] = acc;
   else db[c] = acc;
 }
@@ -139,19 +148,32 @@ extern "C" int bigcn_head_forward(const float* feat, int64_t B, int64_t C, const
   return 0;
 }
 
+extern "C" size_t bigcn_head_backward_scratch_floats(int64_t B, int64_t C) {
+  const int64_t nchunk = B > 0 ? ceil_div(B, HB_TREES) : 1;
+  return (size_t)(B * C + nchunk * C * (FEAT + 1));
+}
+
 extern "C" int bigcn_head_backward(const float* grad_logp, const float* logp, const float* feat,
                                    int64_t B, int64_t C, const float* fc_w, float* grad_feat,
-                                   float* d_fc_w, float* d_fc_b, bigcn_stream_t stream) {
+                                   float* d_fc_w, float* d_fc_b, float* scratch,
+                                   size_t scratch_floats, bigcn_stream_t stream) {
   BIGCN_CHECK_ARG(C >= 1 && C <= 32, "head_backward: C must be in [1,32]");
+  BIGCN_CHECK_ARG(scratch && scratch_floats >= bigcn_head_backward_scratch_floats(B, C),
+                  "head_backward: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
-  if (B > 0 && grad_feat) {
-    k_head_bwd_feat<<<(int)ceil_div(B, 8), 256, 0, st>>>(grad_logp, logp, B, (int)C, fc_w, grad_feat);
+  float* dl = scratch;
+  float* part = scratch + B * C;
+  const int nchunk = B > 0 ? (int)ceil_div(B, HB_TREES) : 1;
+  if (B > 0) {
+    k_head_bwd_feat<<<(int)ceil_div(B, 8), 256, 0, st>>>(grad_logp, logp, B, (int)C, fc_w, grad_feat, dl);
     BIGCN_CHECK_LAUNCH("k_head_bwd_feat");
   }
   if (d_fc_w) {
     const int tot = (int)C * (FEAT + 1);
-    k_head_bwd_w<<<(tot + 127) / 128, 128, 0, st>>>(grad_logp, logp, feat, B, (int)C, d_fc_w, d_fc_b);
+    k_head_bwd_w<<<dim3((tot + 127) / 128, nchunk), 128, 0, st>>>(dl, feat, B, (int)C, part);
     BIGCN_CHECK_LAUNCH("k_head_bwd_w");
+    k_head_bwd_red<<<(tot + 127) / 128, 128, 0, st>>>(part, nchunk, (int)C, d_fc_w, d_fc_b);
+    BIGCN_CHECK_LAUNCH("k_head_bwd_red");
   }
   return 0;
 }

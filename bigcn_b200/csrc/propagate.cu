@@ -102,32 +102,61 @@ int propagate_launch(const PropArgs& a, int ndir, cudaStream_t st) {
 // Per tree: the columns k with relu(x[root,k]) > 0, ascending, and their values.
 // (root_extend of BiGCN_Twitter.py:45-50 is x1[rootindex[batch]]: only these columns
 // can contribute to conv2 after the relu of :53.)
+// CTA per tree: 8 warps ballot 32-column strips, a strip-count scan orders them, a second
+// pass writes (col, val) at its rank and slot[b][k] = rank or -1 for every column (the map
+// the dW2b reduce uses to find a column's slot in a tree).
 __global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= a.B) return;
+  extern __shared__ int strip[];  // [nstrips] counts -> exclusive offsets
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int nstrips = (int)((a.K + 31) / 32);
   const int64_t r = a.rootindex[b];
-  if (r < 0 || r >= a.N) {
-    if (lane == 0) {
-      atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
-      a.cnt[b] = 0;
-    }
-    return;
-  }
-  const float* xr = a.x + r * a.K;
-  int base = 0;
-  for (int64_t k0 = 0; k0 < a.K; k0 += 32) {
-    const int64_t k = k0 + lane;
-    const float v = k < a.K ? xr[k] : 0.f;
+  const bool ok = r >= 0 && r < a.N;
+  if (!ok && threadIdx.x == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+  const float* xr = a.x + (ok ? r : 0) * a.K;
+  for (int s = w; s < nstrips; s += 8) {
+    const int64_t k = (int64_t)s * 32 + lane;
+    const float v = (ok && k < a.K) ? xr[k] : 0.f;
     const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
+    if (lane == 0) strip[s] = __popc(m);
+  }
+  __syncthreads();
+  if (w == 0) {  // exclusive scan of the strip counts: contiguous chunk per lane
+    const int per = (nstrips + 31) / 32;
+    const int lo = min(lane * per, nstrips), hi = min(lo + per, nstrips);
+    int sum = 0;
+    for (int s = lo; s < hi; ++s) sum += strip[s];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL_MASK, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - sum;
+    for (int s = lo; s < hi; ++s) {
+      const int t = strip[s];
+      strip[s] = run;
+      run += t;
+    }
+    if (lane == 31) s_total = inc;
+  }
+  __syncthreads();
+  for (int s = w; s < nstrips; s += 8) {
+    const int64_t k = (int64_t)s * 32 + lane;
+    const float v = (ok && k < a.K) ? xr[k] : 0.f;
+    const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
+    const int pos = strip[s] + __popc(m & ((1u << lane) - 1u));
     if (v > 0.f) {
-      const int pos = base + __popc(m & ((1u << lane) - 1u));
       a.col[b * a.K + pos] = (int32_t)k;
       a.val[b * a.K + pos] = v;
     }
-    base += __popc(m);
+    if (k < a.K) a.slot[b * a.K + k] = v > 0.f ? pos : -1;
   }
-  if (lane == 0) a.cnt[b] = base;
+  if (threadIdx.x == 0) {
+    a.cnt[b] = s_total;
+    if (s_total > a.cap) atomicOr(a.overflow, 1);
+  }
 }
 
 // eval mode: P[d][b][:] = relu(x_root[b]) * W2b_d^T, once per tree
@@ -246,10 +275,12 @@ __global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
 // CTA per tree: 4 row-lanes x 64 features per direction, fixed-order combine.
 __global__ void __launch_bounds__(512) k_readout(ReadoutArgs a) {
   __shared__ float part[2][4][H];
+  __shared__ int cpos[2][4][H];
   const int64_t b = blockIdx.x;
   const int d = threadIdx.x >> 8, g = (threadIdx.x >> 6) & 3, f = threadIdx.x & 63;
   const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
   float acc = 0.f;
+  int npos = 0;
   if (d < a.ndir) {
     const float* h2 = a.h2[d];
     int i = s + g;
@@ -257,13 +288,20 @@ __global__ void __launch_bounds__(512) k_readout(ReadoutArgs a) {
       const float v0 = h2[(int64_t)i * H + f], v1 = h2[(int64_t)(i + 4) * H + f];
       const float v2 = h2[(int64_t)(i + 8) * H + f], v3 = h2[(int64_t)(i + 12) * H + f];
       acc += v0; acc += v1; acc += v2; acc += v3;
+      npos += (v0 > 0.f) + (v1 > 0.f) + (v2 > 0.f) + (v3 > 0.f);
     }
-    for (; i < e; i += 4) acc += h2[(int64_t)i * H + f];
+    for (; i < e; i += 4) {
+      const float v = h2[(int64_t)i * H + f];
+      acc += v;
+      npos += v > 0.f;
+    }
     part[d][g][f] = acc;
+    cpos[d][g][f] = npos;
   }
   __syncthreads();
   if (d < a.ndir && g == 0) {
     const float sum = ((part[d][0][f] + part[d][1][f]) + part[d][2][f]) + part[d][3][f];
+    if (a.pos[d]) a.pos[d][b * H + f] = (float)(cpos[d][0][f] + cpos[d][1][f] + cpos[d][2][f] + cpos[d][3][f]);
     const int n = e - s;
     float* fr = a.feat + b * 4 * H + a.feat_base[d];
     fr[f] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
@@ -278,34 +316,79 @@ __global__ void __launch_bounds__(512) k_readout(ReadoutArgs a) {
 }
 
 // ---------------------------------------------------------------- backward pieces
-// G2[d][i][f] = grad_feat[b_i][base_d + f] / n_b * [H2 > 0]; partial column sums for db2
-__global__ void __launch_bounds__(256) k_g2(G2Args a) {
+// Per tree: gs[d][b][f] = grad_feat[b][base_d + f] / n_b (scatter_mean backward), and the
+// partial column sums of db2 = sum_i G2[i] = sum_b gs[b] * #{i in b : H2[i] > 0} using the
+// positive counts the readout kept.  G2 itself is never materialised: k_propagate_g2 forms
+// it on the fly while gathering.
+__global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
   __shared__ float red[4][H];
   const int d = blockIdx.y;
   const int g = threadIdx.x >> 6, f = threadIdx.x & 63;
   const int64_t base = (int64_t)blockIdx.x * CS_ROWS;
-  const int64_t end = min(a.N, base + CS_ROWS);
+  const int64_t end = min(a.B, base + CS_ROWS);
   float acc = 0.f;
-  for (int64_t i = base + g; i < end; i += 4) {
-    const int64_t b = a.batch[i];
+  for (int64_t b = base + g; b < end; b += 4) {
     const int n = a.node_ptr[b + 1] - a.node_ptr[b];
-    float gv = __fdiv_rn(a.grad_feat[b * 4 * H + a.feat_base[d] + f], (float)(n > 0 ? n : 1));
-    gv = a.h2[d][i * H + f] > 0.f ? gv : 0.f;
-    a.g2[d][i * H + f] = gv;
-    acc += gv;
+    const float gv = __fdiv_rn(a.grad_feat[b * 4 * H + a.feat_base[d] + f], (float)(n > 0 ? n : 1));
+    a.gs[d][b * H + f] = gv;
+    acc = fmaf(gv, a.pos[d][b * H + f], acc);
   }
   red[g][f] = acc;
   __syncthreads();
   if (g == 0) a.part[d][(int64_t)blockIdx.x * H + f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
 }
 
-// out[f] = sum_chunk part[chunk][f], chunks in order
-__global__ void k_colsum_reduce(ColsumArgs a) {
+// T2[j] = sum_{x in out(j)} (dis[j]*dis[x]) * G2[x] + dis[j]^2 * G2[j],
+// G2[x] = [H2[x] > 0] * gs[batch[x]]   (relu and scatter_mean backward fused into the gather)
+__global__ void __launch_bounds__(256) k_propagate_g2(PropG2Args a) {
+  const PropG2Dir& p = a.d[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < a.N; i += nwarp) {
+    const int s = p.ptr[i], e = p.ptr[i + 1];
+    const float di = p.dis[i];
+    float2 acc = make_float2(0.f, 0.f);
+    for (int b0 = s; b0 < e; b0 += 32) {
+      const int n = min(32, e - b0);
+      int j = 0, tb = 0;
+      float dj = 0.f;
+      if (lane < n) {
+        j = p.idx[b0 + lane];
+        dj = p.dis[j];
+        tb = (int)a.batch[j];
+      }
+      for (int l = 0; l < n; ++l) {
+        const int jj = __shfl_sync(FULL_MASK, j, l);
+        const int bb = __shfl_sync(FULL_MASK, tb, l);
+        const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l), di);
+        const float2 hv = *reinterpret_cast<const float2*>(p.h2 + (int64_t)jj * H + 2 * lane);
+        const float2 gv = *reinterpret_cast<const float2*>(p.gs + (int64_t)bb * H + 2 * lane);
+        acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
+        acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+      }
+    }
+    {
+      const float w = __fmul_rn(di, di);
+      const float2 hv = *reinterpret_cast<const float2*>(p.h2 + i * H + 2 * lane);
+      const float2 gv = *reinterpret_cast<const float2*>(p.gs + a.batch[i] * H + 2 * lane);
+      acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
+      acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+    }
+    *reinterpret_cast<float2*>(p.out + i * H + 2 * lane) = acc;
+  }
+}
+
+// out[f] = sum_chunk part[chunk][f]: 4 strided groups, fixed-order combine
+__global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {
+  __shared__ float red[4][H];
   const int j = blockIdx.x;
-  const int f = threadIdx.x;
+  const int g = threadIdx.x >> 6, f = threadIdx.x & 63;
   float s = 0.f;
-  for (int c = 0; c < a.nchunk; ++c) s += a.part[j][(int64_t)c * H + f];
-  a.out[j][f] = s;
+  for (int c = g; c < a.nchunk; c += 4) s += a.part[j][(int64_t)c * H + f];
+  red[g][f] = s;
+  __syncthreads();
+  if (g == 0) a.out[j][f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
 }
 
 // G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1
@@ -422,6 +505,7 @@ __global__ void __launch_bounds__(256) k_segsum(SegSumArgs a) {
 //   eval : sum_b relu(x_root_b[k]) * dP[b][o]
 // Trees ascending, rows ascending inside a warp's strip, warps combined in order.
 __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
+  if (*a.overflow == 0) return;   // sparse roots: the (part, reduce) pair below did the work
   __shared__ float red[4][H];
   __shared__ int s_hit_b[128];
   __shared__ float s_hit_v[128];
@@ -495,6 +579,100 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
   }
 }
 
+// ---- dW2b, sparse-root fast path (every root row has <= DW2B_CAP positive columns) -----
+// part: CTA = DW2B_ROWS consecutive rows of the batch, T2 rows staged in shared memory.
+//   For every tree segment in the block and every root slot t of that tree (warps take
+//   slots round-robin): S[(blk + b)][t][:] = sum_{i in segment, keep(i, 64 + col_t)} T2[i][:]
+//   (lanes decide keep for 32 rows with one Philox block each, then add the kept rows).
+//   (blk + b) is unique per (block, tree) pair because trees are contiguous and sorted.
+// reduce: warp per column k: trees ascending (slot map), blocks ascending:
+//   dW2[o][64 + k] = scale * sum_b relu(x_root_b[k]) * sum_blk S[(blk + b)][slot][o]
+//   eval / p = 0:   dW2[o][64 + k] = sum_b relu(x_root_b[k]) * dP[b][o]
+__global__ void __launch_bounds__(256) k_dw2b_part(Dw2bArgs a) {
+  if (*a.overflow != 0) return;
+  __shared__ __align__(16) float sT[DW2B_ROWS * H];
+  const Dw2bDir& p = a.d[blockIdx.y];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * DW2B_ROWS;
+  const int64_t r1 = min(a.N, r0 + DW2B_ROWS);
+  for (int i = threadIdx.x; i < DW2B_ROWS * H / 4; i += 256) {
+    const int64_t r = r0 + (i >> 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < r1) v = *reinterpret_cast<const float4*>(p.t2 + r * H + (i & 15) * 4);
+    *reinterpret_cast<float4*>(sT + (size_t)i * 4) = v;
+  }
+  __syncthreads();
+  const int64_t b_first = a.batch[r0], b_last = a.batch[r1 - 1];
+  for (int64_t b = b_first; b <= b_last; ++b) {
+    const int s = max((int)r0, a.node_ptr[b]), e = min((int)r1, a.node_ptr[b + 1]);
+    if (s >= e) continue;
+    const int cnt = a.rnz_cnt[b];
+    float* Sb = p.S + ((size_t)(blockIdx.x + b) * DW2B_CAP) * H;
+    for (int t = w; t < cnt; t += 8) {
+      const uint32_t c = (uint32_t)(H + a.rnz_col[b * a.K + t]);
+      float2 acc = make_float2(0.f, 0.f);
+      for (int i0 = s; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        if (i < e) {
+          const Philox4 r = drop_block(p.drop, a.node_id_base + i, c >> 2);
+          keep = philox_elem(r, c & 3) >= p.drop.thresh;
+        }
+        unsigned m = __ballot_sync(FULL_MASK, keep);
+        while (m) {
+          const int sl = __ffs(m) - 1;
+          m &= m - 1;
+          const float2 tv = *reinterpret_cast<const float2*>(sT + (size_t)(i0 + sl - r0) * H + 2 * lane);
+          acc.x += tv.x;
+          acc.y += tv.y;
+        }
+      }
+      *reinterpret_cast<float2*>(Sb + (size_t)t * H + 2 * lane) = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
+  if (*a.overflow != 0) return;
+  const Dw2bDir& p = a.d[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= a.K) return;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int64_t b0 = 0; b0 < a.B; b0 += 32) {
+    const int64_t b = b0 + lane;
+    const int t = b < a.B ? a.slot[b * a.K + k] : -1;
+    unsigned m = __ballot_sync(FULL_MASK, t >= 0);
+    while (m) {
+      const int sl = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t bb = b0 + sl;
+      const int tt = __shfl_sync(FULL_MASK, t, sl);
+      const float v = a.rnz_val[bb * a.K + tt];
+      float2 sub = make_float2(0.f, 0.f);
+      if (p.drop.on) {
+        const int s = a.node_ptr[bb], e = a.node_ptr[bb + 1];
+        if (e > s) {
+          const int j0 = s / DW2B_ROWS, j1 = (e - 1) / DW2B_ROWS;
+          for (int j = j0; j <= j1; ++j) {
+            const float2 q = *reinterpret_cast<const float2*>(
+                p.S + ((size_t)(j + bb) * DW2B_CAP + tt) * H + 2 * lane);
+            sub.x += q.x;
+            sub.y += q.y;
+          }
+        }
+      } else {
+        sub = *reinterpret_cast<const float2*>(p.dP + bb * H + 2 * lane);
+      }
+      acc.x = fmaf(v, sub.x, acc.x);
+      acc.y = fmaf(v, sub.y, acc.y);
+    }
+  }
+  const float sc = p.drop.on ? p.drop.scale : 1.f;
+  p.dw2[(int64_t)(2 * lane) * a.ld + H + k] = acc.x * sc;
+  p.dw2[(int64_t)(2 * lane + 1) * a.ld + H + k] = acc.y * sc;
+}
+
 // ---------------------------------------------------------------- dropout mask materialisation (tests)
 __global__ void k_dropout_mask(DropSpec ds, int64_t node_id_base, int64_t N, int64_t n_cols,
                                uint8_t* keep) {
@@ -514,8 +692,11 @@ __global__ void k_dropout_mask(DropSpec ds, int64_t node_id_base, int64_t N, int
 
 // ---------------------------------------------------------------- host-side launchers
 int root_nz_launch(const RootNzArgs& a, cudaStream_t st) {
+  cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st);
   if (a.B == 0) return 0;
-  k_root_nz<<<(int)ceil_div(a.B, 8), 256, 0, st>>>(a);
+  const size_t smem = (size_t)((a.K + 31) / 32) * sizeof(int);
+  BIGCN_CHECK_ARG(smem <= 48 * 1024, "root_nz: in_feats too large (%lld)", (long long)a.K);
+  k_root_nz<<<(int)a.B, 256, smem, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_root_nz");
   return 0;
 }
@@ -541,14 +722,20 @@ int cs_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, CS_ROWS); }
 int bm_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, BM_ROWS); }
 int op_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, OP_ROWS); }
 
-int g2_launch(const G2Args& a, int ndir, cudaStream_t st) {
+int gscale_launch(const GScaleArgs& a, int ndir, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  k_gscale<<<dim3(cs_chunks(a.B), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_gscale");
+  return 0;
+}
+int propagate_g2_launch(const PropG2Args& a, int ndir, cudaStream_t st) {
   if (a.N == 0) return 0;
-  k_g2<<<dim3(cs_chunks(a.N), ndir), 256, 0, st>>>(a);
-  BIGCN_CHECK_LAUNCH("k_g2");
+  k_propagate_g2<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_propagate_g2");
   return 0;
 }
 int colsum_reduce_launch(const ColsumArgs& a, int njobs, cudaStream_t st) {
-  k_colsum_reduce<<<njobs, H, 0, st>>>(a);
+  k_colsum_reduce<<<njobs, 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_colsum_reduce");
   return 0;
 }
@@ -573,12 +760,19 @@ int segsum_launch(const SegSumArgs& a, int64_t B, int ndir, cudaStream_t st) {
   BIGCN_CHECK_LAUNCH("k_segsum");
   return 0;
 }
-int dw2b_launch(const Dw2bArgs& a, int ndir, cudaStream_t st) {
+int dw2b_launch(const Dw2bArgs& a, int ndir, bool dropping, cudaStream_t st) {
   if (a.K == 0) return 0;
-  k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);
+  if (dropping && a.N > 0) {
+    k_dw2b_part<<<dim3(dw2b_blocks(a.N), ndir), 256, 0, st>>>(a);
+    BIGCN_CHECK_LAUNCH("k_dw2b_part");
+  }
+  k_dw2b_reduce<<<dim3((int)ceil_div(a.K, 8), ndir), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_dw2b_reduce");
+  k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);   // dense-root fallback, returns at once otherwise
   BIGCN_CHECK_LAUNCH("k_dw2b");
   return 0;
 }
+int dw2b_blocks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, DW2B_ROWS); }
 int dropout_mask_launch(const DropSpec& ds, int64_t base, int64_t N, int64_t n_cols, uint8_t* keep,
                         cudaStream_t st) {
   if (N == 0 || n_cols == 0) return 0;

@@ -130,84 +130,106 @@ int transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K, float* 
 }
 
 // ------------------------------------------------------- gT[k, :] = sum_i x[i,k] * t[i, :]
-// CTA = 8 warps x 8 columns = one 64-column slab of X, one chunk of rows.  A warp owns its
-// 8 columns (one 32 B sector per row) and their NOUT accumulators in shared memory, so no
-// two warps ever add into the same address and each column's contributions arrive in
-// ascending row order.  Lanes (2j, 2j+1) read the sector of row r0+j: 16 rows per load,
-// DW_U loads in flight.  Row chunks produce partial[chunk][K][NOUT]; k_dw_reduce sums the
-// chunks in order and writes PyG's [out, in] layout.
+// CTA = one 16-column slab of X (64 B = 2 sectors per row) x one chunk of rows.  EVERY warp
+// covers all 16 columns for its own rows (4 lanes x float4 per row, 8 rows per load, DW_U
+// loads in flight) and keeps the 16 x NOUT accumulators in registers, so a column that is
+// non-zero in every row (common words in a bag-of-words matrix) costs the same as any other:
+// its hits are spread over all warps of all row chunks instead of serialising in one owner.
+// Per column the contributions are added in ascending row order inside a warp, warps are
+// combined in index order through shared memory, and row chunks in order by k_dw_reduce:
+// no atomics, bit-reproducible.
 constexpr int DW_U = 8;
-constexpr int DW_COLS = 64;
+constexpr int DW_COLS = 16;
+constexpr int DW_WARP_ROWS = 8 * DW_U;        // rows a warp covers per outer iteration
+constexpr int DW_CTA_ROWS = 8 * DW_WARP_ROWS;  // 512
+
+template <int V>
+__device__ __forceinline__ void dw_hit(float (&acc)[DW_COLS][V], int cl, float val, const float* tr) {
+  float tv[V];
+  if (V == 4) {
+    const float4 q = *reinterpret_cast<const float4*>(tr);
+    tv[0] = q.x; tv[1] = q.y; tv[2] = q.z; tv[3] = q.w;
+  } else {
+    const float2 q = *reinterpret_cast<const float2*>(tr);
+    tv[0] = q.x; tv[1] = q.y;
+  }
+  switch (cl) {  // warp-uniform: accumulators stay in registers
+#define DW_CASE(c)                                              \
+  case c:                                                       \
+    _Pragma("unroll") for (int j = 0; j < V; ++j) acc[c][j] = fmaf(val, tv[j], acc[c][j]); \
+    break;
+    DW_CASE(0) DW_CASE(1) DW_CASE(2) DW_CASE(3) DW_CASE(4) DW_CASE(5) DW_CASE(6) DW_CASE(7)
+    DW_CASE(8) DW_CASE(9) DW_CASE(10) DW_CASE(11) DW_CASE(12) DW_CASE(13) DW_CASE(14) DW_CASE(15)
+#undef DW_CASE
+  }
+}
 
 template <int NOUT>
-__global__ void __launch_bounds__(256) k_dw_slab(const float* __restrict__ x, int64_t N, int64_t K,
-                                                 const float* __restrict__ t, int64_t ldt,
-                                                 float* __restrict__ partial, int rows_per_chunk) {
+__global__ void __launch_bounds__(256, 2) k_dw_slab(const float* __restrict__ x, int64_t N, int64_t K,
+                                                    const float* __restrict__ t, int64_t ldt,
+                                                    float* __restrict__ partial, int rows_per_chunk) {
   constexpr int V = NOUT / 32;
-  extern __shared__ float acc_s[];  // [64][NOUT]
+  __shared__ float red[DW_COLS * NOUT];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t c0 = (int64_t)blockIdx.x * DW_COLS + w * 8;  // first column of this warp
+  const int64_t c0 = (int64_t)blockIdx.x * DW_COLS;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_chunk;
   const int64_t r_end = min(N, r_begin + rows_per_chunk);
-  float* acc = acc_s + (size_t)w * 8 * NOUT;
-  for (int i = lane; i < 8 * NOUT; i += 32) acc[i] = 0.f;
-  __syncwarp();
-  const int sub = lane & 1;       // which half of the sector
-  const int rl = lane >> 1;       // row within the 16-row group
-  const int64_t col = c0 + sub * 4;
-  const bool col_ok = col < K;    // K % 4 == 0 -> whole float4 valid
-  if (c0 < K) {
-    for (int64_t rb = r_begin; rb < r_end; rb += 16 * DW_U) {
-      float4 v[DW_U];
+  const int q = lane & 3;    // which float4 of the slab
+  const int rl = lane >> 2;  // row within the 8-row group
+  const int64_t col = c0 + q * 4;
+  const bool col_ok = col < K;  // K % 4 == 0 -> whole float4 valid
+  float acc[DW_COLS][V];
 #pragma unroll
-      for (int u = 0; u < DW_U; ++u) {
-        const int64_t r = rb + u * 16 + rl;
-        v[u] = (col_ok && r < r_end) ? ldg_stream_f4(x + r * K + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  for (int c = 0; c < DW_COLS; ++c)
 #pragma unroll
-      for (int u = 0; u < DW_U; ++u) {
-        const bool any = (v[u].x != 0.f) | (v[u].y != 0.f) | (v[u].z != 0.f) | (v[u].w != 0.f);
-        if (__ballot_sync(FULL_MASK, any) == 0u) continue;
+    for (int j = 0; j < V; ++j) acc[c][j] = 0.f;
+  for (int64_t rb = r_begin + w * DW_WARP_ROWS; rb < r_end; rb += DW_CTA_ROWS) {
+    float4 v[DW_U];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float comp = c == 0 ? v[u].x : (c == 1 ? v[u].y : (c == 2 ? v[u].z : v[u].w));
-          unsigned m = __ballot_sync(FULL_MASK, comp != 0.f);
-          while (m) {
-            const int sl = __ffs(m) - 1;
-            m &= m - 1;
-            const float val = __shfl_sync(FULL_MASK, comp, sl);
-            const int64_t r = rb + u * 16 + (sl >> 1);
-            const int cl = (sl & 1) * 4 + c;
-            const float* tr = t + r * ldt + lane * V;
-            float* a = acc + cl * NOUT + lane * V;
-            if (V == 4) {
-              const float4 tv = *reinterpret_cast<const float4*>(tr);
-              float4 av = *reinterpret_cast<float4*>(a);
-              av.x = fmaf(val, tv.x, av.x);
-              av.y = fmaf(val, tv.y, av.y);
-              av.z = fmaf(val, tv.z, av.z);
-              av.w = fmaf(val, tv.w, av.w);
-              *reinterpret_cast<float4*>(a) = av;
-            } else {
-              const float2 tv = *reinterpret_cast<const float2*>(tr);
-              float2 av = *reinterpret_cast<float2*>(a);
-              av.x = fmaf(val, tv.x, av.x);
-              av.y = fmaf(val, tv.y, av.y);
-              *reinterpret_cast<float2*>(a) = av;
-            }
-            __syncwarp();
-          }
+    for (int u = 0; u < DW_U; ++u) {
+      const int64_t r = rb + u * 8 + rl;
+      v[u] = (col_ok && r < r_end) ? ldg_stream_f4(x + r * K + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < DW_U; ++u) {
+      const bool any = (v[u].x != 0.f) | (v[u].y != 0.f) | (v[u].z != 0.f) | (v[u].w != 0.f);
+      unsigned rows_hit = __ballot_sync(FULL_MASK, any);
+      // rows ascending; inside a row the columns ascending
+      while (rows_hit) {
+        const int first = __ffs(rows_hit) - 1;
+        const int rr = first >> 2;
+        rows_hit &= ~(0xfu << (rr * 4));
+        const float* tr = t + (rb + u * 8 + rr) * ldt + lane * V;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int sl = rr * 4 + qq;
+          const float a0 = __shfl_sync(FULL_MASK, v[u].x, sl), a1 = __shfl_sync(FULL_MASK, v[u].y, sl);
+          const float a2 = __shfl_sync(FULL_MASK, v[u].z, sl), a3 = __shfl_sync(FULL_MASK, v[u].w, sl);
+          if (a0 != 0.f) dw_hit<V>(acc, qq * 4 + 0, a0, tr);
+          if (a1 != 0.f) dw_hit<V>(acc, qq * 4 + 1, a1, tr);
+          if (a2 != 0.f) dw_hit<V>(acc, qq * 4 + 2, a2, tr);
+          if (a3 != 0.f) dw_hit<V>(acc, qq * 4 + 3, a3, tr);
         }
       }
     }
   }
-  __syncwarp();
-  float* out = partial + ((size_t)blockIdx.y * K) * NOUT;
-  for (int cl = 0; cl < 8; ++cl) {
-    const int64_t k = c0 + cl;
-    if (k < K) {
-      for (int j = lane; j < NOUT; j += 32) out[k * NOUT + j] = acc[cl * NOUT + j];
+  // ordered combine of the 8 warps, then one coalesced store of the slab's partial
+  for (int ww = 0; ww < 8; ++ww) {
+    if (w == ww) {
+#pragma unroll
+      for (int c = 0; c < DW_COLS; ++c)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float* p = red + c * NOUT + lane * V + j;
+          *p = (ww == 0) ? acc[c][j] : (*p + acc[c][j]);
+        }
     }
+    __syncthreads();
+  }
+  float* out = partial + ((size_t)blockIdx.y * K) * NOUT;
+  for (int i = threadIdx.x; i < DW_COLS * NOUT; i += 256) {
+    const int64_t k = c0 + i / NOUT;
+    if (k < K) out[k * NOUT + (i % NOUT)] = red[i];
   }
 }
 
@@ -262,12 +284,12 @@ DwPlan dw_plan(int64_t N, int64_t K, const float* x) {
     return p;
   }
   const int64_t slabs = ceil_div(K, DW_COLS);
-  int64_t want = ceil_div((int64_t)num_sms() * 4, slabs);
-  const int64_t max_chunks = ceil_div(N, 16 * DW_U);  // at least one full load group per chunk
+  int64_t want = ceil_div((int64_t)num_sms() * 8, slabs);
+  const int64_t max_chunks = ceil_div(N, DW_CTA_ROWS);  // at least one full CTA pass per chunk
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
   int64_t rpc = ceil_div(N, want);
-  rpc = ceil_div(rpc, 16) * 16;
+  rpc = ceil_div(rpc, DW_WARP_ROWS) * DW_WARP_ROWS;
   p.rows_per_chunk = (int)rpc;
   p.nchunk = (int)ceil_div(N, rpc);
   return p;
@@ -275,7 +297,7 @@ DwPlan dw_plan(int64_t N, int64_t K, const float* x) {
 size_t dw_partial_floats(int64_t N, int64_t K, int n_out) {
   // upper bound independent of the pointer alignment
   const int64_t slabs = ceil_div(K, DW_COLS);
-  int64_t want = ceil_div((int64_t)num_sms() * 4, slabs > 0 ? slabs : 1);
+  int64_t want = ceil_div((int64_t)num_sms() * 8, slabs > 0 ? slabs : 1);
   if (want < 1) want = 1;
   return (size_t)(want + 1) * (size_t)K * (size_t)n_out;
 }
@@ -290,11 +312,10 @@ int dw_fp32(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, i
     cudaMemsetAsync(partial, 0, (size_t)K * n_out * sizeof(float), st);
   } else if (p.fast) {
     dim3 grid((unsigned)ceil_div(K, DW_COLS), (unsigned)p.nchunk);
-    const size_t smem = (size_t)DW_COLS * n_out * sizeof(float);
     if (n_out == 128) {
-      k_dw_slab<128><<<grid, 256, smem, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+      k_dw_slab<128><<<grid, 256, 0, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
     } else {
-      k_dw_slab<64><<<grid, 256, smem, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+      k_dw_slab<64><<<grid, 256, 0, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
     }
     BIGCN_CHECK_LAUNCH("k_dw_slab");
   } else {

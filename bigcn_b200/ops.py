@@ -265,8 +265,10 @@ class HeadFunction(torch.autograd.Function):
         gfeat = torch.empty_like(feat)
         dw = torch.empty_like(fc_w)
         db = torch.empty(c, dtype=torch.float32, device=feat.device)
+        nscr = lib().bigcn_head_backward_scratch_floats(b, c)
+        scr = torch.empty(nscr, dtype=torch.float32, device=feat.device)
         check(lib().bigcn_head_backward(_p(g), _p(logp), _p(feat), b, c, _p(fc_w), _p(gfeat), _p(dw), _p(db),
-                                        _stream()), "head_backward")
+                                        _p(scr), nscr, _stream()), "head_backward")
         return gfeat, dw, db
 
 

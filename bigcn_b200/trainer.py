@@ -109,8 +109,10 @@ class FusedTrainer:
                                        _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
         check(l.bigcn_head_forward(_p(feat), b, c, self._pr.fc_w, self._pr.fc_b, _p(logp), st), "head_forward")
         check(l.bigcn_nll_loss(_p(logp), _p(y), b, c, int(b_global or b), _p(loss), _p(glogp), st), "nll_loss")
+        nscr = l.bigcn_head_backward_scratch_floats(b, c)
+        scr = torch.empty(nscr, dtype=torch.float32, device=dev)
         check(l.bigcn_head_backward(_p(glogp), _p(logp), _p(feat), b, c, self._pr.fc_w, _p(gfeat),
-                                    self._gr.fc_w, self._gr.fc_b, st), "head_backward")
+                                    self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_backward")
         check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                         C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
         if self.world > 1:
@@ -136,7 +138,9 @@ def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True) -> i
     passes = (bits + 7) // 8
     prep = 1 + 2 + 3 * passes + 1            # count, scan x2, radix passes, deg  (memset not counted)
     fwd = prep + 3 * n_dirs + 1 + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
-    head = 1 + 1 + 2                           # head fwd, nll, head bwd x2
-    bwd = 2 + 1 + 2 + (0 if training else 1) + 1 + 2 + 1 + 1 + n_dirs   # g2+colsum, propT, outer x2, [segsum], dw2b, bwdmix+colsum, propT, dw slab, dw reduce x dirs
+    head = 1 + 1 + 3                           # head fwd, nll, head bwd (feat, w partial, w reduce)
+    # gscale+colsum, propT(g2), outer x2, [segsum | dw2b part], dw2b reduce + dense fallback,
+    # bwdmix+colsum, propT, dw slab, dw reduce x dirs
+    bwd = 2 + 1 + 2 + 1 + 2 + 2 + 1 + 1 + n_dirs
     adam = 2
     return fwd + head + bwd + adam

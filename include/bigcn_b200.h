@@ -186,9 +186,11 @@ int bigcn_features_backward(const bigcn_dims_t* dims, const bigcn_batch_t* batch
  * Replaces fc + log_softmax (BiGCN_Twitter.py:129-130). */
 int bigcn_head_forward(const float* feat, int64_t B, int64_t C, const float* fc_w,
                        const float* fc_b, float* logp /*[B,C]*/, bigcn_stream_t stream);
+size_t bigcn_head_backward_scratch_floats(int64_t B, int64_t C);
 int bigcn_head_backward(const float* grad_logp, const float* logp, const float* feat, int64_t B,
                         int64_t C, const float* fc_w, float* grad_feat /*[B,256]*/,
-                        float* d_fc_w, float* d_fc_b, bigcn_stream_t stream);
+                        float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
+                        bigcn_stream_t stream);
 
 /* ---- loss and optimiser (the step around the path, :184-189, :146-153) --
  * loss = -(1/B_global) sum_b logp[b,y[b]] (F.nll_loss, mean); grad_logp = dloss/dlogp. */

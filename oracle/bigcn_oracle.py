@@ -32,7 +32,7 @@ def _dropout(x, p, training, keep):
         return x
     if keep is None:
         return F.dropout(x, p=p, training=True)
-    scale = torch.tensor(1.0, dtype=torch.float32) / torch.tensor(1.0 - p, dtype=torch.float32)
+    scale = torch.tensor(1.0, dtype=torch.float32) / torch.tensor(1.0 - p, dtype=torch.float32)  # fp32 1/(1-p), as F.dropout
     return x * (keep.to(x.dtype) * scale.to(x.dtype))
 
 
@@ -62,7 +62,8 @@ class _RumorGCN(torch.nn.Module):
 
     def forward(self, data, keep=None):
         x, edge_index = data.x, getattr(data, self.edge_attr)         # :27 / :78
-        x1 = copy.copy(x.float())                                      # :28
+        x1 = copy.copy(x.to(self.conv1.lin.weight.dtype))              # :28 x.float(); fp64 when the oracle is .double() (truth mode)
+        x = x1
         x = self.conv1(x, edge_index)                                  # :42
         x2 = copy.copy(x)                                              # :44  (detached leaf sharing storage)
         if x2.requires_grad and x2.grad_fn is not None:                # torch<2 semantics guard

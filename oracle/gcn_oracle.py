@@ -48,7 +48,7 @@ def gcn_norm(edge_index: torch.Tensor, num_nodes: int, edge_weight=None,
     edge_index, edge_weight = add_remaining_self_loops(edge_index, edge_weight, 1.0, num_nodes)
     row, col = edge_index[0], edge_index[1]
     idx = col if deg_by == "target" else row
-    deg = torch.zeros(num_nodes, dtype=dtype).scatter_add_(0, idx, edge_weight)
+    deg = torch.zeros(num_nodes, dtype=edge_weight.dtype).scatter_add_(0, idx, edge_weight)
     dis = deg.pow(-0.5)
     dis.masked_fill_(dis == float("inf"), 0)
     w = dis[row] * edge_weight * dis[col]

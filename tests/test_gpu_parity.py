@@ -34,6 +34,22 @@ def rel_err(got, want):
     return float((got - want).abs().max()) / scale
 
 
+def assert_logp_parity(got, ref, b, keep_td=None, keep_bu=None, what=""):
+    """north_star bar: fp32 log-probs within 1e-5 (max|d| / max|ref|).  Checked against the
+    fp64 oracle (truth) outright, and against the fp32 oracle with the fp32 oracle's own
+    distance from the truth as allowance (its sequential index_add_ sums drift by ~1e-5 on
+    trees of thousands of nodes; triangle inequality)."""
+    want32 = ref(b, keep_td, keep_bu).detach()
+    ref64 = copy.deepcopy(ref).double()
+    want64 = ref64(b, keep_td, keep_bu).detach()
+    own = rel_err(want32, want64)
+    e64, e32 = rel_err(got, want64), rel_err(got, want32)
+    assert e64 < LOGP_TOL, f"{what}: vs fp64 oracle {e64:.3e}"
+    assert e32 < LOGP_TOL + own, f"{what}: vs fp32 oracle {e32:.3e} (oracle fp32-vs-fp64 {own:.3e})"
+    assert torch.equal(got.argmax(1).cpu(), want32.argmax(1)), what
+    return want32
+
+
 def clone_batch(b, dev):
     return Batch(x=b.x.to(dev), edge_index=b.edge_index.to(dev), BU_edge_index=b.BU_edge_index.to(dev),
                  batch=b.batch.to(dev), rootindex=b.rootindex.to(dev), y=b.y.to(dev))
@@ -345,7 +361,7 @@ def test_weibo_and_pheme_shapes(dev):
     assert torch.equal(b.BU_edge_index, b.edge_index.flip(0))
     ref, m = make_pair(200, 2, dev, seed=4)
     ref.eval(); m.eval()
-    assert rel_err(m(clone_batch(b, dev)), ref(b)) < LOGP_TOL
+    assert_logp_parity(m(clone_batch(b, dev)), ref, b, what="weibo")
     # PHEME: K=768 dense signed features, B=24, 21 % single-node trees
     b = make_batch("pheme", 24, seed=6, train=True)
     ref, m = make_pair(768, 4, dev, seed=5)
