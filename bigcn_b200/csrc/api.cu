@@ -94,7 +94,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   w.h2[0] = c.take<float>(2 * nh);
   w.h2[1] = w.h2[0] + nh;
   int csn = cs_chunks(N) > bm_chunks(N) ? cs_chunks(N) : bm_chunks(N);
-  if (cs_chunks(B) > csn) csn = cs_chunks(B);
+  if (gs_chunks(B) > csn) csn = gs_chunks(B);
   for (int d = 0; d < 2; ++d) w.cs_part[d] = c.take<float>((size_t)csn * H);
   for (int d = 0; d < 2; ++d) w.op_part[d] = c.take<float>((size_t)op_chunks(N) * H * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
@@ -161,11 +161,15 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   }
   // 2. weights in the layouts the kernels stream
   const int n_out = dirs.n == 2 ? 128 : 64;
-  for (int q = 0; q < dirs.n; ++q) {
-    const int d = dirs.id[q];
-    if (int rc = transpose_weight(dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H, st)) return rc;
-    if (int rc = transpose_weight(dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0, st)) return rc;
-    if (int rc = transpose_weight(dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0, st)) return rc;
+  {
+    TransposeJobs js{};
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];
+      js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
+      js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0};
+      js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0};
+    }
+    if (int rc = transpose_jobs_launch(js, st)) return rc;
   }
   // 3. X W1^T for all active directions in one pass over X
   if (int rc = xw_dispatch(bt->x, N, K, w.w1T, n_out, w.xw, n_out, o->gemm_mode, st)) return rc;
@@ -245,7 +249,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     GScaleArgs a{};
     a.grad_feat = grad_feat; a.node_ptr = w.node_ptr; a.B = B;
     ColsumArgs c{};
-    c.nchunk = B > 0 ? cs_chunks(B) : 0;
+    c.nchunk = B > 0 ? gs_chunks(B) : 0;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
       a.pos[q] = w.pos[d]; a.gs[q] = w.gs[d]; a.part[q] = w.cs_part[d]; a.feat_base[q] = feat_base(d);

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__
 
 // dW[c][f] = sum_b dl[b][c] feat[b][f] (+ bias column f == 256): thread per (c, f), a chunk
 // of HB_TREES trees per blockIdx.y, trees in order; chunks are summed in order by k_head_bwd_red.
-constexpr int HB_TREES = 256;
+constexpr int HB_TREES = 32;
 __global__ void k_head_bwd_w(const float* __restrict__ dl, const float* __restrict__ feat, int64_t B,
                              int C, float* __restrict__ part) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -5,6 +5,7 @@
 namespace bigcn {
 
 constexpr int CS_ROWS = 256;  // rows per CTA for column-sum partials
+constexpr int GS_TREES = 16;  // trees per CTA in k_gscale
 constexpr int BM_ROWS = 128;  // rows per CTA in k_bwd_mix (8 warps x 16 rows)
 constexpr int OP_ROWS = 512;  // rows per CTA in k_outer64
 constexpr int DW2B_ROWS = 128; // rows per CTA in k_dw2b_part
@@ -15,6 +16,9 @@ int graph_prep_impl(int32_t, const int64_t* const*, const int64_t*, int64_t, con
 size_t graph_prep_ws_bytes(int64_t N, int64_t Emax, int ndir);
 int xw_fp32(const float*, int64_t, int64_t, const float*, int, float*, int64_t, cudaStream_t);
 int transpose_weight(const float*, int64_t, int64_t, int64_t, float*, int64_t, int64_t, cudaStream_t);
+struct TransposeJob { const float* w; int64_t ldw, k0, K; float* wt; int64_t ldwt, col0; };
+struct TransposeJobs { TransposeJob job[6]; int n; };
+int transpose_jobs_launch(const TransposeJobs&, cudaStream_t);
 size_t dw_partial_floats(int64_t N, int64_t K, int n_out);
 int dw_fp32(const float*, int64_t, int64_t, const float*, int64_t, int, float*, float*, int64_t, int64_t,
             float*, int64_t, int64_t, cudaStream_t);
@@ -52,6 +56,7 @@ int dw2b_launch(const Dw2bArgs&, int, bool, cudaStream_t);
 int dw2b_blocks(int64_t N);
 int dropout_mask_launch(const DropSpec&, int64_t, int64_t, int64_t, uint8_t*, cudaStream_t);
 int cs_chunks(int64_t N);
+int gs_chunks(int64_t B);
 int bm_chunks(int64_t N);
 int op_chunks(int64_t N);
 int xw_tc(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,

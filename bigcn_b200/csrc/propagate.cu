@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
   __shared__ float red[4][H];
   const int d = blockIdx.y;
   const int g = threadIdx.x >> 6, f = threadIdx.x & 63;
-  const int64_t base = (int64_t)blockIdx.x * CS_ROWS;
-  const int64_t end = min(a.B, base + CS_ROWS);
+  const int64_t base = (int64_t)blockIdx.x * GS_TREES;
+  const int64_t end = min(a.B, base + GS_TREES);
   float acc = 0.f;
   for (int64_t b = base + g; b < end; b += 4) {
     const int n = a.node_ptr[b + 1] - a.node_ptr[b];
@@ -634,43 +634,64 @@ __global__ void __launch_bounds__(256) k_dw2b_part(Dw2bArgs a) {
 
 __global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
   if (*a.overflow != 0) return;
+  // CTA = 2 columns x 4 warps; warp g of a column takes the 32-tree rounds r = g, g+4, ...;
+  // the four partial sums are combined in warp order.
+  __shared__ float red[2][4][H];
   const Dw2bDir& p = a.d[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (k >= a.K) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cg = w >> 2, g = w & 3;
+  const int64_t k = (int64_t)blockIdx.x * 2 + cg;
   float2 acc = make_float2(0.f, 0.f);
-  for (int64_t b0 = 0; b0 < a.B; b0 += 32) {
-    const int64_t b = b0 + lane;
-    const int t = b < a.B ? a.slot[b * a.K + k] : -1;
-    unsigned m = __ballot_sync(FULL_MASK, t >= 0);
-    while (m) {
-      const int sl = __ffs(m) - 1;
-      m &= m - 1;
-      const int64_t bb = b0 + sl;
-      const int tt = __shfl_sync(FULL_MASK, t, sl);
-      const float v = a.rnz_val[bb * a.K + tt];
-      float2 sub = make_float2(0.f, 0.f);
-      if (p.drop.on) {
-        const int s = a.node_ptr[bb], e = a.node_ptr[bb + 1];
-        if (e > s) {
-          const int j0 = s / DW2B_ROWS, j1 = (e - 1) / DW2B_ROWS;
-          for (int j = j0; j <= j1; ++j) {
-            const float2 q = *reinterpret_cast<const float2*>(
-                p.S + ((size_t)(j + bb) * DW2B_CAP + tt) * H + 2 * lane);
-            sub.x += q.x;
-            sub.y += q.y;
-          }
-        }
-      } else {
-        sub = *reinterpret_cast<const float2*>(p.dP + bb * H + 2 * lane);
+  if (k < a.K) {
+    for (int64_t b0 = (int64_t)g * 32; b0 < a.B; b0 += 128) {
+      const int64_t b = b0 + lane;
+      const int t = b < a.B ? a.slot[b * a.K + k] : -1;
+      float v = 0.f;
+      int s = 0, e = 0;
+      if (t >= 0) {                       // lanes fetch their tree's operands in parallel
+        v = a.rnz_val[b * a.K + t];
+        s = a.node_ptr[b];
+        e = a.node_ptr[b + 1];
       }
-      acc.x = fmaf(v, sub.x, acc.x);
-      acc.y = fmaf(v, sub.y, acc.y);
+      unsigned m = __ballot_sync(FULL_MASK, t >= 0);
+      while (m) {
+        const int sl = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t bb = b0 + sl;
+        const int tt = __shfl_sync(FULL_MASK, t, sl);
+        const float vv = __shfl_sync(FULL_MASK, v, sl);
+        float2 sub = make_float2(0.f, 0.f);
+        if (p.drop.on) {
+          const int ss = __shfl_sync(FULL_MASK, s, sl), ee = __shfl_sync(FULL_MASK, e, sl);
+          if (ee > ss) {
+            const int j0 = ss / DW2B_ROWS, j1 = (ee - 1) / DW2B_ROWS;
+            for (int j = j0; j <= j1; ++j) {
+              const float2 q = *reinterpret_cast<const float2*>(
+                  p.S + ((size_t)(j + bb) * DW2B_CAP + tt) * H + 2 * lane);
+              sub.x += q.x;
+              sub.y += q.y;
+            }
+          }
+        } else {
+          sub = *reinterpret_cast<const float2*>(p.dP + bb * H + 2 * lane);
+        }
+        acc.x = fmaf(vv, sub.x, acc.x);
+        acc.y = fmaf(vv, sub.y, acc.y);
+      }
     }
   }
-  const float sc = p.drop.on ? p.drop.scale : 1.f;
-  p.dw2[(int64_t)(2 * lane) * a.ld + H + k] = acc.x * sc;
-  p.dw2[(int64_t)(2 * lane + 1) * a.ld + H + k] = acc.y * sc;
+  red[cg][g][2 * lane] = acc.x;
+  red[cg][g][2 * lane + 1] = acc.y;
+  __syncthreads();
+  if (g == 0 && k < a.K) {
+    const float sc = p.drop.on ? p.drop.scale : 1.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = 2 * lane + h;
+      const float tot = ((red[cg][0][o] + red[cg][1][o]) + red[cg][2][o]) + red[cg][3][o];
+      p.dw2[(int64_t)o * a.ld + H + k] = tot * sc;
+    }
+  }
 }
 
 // ---------------------------------------------------------------- dropout mask materialisation (tests)
@@ -719,12 +740,13 @@ int readout_launch(const ReadoutArgs& a, cudaStream_t st) {
   return 0;
 }
 int cs_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, CS_ROWS); }
+int gs_chunks(int64_t B) { return (int)ceil_div(B > 0 ? B : 1, GS_TREES); }
 int bm_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, BM_ROWS); }
 int op_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, OP_ROWS); }
 
 int gscale_launch(const GScaleArgs& a, int ndir, cudaStream_t st) {
   if (a.B == 0) return 0;
-  k_gscale<<<dim3(cs_chunks(a.B), ndir), 256, 0, st>>>(a);
+  k_gscale<<<dim3(gs_chunks(a.B), ndir), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_gscale");
   return 0;
 }
@@ -766,7 +788,7 @@ int dw2b_launch(const Dw2bArgs& a, int ndir, bool dropping, cudaStream_t st) {
     k_dw2b_part<<<dim3(dw2b_blocks(a.N), ndir), 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_dw2b_part");
   }
-  k_dw2b_reduce<<<dim3((int)ceil_div(a.K, 8), ndir), 256, 0, st>>>(a);
+  k_dw2b_reduce<<<dim3((int)ceil_div(a.K, 2), ndir), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_dw2b_reduce");
   k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);   // dense-root fallback, returns at once otherwise
   BIGCN_CHECK_LAUNCH("k_dw2b");

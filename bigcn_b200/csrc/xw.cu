@@ -8,7 +8,7 @@
 // so results are exact fp32 sums and bit-reproducible.  Dense inputs stay correct
 // (every entry then takes the FFMA branch); the tcgen05 kind::tf32 GEMM in
 // gemm_tc.cu is the path for those.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace bigcn {
 
@@ -121,6 +121,35 @@ __global__ void k_transpose_w(const float* __restrict__ w, int64_t ldw, int64_t 
   }
 }
 
+// several transposes in one launch (blockIdx.y = job): the per-step weight re-layout
+__global__ void k_transpose_jobs(TransposeJobs js) {
+  const TransposeJob& j = js.job[blockIdx.y];
+  __shared__ float t[64][33];
+  const int64_t kb = (int64_t)blockIdx.x * 32;
+  if (kb >= j.K) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int o = ty; o < 64; o += 8) {
+    const int64_t k = kb + tx;
+    t[o][tx] = k < j.K ? j.w[o * j.ldw + j.k0 + k] : 0.f;
+  }
+  __syncthreads();
+  for (int kk = ty; kk < 32; kk += 8) {
+    const int64_t k = kb + kk;
+    if (k < j.K) {
+      j.wt[k * j.ldwt + j.col0 + tx] = t[tx][kk];
+      j.wt[k * j.ldwt + j.col0 + 32 + tx] = t[tx + 32][kk];
+    }
+  }
+}
+int transpose_jobs_launch(const TransposeJobs& js, cudaStream_t st) {
+  int64_t kmax = 0;
+  for (int i = 0; i < js.n; ++i) kmax = js.job[i].K > kmax ? js.job[i].K : kmax;
+  if (js.n == 0 || kmax == 0) return 0;
+  k_transpose_jobs<<<dim3((int)ceil_div(kmax, 32), js.n), 256, 0, st>>>(js);
+  BIGCN_CHECK_LAUNCH("k_transpose_jobs");
+  return 0;
+}
+
 int transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K, float* wt, int64_t ldwt,
                      int64_t col0, cudaStream_t st) {
   if (K == 0) return 0;
@@ -131,46 +160,39 @@ int transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K, float* 
 
 // ------------------------------------------------------- gT[k, :] = sum_i x[i,k] * t[i, :]
 // CTA = one 16-column slab of X (64 B = 2 sectors per row) x one chunk of rows.  EVERY warp
-// covers all 16 columns for its own rows (4 lanes x float4 per row, 8 rows per load, DW_U
-// loads in flight) and keeps the 16 x NOUT accumulators in registers, so a column that is
-// non-zero in every row (common words in a bag-of-words matrix) costs the same as any other:
-// its hits are spread over all warps of all row chunks instead of serialising in one owner.
-// Per column the contributions are added in ascending row order inside a warp, warps are
-// combined in index order through shared memory, and row chunks in order by k_dw_reduce:
-// no atomics, bit-reproducible.
-constexpr int DW_U = 8;
+// covers all 16 columns for its own rows and keeps the 16 x NOUT accumulators in registers,
+// so a column that is non-zero in every row (common words in a bag-of-words matrix) costs the
+// same as any other: its hits are spread over all warps of all row chunks instead of
+// serialising in one owner.  X never passes through registers: each warp streams 64-row
+// stages (4 KB) into its private shared-memory ring with cp.async (two stages, 16 B per
+// lane), ballots the non-zero rows of a landed stage, fetches the T rows of up to four hit
+// rows at once (L2) and adds x[row][c] * T[row][:] for the non-zero c, broadcast-reading the
+// row's 16 values from shared memory.  Per column the contributions arrive in ascending row
+// order inside a warp, warps are combined in index order, row chunks in order by
+// k_dw_reduce: no atomics, bit-reproducible.
+constexpr int DW_U = 8;                         // cp.async per lane per stage
 constexpr int DW_COLS = 16;
-constexpr int DW_WARP_ROWS = 8 * DW_U;        // rows a warp covers per outer iteration
-constexpr int DW_CTA_ROWS = 8 * DW_WARP_ROWS;  // 512
+constexpr int DW_WARP_ROWS = 8 * DW_U;          // 64 rows per stage
+constexpr int DW_CTA_ROWS = 8 * DW_WARP_ROWS;   // 512 rows per CTA pass
+constexpr int DW_STAGE_FLOATS = DW_WARP_ROWS * DW_COLS;  // 1024
+constexpr int DW_SMEM_BYTES = 8 * 2 * DW_STAGE_FLOATS * 4;  // 64 KB
 
-template <int V>
-__device__ __forceinline__ void dw_hit(float (&acc)[DW_COLS][V], int cl, float val, const float* tr) {
-  float tv[V];
-  if (V == 4) {
-    const float4 q = *reinterpret_cast<const float4*>(tr);
-    tv[0] = q.x; tv[1] = q.y; tv[2] = q.z; tv[3] = q.w;
-  } else {
-    const float2 q = *reinterpret_cast<const float2*>(tr);
-    tv[0] = q.x; tv[1] = q.y;
-  }
-  switch (cl) {  // warp-uniform: accumulators stay in registers
-#define DW_CASE(c)                                              \
-  case c:                                                       \
-    _Pragma("unroll") for (int j = 0; j < V; ++j) acc[c][j] = fmaf(val, tv[j], acc[c][j]); \
-    break;
-    DW_CASE(0) DW_CASE(1) DW_CASE(2) DW_CASE(3) DW_CASE(4) DW_CASE(5) DW_CASE(6) DW_CASE(7)
-    DW_CASE(8) DW_CASE(9) DW_CASE(10) DW_CASE(11) DW_CASE(12) DW_CASE(13) DW_CASE(14) DW_CASE(15)
-#undef DW_CASE
-  }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
 
 template <int NOUT>
 __global__ void __launch_bounds__(256, 2) k_dw_slab(const float* __restrict__ x, int64_t N, int64_t K,
                                                     const float* __restrict__ t, int64_t ldt,
                                                     float* __restrict__ partial, int rows_per_chunk) {
   constexpr int V = NOUT / 32;
-  __shared__ float red[DW_COLS * NOUT];
+  extern __shared__ __align__(16) float dw_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* xs = dw_smem + (size_t)w * 2 * DW_STAGE_FLOATS;
   const int64_t c0 = (int64_t)blockIdx.x * DW_COLS;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_chunk;
   const int64_t r_end = min(N, r_begin + rows_per_chunk);
@@ -183,37 +205,86 @@ __global__ void __launch_bounds__(256, 2) k_dw_slab(const float* __restrict__ x,
   for (int c = 0; c < DW_COLS; ++c)
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[c][j] = 0.f;
-  for (int64_t rb = r_begin + w * DW_WARP_ROWS; rb < r_end; rb += DW_CTA_ROWS) {
-    float4 v[DW_U];
+
+  auto issue = [&](int stage, int64_t rb) {
 #pragma unroll
     for (int u = 0; u < DW_U; ++u) {
       const int64_t r = rb + u * 8 + rl;
-      v[u] = (col_ok && r < r_end) ? ldg_stream_f4(x + r * K + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ok = col_ok && r < r_end;
+      cp_async16(xs + stage * DW_STAGE_FLOATS + (u * 32 + lane) * 4, ok ? x + r * K + col : x, ok ? 16 : 0);
     }
+    cp_async_commit();
+  };
+
+  int64_t rb = r_begin + (int64_t)w * DW_WARP_ROWS;
+  int stage = 0;
+  if (rb < r_end) issue(0, rb);
+  for (; rb < r_end; rb += DW_CTA_ROWS, stage ^= 1) {
+    const bool more = rb + DW_CTA_ROWS < r_end;
+    if (more) {
+      issue(stage ^ 1, rb + DW_CTA_ROWS);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const float* st = xs + stage * DW_STAGE_FLOATS;
+    // which of the 64 rows of this stage hold a non-zero
+    unsigned long long hits = 0ull;
 #pragma unroll
     for (int u = 0; u < DW_U; ++u) {
-      const bool any = (v[u].x != 0.f) | (v[u].y != 0.f) | (v[u].z != 0.f) | (v[u].w != 0.f);
-      unsigned rows_hit = __ballot_sync(FULL_MASK, any);
-      // rows ascending; inside a row the columns ascending
-      while (rows_hit) {
-        const int first = __ffs(rows_hit) - 1;
-        const int rr = first >> 2;
-        rows_hit &= ~(0xfu << (rr * 4));
-        const float* tr = t + (rb + u * 8 + rr) * ldt + lane * V;
+      const float4 v = *reinterpret_cast<const float4*>(st + (u * 32 + lane) * 4);
+      const bool any = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+      unsigned m = __ballot_sync(FULL_MASK, any);
+      m |= m >> 1;
+      m |= m >> 2;
+      m &= 0x11111111u;   // bit 4*rr set <=> row rr hit
+      m = (m | (m >> 3)) & 0x03030303u;
+      m = (m | (m >> 6)) & 0x000f000fu;
+      m = (m | (m >> 12)) & 0xffu;
+      hits |= (unsigned long long)m << (u * 8);
+    }
+    const float* trow = t + rb * ldt + lane * V;
+    while (hits) {
+      int rows[4];
+      float tv[4][V];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rows[j] = -1;
+        if (hits) {
+          rows[j] = __ffsll((long long)hits) - 1;
+          hits &= hits - 1;
+          if (V == 4) {
+            const float4 g = *reinterpret_cast<const float4*>(trow + (int64_t)rows[j] * ldt);
+            tv[j][0] = g.x; tv[j][1] = g.y; tv[j][2] = g.z; tv[j][3] = g.w;
+          } else {
+            const float2 g = *reinterpret_cast<const float2*>(trow + (int64_t)rows[j] * ldt);
+            tv[j][0] = g.x; tv[j][1] = g.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (rows[j] < 0) continue;
+        const float4* xr = reinterpret_cast<const float4*>(st + rows[j] * DW_COLS);
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          const int sl = rr * 4 + qq;
-          const float a0 = __shfl_sync(FULL_MASK, v[u].x, sl), a1 = __shfl_sync(FULL_MASK, v[u].y, sl);
-          const float a2 = __shfl_sync(FULL_MASK, v[u].z, sl), a3 = __shfl_sync(FULL_MASK, v[u].w, sl);
-          if (a0 != 0.f) dw_hit<V>(acc, qq * 4 + 0, a0, tr);
-          if (a1 != 0.f) dw_hit<V>(acc, qq * 4 + 1, a1, tr);
-          if (a2 != 0.f) dw_hit<V>(acc, qq * 4 + 2, a2, tr);
-          if (a3 != 0.f) dw_hit<V>(acc, qq * 4 + 3, a3, tr);
+          const float4 xv = xr[qq];   // broadcast read
+          const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (xa[c] != 0.f) {
+#pragma unroll
+              for (int jj = 0; jj < V; ++jj) acc[qq * 4 + c][jj] = fmaf(xa[c], tv[j][jj], acc[qq * 4 + c][jj]);
+            }
         }
       }
     }
+    __syncwarp();
   }
-  // ordered combine of the 8 warps, then one coalesced store of the slab's partial
+  // ordered combine of the 8 warps (reusing the ring), then one coalesced store of the slab's partial
+  __syncthreads();
+  float* red = dw_smem;
   for (int ww = 0; ww < 8; ++ww) {
     if (w == ww) {
 #pragma unroll
@@ -312,10 +383,16 @@ int dw_fp32(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, i
     cudaMemsetAsync(partial, 0, (size_t)K * n_out * sizeof(float), st);
   } else if (p.fast) {
     dim3 grid((unsigned)ceil_div(K, DW_COLS), (unsigned)p.nchunk);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_dw_slab<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES);
+      cudaFuncSetAttribute(k_dw_slab<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES);
+      attr_set = true;
+    }
     if (n_out == 128) {
-      k_dw_slab<128><<<grid, 256, 0, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+      k_dw_slab<128><<<grid, 256, DW_SMEM_BYTES, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
     } else {
-      k_dw_slab<64><<<grid, 256, 0, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
+      k_dw_slab<64><<<grid, 256, DW_SMEM_BYTES, st>>>(x, N, K, t, ldt, partial, p.rows_per_chunk);
     }
     BIGCN_CHECK_LAUNCH("k_dw_slab");
   } else {

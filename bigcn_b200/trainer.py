@@ -137,7 +137,7 @@ def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True) -> i
         bits += 1
     passes = (bits + 7) // 8
     prep = 1 + 2 + 3 * passes + 1            # count, scan x2, radix passes, deg  (memset not counted)
-    fwd = prep + 3 * n_dirs + 1 + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
+    fwd = prep + 1 + 1 + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
     head = 1 + 1 + 3                           # head fwd, nll, head bwd (feat, w partial, w reduce)
     # gscale+colsum, propT(g2), outer x2, [segsum | dw2b part], dw2b reduce + dense fallback,
     # bwdmix+colsum, propT, dw slab, dw reduce x dirs
