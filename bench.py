@@ -277,13 +277,15 @@ def run_ours(args):
     lib = L.lib()
     st = torch.cuda.current_stream().cuda_stream
     n0 = nodes[0]
-    wt = torch.randn(K_FEATS, 128, device=dev) * 0.02
+    w0 = torch.randn(64, K_FEATS, device=dev) * 0.02
+    w1 = torch.randn(64, K_FEATS, device=dev) * 0.02
+    scr = torch.empty(lib.bigcn_xw_scratch_floats(K_FEATS, 2), device=dev)
     ys = [torch.empty(n, 128, device=dev) for n in nodes]
 
     def xw_fn(i):
         j = i % N_ROTATE
-        L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, wt.data_ptr(), 128, ys[j].data_ptr(),
-                             128, L.GEMM_MODE[args.gemm_mode], st))
+        L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
+                             ys[j].data_ptr(), 128, L.GEMM_MODE[args.gemm_mode], scr.data_ptr(), st))
     xw_ms = time_kernel(xw_fn, 12, torch)
     mean_nodes = sum(nodes[i % N_ROTATE] for i in range(12)) / 12
     xw_bytes = mean_nodes * K_FEATS * 4 + K_FEATS * 128 * 4 + mean_nodes * 128 * 4

@@ -58,7 +58,9 @@ _SIGS = {
     "bigcn_graph_prep": (C.c_int, [C.c_int32, C.POINTER(c_ptr), C.POINTER(C.c_int64), C.c_int64, c_ptr,
                                    C.c_int64, C.c_int32, C.POINTER(Graph), c_ptr, c_ptr, c_ptr,
                                    C.c_size_t, c_ptr]),
-    "bigcn_xw": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, C.c_int64, C.c_int32, c_ptr]),
+    "bigcn_xw_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "bigcn_xw": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int32,
+                           c_ptr, c_ptr]),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
     "bigcn_propagate": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, c_ptr, C.c_int32,

@@ -26,19 +26,27 @@ int num_sms() {
   return n;
 }
 
-int xw_dispatch(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y,
-                int64_t ldy, int mode, cudaStream_t st) {
-  BIGCN_CHECK_ARG(n_out == 64 || n_out == 128, "xw: n_out must be 64 or 128");
-  if (mode == BIGCN_GEMM_FP32) return xw_fp32(x, N, K, wt, n_out, y, ldy, st);
+// w[0..n_w): PyG [64, K] weights (row pitch ldw).  scratch: 2 * 64 * n_w * K floats -- the
+// transposed copy the fp32 scan streams, or the TF32 hi/lo split of the tensor-core modes.
+int xw_dispatch(const float* x, int64_t N, int64_t K, const float* const* w, int n_w, int64_t ldw,
+                float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st) {
+  BIGCN_CHECK_ARG(n_w == 1 || n_w == 2, "xw: one or two weight matrices");
+  const int n_out = H * n_w;
+  if (mode == BIGCN_GEMM_FP32) {
+    TransposeJobs js{};
+    for (int q = 0; q < n_w; ++q) js.job[js.n++] = TransposeJob{w[q], ldw, 0, K, scratch, n_out, q * H};
+    if (int rc = transpose_jobs_launch(js, st)) return rc;
+    return xw_fp32(x, N, K, scratch, n_out, y, ldy, st);
+  }
   BIGCN_CHECK_ARG(mode == BIGCN_GEMM_TF32 || mode == BIGCN_GEMM_TF32X3, "xw: unknown gemm_mode %d", mode);
-  return xw_tc(x, N, K, wt, n_out, y, ldy, mode, st);
+  return xw_tc_weights(x, N, K, w, ldw, n_out, scratch, y, ldy, mode, st);
 }
 
 // ---- workspace of the feature path -----------------------------------------------
 struct FeatWs {
   bigcn_graph_t g[2];       // [0] = TD, [1] = BU
   int32_t* node_ptr;
-  float* w1T;               // [K][128]  (TD cols 0..63, BU cols 64..127)
+  float* w1T;               // [K][128]  (TD cols 0..63, BU cols 64..127) | hi/lo split [4][64][K]
   float* w2aT[2];           // [64][64]
   float* w2bT[2];           // [K][64]
   int32_t* rnz_cnt; int32_t* rnz_col; float* rnz_val;
@@ -76,7 +84,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
     w.g[d].rowsum = nullptr;
   }
   w.node_ptr = c.take<int32_t>(B + 1);
-  w.w1T = c.take<float>((size_t)K * 128);
+  w.w1T = c.take<float>((size_t)K * 256);   // fp32: [K][128] transposed; tensor-core modes: hi/lo split
   for (int d = 0; d < 2; ++d) {
     w.w2aT[d] = c.take<float>(H * H);
     w.w2bT[d] = c.take<float>((size_t)K * H);
@@ -165,14 +173,20 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     TransposeJobs js{};
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
+      if (o->gemm_mode == BIGCN_GEMM_FP32)
+        js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0};
     }
     if (int rc = transpose_jobs_launch(js, st)) return rc;
   }
   // 3. X W1^T for all active directions in one pass over X
-  if (int rc = xw_dispatch(bt->x, N, K, w.w1T, n_out, w.xw, n_out, o->gemm_mode, st)) return rc;
+  if (o->gemm_mode == BIGCN_GEMM_FP32) {
+    if (int rc = xw_fp32(bt->x, N, K, w.w1T, n_out, w.xw, n_out, st)) return rc;
+  } else {
+    const float* ws[2] = {dir_w1(pr, dirs.id[0]), dirs.n == 2 ? dir_w1(pr, dirs.id[1]) : nullptr};
+    if (int rc = xw_tc_weights(bt->x, N, K, ws, K, n_out, w.w1T, w.xw, n_out, o->gemm_mode, st)) return rc;
+  }
   // 4. root columns (and, without dropout, the per-tree projection)
   {
     RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
@@ -355,7 +369,7 @@ static ConvWs carve_conv(int64_t N, int64_t E, int64_t K, void* ws, size_t bytes
   w.g.deg = c.take<int32_t>(N > 0 ? N : 1);
   w.g.dis = c.take<float>(N > 0 ? N : 1);
   w.g.rowsum = nullptr;
-  w.wT = c.take<float>((size_t)K * H);
+  w.wT = c.take<float>((size_t)K * H * 2);
   w.xw = c.take<float>((size_t)(N > 0 ? N : 1) * H);
   w.cs_part = c.take<float>((size_t)cs_chunks(N) * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 64));
@@ -392,9 +406,13 @@ extern "C" int bigcn_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
-extern "C" int bigcn_xw(const float* x, int64_t N, int64_t K, const float* wt, int32_t n_out, float* y,
-                        int64_t ldy, int32_t gemm_mode, bigcn_stream_t stream) {
-  return xw_dispatch(x, N, K, wt, n_out, y, ldy, gemm_mode, (cudaStream_t)stream);
+extern "C" size_t bigcn_xw_scratch_floats(int64_t K, int32_t n_w) { return (size_t)2 * H * n_w * K; }
+
+extern "C" int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
+                        float* y, int64_t ldy, int32_t gemm_mode, float* scratch, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(x && w0 && y && scratch, "xw: NULL argument");
+  const float* ws[2] = {w0, w1};
+  return xw_dispatch(x, N, K, ws, w1 ? 2 : 1, ldw, scratch, y, ldy, gemm_mode, (cudaStream_t)stream);
 }
 
 extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N,
@@ -457,8 +475,8 @@ extern "C" int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const
   if (int rc = graph_prep_impl(1, ei, Es, N, nullptr, 0, deg_by, &cw.g, nullptr, flags, cw.prep_ws,
                                cw.prep_bytes, st))
     return rc;
-  if (int rc = transpose_weight(w, K, 0, K, cw.wT, H, 0, st)) return rc;
-  if (int rc = xw_dispatch(x, N, K, cw.wT, H, cw.xw, H, gemm_mode, st)) return rc;
+  const float* ws1[1] = {w};
+  if (int rc = xw_dispatch(x, N, K, ws1, 1, K, cw.wT, cw.xw, H, gemm_mode, st)) return rc;
   PropArgs a{};
   a.N = N; a.relu = 0;
   a.d[0] = PropDir{cw.g.in_ptr, cw.g.in_idx, cw.g.dis, cw.xw, bias, out, H, H};

@@ -1,10 +1,347 @@
-// tcgen05 / TMA GEMM for X * W^T (kind::tf32).  Placeholder until the tensor-core path lands.
+// tcgen05 / TMA / TMEM GEMM for the feature transform  Y[N, n_out] = X[N, K] * W^T.
+//
+// Replaces GCNConv.lin (cuBLAS SGEMM) at BiGCN_Twitter.py:42,92 in the tensor-core modes:
+//   BIGCN_GEMM_TF32   : one kind::tf32 MMA per K step (operands truncated to TF32 by the MMA)
+//   BIGCN_GEMM_TF32X3 : W = W_hi + W_lo with W_lo = W - tf32(W) as a second B operand (two
+//                       MMAs per K step); exact to ~2^-22 whenever X is representable in TF32
+//                       (bag-of-words counts are).  [third term X_lo * W_hi: see DESIGN.md]
+// Both operands are K-major exactly as they sit in HBM: X is [N, K] row-major and the PyG
+// weights are [64, K] row-major, so TMA loads them straight into 128B-swizzled shared memory
+// (no transposed copy).  The TD and BU weights are two 64-row boxes of one B tile, so X is
+// read ONCE for both directions.  One CTA owns 256 rows of X: two M=128 accumulators in TMEM
+// share every B tile, halving the L2 traffic for W.  Warp-specialised, mbarrier ring:
+//   warp 0 : TMA producer            warp 1 : tcgen05.mma issuer (one elected lane)
+//   warp 2 : TMEM allocator          warps 4-7 : epilogue (tcgen05.ld -> registers -> HBM)
+// The kernel is HBM-bound on X (64 flop/B at n_out = 128 < the TF32 ridge).
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 namespace bigcn {
-bool xw_tc_available() { return false; }
-int xw_tc(const float*, int64_t, int64_t, const float*, int, float*, int64_t, int, cudaStream_t) {
-  set_error("xw: the tcgen05 GEMM modes are not built in this version; use BIGCN_GEMM_FP32");
-  return 1;
+
+constexpr int TC_BLOCK_M = 256;
+constexpr int TC_BLOCK_K = 32;                      // 32 fp32 = 128 B = one swizzle atom
+constexpr int TC_UMMA_K = 8;                        // kind::tf32
+constexpr int TC_A_BYTES = TC_BLOCK_M * 128;        // 32 KB
+constexpr int TC_THREADS = 256;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1, unused for swizzled K-major),
+//   [32,46) SBO >> 4 (1024 B between 8-row groups), [46,48) version = 1, [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6),
+// a/b_format TF32 (2) at [7,10)/[10,13), K-major A and B, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+  float* y;
+  int64_t ldy;
+  int64_t N, K;
+  int n_out;       // 64 or 128
+  int num_tiles;   // ceil(N / 256)
+  int num_kb;      // ceil(K / 32)
+};
+
+// NB = number of B operands per stage (1: W, 2: W and W_lo)
+template <int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w0,
+        const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_l0,
+        const __grid_constant__ CUtensorMap map_l1, const TcParams p) {
+  constexpr int STAGES = NB == 1 ? 4 : 3;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  const int b_bytes = p.n_out * 128;                           // one B operand tile
+  const int stage_bytes = TC_A_BYTES + NB * 16384;             // B slots are 16 KB apart (1024 B aligned)
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full, bar_tmem_empty;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024 B alignment of the dynamic region (SWIZZLE_128B atoms)
+  const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w0);
+    if (p.n_out == 128) tma_prefetch_desc(&map_w1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_tmem_full), 1);
+    mbar_init(smem_u32(&bar_tmem_empty), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // 256 TMEM columns: two fp32 accumulators of up to 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(TC_A_BYTES + NB * b_bytes);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = tile * TC_BLOCK_M;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          const uint32_t sa = smem0 + s * stage_bytes;
+          mbar_expect_tx(full, tx);
+          tma_load_2d(sa, &map_x, full, kb * TC_BLOCK_K, m0);
+          tma_load_2d(sa + TC_A_BYTES, &map_w0, full, kb * TC_BLOCK_K, 0);
+          if (p.n_out == 128) tma_load_2d(sa + TC_A_BYTES + 64 * 128, &map_w1, full, kb * TC_BLOCK_K, 0);
+          if (NB == 2) {
+            tma_load_2d(sa + TC_A_BYTES + 16384, &map_l0, full, kb * TC_BLOCK_K, 0);
+            if (p.n_out == 128) tma_load_2d(sa + TC_A_BYTES + 16384 + 64 * 128, &map_l1, full, kb * TC_BLOCK_K, 0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc_tf32(128, p.n_out);
+      int s = 0;
+      uint32_t ph = 0, tile_ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_ph ^= 1) {
+        mbar_wait(smem_u32(&bar_tmem_empty), tile_ph ^ 1);   // epilogue has drained the accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + s * stage_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            const uint32_t koff = k * TC_UMMA_K * 4;           // 32 B per K step inside the 128 B atom
+            const uint64_t da0 = make_desc_k_sw128(sa + koff);
+            const uint64_t da1 = make_desc_k_sw128(sa + 128 * 128 + koff);
+            const uint64_t db = make_desc_k_sw128(sa + TC_A_BYTES + koff);
+            const uint32_t acc = (kb | k) ? 1u : 0u;
+            tc_mma_tf32(tmem_base, da0, db, idesc, acc);
+            tc_mma_tf32(tmem_base + 128, da1, db, idesc, acc);
+            if (NB == 2) {
+              const uint64_t dl = make_desc_k_sw128(sa + TC_A_BYTES + 16384 + koff);
+              tc_mma_tf32(tmem_base, da0, dl, idesc, 1u);
+              tc_mma_tf32(tmem_base + 128, da1, dl, idesc, 1u);
+            }
+          }
+          tc_commit(smem_u32(&bar_empty[s]));                 // frees the stage when the MMAs retire
+          if (kb == p.num_kb - 1) tc_commit(smem_u32(&bar_tmem_full));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    uint32_t tile_ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_ph ^= 1) {
+      mbar_wait(smem_u32(&bar_tmem_full), tile_ph);
+      tc_fence_after();
+      const int64_t m0 = (int64_t)tile * TC_BLOCK_M;
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        const int64_t row = m0 + a * 128 + q * 32 + lane;
+        for (int c0 = 0; c0 < p.n_out; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c0), r);
+          tc_wait_ld();
+          if (row < p.N) {
+            float4* dst = reinterpret_cast<float4*>(p.y + row * p.ldy + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  }
+}
+
+// hi = w with the 13 low mantissa bits cleared (exactly a TF32 value, whatever rounding the MMA
+// applies to fp32 operands); lo = tf32(w - hi).  hi + lo == w to ~2^-22 relative.
+__global__ void k_split_hi_lo(const float* __restrict__ w, int64_t ldw, int64_t K, float* __restrict__ hi,
+                              float* __restrict__ lo) {
+  const int64_t n = 64 * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[(i / K) * ldw + (i % K)];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+bool xw_tc_available() { return encode_fn() != nullptr; }
+
+// 2-D fp32 row-major [rows, cols] with row pitch ld (elements); box = 32 cols x box_rows, SW128
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("xw_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 2;
+  }
+  return 0;
+}
+
+// w[0], w[1]: the [64, K] PyG weights of the active directions (row pitch ldw); scratch:
+// 2 * n_out * K floats for the TF32X3 split (may be NULL in TF32 mode)
+int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, int64_t ldw, int n_out,
+                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st) {
+  BIGCN_CHECK_ARG(encode_fn() != nullptr, "xw_tc: cuTensorMapEncodeTiled is unavailable in this driver");
+  BIGCN_CHECK_ARG(K % 4 == 0 && ldw % 4 == 0, "xw_tc: in_feats must be a multiple of 4 for TMA (got %lld)", (long long)K);
+  BIGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "xw_tc: x must be 16-byte aligned");
+  BIGCN_CHECK_ARG(n_out == 64 || n_out == 128, "xw_tc: n_out must be 64 or 128");
+  if (N == 0) return 0;
+  const int nb = mode == BIGCN_GEMM_TF32X3 ? 2 : 1;
+  BIGCN_CHECK_ARG(nb == 1 || scratch != nullptr, "xw_tc: TF32X3 needs the split scratch");
+  CUtensorMap mx, mw0, mw1, ml0, ml1;
+  if (int rc = make_map(&mx, x, N, K, K, 256)) return rc;
+  if (nb == 1) {
+    if (int rc = make_map(&mw0, w[0], 64, K, ldw, 64)) return rc;
+    mw1 = mw0;
+    if (n_out == 128)
+      if (int rc = make_map(&mw1, w[1], 64, K, ldw, 64)) return rc;
+    ml0 = mw0;
+    ml1 = mw1;
+  } else {
+    for (int d = 0; d < n_out / 64; ++d) {
+      float* hi = scratch + (size_t)(2 * d) * 64 * K;
+      float* lo = scratch + (size_t)(2 * d + 1) * 64 * K;
+      k_split_hi_lo<<<num_sms() * 2, 256, 0, st>>>(w[d], ldw, K, hi, lo);
+      BIGCN_CHECK_LAUNCH("k_split_hi_lo");
+      if (int rc = make_map(d == 0 ? &mw0 : &mw1, hi, 64, K, K, 64)) return rc;
+      if (int rc = make_map(d == 0 ? &ml0 : &ml1, lo, 64, K, K, 64)) return rc;
+    }
+    if (n_out == 64) { mw1 = mw0; ml1 = ml0; }
+  }
+  TcParams p;
+  p.y = y; p.ldy = ldy; p.N = N; p.K = K; p.n_out = n_out;
+  p.num_tiles = (int)ceil_div(N, TC_BLOCK_M);
+  p.num_kb = (int)ceil_div(K, TC_BLOCK_K);
+  const int stage_bytes = TC_A_BYTES + nb * 16384;
+  const int stages = nb == 1 ? 4 : 3;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_xw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (TC_A_BYTES + 16384) + 1024);
+    cudaFuncSetAttribute(k_xw_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (TC_A_BYTES + 32768) + 1024);
+    attr = true;
+  }
+  if (nb == 1) k_xw_tc<1><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
+  else k_xw_tc<2><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
+  BIGCN_CHECK_LAUNCH("k_xw_tc");
+  return 0;
+}
+
 }  // namespace bigcn

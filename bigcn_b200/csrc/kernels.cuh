@@ -59,8 +59,8 @@ int cs_chunks(int64_t N);
 int gs_chunks(int64_t B);
 int bm_chunks(int64_t N);
 int op_chunks(int64_t N);
-int xw_tc(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
-          int mode, cudaStream_t st);
+int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, int64_t ldw, int n_out,
+                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st);
 bool xw_tc_available();
 
 

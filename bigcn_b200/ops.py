@@ -90,11 +90,14 @@ def xw(x, weights, gemm_mode="fp32"):
     _need_cuda(x, *weights)
     n, k = x.shape
     n_out = H * len(weights)
-    wt = torch.empty(k, n_out, dtype=torch.float32, device=x.device)
-    for q, w in enumerate(weights):
-        transpose_weight(_f32(w), 0, k, wt, q * H)
+    ws = [_f32(w) for w in weights]
+    if len(ws) == 2 and ws[0].stride(0) != ws[1].stride(0):
+        raise L.BigcnError("xw: the two weight matrices must share a row pitch")
+    nscr = lib().bigcn_xw_scratch_floats(k, len(ws))
+    scr = torch.empty(nscr, dtype=torch.float32, device=x.device)
     y = torch.empty(n, n_out, dtype=torch.float32, device=x.device)
-    check(lib().bigcn_xw(_p(x), n, k, _p(wt), n_out, _p(y), n_out, L.GEMM_MODE[gemm_mode], _stream()), "xw")
+    check(lib().bigcn_xw(_p(x), n, k, _p(ws[0]), _p(ws[1]) if len(ws) == 2 else None, ws[0].stride(0), _p(y),
+                         n_out, L.GEMM_MODE[gemm_mode], _p(scr), _stream()), "xw")
     return y
 
 

@@ -126,10 +126,13 @@ int bigcn_graph_prep(int32_t n_dirs, const int64_t* const* edge_index, const int
 
 /* ---- X * W^T ------------------------------------------------------------
  * Replaces GCNConv.lin (cuBLAS SGEMM) at BiGCN_Twitter.py:42,92.
- * y[N,n_out] = x[N,K] * wt[K,n_out]  (wt = transposed, concatenated weights;
- * n_out = 64 or 128 so TD and BU share one pass over x).  ldy = row pitch of y. */
-int bigcn_xw(const float* x, int64_t N, int64_t K, const float* wt, int32_t n_out,
-             float* y, int64_t ldy, int32_t gemm_mode, bigcn_stream_t stream);
+ * y[N, 64*n_w] = x[N,K] * [w0; w1]^T with w0, w1 the [64,K] lin.weight tensors (row pitch
+ * ldw) of one or two directions (w1 = NULL for one), so TD and BU share ONE pass over x.
+ * gemm_mode FP32: exact-fp32 streaming scan; TF32 / TF32X3: tcgen05 + TMA + TMEM GEMM.
+ * scratch: bigcn_xw_scratch_floats(K, n_w) floats.  ldy = row pitch of y. */
+size_t bigcn_xw_scratch_floats(int64_t K, int32_t n_w);
+int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
+             float* y, int64_t ldy, int32_t gemm_mode, float* scratch, bigcn_stream_t stream);
 /* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
 int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
                            float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);
