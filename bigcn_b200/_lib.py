@@ -71,7 +71,7 @@ _SIGS = {
     "bigcn_gcnconv_forward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int64, c_ptr, c_ptr,
                                         C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_gcnconv_backward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr,
-                                         c_ptr, C.c_size_t, c_ptr]),
+                                         C.c_int32, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_features_workspace_bytes": (C.c_size_t, [C.POINTER(Dims)]),
     "bigcn_features_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(BatchPtrs), C.POINTER(Params),
                                          C.POINTER(Opts), c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

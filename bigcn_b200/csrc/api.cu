@@ -344,7 +344,13 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   {
     float* da = gdir_w1(gr, dirs.id[0]);
     float* db = dirs.n == 2 ? gdir_w1(gr, dirs.id[1]) : nullptr;
-    if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
+    if (o->gemm_mode == BIGCN_GEMM_FP32) {
+      if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
+    } else {   // G1 (w.z) and T2 (w.xw) are dead here: they hold the TF32 hi / lo split of T1
+      if (int rc = dw_tc(bt->x, N, K, t1cat, n_out, n_out, w.z[0], w.xw, w.dw_part, da, K, 0, db, K, 0,
+                         o->gemm_mode, st))
+        return rc;
+    }
   }
   return 0;
 }
@@ -354,6 +360,7 @@ struct ConvWs {
   bigcn_graph_t g;
   float* wT;      // [K][64]
   float* xw;      // [N][64]  (backward: T)
+  float* split;   // [2][N][64] TF32 hi / lo of T (tensor-core modes)
   float* cs_part;
   float* dw_part;
   void* prep_ws; size_t prep_bytes;
@@ -371,6 +378,7 @@ static ConvWs carve_conv(int64_t N, int64_t E, int64_t K, void* ws, size_t bytes
   w.g.rowsum = nullptr;
   w.wT = c.take<float>((size_t)K * H * 2);
   w.xw = c.take<float>((size_t)(N > 0 ? N : 1) * H);
+  w.split = c.take<float>((size_t)(N > 0 ? N : 1) * H * 2);
   w.cs_part = c.take<float>((size_t)cs_chunks(N) * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 64));
   w.prep_bytes = graph_prep_ws_bytes(N, E, 1);
@@ -484,8 +492,8 @@ extern "C" int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const
 }
 
 extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int64_t E,
-                                      const float* grad_out, float* dw, float* db, void* workspace,
-                                      size_t workspace_bytes, bigcn_stream_t stream) {
+                                      const float* grad_out, float* dw, float* db, int32_t gemm_mode,
+                                      void* workspace, size_t workspace_bytes, bigcn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ConvWs cw = carve_conv(N, E, K, workspace, workspace_bytes);
   BIGCN_CHECK_ARG(workspace && workspace_bytes >= cw.total, "gcnconv_backward: workspace too small");
@@ -504,5 +512,7 @@ extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int6
   a.d[0] = PropDir{cw.g.out_ptr, cw.g.out_idx, cw.g.dis, grad_out, nullptr, cw.xw, H, H};
   if (int rc = propagate_launch(a, 1, st)) return rc;
   // dw = T^T x
-  return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);
+  if (gemm_mode == BIGCN_GEMM_FP32) return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);
+  return dw_tc(x, N, K, cw.xw, H, 64, cw.split, cw.split + (size_t)(N > 0 ? N : 1) * H, cw.dw_part, dw, K, 0,
+               nullptr, 0, 0, gemm_mode, st);
 }

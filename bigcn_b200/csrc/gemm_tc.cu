@@ -344,4 +344,241 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
   return 0;
 }
 
+
+// =====================================================================================
+// Weight gradient  dW^T[k, o] = sum_i X[i, k] * T[i, o]   (dW1 = T1^T X)
+// as D[M = 128 outputs, N = 256 columns of X] += A^T B over the node axis, kind::tf32.
+// Both operands are "MN-major" as they sit in HBM (X[i, :] and T[i, :] are contiguous along
+// the M / N axis), which for 32-bit operands is the SWIZZLE_128B_BASE32B shared-memory layout:
+// TMA boxes of 32 columns x 32 node rows with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// Grid = (256-column tiles of X) x (node-range splits), one wave: every CTA streams its slice
+// of X exactly once; T (16 MB, L2 resident) is re-read once per column tile.  The accumulator
+// (128 x 256 fp32) lives in TMEM; split partials go to partial[split][k][o] and are summed in
+// order by k_dw_reduce.  Cost is independent of the sparsity pattern of X.
+// NA = 1: T as is (TF32);  NA = 2: T = T_hi + T_lo (fp32-class when X is TF32-exact).
+constexpr int DWT_BK = 32;            // node rows per stage
+constexpr int DWT_N = 256;            // columns of X per CTA
+constexpr int DWT_A_BYTES = 4 * DWT_BK * 128;   // 128 outputs = 4 blocks of 32
+constexpr int DWT_B_BYTES = 8 * DWT_BK * 128;   // 256 columns = 8 blocks of 32
+
+// MN-major SWIZZLE_128B_BASE32B descriptor: 128 B (32 fp32) contiguous along MN, rows of the
+// K axis 128 B apart, 4-row swizzle atoms (SBO = 512 B), LBO = bytes between 32-element MN blocks
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;   // LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
+  return make_idesc_tf32(m, n) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+
+struct DwtParams {
+  float* partial;     // [nsplit][K][n_out]
+  int64_t N, K;
+  int n_out;
+  int rows_per_split; // multiple of DWT_BK
+};
+
+template <int NA>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_t,
+        const __grid_constant__ CUtensorMap map_tlo, const DwtParams p) {
+  constexpr int STAGES = NA == 1 ? 4 : 3;
+  constexpr int STAGE_BYTES = NA * DWT_A_BYTES + DWT_B_BYTES;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const int col0 = blockIdx.x * DWT_N;
+  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
+  const int64_t r_end = min(p.N, r_begin + p.rows_per_split);
+  const int num_kb = r_end > r_begin ? (int)((r_end - r_begin + DWT_BK - 1) / DWT_BK) : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_t);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int m_blocks = p.n_out / 32;   // 4 (both directions) or 2
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      // all 4 output blocks are always loaded: blocks beyond n_out are out of bounds -> zero filled
+      const uint32_t tx = (uint32_t)STAGE_BYTES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+        const uint32_t full = smem_u32(&bar_full[s]);
+        const uint32_t sa = smem0 + s * STAGE_BYTES;
+        const int row = (int)(r_begin + (int64_t)kb * DWT_BK);
+        mbar_expect_tx(full, tx);
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          tma_load_2d(sa + mb * (DWT_BK * 128), &map_t, full, mb * 32, row);
+          if (NA == 2) tma_load_2d(sa + DWT_A_BYTES + mb * (DWT_BK * 128), &map_tlo, full, mb * 32, row);
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+          tma_load_2d(sa + NA * DWT_A_BYTES + nb * (DWT_BK * 128), &map_x, full, col0 + nb * 32, row);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc_tf32_mn(128, DWT_N);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem0 + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < DWT_BK / TC_UMMA_K; ++k) {
+          const uint32_t koff = k * TC_UMMA_K * 128;           // 8 node rows of 128 B
+          const uint64_t da = make_desc_mn_sw128_32b(sa + koff, DWT_BK * 128);
+          const uint64_t db = make_desc_mn_sw128_32b(sa + NA * DWT_A_BYTES + koff, DWT_BK * 128);
+          tc_mma_tf32(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+          if (NA == 2) {
+            const uint64_t dl = make_desc_mn_sw128_32b(sa + DWT_A_BYTES + koff, DWT_BK * 128);
+            tc_mma_tf32(tmem_base, dl, db, idesc, 1u);
+          }
+        }
+        tc_commit(smem_u32(&bar_empty[s]));
+        if (kb == num_kb - 1) tc_commit(smem_u32(&bar_tmem_full));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {   // ===== epilogue =====
+    const int q = warp & 3;
+    float* out = p.partial + (size_t)blockIdx.y * p.K * p.n_out;
+    const int m = q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(&bar_tmem_full), 0);
+      tc_fence_after();
+    }
+    if (q < m_blocks) {
+      for (int c0 = 0; c0 < DWT_N; c0 += 32) {
+        uint32_t r[32];
+        if (num_kb > 0) {
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t col = (int64_t)col0 + c0 + j;
+          if (col < p.K) out[col * p.n_out + m] = __uint_as_float(r[j]);   // 32 lanes -> 128 B
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  }
+}
+
+// [rows, cols] fp32 row-major, box = 32 cols x 32 rows, SWIZZLE_128B with 32 B atoms (MN-major tf32)
+static int make_map_mn(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)DWT_BK};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("dw_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 2;
+  }
+  return 0;
+}
+
+__global__ void k_split_rows_hi_lo(const float* __restrict__ t, int64_t n, float* __restrict__ hi,
+                                   float* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = t[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xFFFFE000u);
+  }
+}
+
+// t: [N, n_out] (row pitch ldt == n_out).  hi_scratch / lo_scratch: N * n_out floats each (TF32X3 only).
+int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int n_out, float* hi_scratch,
+          float* lo_scratch, float* partial, float* dw_a, int64_t ldw_a, int64_t k0_a, float* dw_b, int64_t ldw_b, int64_t k0_b,
+          int mode, cudaStream_t st) {
+  BIGCN_CHECK_ARG(encode_fn() != nullptr, "dw_tc: cuTensorMapEncodeTiled is unavailable in this driver");
+  BIGCN_CHECK_ARG(K % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "dw_tc: x must be TMA-addressable");
+  BIGCN_CHECK_ARG(ldt == n_out && (n_out == 64 || n_out == 128), "dw_tc: t must be dense [N, 64|128]");
+  if (K == 0) return 0;
+  const int na = mode == BIGCN_GEMM_TF32X3 ? 2 : 1;
+  const int tiles = (int)ceil_div(K, DWT_N);
+  int nsplit = 1;
+  if (N == 0) {
+    cudaMemsetAsync(partial, 0, (size_t)K * n_out * sizeof(float), st);
+  } else {
+    nsplit = num_sms() / tiles;
+    const int64_t max_split = ceil_div(N, 4 * DWT_BK);
+    if (nsplit > max_split) nsplit = (int)max_split;
+    if (nsplit < 1) nsplit = 1;
+    int64_t rps = ceil_div(ceil_div(N, nsplit), DWT_BK) * DWT_BK;
+    nsplit = (int)ceil_div(N, rps);
+    const float* t_hi = t;
+    const float* t_lo = t;
+    if (na == 2) {
+      BIGCN_CHECK_ARG(hi_scratch != nullptr && lo_scratch != nullptr, "dw_tc: TF32X3 needs the split scratch");
+      float* hi = hi_scratch;
+      float* lo = lo_scratch;
+      k_split_rows_hi_lo<<<num_sms() * 4, 256, 0, st>>>(t, N * n_out, hi, lo);
+      BIGCN_CHECK_LAUNCH("k_split_rows_hi_lo");
+      t_hi = hi;
+      t_lo = lo;
+    }
+    CUtensorMap mx, mt, ml;
+    if (int rc = make_map_mn(&mx, x, N, K, K)) return rc;
+    if (int rc = make_map_mn(&mt, t_hi, N, n_out, n_out)) return rc;
+    if (int rc = make_map_mn(&ml, t_lo, N, n_out, n_out)) return rc;
+    DwtParams p;
+    p.partial = partial; p.N = N; p.K = K; p.n_out = n_out; p.rows_per_split = (int)rps;
+    const int stages = na == 1 ? 4 : 3;
+    const size_t smem = (size_t)stages * (na * DWT_A_BYTES + DWT_B_BYTES) + 1024;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(k_dw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (DWT_A_BYTES + DWT_B_BYTES) + 1024);
+      cudaFuncSetAttribute(k_dw_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * DWT_A_BYTES + DWT_B_BYTES) + 1024);
+      attr = true;
+    }
+    if (na == 1) k_dw_tc<1><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
+    else k_dw_tc<2><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
+    BIGCN_CHECK_LAUNCH("k_dw_tc");
+  }
+  return dw_reduce_launch(partial, nsplit, K, n_out, dw_a, ldw_a, k0_a, dw_b, ldw_b, k0_b, st);
+}
+
 }  // namespace bigcn

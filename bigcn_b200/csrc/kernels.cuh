@@ -20,6 +20,11 @@ struct TransposeJob { const float* w; int64_t ldw, k0, K; float* wt; int64_t ldw
 struct TransposeJobs { TransposeJob job[6]; int n; };
 int transpose_jobs_launch(const TransposeJobs&, cudaStream_t);
 size_t dw_partial_floats(int64_t N, int64_t K, int n_out);
+int dw_reduce_launch(const float* partial, int nchunk, int64_t K, int n_out, float* dw_a, int64_t ldw_a,
+                     int64_t k0_a, float* dw_b, int64_t ldw_b, int64_t k0_b, cudaStream_t st);
+int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int n_out, float* hi_scratch,
+          float* lo_scratch, float* partial, float* dw_a, int64_t ldw_a, int64_t k0_a, float* dw_b, int64_t ldw_b, int64_t k0_b,
+          int mode, cudaStream_t st);
 int dw_fp32(const float*, int64_t, int64_t, const float*, int64_t, int, float*, float*, int64_t, int64_t,
             float*, int64_t, int64_t, cudaStream_t);
 

@@ -370,7 +370,9 @@ size_t dw_partial_floats(int64_t N, int64_t K, int n_out) {
   const int64_t slabs = ceil_div(K, DW_COLS);
   int64_t want = ceil_div((int64_t)num_sms() * 8, slabs > 0 ? slabs : 1);
   if (want < 1) want = 1;
-  return (size_t)(want + 1) * (size_t)K * (size_t)n_out;
+  const size_t scan = (size_t)(want + 1) * (size_t)K * (size_t)n_out;
+  const size_t tc = (size_t)(num_sms() + 1) * 256 * (size_t)n_out;   // tcgen05 split-K partials (gemm_tc.cu)
+  return scan > tc ? scan : tc;
 }
 
 // grad of x*wt wrt the weights: writes dw_a (cols [0,64) of t) and, if n_out == 128, dw_b (cols [64,128))
@@ -402,6 +404,11 @@ int dw_fp32(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, i
     BIGCN_CHECK_LAUNCH("k_dw_naive");
   }
   const int nchunk = N == 0 ? 1 : p.nchunk;
+  return dw_reduce_launch(partial, nchunk, K, n_out, dw_a, ldw_a, k0_a, dw_b, ldw_b, k0_b, st);
+}
+
+int dw_reduce_launch(const float* partial, int nchunk, int64_t K, int n_out, float* dw_a, int64_t ldw_a,
+                     int64_t k0_a, float* dw_b, int64_t ldw_b, int64_t k0_b, cudaStream_t st) {
   k_dw_reduce<<<(int)ceil_div(K, 32), 256, 0, st>>>(partial, nchunk, K, n_out, 0, dw_a, ldw_a, k0_a);
   BIGCN_CHECK_LAUNCH("k_dw_reduce");
   if (n_out == 128 && dw_b != nullptr) {

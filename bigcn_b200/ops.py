@@ -160,6 +160,7 @@ class GCNConvFunction(torch.autograd.Function):
         ctx.save_for_backward(x, ws)
         ctx.dims = (n, k, e)
         ctx.flags = flags
+        ctx.gemm_mode = gemm_mode
         return out
 
     @staticmethod
@@ -169,8 +170,8 @@ class GCNConvFunction(torch.autograd.Function):
         g = _f32(grad_out)
         dw = torch.empty(H, k, dtype=torch.float32, device=x.device)
         db = torch.empty(H, dtype=torch.float32, device=x.device)
-        check(lib().bigcn_gcnconv_backward(_p(x), n, k, e, _p(g), _p(dw), _p(db), _p(ws), ws.numel(),
-                                           _stream()), "gcnconv_backward")
+        check(lib().bigcn_gcnconv_backward(_p(x), n, k, e, _p(g), _p(dw), _p(db), L.GEMM_MODE[ctx.gemm_mode],
+                                           _p(ws), ws.numel(), _stream()), "gcnconv_backward")
         return None, None, dw, db, None, None
 
 

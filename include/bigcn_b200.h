@@ -165,7 +165,7 @@ int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const int64_t* e
                           size_t workspace_bytes, bigcn_stream_t stream);
 int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int64_t E,
                            const float* grad_out /*[N,64]*/, float* dw /*[64,K]*/, float* db /*[64]*/,
-                           void* workspace /* the forward's */, size_t workspace_bytes,
+                           int32_t gemm_mode, void* workspace /* the forward's */, size_t workspace_bytes,
                            bigcn_stream_t stream);
 
 /* ---- the two-direction feature path ------------------------------------
