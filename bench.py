@@ -40,10 +40,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="bigcn_b200", choices=["bigcn_b200", "reference"])
-    ap.add_argument("--gemm-mode", default="fp32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--gemm-mode", default="mixed", choices=["fp32", "tf32", "tf32x3", "mixed"])
     ap.add_argument("--cpu-sample-trees", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernels", action="store_true", help="also time propagate/readout-size kernels at large N")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the large-N propagate micro-benchmark")
     return ap.parse_args()
 
 
@@ -288,15 +288,39 @@ def run_ours(args):
                              ys[j].data_ptr(), 128, L.GEMM_MODE[args.gemm_mode], scr.data_ptr(), st))
     xw_ms = time_kernel(xw_fn, 12, torch)
     mean_nodes = sum(nodes[i % N_ROTATE] for i in range(12)) / 12
+    # conv1 GEMM (TD|BU fused) bytes = N*K*4 + 128*K*4 + N*128*4
     xw_bytes = mean_nodes * K_FEATS * 4 + K_FEATS * 128 * 4 + mean_nodes * 128 * 4
     xw_gbs = xw_bytes / (xw_ms * 1e-3) / 1e9
-    roof = {"kernel": "k_xw_scan<128> (X * [W1_td;W1_bu]^T, conv1 lin of both directions in one pass over X)",
-            "bound": "hbm", "achieved": xw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xw_gbs / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "ms": xw_ms,
-            "algorithmic_bytes": xw_bytes, "frac_of_8TBs_nominal": xw_gbs / 8000.0}
-    others = {}
-    if args.kernels:
-        others = kernel_microbench(torch, L, ops, dev, hbm_peak)
+    fwd_kernel = {"fp32": "k_xw_scan<128>", "mixed": "k_xw_scan<128>", "tf32": "k_xw_tc<1> (tcgen05 kind::tf32)",
+                  "tf32x3": "k_xw_tc<2> (tcgen05 kind::tf32, W hi+lo)"}[args.gemm_mode]
+    roof_fwd = {"kernel": fwd_kernel + ": X * [W1_td;W1_bu]^T, conv1.lin of both directions in one pass over X",
+                "bound": "hbm", "achieved": xw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xw_gbs / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "ms": xw_ms, "algorithmic_bytes": xw_bytes,
+                "frac_of_8TBs_nominal": xw_gbs / 8000.0}
+    # the weight gradient dW1 = T1^T X: the second pass over X (backward)
+    ts = [torch.randn(n, 128, device=dev) for n in nodes]
+    dws = [torch.empty(64, K_FEATS, device=dev) for _ in range(2)]
+    wscr = torch.empty(max(lib.bigcn_xw_wgrad_scratch_floats(n, K_FEATS, 2) for n in nodes), device=dev)
+
+    def dw_fn(i):
+        j = i % N_ROTATE
+        L.check(lib.bigcn_xw_wgrad(resident[j].x.data_ptr(), nodes[j], K_FEATS, ts[j].data_ptr(), 2, dws[0].data_ptr(),
+                                   dws[1].data_ptr(), K_FEATS, L.GEMM_MODE[args.gemm_mode], wscr.data_ptr(), st))
+    dw_ms = time_kernel(dw_fn, 12, torch)
+    # same algorithmic bytes: X once, T [N,128] once, dW [128,K] once
+    dw_gbs = xw_bytes / (dw_ms * 1e-3) / 1e9
+    bwd_kernel = {"fp32": "k_dw_slab<128> + k_dw_reduce", "tf32": "k_dw_tc<1> (tcgen05 kind::tf32, MN-major) + k_dw_reduce",
+                  "tf32x3": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce",
+                  "mixed": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce"}[args.gemm_mode]
+    roof_bwd = {"kernel": bwd_kernel + ": dW1 = T1^T X for both directions, second pass over X",
+                "bound": "hbm", "achieved": dw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dw_gbs / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "ms": dw_ms, "algorithmic_bytes": xw_bytes,
+                "frac_of_8TBs_nominal": dw_gbs / 8000.0,
+                "note": "ms covers the split-K reduce (and the T split) launched with the GEMM"}
+    roof, other_gemm = (roof_bwd, roof_fwd) if dw_ms >= xw_ms else (roof_fwd, roof_bwd)
+    others = {"other_x_stream": other_gemm}
+    if not args.no_kernels:
+        others.update(kernel_microbench(torch, L, ops, dev, hbm_peak))
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -314,7 +338,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps},
-            "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True),
+            "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode),
             "roofline": roof, "final_loss": final_loss}
     if others:
         line["roofline_others"] = others

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libbigcn_b200.so")
 H = 64
 FLAG_EDGE_RANGE, FLAG_BATCH_ORDER, FLAG_ROOT_RANGE = 1, 2, 4
 DEG_BY = {"target": 0, "source": 1}
-GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3}
 DIR_TD, DIR_BU = 1, 2
 
 c_f32p = C.c_void_p  # device pointers travel as integers
@@ -61,6 +61,9 @@ _SIGS = {
     "bigcn_xw_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
     "bigcn_xw": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int32,
                            c_ptr, c_ptr]),
+    "bigcn_xw_wgrad_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "bigcn_xw_wgrad": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, C.c_int64, C.c_int32,
+                                 c_ptr, c_ptr]),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
     "bigcn_propagate": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, c_ptr, C.c_int32,

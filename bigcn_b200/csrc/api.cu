@@ -32,7 +32,7 @@ int xw_dispatch(const float* x, int64_t N, int64_t K, const float* const* w, int
                 float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st) {
   BIGCN_CHECK_ARG(n_w == 1 || n_w == 2, "xw: one or two weight matrices");
   const int n_out = H * n_w;
-  if (mode == BIGCN_GEMM_FP32) {
+  if (mode == BIGCN_GEMM_FP32 || mode == BIGCN_GEMM_MIXED) {
     TransposeJobs js{};
     for (int q = 0; q < n_w; ++q) js.job[js.n++] = TransposeJob{w[q], ldw, 0, K, scratch, n_out, q * H};
     if (int rc = transpose_jobs_launch(js, st)) return rc;
@@ -173,7 +173,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     TransposeJobs js{};
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      if (o->gemm_mode == BIGCN_GEMM_FP32)
+      if (o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED)
         js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0};
@@ -181,7 +181,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     if (int rc = transpose_jobs_launch(js, st)) return rc;
   }
   // 3. X W1^T for all active directions in one pass over X
-  if (o->gemm_mode == BIGCN_GEMM_FP32) {
+  if (o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED) {
     if (int rc = xw_fp32(bt->x, N, K, w.w1T, n_out, w.xw, n_out, st)) return rc;
   } else {
     const float* ws[2] = {dir_w1(pr, dirs.id[0]), dirs.n == 2 ? dir_w1(pr, dirs.id[1]) : nullptr};
@@ -515,4 +515,24 @@ extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int6
   if (gemm_mode == BIGCN_GEMM_FP32) return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);
   return dw_tc(x, N, K, cw.xw, H, 64, cw.split, cw.split + (size_t)(N > 0 ? N : 1) * H, cw.dw_part, dw, K, 0,
                nullptr, 0, 0, gemm_mode, st);
+}
+
+// ---- weight gradient of X * W^T on its own (the autograd transpose of GCNConv.lin) -------
+extern "C" size_t bigcn_xw_wgrad_scratch_floats(int64_t N, int64_t K, int32_t n_w) {
+  const int n_out = H * n_w;
+  return dw_partial_floats(N, K, n_out) + (size_t)2 * (size_t)(N > 0 ? N : 1) * n_out;
+}
+
+extern "C" int bigcn_xw_wgrad(const float* x, int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0,
+                              float* dw1, int64_t ldw, int32_t gemm_mode, float* scratch,
+                              bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(x && t && dw0 && scratch && (n_w == 1 || (n_w == 2 && dw1)), "xw_wgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_out = H * n_w;
+  float* partial = scratch;
+  float* hi = scratch + dw_partial_floats(N, K, n_out);
+  float* lo = hi + (size_t)(N > 0 ? N : 1) * n_out;
+  if (gemm_mode == BIGCN_GEMM_FP32)
+    return dw_fp32(x, N, K, t, n_out, n_out, partial, dw0, ldw, 0, dw1, ldw, 0, st);
+  return dw_tc(x, N, K, t, n_out, n_out, hi, lo, partial, dw0, ldw, 0, dw1, ldw, 0, gemm_mode, st);
 }

@@ -537,7 +537,7 @@ int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int
   BIGCN_CHECK_ARG(K % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "dw_tc: x must be TMA-addressable");
   BIGCN_CHECK_ARG(ldt == n_out && (n_out == 64 || n_out == 128), "dw_tc: t must be dense [N, 64|128]");
   if (K == 0) return 0;
-  const int na = mode == BIGCN_GEMM_TF32X3 ? 2 : 1;
+  const int na = mode == BIGCN_GEMM_TF32 ? 1 : 2;   // TF32X3 and MIXED split T
   const int tiles = (int)ceil_div(K, DWT_N);
   int nsplit = 1;
   if (N == 0) {

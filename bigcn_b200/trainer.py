@@ -129,7 +129,7 @@ class FusedTrainer:
         raise_on_flags(self.flags)
 
 
-def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True) -> int:
+def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm_mode: str = "fp32") -> int:
     """How many kernels of this library one FusedTrainer.step enqueues (for bench.py's
     gpu_launches claim); mirrors the launch sequence in csrc/api.cu + graph_prep.cu."""
     bits = 1
@@ -137,10 +137,12 @@ def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True) -> i
         bits += 1
     passes = (bits + 7) // 8
     prep = 1 + 2 + 3 * passes + 1            # count, scan x2, radix passes, deg  (memset not counted)
-    fwd = prep + 1 + 1 + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
+    xw = 1 + (n_dirs if gemm_mode == "tf32x3" else 0)     # [W hi/lo split per direction], X*W
+    fwd = prep + 1 + xw + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
     head = 1 + 1 + 3                           # head fwd, nll, head bwd (feat, w partial, w reduce)
+    dw = 1 + (1 if gemm_mode in ("tf32x3", "mixed") else 0) + n_dirs   # [T hi/lo split], dW GEMM/scan, reduce x dirs
     # gscale+colsum, propT(g2), outer x2, [segsum | dw2b part], dw2b reduce + dense fallback,
-    # bwdmix+colsum, propT, dw slab, dw reduce x dirs
-    bwd = 2 + 1 + 2 + 1 + 2 + 2 + 1 + 1 + n_dirs
+    # bwdmix+colsum, propT, dW
+    bwd = 2 + 1 + 2 + 1 + 2 + 2 + 1 + dw
     adam = 2
     return fwd + head + bwd + adam

@@ -48,6 +48,8 @@ extern "C" {
 #define BIGCN_GEMM_FP32 0
 #define BIGCN_GEMM_TF32 1
 #define BIGCN_GEMM_TF32X3 2
+/* exact fp32 scan for X*W (forward), tcgen05 hi/lo-split GEMM for the weight gradient */
+#define BIGCN_GEMM_MIXED 3
 
 /* direction bits */
 #define BIGCN_DIR_TD 1
@@ -133,6 +135,12 @@ int bigcn_graph_prep(int32_t n_dirs, const int64_t* const* edge_index, const int
 size_t bigcn_xw_scratch_floats(int64_t K, int32_t n_w);
 int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
              float* y, int64_t ldy, int32_t gemm_mode, float* scratch, bigcn_stream_t stream);
+/* The autograd transpose of the above (dW1 = T1^T X):
+ * dw_d[o, k] = sum_i t[i, 64*d + o] * x[i, k] for d < n_w; t is [N, 64*n_w] dense.
+ * FP32: exact streaming scan; TF32: one tcgen05 pass; TF32X3 / MIXED: T split hi + lo. */
+size_t bigcn_xw_wgrad_scratch_floats(int64_t N, int64_t K, int32_t n_w);
+int bigcn_xw_wgrad(const float* x, int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0,
+                   float* dw1, int64_t ldw, int32_t gemm_mode, float* scratch, bigcn_stream_t stream);
 /* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
 int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
                            float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);
