@@ -418,6 +418,7 @@ extern "C" size_t bigcn_xw_scratch_floats(int64_t K, int32_t n_w) { return (size
 
 extern "C" int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
                         float* y, int64_t ldy, int32_t gemm_mode, float* scratch, bigcn_stream_t stream) {
+  if (N == 0) return 0;   // empty batch: nothing to write (x / y may be NULL)
   BIGCN_CHECK_ARG(x && w0 && y && scratch, "xw: NULL argument");
   const float* ws[2] = {w0, w1};
   return xw_dispatch(x, N, K, ws, w1 ? 2 : 1, ldw, scratch, y, ldy, gemm_mode, (cudaStream_t)stream);

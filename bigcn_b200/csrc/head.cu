@@ -110,27 +110,56 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
                        float* __restrict__ v, int64_t n, const int64_t* __restrict__ seg_end,
                        const float* __restrict__ seg_lr, int n_seg, double beta1d, double beta2d,
                        float eps, float wd, float gscale, const int64_t* step_count) {
-  const double step = (double)(*step_count + 1);
-  const float bc1 = (float)(1.0 - pow(beta1d, step));
-  const float bc2s = (float)sqrt(1.0 - pow(beta2d, step));
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {   // the double-precision pow() runs once per block, not per thread
+    const double step = (double)(*step_count + 1);
+    s_bc[0] = (float)(1.0 - pow(beta1d, step));
+    s_bc[1] = (float)sqrt(1.0 - pow(beta2d, step));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2s = s_bc[1];
   const float beta2 = (float)beta2d;
   const float omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  auto lr_of = [&](int64_t i) {
     float lr = seg_lr[n_seg - 1];
     for (int s = 0; s < n_seg; ++s)
       if (i < seg_end[s]) {
         lr = seg_lr[s];
         break;
       }
-    const float pv = p[i];
-    const float gr = fmaf(wd, pv, g[i] * gscale);
-    const float mi = m[i] + (gr - m[i]) * omb1;
-    const float vi = v[i] * beta2 + omb2 * (gr * gr);
+    return lr;
+  };
+  auto upd = [&](float pv, float gv, float& mi, float& vi, float lr) {
+    const float gr = fmaf(wd, pv, gv * gscale);
+    mi = mi + (gr - mi) * omb1;
+    vi = vi * beta2 + omb2 * (gr * gr);
+    const float denom = sqrtf(vi) / bc2s + eps;
+    return pv - (lr / bc1) * (mi / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = tid; q < n4; q += nth) {
+    float4 pv = reinterpret_cast<float4*>(p)[q];
+    const float4 gv = reinterpret_cast<const float4*>(g)[q];
+    float4 mv = reinterpret_cast<float4*>(m)[q];
+    float4 vv = reinterpret_cast<float4*>(v)[q];
+    // lr groups may change inside a quad only if a segment end is not a multiple of 4
+    pv.x = upd(pv.x, gv.x, mv.x, vv.x, lr_of(4 * q + 0));
+    pv.y = upd(pv.y, gv.y, mv.y, vv.y, lr_of(4 * q + 1));
+    pv.z = upd(pv.z, gv.z, mv.z, vv.z, lr_of(4 * q + 2));
+    pv.w = upd(pv.w, gv.w, mv.w, vv.w, lr_of(4 * q + 3));
+    reinterpret_cast<float4*>(p)[q] = pv;
+    reinterpret_cast<float4*>(m)[q] = mv;
+    reinterpret_cast<float4*>(v)[q] = vv;
+  }
+  for (int64_t i = 4 * n4 + tid; i < n; i += nth) {
+    float mi = m[i], vi = v[i];
+    p[i] = upd(p[i], g[i], mi, vi, lr_of(i));
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2s + eps;
-    p[i] = pv - (lr / bc1) * (mi / denom);
   }
 }
 __global__ void k_step_inc(int64_t* step_count) { *step_count += 1; }

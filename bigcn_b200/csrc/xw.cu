@@ -322,8 +322,14 @@ __global__ void k_dw_naive(const float* __restrict__ x, int64_t N, int64_t K,
 
 // dw[o*ldw + k0 + k] = sum_chunk partial[chunk][k][col0 + o]   (o < 64), chunks in order
 __global__ void k_dw_reduce(const float* __restrict__ partial, int nchunk, int64_t K, int nout,
-                            int col0, float* __restrict__ dw, int64_t ldw, int64_t k0) {
+                            float* __restrict__ dw_a, int64_t ldw_a, int64_t k0_a,
+                            float* __restrict__ dw_b, int64_t ldw_b, int64_t k0_b) {
   __shared__ float tile[32][65];
+  // blockIdx.y = which 64-output half (direction) of the partials
+  const int col0 = blockIdx.y * 64;
+  float* __restrict__ dw = blockIdx.y ? dw_b : dw_a;
+  const int64_t ldw = blockIdx.y ? ldw_b : ldw_a;
+  const int64_t k0 = blockIdx.y ? k0_b : k0_a;
   const int64_t kb = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 256 threads: 4 x 64
   for (int kk = ty; kk < 32; kk += 4) {
@@ -409,12 +415,10 @@ int dw_fp32(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, i
 
 int dw_reduce_launch(const float* partial, int nchunk, int64_t K, int n_out, float* dw_a, int64_t ldw_a,
                      int64_t k0_a, float* dw_b, int64_t ldw_b, int64_t k0_b, cudaStream_t st) {
-  k_dw_reduce<<<(int)ceil_div(K, 32), 256, 0, st>>>(partial, nchunk, K, n_out, 0, dw_a, ldw_a, k0_a);
+  const int halves = (n_out == 128 && dw_b != nullptr) ? 2 : 1;
+  k_dw_reduce<<<dim3((int)ceil_div(K, 32), halves), 256, 0, st>>>(partial, nchunk, K, n_out, dw_a, ldw_a, k0_a,
+                                                                  dw_b, ldw_b, k0_b);
   BIGCN_CHECK_LAUNCH("k_dw_reduce");
-  if (n_out == 128 && dw_b != nullptr) {
-    k_dw_reduce<<<(int)ceil_div(K, 32), 256, 0, st>>>(partial, nchunk, K, n_out, 64, dw_b, ldw_b, k0_b);
-    BIGCN_CHECK_LAUNCH("k_dw_reduce");
-  }
   return 0;
 }
 
