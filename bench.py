@@ -317,6 +317,17 @@ def run_ours(args):
                 "traffic": None, "peak_source": peak_src, "ms": dw_ms, "algorithmic_bytes": xw_bytes,
                 "frac_of_8TBs_nominal": dw_gbs / 8000.0,
                 "note": "ms covers the split-K reduce (and the T split) launched with the GEMM"}
+    # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.gemm_mode in ("fp32", "mixed"):
+            roof_fwd["traffic"] = tr["k_xw_scan"]["bytes"]
+            roof_fwd["traffic_note"] = f"ncu capture at N = {tr['k_xw_scan']['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
+        if args.gemm_mode in ("tf32x3", "mixed"):
+            roof_bwd["traffic"] = tr["k_dw_tc"]["bytes"]
+            roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {tr['k_dw_tc']['nodes']} nodes"
+    except Exception:  # noqa: BLE001
+        pass
     roof, other_gemm = (roof_bwd, roof_fwd) if dw_ms >= xw_ms else (roof_fwd, roof_bwd)
     others = {"other_x_stream": other_gemm}
     if not args.no_kernels:

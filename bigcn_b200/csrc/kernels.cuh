@@ -7,7 +7,7 @@ namespace bigcn {
 constexpr int CS_ROWS = 256;  // rows per CTA for column-sum partials
 constexpr int GS_TREES = 16;  // trees per CTA in k_gscale
 constexpr int BM_ROWS = 128;  // rows per CTA in k_bwd_mix (8 warps x 16 rows)
-constexpr int OP_ROWS = 512;  // rows per CTA in k_outer64
+constexpr int OP_ROWS = 128;  // rows per CTA in k_outer64
 constexpr int DW2B_ROWS = 128; // rows per CTA in k_dw2b_part
 constexpr int DW2B_CAP = 64;   // root slots per tree on the sparse-root fast path
 

@@ -13,78 +13,86 @@
 namespace bigcn {
 
 // ---------------------------------------------------------------- A-hat row gather
+// Half-warp per row: 16 lanes x float4 cover the 64 features (256 B coalesced), so a warp
+// walks TWO rows at once (twice the rows in flight, half the per-row instruction overhead).
 // acc = sum_{e in row} (dis[src]*dis[i]) * h[src]  (edge order)  + (dis[i]*dis[i]) * h[i]
-__device__ __forceinline__ float2 gather_row(const int32_t* __restrict__ ptr,
-                                             const int32_t* __restrict__ idx,
-                                             const float* __restrict__ dis,
-                                             const float* __restrict__ h, int64_t ldh, int64_t i,
-                                             int lane) {
-  const int s = ptr[i], e = ptr[i + 1];
-  const float di = dis[i];
-  float2 acc = make_float2(0.f, 0.f);
-  for (int b = s; b < e; b += 32) {
-    const int n = min(32, e - b);
+// with separate multiply and add: bit-identical to the CPU index_add_ order of the oracle.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float comp4(const float4& v, int c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void wadd4(float4& acc, float w, const float4& h) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(w, h.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(w, h.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(w, h.z));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(w, h.w));
+}
+
+__device__ __forceinline__ float4 gather_row16(const int32_t* __restrict__ ptr,
+                                               const int32_t* __restrict__ idx,
+                                               const float* __restrict__ dis,
+                                               const float* __restrict__ h, int64_t ldh, int64_t i,
+                                               bool valid, int sub) {
+  int s = 0, e = 0;
+  float di = 0.f;
+  if (valid) {
+    s = ptr[i];
+    e = ptr[i + 1];
+    di = dis[i];
+  }
+  const int n = e - s;
+  const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));   // the two halves loop together
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < nmax; b += 16) {
+    const int cnt = min(16, n - b);
     int j = 0;
     float dj = 0.f;
-    if (lane < n) {
-      j = idx[b + lane];
+    if (sub < cnt) {
+      j = idx[s + b + sub];
       dj = dis[j];
     }
-    int l = 0;
-    for (; l + 4 <= n; l += 4) {
-      float2 hv[4];
-      float w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int jj = __shfl_sync(FULL_MASK, j, l + q);
-        w[q] = __fmul_rn(__shfl_sync(FULL_MASK, dj, l + q), di);
-        hv[q] = *reinterpret_cast<const float2*>(h + (int64_t)jj * ldh + 2 * lane);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        acc.x = __fadd_rn(acc.x, __fmul_rn(w[q], hv[q].x));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(w[q], hv[q].y));
-      }
-    }
-    for (; l < n; ++l) {
-      const int jj = __shfl_sync(FULL_MASK, j, l);
-      const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l), di);
-      const float2 hv = *reinterpret_cast<const float2*>(h + (int64_t)jj * ldh + 2 * lane);
-      acc.x = __fadd_rn(acc.x, __fmul_rn(w, hv.x));
-      acc.y = __fadd_rn(acc.y, __fmul_rn(w, hv.y));
+    const int cmax = min(16, nmax - b);
+    for (int l = 0; l < cmax; ++l) {
+      const int jj = __shfl_sync(FULL_MASK, j, l, 16);
+      const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l, 16), di);
+      if (l < cnt) wadd4(acc, w, ld4(h + (int64_t)jj * ldh + 4 * sub));
     }
   }
-  const float ws = __fmul_rn(di, di);
-  const float2 hs = *reinterpret_cast<const float2*>(h + i * ldh + 2 * lane);
-  acc.x = __fadd_rn(acc.x, __fmul_rn(ws, hs.x));
-  acc.y = __fadd_rn(acc.y, __fmul_rn(ws, hs.y));
+  if (valid) wadd4(acc, __fmul_rn(di, di), ld4(h + i * ldh + 4 * sub));
   return acc;
 }
 
-
 __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
   const PropDir& p = a.d[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float2 b = make_float2(0.f, 0.f);
-  if (p.bias) b = *reinterpret_cast<const float2*>(p.bias + 2 * lane);
-  for (int64_t i = warp0; i < a.N; i += nwarp) {
-    float2 acc = gather_row(p.ptr, p.idx, p.dis, p.h, p.ldh, i, lane);
+  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) b = ld4(p.bias + 4 * sub);
+  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
+    const int64_t i = 2 * pr + half;
+    const bool valid = i < a.N;
+    float4 acc = gather_row16(p.ptr, p.idx, p.dis, p.h, p.ldh, i, valid, sub);
     if (p.bias) {
       acc.x = __fadd_rn(acc.x, b.x);
       acc.y = __fadd_rn(acc.y, b.y);
+      acc.z = __fadd_rn(acc.z, b.z);
+      acc.w = __fadd_rn(acc.w, b.w);
     }
     if (a.relu) {
       acc.x = fmaxf(acc.x, 0.f);
       acc.y = fmaxf(acc.y, 0.f);
+      acc.z = fmaxf(acc.z, 0.f);
+      acc.w = fmaxf(acc.w, 0.f);
     }
-    *reinterpret_cast<float2*>(p.out + i * p.ldo + 2 * lane) = acc;
+    if (valid) st4(p.out + i * p.ldo + 4 * sub, acc);
   }
 }
 
+// CTAs for a warp-per-row-pair sweep over N rows: enough to fill the machine, no more
 static int row_blocks(int64_t N) {
-  int64_t blocks = ceil_div(N, 8);
+  int64_t blocks = ceil_div(N, 16);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -193,49 +201,60 @@ __global__ void __launch_bounds__(256) k_root_proj(RootProjArgs a) {
 //   a1 = dropout(relu(h1))                        (:53-54) -> A1 (kept for dW2a)
 //   z  = a1 W2a^T + dropout(relu(x_root[b_i])) W2b^T   (:51-56, the lin of conv2 on the cat)
 // The root part touches only the non-zero root columns (k_root_nz); one Philox block per
-// lane decides which of them survive for this node.
-
-__device__ __forceinline__ void drop_pair(const DropSpec& ds, int64_t node, int lane, float2& a) {
-  // lane holds columns 2*lane, 2*lane+1 -> Philox block lane>>1, elements (lane&1)*2 + {0,1}
-  const Philox4 r = drop_block(ds, node, (uint32_t)(lane >> 1));
-  const uint32_t r0 = (lane & 1) ? r.z : r.x;
-  const uint32_t r1 = (lane & 1) ? r.w : r.y;
-  a.x = r0 >= ds.thresh ? __fmul_rn(a.x, ds.scale) : 0.f;
-  a.y = r1 >= ds.thresh ? __fmul_rn(a.y, ds.scale) : 0.f;
+// lane decides which of them survive for this node.  Half-warp per row (float4 per lane):
+// a lane's four columns are exactly one Philox block.
+__device__ __forceinline__ void drop_quad(const DropSpec& ds, int64_t node, int sub, float4& a) {
+  const Philox4 r = drop_block(ds, node, (uint32_t)sub);
+  a.x = r.x >= ds.thresh ? __fmul_rn(a.x, ds.scale) : 0.f;
+  a.y = r.y >= ds.thresh ? __fmul_rn(a.y, ds.scale) : 0.f;
+  a.z = r.z >= ds.thresh ? __fmul_rn(a.z, ds.scale) : 0.f;
+  a.w = r.w >= ds.thresh ? __fmul_rn(a.w, ds.scale) : 0.f;
+}
+// out[4*sub..] = sum_k v[k] * sW[k][4*sub..]  with v spread over the 16 lanes of the half
+__device__ __forceinline__ float4 matvec16(const float4& v, const float* __restrict__ sW, int sub) {
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 16
+  for (int k = 0; k < H; ++k) {
+    const float s = __shfl_sync(FULL_MASK, comp4(v, k & 3), k >> 2, 16);
+    const float4 w = ld4(sW + k * H + 4 * sub);
+    z.x = fmaf(s, w.x, z.x);
+    z.y = fmaf(s, w.y, z.y);
+    z.z = fmaf(s, w.z, z.z);
+    z.w = fmaf(s, w.w, z.w);
+  }
+  return z;
 }
 
 __global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
-  __shared__ float sW[H * H];
+  __shared__ __align__(16) float sW[H * H];
   const MixDir& p = a.d[blockIdx.y];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2aT[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const float2 b1 = *reinterpret_cast<const float2*>(p.b1 + 2 * lane);
-  for (int64_t i = warp0; i < a.N; i += nwarp) {
-    float2 h1 = gather_row(p.ptr, p.idx, p.dis, p.xw, a.ldxw, i, lane);
+  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4 b1 = ld4(p.b1 + 4 * sub);
+  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
+    const int64_t i = 2 * pr + half;
+    const bool valid = i < a.N;
+    float4 h1 = gather_row16(p.ptr, p.idx, p.dis, p.xw, a.ldxw, i, valid, sub);
     h1.x = __fadd_rn(h1.x, b1.x);
     h1.y = __fadd_rn(h1.y, b1.y);
-    *reinterpret_cast<float2*>(p.h1 + i * H + 2 * lane) = h1;
-    float2 av = make_float2(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f));
+    h1.z = __fadd_rn(h1.z, b1.z);
+    h1.w = __fadd_rn(h1.w, b1.w);
+    if (valid) st4(p.h1 + i * H + 4 * sub, h1);
+    float4 av = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
     const int64_t node = a.node_id_base + i;
-    if (p.drop.on) drop_pair(p.drop, node, lane, av);
-    *reinterpret_cast<float2*>(p.a1 + i * H + 2 * lane) = av;
-    float2 z = make_float2(0.f, 0.f);
-#pragma unroll 16
-    for (int k = 0; k < H; ++k) {
-      const float s = __shfl_sync(FULL_MASK, (k & 1) ? av.y : av.x, k >> 1);
-      const float2 w = *reinterpret_cast<const float2*>(sW + k * H + 2 * lane);
-      z.x = fmaf(s, w.x, z.x);
-      z.y = fmaf(s, w.y, z.y);
-    }
-    const int64_t b = a.batch[i];
+    if (p.drop.on) drop_quad(p.drop, node, sub, av);
+    if (valid) st4(p.a1 + i * H + 4 * sub, av);
+    float4 z = matvec16(av, sW, sub);
+    const int64_t b = valid ? a.batch[i] : 0;
     if (p.drop.on) {
-      const int n = a.rnz_cnt[b];
-      float2 racc = make_float2(0.f, 0.f);
-      for (int t0 = 0; t0 < n; t0 += 32) {
-        const int t = t0 + lane;
+      const int n = valid ? a.rnz_cnt[b] : 0;
+      const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));
+      float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t0 = 0; t0 < nmax; t0 += 16) {
+        const int t = t0 + sub;
         int k = 0;
         float v = 0.f;
         bool keep = false;
@@ -246,27 +265,38 @@ __global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
           const Philox4 r = drop_block(p.drop, node, c >> 2);
           keep = philox_elem(r, c & 3) >= p.drop.thresh;
         }
-        unsigned m = __ballot_sync(FULL_MASK, keep);
-        while (m) {
-          const int sl = __ffs(m) - 1;
-          m &= m - 1;
-          const int kk = __shfl_sync(FULL_MASK, k, sl);
-          const float vv = __shfl_sync(FULL_MASK, v, sl);
-          const float2 w = *reinterpret_cast<const float2*>(p.w2bT + (int64_t)kk * H + 2 * lane);
-          racc.x = fmaf(vv, w.x, racc.x);
-          racc.y = fmaf(vv, w.y, racc.y);
+        unsigned mine = (__ballot_sync(FULL_MASK, keep) >> (16 * half)) & 0xffffu;
+        const int cnt = __popc(mine);
+        const int cmax = max(cnt, __shfl_xor_sync(FULL_MASK, cnt, 16));
+        for (int q = 0; q < cmax; ++q) {       // kept entries in ascending order
+          const int src = mine ? __ffs(mine) - 1 : 0;
+          mine &= mine - 1;
+          const int kk = __shfl_sync(FULL_MASK, k, src, 16);
+          const float vv = __shfl_sync(FULL_MASK, v, src, 16);
+          if (q < cnt) {
+            const float4 w = ld4(p.w2bT + (int64_t)kk * H + 4 * sub);
+            racc.x = fmaf(vv, w.x, racc.x);
+            racc.y = fmaf(vv, w.y, racc.y);
+            racc.z = fmaf(vv, w.z, racc.z);
+            racc.w = fmaf(vv, w.w, racc.w);
+          }
         }
       }
       z.x = fmaf(p.drop.scale, racc.x, z.x);
       z.y = fmaf(p.drop.scale, racc.y, z.y);
-    } else {
-      const float2 pv = *reinterpret_cast<const float2*>(p.P + b * H + 2 * lane);
+      z.z = fmaf(p.drop.scale, racc.z, z.z);
+      z.w = fmaf(p.drop.scale, racc.w, z.w);
+    } else if (valid) {
+      const float4 pv = ld4(p.P + b * H + 4 * sub);
       z.x += pv.x;
       z.y += pv.y;
+      z.z += pv.z;
+      z.w += pv.w;
     }
-    *reinterpret_cast<float2*>(p.z + i * H + 2 * lane) = z;
+    if (valid) st4(p.z + i * H + 4 * sub, z);
   }
 }
+
 
 // ---------------------------------------------------------------- readout
 // feat[b, base_d + f]      = mean_{i in tree b} H2_d[i, f]           (scatter_mean, :65)
@@ -342,42 +372,60 @@ __global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
 // G2[x] = [H2[x] > 0] * gs[batch[x]]   (relu and scatter_mean backward fused into the gather)
 __global__ void __launch_bounds__(256) k_propagate_g2(PropG2Args a) {
   const PropG2Dir& p = a.d[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp0; i < a.N; i += nwarp) {
-    const int s = p.ptr[i], e = p.ptr[i + 1];
-    const float di = p.dis[i];
-    float2 acc = make_float2(0.f, 0.f);
-    for (int b0 = s; b0 < e; b0 += 32) {
-      const int n = min(32, e - b0);
+  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
+    const int64_t i = 2 * pr + half;
+    const bool valid = i < a.N;
+    int s = 0, e = 0, bi = 0;
+    float di = 0.f;
+    if (valid) {
+      s = p.ptr[i];
+      e = p.ptr[i + 1];
+      di = p.dis[i];
+      bi = (int)a.batch[i];
+    }
+    const int n = e - s;
+    const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b0 = 0; b0 < nmax; b0 += 16) {
+      const int cnt = min(16, n - b0);
       int j = 0, tb = 0;
       float dj = 0.f;
-      if (lane < n) {
-        j = p.idx[b0 + lane];
+      if (sub < cnt) {
+        j = p.idx[s + b0 + sub];
         dj = p.dis[j];
         tb = (int)a.batch[j];
       }
-      for (int l = 0; l < n; ++l) {
-        const int jj = __shfl_sync(FULL_MASK, j, l);
-        const int bb = __shfl_sync(FULL_MASK, tb, l);
-        const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l), di);
-        const float2 hv = *reinterpret_cast<const float2*>(p.h2 + (int64_t)jj * H + 2 * lane);
-        const float2 gv = *reinterpret_cast<const float2*>(p.gs + (int64_t)bb * H + 2 * lane);
-        acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
-        acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+      const int cmax = min(16, nmax - b0);
+      for (int l = 0; l < cmax; ++l) {
+        const int jj = __shfl_sync(FULL_MASK, j, l, 16);
+        const int bb = __shfl_sync(FULL_MASK, tb, l, 16);
+        const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l, 16), di);
+        if (l < cnt) {
+          const float4 hv = ld4(p.h2 + (int64_t)jj * H + 4 * sub);
+          const float4 gv = ld4(p.gs + (int64_t)bb * H + 4 * sub);
+          acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
+          acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+          acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
+          acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
+        }
       }
     }
-    {
+    if (valid) {
       const float w = __fmul_rn(di, di);
-      const float2 hv = *reinterpret_cast<const float2*>(p.h2 + i * H + 2 * lane);
-      const float2 gv = *reinterpret_cast<const float2*>(p.gs + a.batch[i] * H + 2 * lane);
+      const float4 hv = ld4(p.h2 + i * H + 4 * sub);
+      const float4 gv = ld4(p.gs + (int64_t)bi * H + 4 * sub);
       acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
       acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+      acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
+      acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
+      st4(p.out + i * H + 4 * sub, acc);
     }
-    *reinterpret_cast<float2*>(p.out + i * H + 2 * lane) = acc;
   }
 }
+
 
 // out[f] = sum_chunk part[chunk][f]: 4 strided groups, fixed-order combine
 __global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {
@@ -391,46 +439,44 @@ __global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {
   if (g == 0) a.out[j][f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
 }
 
-// G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1
+// G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1.
+// CTA = BM_ROWS rows: 8 warps x 8 row pairs, half-warp per row.
 __global__ void __launch_bounds__(256) k_bwd_mix(BwdMixArgs a) {
-  __shared__ float sW[H * H];
-  __shared__ float red[8][H];
+  __shared__ __align__(16) float sW[H * H];   // [o][k] = W2[o][k], k < 64
+  __shared__ float red[16][H];
   const BwdMixDir& p = a.d[blockIdx.y];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2[(int64_t)(i >> 6) * a.ldw2 + (i & 63)];
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane & 15, half = lane >> 4;
   const int64_t base = (int64_t)blockIdx.x * BM_ROWS + w * 16;
-  float2 cs = make_float2(0.f, 0.f);
-  for (int r = 0; r < 16; ++r) {
-    const int64_t i = base + r;
-    if (i >= a.N) break;
-    const float2 t = *reinterpret_cast<const float2*>(p.t2 + i * H + 2 * lane);
-    float2 g = make_float2(0.f, 0.f);
-#pragma unroll 16
-    for (int o = 0; o < H; ++o) {
-      const float s = __shfl_sync(FULL_MASK, (o & 1) ? t.y : t.x, o >> 1);
-      const float2 wv = *reinterpret_cast<const float2*>(sW + o * H + 2 * lane);
-      g.x = fmaf(s, wv.x, g.x);
-      g.y = fmaf(s, wv.y, g.y);
-    }
-    if (p.drop.on) drop_pair(p.drop, a.node_id_base + i, lane, g);
-    const float2 h = *reinterpret_cast<const float2*>(p.h1 + i * H + 2 * lane);
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = base + 2 * r + half;
+    const bool valid = i < a.N;
+    const float4 t = valid ? ld4(p.t2 + i * H + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g = matvec16(t, sW, sub);
+    if (p.drop.on) drop_quad(p.drop, a.node_id_base + i, sub, g);
+    const float4 h = valid ? ld4(p.h1 + i * H + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
     g.x = h.x > 0.f ? g.x : 0.f;
     g.y = h.y > 0.f ? g.y : 0.f;
-    *reinterpret_cast<float2*>(p.g1 + i * H + 2 * lane) = g;
+    g.z = h.z > 0.f ? g.z : 0.f;
+    g.w = h.w > 0.f ? g.w : 0.f;
+    if (valid) st4(p.g1 + i * H + 4 * sub, g);
     cs.x += g.x;
     cs.y += g.y;
+    cs.z += g.z;
+    cs.w += g.w;
   }
-  red[w][2 * lane] = cs.x;
-  red[w][2 * lane + 1] = cs.y;
+  st4(&red[w * 2 + half][4 * sub], cs);
   __syncthreads();
   if (threadIdx.x < H) {
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x];
+    for (int q = 0; q < 16; ++q) s += red[q][threadIdx.x];
     p.part[(int64_t)blockIdx.x * H + threadIdx.x] = s;
   }
 }
+
 
 // C[o][k] = sum_i U[i][o] * V[i][k]  (64 x 64), rows chunked; partial[chunk][64*64]
 __global__ void __launch_bounds__(256) k_outer64(OuterArgs a) {
@@ -481,9 +527,16 @@ __global__ void __launch_bounds__(256) k_outer64(OuterArgs a) {
 __global__ void k_outer_reduce(OuterReduceArgs a) {
   const int d = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 0..4095
-  float s = 0.f;
-  for (int c = 0; c < a.nchunk; ++c) s += a.part[d][(int64_t)c * H * H + idx];
-  a.dst[d][(int64_t)(idx >> 6) * a.ld + (idx & 63)] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains, fixed combine order
+  int c = 0;
+  for (; c + 4 <= a.nchunk; c += 4) {
+    s0 += a.part[d][(int64_t)(c + 0) * H * H + idx];
+    s1 += a.part[d][(int64_t)(c + 1) * H * H + idx];
+    s2 += a.part[d][(int64_t)(c + 2) * H * H + idx];
+    s3 += a.part[d][(int64_t)(c + 3) * H * H + idx];
+  }
+  for (; c < a.nchunk; ++c) s0 += a.part[d][(int64_t)c * H * H + idx];
+  a.dst[d][(int64_t)(idx >> 6) * a.ld + (idx & 63)] = (s0 + s1) + (s2 + s3);
 }
 
 // per-tree segment sum: dP[d][b][f] = sum_{i in b} T2_d[i][f]   (eval-mode dW2b)
