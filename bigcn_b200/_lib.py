@@ -43,7 +43,8 @@ class Graph(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("training", C.c_int32), ("p_drop", C.c_float), ("seed", C.c_uint64),
-                ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32)]
+                ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32),
+                ("bwd_phase", C.c_int32)]
 
 
 class BigcnError(RuntimeError):

@@ -258,6 +258,10 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   float* t2[2] = {w.xw, w.xw + nh};      // XW is dead after forward
   float* g1[2] = {w.z[0], w.z[1]};       // Z is dead after forward
   float* t1cat = w.h2[0];                // H2 is dead once T2 exists
+  // bwd_phase: 0 = everything, 1 = all but dW1, 2 = dW1 only (lets the caller all-reduce the
+  // other gradients while the second X stream runs)
+  const int phase = o->bwd_phase;
+  if (phase == 2) goto dw1_only;
   // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
     GScaleArgs a{};
@@ -340,6 +344,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
+  if (phase == 1) return 0;
+dw1_only:
   // 7. dW1 = T1^T X, one more pass over X
   {
     float* da = gdir_w1(gr, dirs.id[0]);

@@ -29,70 +29,101 @@ __device__ __forceinline__ void wadd4(float4& acc, float w, const float4& h) {
   acc.w = __fadd_rn(acc.w, __fmul_rn(w, h.w));
 }
 
-__device__ __forceinline__ float4 gather_row16(const int32_t* __restrict__ ptr,
-                                               const int32_t* __restrict__ idx,
-                                               const float* __restrict__ dis,
-                                               const float* __restrict__ h, int64_t ldh, int64_t i,
-                                               bool valid, int sub) {
-  int s = 0, e = 0;
-  float di = 0.f;
-  if (valid) {
-    s = ptr[i];
-    e = ptr[i + 1];
-    di = dis[i];
-  }
-  const int n = e - s;
-  const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));   // the two halves loop together
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int b = 0; b < nmax; b += 16) {
-    const int cnt = min(16, n - b);
-    int j = 0;
-    float dj = 0.f;
-    if (sub < cnt) {
-      j = idx[s + b + sub];
-      dj = dis[j];
+// GU row pairs per warp iteration.  All loads of one dependency level are issued for the GU
+// rows before anything is consumed (ptr/dis/self row -> first neighbour index -> its dis and
+// row), so a warp keeps 2*GU rows of gathers in flight instead of one dependent chain; further
+// neighbours (rows with more than one in-edge) are added by an unrolled loop.  The additions
+// still run in COO' order per row: neighbours in edge order, then the self-loop.
+template <int GU>
+struct RowGather {
+  int64_t i[GU];
+  bool valid[GU];
+  float4 acc[GU];
+};
+
+template <int GU>
+__device__ __forceinline__ void gather_rows(RowGather<GU>& r, const int32_t* __restrict__ ptr,
+                                            const int32_t* __restrict__ idx,
+                                            const float* __restrict__ dis,
+                                            const float* __restrict__ h, int64_t ldh, int64_t first_pair,
+                                            int64_t N, int sub, int half) {
+  int s[GU], n[GU], j[GU];
+  float di[GU], dj[GU];
+  float4 self[GU], hv[GU];
+#pragma unroll
+  for (int u = 0; u < GU; ++u) {
+    r.i[u] = (first_pair + u) * 2 + half;
+    r.valid[u] = r.i[u] < N;
+    s[u] = 0; n[u] = 0; di[u] = 0.f;
+    self[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r.valid[u]) {
+      s[u] = ptr[r.i[u]];
+      n[u] = ptr[r.i[u] + 1] - s[u];
+      di[u] = dis[r.i[u]];
+      self[u] = ld4(h + r.i[u] * ldh + 4 * sub);
     }
-    const int cmax = min(16, nmax - b);
-    for (int l = 0; l < cmax; ++l) {
-      const int jj = __shfl_sync(FULL_MASK, j, l, 16);
-      const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l, 16), di);
-      if (l < cnt) wadd4(acc, w, ld4(h + (int64_t)jj * ldh + 4 * sub));
+  }
+#pragma unroll
+  for (int u = 0; u < GU; ++u) j[u] = n[u] > 0 ? idx[s[u]] : 0;
+#pragma unroll
+  for (int u = 0; u < GU; ++u) {
+    dj[u] = 0.f;
+    hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n[u] > 0) {
+      dj[u] = dis[j[u]];
+      hv[u] = ld4(h + (int64_t)j[u] * ldh + 4 * sub);
     }
   }
-  if (valid) wadd4(acc, __fmul_rn(di, di), ld4(h + i * ldh + 4 * sub));
-  return acc;
+#pragma unroll
+  for (int u = 0; u < GU; ++u) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n[u] > 0) wadd4(acc, __fmul_rn(dj[u], di[u]), hv[u]);
+#pragma unroll 4
+    for (int l = 1; l < n[u]; ++l) {
+      const int jj = idx[s[u] + l];
+      wadd4(acc, __fmul_rn(dis[jj], di[u]), ld4(h + (int64_t)jj * ldh + 4 * sub));
+    }
+    if (r.valid[u]) wadd4(acc, __fmul_rn(di[u], di[u]), self[u]);
+    r.acc[u] = acc;
+  }
 }
+
+constexpr int PROP_GU = 4;
 
 __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
   const PropDir& p = a.d[blockIdx.y];
   const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias) b = ld4(p.bias + 4 * sub);
-  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
-    const int64_t i = 2 * pr + half;
-    const bool valid = i < a.N;
-    float4 acc = gather_row16(p.ptr, p.idx, p.dis, p.h, p.ldh, i, valid, sub);
-    if (p.bias) {
-      acc.x = __fadd_rn(acc.x, b.x);
-      acc.y = __fadd_rn(acc.y, b.y);
-      acc.z = __fadd_rn(acc.z, b.z);
-      acc.w = __fadd_rn(acc.w, b.w);
+  const int64_t ngroups = (a.N + 2 * PROP_GU - 1) / (2 * PROP_GU);
+  for (int64_t g = w0; g < ngroups; g += nw) {
+    RowGather<PROP_GU> r;
+    gather_rows<PROP_GU>(r, p.ptr, p.idx, p.dis, p.h, p.ldh, g * PROP_GU, a.N, sub, half);
+#pragma unroll
+    for (int u = 0; u < PROP_GU; ++u) {
+      float4 acc = r.acc[u];
+      if (p.bias) {
+        acc.x = __fadd_rn(acc.x, b.x);
+        acc.y = __fadd_rn(acc.y, b.y);
+        acc.z = __fadd_rn(acc.z, b.z);
+        acc.w = __fadd_rn(acc.w, b.w);
+      }
+      if (a.relu) {
+        acc.x = fmaxf(acc.x, 0.f);
+        acc.y = fmaxf(acc.y, 0.f);
+        acc.z = fmaxf(acc.z, 0.f);
+        acc.w = fmaxf(acc.w, 0.f);
+      }
+      if (r.valid[u]) st4(p.out + r.i[u] * p.ldo + 4 * sub, acc);
     }
-    if (a.relu) {
-      acc.x = fmaxf(acc.x, 0.f);
-      acc.y = fmaxf(acc.y, 0.f);
-      acc.z = fmaxf(acc.z, 0.f);
-      acc.w = fmaxf(acc.w, 0.f);
-    }
-    if (valid) st4(p.out + i * p.ldo + 4 * sub, acc);
   }
 }
 
 // CTAs for a warp-per-row-pair sweep over N rows: enough to fill the machine, no more
 static int row_blocks(int64_t N) {
-  int64_t blocks = ceil_div(N, 16);
+  int64_t blocks = ceil_div(N, 8 * 2 * PROP_GU);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -235,9 +266,11 @@ __global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
   const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float4 b1 = ld4(p.b1 + 4 * sub);
   for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
-    const int64_t i = 2 * pr + half;
-    const bool valid = i < a.N;
-    float4 h1 = gather_row16(p.ptr, p.idx, p.dis, p.xw, a.ldxw, i, valid, sub);
+    RowGather<1> rg;
+    gather_rows<1>(rg, p.ptr, p.idx, p.dis, p.xw, a.ldxw, pr, a.N, sub, half);
+    const int64_t i = rg.i[0];
+    const bool valid = rg.valid[0];
+    float4 h1 = rg.acc[0];
     h1.x = __fadd_rn(h1.x, b1.x);
     h1.y = __fadd_rn(h1.y, b1.y);
     h1.z = __fadd_rn(h1.z, b1.z);
@@ -370,62 +403,69 @@ __global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
 
 // T2[j] = sum_{x in out(j)} (dis[j]*dis[x]) * G2[x] + dis[j]^2 * G2[j],
 // G2[x] = [H2[x] > 0] * gs[batch[x]]   (relu and scatter_mean backward fused into the gather)
+__device__ __forceinline__ void gadd4(float4& acc, float w, const float4& hv, const float4& gv) {
+  acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
+  acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
+  acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
+  acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
+}
 __global__ void __launch_bounds__(256) k_propagate_g2(PropG2Args a) {
+  constexpr int GU = PROP_GU;
   const PropG2Dir& p = a.d[blockIdx.y];
   const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
-    const int64_t i = 2 * pr + half;
-    const bool valid = i < a.N;
-    int s = 0, e = 0, bi = 0;
-    float di = 0.f;
-    if (valid) {
-      s = p.ptr[i];
-      e = p.ptr[i + 1];
-      di = p.dis[i];
-      bi = (int)a.batch[i];
-    }
-    const int n = e - s;
-    const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b0 = 0; b0 < nmax; b0 += 16) {
-      const int cnt = min(16, n - b0);
-      int j = 0, tb = 0;
-      float dj = 0.f;
-      if (sub < cnt) {
-        j = p.idx[s + b0 + sub];
-        dj = p.dis[j];
-        tb = (int)a.batch[j];
-      }
-      const int cmax = min(16, nmax - b0);
-      for (int l = 0; l < cmax; ++l) {
-        const int jj = __shfl_sync(FULL_MASK, j, l, 16);
-        const int bb = __shfl_sync(FULL_MASK, tb, l, 16);
-        const float w = __fmul_rn(__shfl_sync(FULL_MASK, dj, l, 16), di);
-        if (l < cnt) {
-          const float4 hv = ld4(p.h2 + (int64_t)jj * H + 4 * sub);
-          const float4 gv = ld4(p.gs + (int64_t)bb * H + 4 * sub);
-          acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
-          acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
-          acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
-          acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
-        }
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ngroups = (a.N + 2 * GU - 1) / (2 * GU);
+  for (int64_t g = w0; g < ngroups; g += nw) {
+    int64_t i[GU];
+    bool valid[GU];
+    int s[GU], n[GU], j[GU], bi[GU], bj[GU];
+    float di[GU], dj[GU];
+    float4 hs[GU], hv[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      i[u] = (g * GU + u) * 2 + half;
+      valid[u] = i[u] < a.N;
+      s[u] = 0; n[u] = 0; di[u] = 0.f; bi[u] = 0;
+      hs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid[u]) {
+        s[u] = p.ptr[i[u]];
+        n[u] = p.ptr[i[u] + 1] - s[u];
+        di[u] = p.dis[i[u]];
+        bi[u] = (int)a.batch[i[u]];
+        hs[u] = ld4(p.h2 + i[u] * H + 4 * sub);
       }
     }
-    if (valid) {
-      const float w = __fmul_rn(di, di);
-      const float4 hv = ld4(p.h2 + i * H + 4 * sub);
-      const float4 gv = ld4(p.gs + (int64_t)bi * H + 4 * sub);
-      acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
-      acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
-      acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
-      acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
-      st4(p.out + i * H + 4 * sub, acc);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) j[u] = n[u] > 0 ? p.idx[s[u]] : 0;
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      dj[u] = 0.f; bj[u] = 0;
+      hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n[u] > 0) {
+        dj[u] = p.dis[j[u]];
+        bj[u] = (int)a.batch[j[u]];
+        hv[u] = ld4(p.h2 + (int64_t)j[u] * H + 4 * sub);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n[u] > 0) gadd4(acc, __fmul_rn(dj[u], di[u]), hv[u], ld4(p.gs + (int64_t)bj[u] * H + 4 * sub));
+#pragma unroll 4
+      for (int l = 1; l < n[u]; ++l) {
+        const int jj = p.idx[s[u] + l];
+        const int bb = (int)a.batch[jj];
+        gadd4(acc, __fmul_rn(p.dis[jj], di[u]), ld4(p.h2 + (int64_t)jj * H + 4 * sub),
+              ld4(p.gs + (int64_t)bb * H + 4 * sub));
+      }
+      if (valid[u]) {
+        gadd4(acc, __fmul_rn(di[u], di[u]), hs[u], ld4(p.gs + (int64_t)bi[u] * H + 4 * sub));
+        st4(p.out + i[u] * H + 4 * sub, acc);
+      }
     }
   }
 }
-
 
 // out[f] = sum_chunk part[chunk][f]: 4 strided groups, fixed-order combine
 __global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {

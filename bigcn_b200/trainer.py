@@ -16,10 +16,12 @@ from . import _lib as L
 from ._lib import H, Opts, Params, check, lib
 from .ops import _make_structs, _p, _stream, _i64, _f32, raise_on_flags
 
-_ORDER = ("TDrumorGCN.conv1.lin.weight", "TDrumorGCN.conv1.bias", "TDrumorGCN.conv2.lin.weight",
-          "TDrumorGCN.conv2.bias", "fc.weight", "fc.bias",
-          "BUrumorGCN.conv1.lin.weight", "BUrumorGCN.conv1.bias", "BUrumorGCN.conv2.lin.weight",
-          "BUrumorGCN.conv2.bias")
+# flat layout: the two conv1 weights (the gradients the second X stream produces LAST) first, so
+# the gradient splits into two contiguous all-reduce buckets: [W1_td | W1_bu] and [everything else]
+_ORDER = ("TDrumorGCN.conv1.lin.weight", "BUrumorGCN.conv1.lin.weight",
+          "TDrumorGCN.conv1.bias", "TDrumorGCN.conv2.lin.weight", "TDrumorGCN.conv2.bias", "fc.weight", "fc.bias",
+          "BUrumorGCN.conv1.bias", "BUrumorGCN.conv2.lin.weight", "BUrumorGCN.conv2.bias")
+_LR_DIV = (1, 5, 1, 1, 1, 1, 1, 5, 5, 5)     # BU conv1 / conv2 at lr/5 (BiGCN_Twitter.py:146-153)
 _STRUCT = {"TDrumorGCN.conv1.lin.weight": "td_w1", "TDrumorGCN.conv1.bias": "td_b1",
            "TDrumorGCN.conv2.lin.weight": "td_w2", "TDrumorGCN.conv2.bias": "td_b2",
            "BUrumorGCN.conv1.lin.weight": "bu_w1", "BUrumorGCN.conv1.bias": "bu_b1",
@@ -59,10 +61,11 @@ class FusedTrainer:
                 p.data = v                         # the module now reads the flat buffer
                 self.views[name] = v
                 self.gviews[name] = self.grad[o:o + s].view(p.shape)
-        # lr groups: [TD convs + fc] at lr, [BU convs] at lr/5  (BiGCN_Twitter.py:146-153)
-        split = offs[6]
-        self.seg_end = torch.tensor([split, self.n], dtype=torch.int64, device=dev)
-        self.seg_lr = torch.tensor([lr, lr / 5], dtype=torch.float32, device=dev)
+        # lr groups: TD convs + fc at lr, BU convs at lr/5  (BiGCN_Twitter.py:146-153)
+        self.seg_end = torch.tensor(offs[1:], dtype=torch.int64, device=dev)
+        self.seg_lr = torch.tensor([lr / d for d in _LR_DIV], dtype=torch.float32, device=dev)
+        self.n_seg = len(_LR_DIV)
+        self.w1_end = offs[2]                    # [0, w1_end) = the two conv1 weight gradients
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pr, self._gr = Params(), Params()
@@ -113,13 +116,24 @@ class FusedTrainer:
         scr = torch.empty(nscr, dtype=torch.float32, device=dev)
         check(l.bigcn_head_backward(_p(glogp), _p(logp), _p(feat), b, c, self._pr.fc_w, _p(gfeat),
                                     self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_backward")
-        check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
-                                        C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
         if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+            # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
+            o.bwd_phase = 1
+            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+            h_rest = torch.distributed.all_reduce(self.grad[self.w1_end:], group=self.pg, async_op=True)
+            o.bwd_phase = 2
+            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+            h_w1 = torch.distributed.all_reduce(self.grad[:self.w1_end], group=self.pg, async_op=True)
+            h_rest.wait()
+            h_w1.wait()
+        else:
+            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
         check(l.bigcn_adam_step(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
-                                _p(self.seg_end), _p(self.seg_lr), 2, self.betas[0], self.betas[1], self.eps,
-                                self.wd, 1.0, _p(self.step_count), st), "adam_step")
+                                _p(self.seg_end), _p(self.seg_lr), self.n_seg, self.betas[0], self.betas[1],
+                                self.eps, self.wd, 1.0, _p(self.step_count), st), "adam_step")
         self.last_logp = logp
         if self.validate:
             raise_on_flags(self.flags)

@@ -105,6 +105,7 @@ typedef struct bigcn_opts {
   int32_t deg_by;     /* BIGCN_DEG_BY_*                                             */
   int32_t gemm_mode;  /* BIGCN_GEMM_*                                               */
   int32_t dir_mask;   /* BIGCN_DIR_TD | BIGCN_DIR_BU                                */
+  int32_t bwd_phase;  /* features_backward: 0 all, 1 all but dW1, 2 dW1 only        */
 } bigcn_opts_t;
 
 const char* bigcn_last_error(void);
