@@ -378,7 +378,8 @@ def kernel_microbench(torch, L, ops, dev, hbm_peak):
         ptr, idx = g["in_ptr"], g["in_idx"]
 
         def fn(i, ptr=ptr, idx=idx, g=g):
-            L.check(lib.bigcn_propagate(ptr.data_ptr(), idx.data_ptr(), g["dis"].data_ptr(), n, hs[i % 2].data_ptr(), 64,
+            L.check(lib.bigcn_propagate(ptr.data_ptr(), idx.data_ptr(), g["dis"].data_ptr(), n, g["E"],
+                                        g["in_long"].data_ptr(), hs[i % 2].data_ptr(), 64,
                                         bias.data_ptr(), 1, outb.data_ptr(), 64, st))
         ms = time_kernel(fn, 10, torch)
         # N*(2*256 + 8) + 4E + 260 bytes (each source row counted once)

@@ -38,7 +38,8 @@ class Params(C.Structure):
 
 
 class Graph(C.Structure):
-    _fields_ = [(n, c_ptr) for n in ("in_ptr", "in_idx", "out_ptr", "out_idx", "deg", "dis", "rowsum")]
+    _fields_ = [(n, c_ptr) for n in ("in_ptr", "in_idx", "out_ptr", "out_idx", "deg", "dis", "rowsum",
+                                     "in_long", "out_long")]
 
 
 class Opts(C.Structure):
@@ -67,8 +68,9 @@ _SIGS = {
                                  c_ptr, c_ptr]),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
-    "bigcn_propagate": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, c_ptr, C.c_int32,
-                                  c_ptr, C.c_int64, c_ptr]),
+    "bigcn_long_ws_ints": (C.c_size_t, [C.c_int64]),
+    "bigcn_propagate": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr,
+                                  C.c_int32, c_ptr, C.c_int64, c_ptr]),
     "bigcn_dropout_mask": (C.c_int, [C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                      c_ptr, c_ptr]),
     "bigcn_gcnconv_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),

@@ -82,6 +82,8 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
     w.g[d].deg = c.take<int32_t>(N > 0 ? N : 1);
     w.g[d].dis = c.take<float>(N > 0 ? N : 1);
     w.g[d].rowsum = nullptr;
+    w.g[d].in_long = c.take<int32_t>(long_ws_ints(E[d]));
+    w.g[d].out_long = c.take<int32_t>(long_ws_ints(E[d]));
   }
   w.node_ptr = c.take<int32_t>(B + 1);
   w.w1T = c.take<float>((size_t)K * 256);   // fp32: [K][128] transposed; tensor-core modes: hi/lo split
@@ -212,6 +214,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       const int d = dirs.id[q];
       MixDir& m = a.d[q];
       m.ptr = w.g[d].in_ptr; m.idx = w.g[d].in_idx; m.dis = w.g[d].dis;
+      m.lng = w.g[d].in_long; m.E = d == 0 ? dm->E_td : dm->E_bu;
       m.xw = w.xw + q * H; m.b1 = dir_b1(pr, d);
       m.w2aT = w.w2aT[d]; m.w2bT = w.w2bT[d]; m.P = w.P[d];
       m.h1 = w.h1[d]; m.a1 = w.a1[d]; m.z = w.z[d];
@@ -225,7 +228,8 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     a.N = N; a.relu = 1;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = PropDir{w.g[d].in_ptr, w.g[d].in_idx, w.g[d].dis, w.z[d], dir_b2(pr, d), w.h2[d], H, H};
+      a.d[q] = PropDir{w.g[d].in_ptr, w.g[d].in_idx, w.g[d].dis, w.z[d], dir_b2(pr, d), w.h2[d], H, H,
+                       w.g[d].in_long, d == 0 ? dm->E_td : dm->E_bu};
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
@@ -282,7 +286,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     a.N = N; a.batch = bt->batch;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = PropG2Dir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, w.h2[d], w.gs[d], t2[d]};
+      a.d[q] = PropG2Dir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, w.h2[d], w.gs[d], t2[d],
+                         w.g[d].out_long, d == 0 ? dm->E_td : dm->E_bu};
     }
     if (int rc = propagate_g2_launch(a, dirs.n, st)) return rc;
   }
@@ -340,7 +345,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     a.N = N; a.relu = 0;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = PropDir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, g1[d], nullptr, t1cat + q * H, H, n_out};
+      a.d[q] = PropDir{w.g[d].out_ptr, w.g[d].out_idx, w.g[d].dis, g1[d], nullptr, t1cat + q * H, H, n_out,
+                       w.g[d].out_long, d == 0 ? dm->E_td : dm->E_bu};
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
@@ -382,6 +388,8 @@ static ConvWs carve_conv(int64_t N, int64_t E, int64_t K, void* ws, size_t bytes
   w.g.deg = c.take<int32_t>(N > 0 ? N : 1);
   w.g.dis = c.take<float>(N > 0 ? N : 1);
   w.g.rowsum = nullptr;
+  w.g.in_long = c.take<int32_t>(long_ws_ints(E));
+  w.g.out_long = c.take<int32_t>(long_ws_ints(E));
   w.wT = c.take<float>((size_t)K * H * 2);
   w.xw = c.take<float>((size_t)(N > 0 ? N : 1) * H);
   w.split = c.take<float>((size_t)(N > 0 ? N : 1) * H * 2);
@@ -430,13 +438,15 @@ extern "C" int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, c
   return xw_dispatch(x, N, K, ws, w1 ? 2 : 1, ldw, scratch, y, ldy, gemm_mode, (cudaStream_t)stream);
 }
 
-extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N,
-                               const float* h, int64_t ldh, const float* bias, int32_t relu, float* out,
-                               int64_t ldo, bigcn_stream_t stream) {
-  BIGCN_CHECK_ARG((ldh % 2 == 0) && (ldo % 2 == 0), "propagate: row pitches must be even");
+extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N, int64_t E,
+                               int32_t* long_ws, const float* h, int64_t ldh, const float* bias, int32_t relu,
+                               float* out, int64_t ldo, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG((ldh % 4 == 0) && (ldo % 4 == 0), "propagate: row pitches must be multiples of 4 floats");
+  BIGCN_CHECK_ARG(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                  "propagate: h and out must be 16 B aligned");
   PropArgs a{};
   a.N = N; a.relu = relu;
-  a.d[0] = PropDir{ptr, idx, dis, h, bias, out, ldh, ldo};
+  a.d[0] = PropDir{ptr, idx, dis, h, bias, out, ldh, ldo, long_ws, E};
   return propagate_launch(a, 1, (cudaStream_t)stream);
 }
 
@@ -494,7 +504,7 @@ extern "C" int bigcn_gcnconv_forward(const float* x, int64_t N, int64_t K, const
   if (int rc = xw_dispatch(x, N, K, ws1, 1, K, cw.wT, cw.xw, H, gemm_mode, st)) return rc;
   PropArgs a{};
   a.N = N; a.relu = 0;
-  a.d[0] = PropDir{cw.g.in_ptr, cw.g.in_idx, cw.g.dis, cw.xw, bias, out, H, H};
+  a.d[0] = PropDir{cw.g.in_ptr, cw.g.in_idx, cw.g.dis, cw.xw, bias, out, H, H, cw.g.in_long, E};
   return propagate_launch(a, 1, st);
 }
 
@@ -516,7 +526,7 @@ extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int6
   // T = A-hat^T grad_out
   PropArgs a{};
   a.N = N; a.relu = 0;
-  a.d[0] = PropDir{cw.g.out_ptr, cw.g.out_idx, cw.g.dis, grad_out, nullptr, cw.xw, H, H};
+  a.d[0] = PropDir{cw.g.out_ptr, cw.g.out_idx, cw.g.dis, grad_out, nullptr, cw.xw, H, H, cw.g.out_long, E};
   if (int rc = propagate_launch(a, 1, st)) return rc;
   // dw = T^T x
   if (gemm_mode == BIGCN_GEMM_FP32) return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);

@@ -13,7 +13,7 @@
 // All of this is HBM/latency-bound integer work: 32-bit keys, 8-bit digits,
 // ceil(bits(N)/8) passes, the four sorts (2 directions x {by target, by source})
 // batched in blockIdx.y so a prep is a fixed, short launch sequence.
-#include "common.cuh"
+#include "gather.cuh"
 
 namespace bigcn {
 
@@ -74,6 +74,13 @@ __global__ void k_prep_count(PrepArgs a) {
     v_in[e] = (int32_t)r;
     k_out[e] = valid ? (int32_t)r : sentinel;
     v_out[e] = (int32_t)c;
+  }
+  // hub-row lists of this direction: counters and arrival flags start at zero
+  for (int o = 0; o < 2; ++o) {
+    int32_t* lng = o ? pd.g.out_long : pd.g.in_long;
+    if (lng == nullptr) continue;
+    const int64_t hdr = long_hdr_ints(pd.E);
+    for (int64_t i = t0; i < hdr; i += stride) lng[i] = 0;
   }
   if (dir == 0 && a.node_ptr != nullptr) {
     for (int64_t i = t0; i <= a.N; i += stride) {
@@ -259,6 +266,30 @@ __global__ void k_prep_deg(PrepArgs a) {
   }
 }
 
+// hub rows of the four CSRs (blockIdx.y = 2*dir + orient): rows with more than LONG_ROW entries
+// get a slot and a run of (row, chunk) items; slot / item numbering depends on the arrival
+// order of the atomics, the sums formed from them do not.
+__global__ void k_prep_long(PrepArgs a) {
+  const int s = blockIdx.y;
+  const PrepDir& pd = a.d[s >> 1];
+  int32_t* lng = (s & 1) ? pd.g.out_long : pd.g.in_long;
+  if (lng == nullptr) return;
+  const int32_t* ptr = (s & 1) ? pd.g.out_ptr : pd.g.in_ptr;
+  const LongView L = long_view(lng, pd.E);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int len = ptr[i + 1] - ptr[i];
+    if (len <= LONG_ROW) continue;
+    int lch, nch;
+    long_chunking(len, lch, nch);
+    const int slot = atomicAdd(&L.cnt[0], 1);
+    const int t0 = atomicAdd(&L.cnt[1], nch);
+    L.row[slot] = (int32_t)i;
+    L.item0[slot] = t0;
+    for (int c = 0; c < nch; ++c) L.item_slot[t0 + c] = slot;
+  }
+}
+
 __global__ void k_prep_rowsum(PrepArgs a) {
   // warp per row, COO' order: in-edges sequentially, then the self-loop
   const int dir = blockIdx.y;
@@ -382,6 +413,12 @@ int graph_prep_impl(int32_t n_dirs, const int64_t* const* edge_index, const int6
     if (blocks > cap) blocks = cap;
     k_prep_deg<<<dim3(blocks, n_dirs), 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_prep_deg");
+    bool want_long = false;
+    for (int d = 0; d < n_dirs; ++d) want_long |= graphs[d].in_long != nullptr || graphs[d].out_long != nullptr;
+    if (want_long && Emax > LONG_ROW) {
+      k_prep_long<<<dim3(blocks, ns), 256, 0, st>>>(a);
+      BIGCN_CHECK_LAUNCH("k_prep_long");
+    }
     bool want_rowsum = false;
     for (int d = 0; d < n_dirs; ++d) want_rowsum |= graphs[d].rowsum != nullptr;
     if (want_rowsum) {
@@ -394,6 +431,8 @@ int graph_prep_impl(int32_t n_dirs, const int64_t* const* edge_index, const int6
   return 0;
 }
 
+size_t long_ws_ints(int64_t E) { return (size_t)long_ws_ints_impl(E > 0 ? E : 0); }
+
 size_t graph_prep_ws_bytes(int64_t N, int64_t Emax, int ndir) {
   return prep_layout(N, Emax, ndir).total;
 }
@@ -403,6 +442,8 @@ size_t graph_prep_ws_bytes(int64_t N, int64_t Emax, int ndir) {
 extern "C" size_t bigcn_graph_prep_workspace_bytes(int64_t N, int64_t E_max, int32_t n_dirs) {
   return bigcn::graph_prep_ws_bytes(N, E_max, n_dirs);
 }
+
+extern "C" size_t bigcn_long_ws_ints(int64_t E) { return bigcn::long_ws_ints(E); }
 
 extern "C" int bigcn_graph_prep(int32_t n_dirs, const int64_t* const* edge_index, const int64_t* E,
                                 int64_t N, const int64_t* batch, int64_t B, int32_t deg_by,

@@ -10,6 +10,9 @@ constexpr int BM_ROWS = 128;  // rows per CTA in k_bwd_mix (8 warps x 16 rows)
 constexpr int OP_ROWS = 128;  // rows per CTA in k_outer64
 constexpr int DW2B_ROWS = 128; // rows per CTA in k_dw2b_part
 constexpr int DW2B_CAP = 64;   // root slots per tree on the sparse-root fast path
+constexpr int LONG_ROW = 32;         // CSR rows with more in-edges are split (gather.cuh)
+constexpr int LONG_MAX_CHUNKS = 64;  // at most this many chunks per hub row
+size_t long_ws_ints(int64_t E);
 
 int graph_prep_impl(int32_t, const int64_t* const*, const int64_t*, int64_t, const int64_t*, int64_t,
                     int32_t, const bigcn_graph_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
@@ -28,22 +31,22 @@ int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int
 int dw_fp32(const float*, int64_t, int64_t, const float*, int64_t, int, float*, float*, int64_t, int64_t,
             float*, int64_t, int64_t, cudaStream_t);
 
-struct PropDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h; const float* bias; float* out; int64_t ldh, ldo; };
-struct PropArgs { PropDir d[2]; int64_t N; int32_t relu; };
+struct PropDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h; const float* bias; float* out; int64_t ldh, ldo; int32_t* lng; int64_t E; };
+struct PropArgs { PropDir d[2]; int64_t N; int32_t relu; int32_t cb; };
 int propagate_launch(const PropArgs&, int, cudaStream_t);
 struct RootNzArgs { const float* x; const int64_t* rootindex; int64_t N, B, K; int32_t* cnt; int32_t* col; float* val; int32_t* flags; int32_t* slot; int32_t* overflow; int32_t cap; };
 int root_nz_launch(const RootNzArgs&, cudaStream_t);
 struct RootProjArgs { const int32_t* cnt; const int32_t* col; const float* val; const float* w2bT[2]; float* P[2]; int64_t B, K; };
 int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
-struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; };
-struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
+struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; };
+struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
 struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t N, B; int32_t* flags; };
 int readout_launch(const ReadoutArgs&, cudaStream_t);
 struct GScaleArgs { const float* grad_feat; const float* pos[2]; float* gs[2]; float* part[2]; int feat_base[2]; const int32_t* node_ptr; int64_t B; };
 int gscale_launch(const GScaleArgs&, int, cudaStream_t);
-struct PropG2Dir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h2; const float* gs; float* out; };
-struct PropG2Args { PropG2Dir d[2]; int64_t N; const int64_t* batch; };
+struct PropG2Dir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h2; const float* gs; float* out; int32_t* lng; int64_t E; };
+struct PropG2Args { PropG2Dir d[2]; int64_t N; const int64_t* batch; int32_t cb; };
 int propagate_g2_launch(const PropG2Args&, int, cudaStream_t);
 struct ColsumArgs { const float* part[4]; float* out[4]; int nchunk; };
 int colsum_reduce_launch(const ColsumArgs&, int, cudaStream_t);

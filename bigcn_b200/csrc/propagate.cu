@@ -8,131 +8,65 @@
 // All kernels are warp-per-row over 64-wide fp32 rows (float2 per lane, 256 B coalesced),
 // gather through the int32 CSR built by graph_prep, sum in COO' order with separate
 // multiply and add (bit-identical to the CPU index_add_ order), and use no atomics.
-#include "kernels.cuh"
+#include "gather.cuh"
 
 namespace bigcn {
 
-// ---------------------------------------------------------------- A-hat row gather
-// Half-warp per row: 16 lanes x float4 cover the 64 features (256 B coalesced), so a warp
-// walks TWO rows at once (twice the rows in flight, half the per-row instruction overhead).
-// acc = sum_{e in row} (dis[src]*dis[i]) * h[src]  (edge order)  + (dis[i]*dis[i]) * h[i]
-// with separate multiply and add: bit-identical to the CPU index_add_ order of the oracle.
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float comp4(const float4& v, int c) {
-  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
-}
-__device__ __forceinline__ void wadd4(float4& acc, float w, const float4& h) {
-  acc.x = __fadd_rn(acc.x, __fmul_rn(w, h.x));
-  acc.y = __fadd_rn(acc.y, __fmul_rn(w, h.y));
-  acc.z = __fadd_rn(acc.z, __fmul_rn(w, h.z));
-  acc.w = __fadd_rn(acc.w, __fmul_rn(w, h.w));
-}
+// ---------------------------------------------------------------- A-hat / A-hat^T propagate
+// out = A-hat h (+ bias)(relu): the CSR sweep of gather.cuh with a bias / relu / store epilogue.
+constexpr int PROP_R = 8, PROP_Q = 8;     // 64 KB stage per CTA, 3 CTAs per SM
+constexpr int MIX_R = 4, MIX_Q = 8;       // 48 KB stage + 16 KB W2a per CTA, 3 CTAs per SM
 
-// GU row pairs per warp iteration.  All loads of one dependency level are issued for the GU
-// rows before anything is consumed (ptr/dis/self row -> first neighbour index -> its dis and
-// row), so a warp keeps 2*GU rows of gathers in flight instead of one dependent chain; further
-// neighbours (rows with more than one in-edge) are added by an unrolled loop.  The additions
-// still run in COO' order per row: neighbours in edge order, then the self-loop.
-template <int GU>
-struct RowGather {
-  int64_t i[GU];
-  bool valid[GU];
-  float4 acc[GU];
+struct PostBiasRelu {
+  const float* bias;
+  float* out;
+  int64_t ldo;
+  int relu;
+  float4 b;
+  __device__ __forceinline__ void operator()(int i, float4 v, int sub, unsigned, float*) const {
+    if (bias) {
+      v.x = __fadd_rn(v.x, b.x);
+      v.y = __fadd_rn(v.y, b.y);
+      v.z = __fadd_rn(v.z, b.z);
+      v.w = __fadd_rn(v.w, b.w);
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f);
+      v.y = fmaxf(v.y, 0.f);
+      v.z = fmaxf(v.z, 0.f);
+      v.w = fmaxf(v.w, 0.f);
+    }
+    st4(out + (int64_t)i * ldo + 4 * sub, v);
+  }
 };
 
-template <int GU>
-__device__ __forceinline__ void gather_rows(RowGather<GU>& r, const int32_t* __restrict__ ptr,
-                                            const int32_t* __restrict__ idx,
-                                            const float* __restrict__ dis,
-                                            const float* __restrict__ h, int64_t ldh, int64_t first_pair,
-                                            int64_t N, int sub, int half) {
-  int s[GU], n[GU], j[GU];
-  float di[GU], dj[GU];
-  float4 self[GU], hv[GU];
-#pragma unroll
-  for (int u = 0; u < GU; ++u) {
-    r.i[u] = (first_pair + u) * 2 + half;
-    r.valid[u] = r.i[u] < N;
-    s[u] = 0; n[u] = 0; di[u] = 0.f;
-    self[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r.valid[u]) {
-      s[u] = ptr[r.i[u]];
-      n[u] = ptr[r.i[u] + 1] - s[u];
-      di[u] = dis[r.i[u]];
-      self[u] = ld4(h + r.i[u] * ldh + 4 * sub);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < GU; ++u) j[u] = n[u] > 0 ? idx[s[u]] : 0;
-#pragma unroll
-  for (int u = 0; u < GU; ++u) {
-    dj[u] = 0.f;
-    hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n[u] > 0) {
-      dj[u] = dis[j[u]];
-      hv[u] = ld4(h + (int64_t)j[u] * ldh + 4 * sub);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < GU; ++u) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n[u] > 0) wadd4(acc, __fmul_rn(dj[u], di[u]), hv[u]);
-#pragma unroll 4
-    for (int l = 1; l < n[u]; ++l) {
-      const int jj = idx[s[u] + l];
-      wadd4(acc, __fmul_rn(dis[jj], di[u]), ld4(h + (int64_t)jj * ldh + 4 * sub));
-    }
-    if (r.valid[u]) wadd4(acc, __fmul_rn(di[u], di[u]), self[u]);
-    r.acc[u] = acc;
-  }
+__global__ void __launch_bounds__(256, 3) k_propagate(PropArgs a) {
+  extern __shared__ __align__(128) float sweep_smem[];
+  const PropDir p = a.d[blockIdx.y];
+  const int sub = threadIdx.x & 15;
+  PostBiasRelu post{p.bias, p.out, p.ldo, a.relu, make_float4(0.f, 0.f, 0.f, 0.f)};
+  if (p.bias) post.b = ld4(p.bias + 4 * sub);
+  csr_sweep<PROP_R, PROP_Q, true>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
+                                         ValRow{p.h, p.ldh}, post);
 }
 
-constexpr int PROP_GU = 4;
+template <class K>
+static void sweep_attr(K kernel, int smem) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
 
-__global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
-  const PropDir& p = a.d[blockIdx.y];
-  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) b = ld4(p.bias + 4 * sub);
-  const int64_t ngroups = (a.N + 2 * PROP_GU - 1) / (2 * PROP_GU);
-  for (int64_t g = w0; g < ngroups; g += nw) {
-    RowGather<PROP_GU> r;
-    gather_rows<PROP_GU>(r, p.ptr, p.idx, p.dis, p.h, p.ldh, g * PROP_GU, a.N, sub, half);
-#pragma unroll
-    for (int u = 0; u < PROP_GU; ++u) {
-      float4 acc = r.acc[u];
-      if (p.bias) {
-        acc.x = __fadd_rn(acc.x, b.x);
-        acc.y = __fadd_rn(acc.y, b.y);
-        acc.z = __fadd_rn(acc.z, b.z);
-        acc.w = __fadd_rn(acc.w, b.w);
-      }
-      if (a.relu) {
-        acc.x = fmaxf(acc.x, 0.f);
-        acc.y = fmaxf(acc.y, 0.f);
-        acc.z = fmaxf(acc.z, 0.f);
-        acc.w = fmaxf(acc.w, 0.f);
-      }
-      if (r.valid[u]) st4(p.out + r.i[u] * p.ldo + 4 * sub, acc);
-    }
+int propagate_launch(const PropArgs& a0, int ndir, cudaStream_t st) {
+  if (a0.N == 0) return 0;
+  constexpr int smem = SweepSmem<PROP_R, PROP_Q>::kBytes;
+  static bool attr = false;
+  if (!attr) {
+    sweep_attr(k_propagate, smem);
+    attr = true;
   }
-}
-
-// CTAs for a warp-per-row-pair sweep over N rows: enough to fill the machine, no more
-static int row_blocks(int64_t N) {
-  int64_t blocks = ceil_div(N, 8 * 2 * PROP_GU);
-  const int64_t cap = (int64_t)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
-}
-
-int propagate_launch(const PropArgs& a, int ndir, cudaStream_t st) {
-  if (a.N == 0) return 0;
-  k_propagate<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+  PropArgs a = a0;
+  const int max_ctas = num_sms() * 3;
+  a.cb = sweep_cb(a.N, PROP_R, max_ctas);
+  k_propagate<<<dim3(sweep_grid(a.N, PROP_R, a.cb, max_ctas), ndir), 256, smem, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_propagate");
   return 0;
 }
@@ -256,78 +190,111 @@ __device__ __forceinline__ float4 matvec16(const float4& v, const float* __restr
   return z;
 }
 
-__global__ void __launch_bounds__(256) k_prop1_mix(MixArgs a) {
-  __shared__ __align__(16) float sW[H * H];
-  const MixDir& p = a.d[blockIdx.y];
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2aT[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-  const int64_t pair0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t npair = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const float4 b1 = ld4(p.b1 + 4 * sub);
-  for (int64_t pr = pair0; 2 * pr < a.N; pr += npair) {
-    RowGather<1> rg;
-    gather_rows<1>(rg, p.ptr, p.idx, p.dis, p.xw, a.ldxw, pr, a.N, sub, half);
-    const int64_t i = rg.i[0];
-    const bool valid = rg.valid[0];
-    float4 h1 = rg.acc[0];
+// z[4*sub..] = sum_k av[k] * sW[k][4*sub..]: the half-warp parks av in shared memory and every
+// lane reads it back as broadcast float4s (no shuffles), k ascending, one fma chain per output
+__device__ __forceinline__ float4 matvec_smem(const float4& av, const float* __restrict__ sW, float* scratch,
+                                              int sub, unsigned hm) {
+  st4(scratch + 4 * sub, av);
+  __syncwarp(hm);
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int k4 = 0; k4 < H / 4; ++k4) {
+    const float4 a4 = ld4(scratch + 4 * k4);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float s = comp4(a4, c);
+      const float4 w = ld4(sW + (4 * k4 + c) * H + 4 * sub);
+      z.x = fmaf(s, w.x, z.x);
+      z.y = fmaf(s, w.y, z.y);
+      z.z = fmaf(s, w.z, z.z);
+      z.w = fmaf(s, w.w, z.w);
+    }
+  }
+  __syncwarp(hm);
+  return z;
+}
+
+struct PostMix {
+  MixDir p;
+  const float* sW;
+  const int64_t* batch;
+  const int32_t* rnz_cnt;
+  const int32_t* rnz_col;
+  const float* rnz_val;
+  int64_t K, node_id_base;
+  float4 b1;
+  __device__ __forceinline__ void operator()(int i, float4 h1, int sub, unsigned hm, float* scratch) const {
     h1.x = __fadd_rn(h1.x, b1.x);
     h1.y = __fadd_rn(h1.y, b1.y);
     h1.z = __fadd_rn(h1.z, b1.z);
     h1.w = __fadd_rn(h1.w, b1.w);
-    if (valid) st4(p.h1 + i * H + 4 * sub, h1);
+    st4(p.h1 + (int64_t)i * H + 4 * sub, h1);
     float4 av = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
-    const int64_t node = a.node_id_base + i;
+    const int64_t node = node_id_base + i;
     if (p.drop.on) drop_quad(p.drop, node, sub, av);
-    if (valid) st4(p.a1 + i * H + 4 * sub, av);
-    float4 z = matvec16(av, sW, sub);
-    const int64_t b = valid ? a.batch[i] : 0;
+    st4(p.a1 + (int64_t)i * H + 4 * sub, av);
+    float4 z = matvec_smem(av, sW, scratch, sub, hm);
+    const int64_t b = batch[i];
     if (p.drop.on) {
-      const int n = valid ? a.rnz_cnt[b] : 0;
-      const int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));
+      const int n = rnz_cnt[b];
       float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t0 = 0; t0 < nmax; t0 += 16) {
+      for (int t0 = 0; t0 < n; t0 += 16) {
         const int t = t0 + sub;
         int k = 0;
         float v = 0.f;
         bool keep = false;
         if (t < n) {
-          k = a.rnz_col[b * a.K + t];
-          v = a.rnz_val[b * a.K + t];
+          k = rnz_col[b * K + t];
+          v = rnz_val[b * K + t];
           const uint32_t c = (uint32_t)(H + k);
           const Philox4 r = drop_block(p.drop, node, c >> 2);
           keep = philox_elem(r, c & 3) >= p.drop.thresh;
         }
-        unsigned mine = (__ballot_sync(FULL_MASK, keep) >> (16 * half)) & 0xffffu;
-        const int cnt = __popc(mine);
-        const int cmax = max(cnt, __shfl_xor_sync(FULL_MASK, cnt, 16));
-        for (int q = 0; q < cmax; ++q) {       // kept entries in ascending order
-          const int src = mine ? __ffs(mine) - 1 : 0;
-          mine &= mine - 1;
-          const int kk = __shfl_sync(FULL_MASK, k, src, 16);
-          const float vv = __shfl_sync(FULL_MASK, v, src, 16);
-          if (q < cnt) {
-            const float4 w = ld4(p.w2bT + (int64_t)kk * H + 4 * sub);
-            racc.x = fmaf(vv, w.x, racc.x);
-            racc.y = fmaf(vv, w.y, racc.y);
-            racc.z = fmaf(vv, w.z, racc.z);
-            racc.w = fmaf(vv, w.w, racc.w);
-          }
+        // kept entries in ascending order: (k, v) pairs go through the scratch row
+        unsigned mine = (__ballot_sync(hm, keep) >> (hm == 0xffffu ? 0 : 16)) & 0xffffu;
+        if (keep) {
+          const int pos = __popc(mine & ((1u << sub) - 1u));
+          reinterpret_cast<int*>(scratch)[pos] = k;
+          scratch[16 + pos] = v;
         }
+        __syncwarp(hm);
+        const int cnt = __popc(mine);
+        for (int q = 0; q < cnt; ++q) {
+          const int kk = reinterpret_cast<const int*>(scratch)[q];
+          const float vv = scratch[16 + q];
+          const float4 w = ld4(p.w2bT + (int64_t)kk * H + 4 * sub);
+          racc.x = fmaf(vv, w.x, racc.x);
+          racc.y = fmaf(vv, w.y, racc.y);
+          racc.z = fmaf(vv, w.z, racc.z);
+          racc.w = fmaf(vv, w.w, racc.w);
+        }
+        __syncwarp(hm);
       }
       z.x = fmaf(p.drop.scale, racc.x, z.x);
       z.y = fmaf(p.drop.scale, racc.y, z.y);
       z.z = fmaf(p.drop.scale, racc.z, z.z);
       z.w = fmaf(p.drop.scale, racc.w, z.w);
-    } else if (valid) {
+    } else {
       const float4 pv = ld4(p.P + b * H + 4 * sub);
       z.x += pv.x;
       z.y += pv.y;
       z.z += pv.z;
       z.w += pv.w;
     }
-    if (valid) st4(p.z + i * H + 4 * sub, z);
+    st4(p.z + (int64_t)i * H + 4 * sub, z);
   }
+};
+
+__global__ void __launch_bounds__(256, 3) k_prop1_mix(MixArgs a) {
+  extern __shared__ __align__(128) float sweep_smem[];
+  __shared__ __align__(16) float sW[H * H];
+  const MixDir p = a.d[blockIdx.y];
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2aT[i];
+  // csr_sweep starts with a __syncthreads()
+  const int sub = threadIdx.x & 15;
+  PostMix post{p, sW, a.batch, a.rnz_cnt, a.rnz_col, a.rnz_val, a.K, a.node_id_base, ld4(p.b1 + 4 * sub)};
+  csr_sweep<MIX_R, MIX_Q, true>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
+                                      ValRow{p.xw, a.ldxw}, post);
 }
 
 
@@ -403,68 +370,32 @@ __global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
 
 // T2[j] = sum_{x in out(j)} (dis[j]*dis[x]) * G2[x] + dis[j]^2 * G2[j],
 // G2[x] = [H2[x] > 0] * gs[batch[x]]   (relu and scatter_mean backward fused into the gather)
-__device__ __forceinline__ void gadd4(float4& acc, float w, const float4& hv, const float4& gv) {
-  acc.x += w * (hv.x > 0.f ? gv.x : 0.f);
-  acc.y += w * (hv.y > 0.f ? gv.y : 0.f);
-  acc.z += w * (hv.z > 0.f ? gv.z : 0.f);
-  acc.w += w * (hv.w > 0.f ? gv.w : 0.f);
-}
-__global__ void __launch_bounds__(256) k_propagate_g2(PropG2Args a) {
-  constexpr int GU = PROP_GU;
-  const PropG2Dir& p = a.d[blockIdx.y];
-  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ngroups = (a.N + 2 * GU - 1) / (2 * GU);
-  for (int64_t g = w0; g < ngroups; g += nw) {
-    int64_t i[GU];
-    bool valid[GU];
-    int s[GU], n[GU], j[GU], bi[GU], bj[GU];
-    float di[GU], dj[GU];
-    float4 hs[GU], hv[GU];
-#pragma unroll
-    for (int u = 0; u < GU; ++u) {
-      i[u] = (g * GU + u) * 2 + half;
-      valid[u] = i[u] < a.N;
-      s[u] = 0; n[u] = 0; di[u] = 0.f; bi[u] = 0;
-      hs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid[u]) {
-        s[u] = p.ptr[i[u]];
-        n[u] = p.ptr[i[u] + 1] - s[u];
-        di[u] = p.dis[i[u]];
-        bi[u] = (int)a.batch[i[u]];
-        hs[u] = ld4(p.h2 + i[u] * H + 4 * sub);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GU; ++u) j[u] = n[u] > 0 ? p.idx[s[u]] : 0;
-#pragma unroll
-    for (int u = 0; u < GU; ++u) {
-      dj[u] = 0.f; bj[u] = 0;
-      hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n[u] > 0) {
-        dj[u] = p.dis[j[u]];
-        bj[u] = (int)a.batch[j[u]];
-        hv[u] = ld4(p.h2 + (int64_t)j[u] * H + 4 * sub);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GU; ++u) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n[u] > 0) gadd4(acc, __fmul_rn(dj[u], di[u]), hv[u], ld4(p.gs + (int64_t)bj[u] * H + 4 * sub));
-#pragma unroll 4
-      for (int l = 1; l < n[u]; ++l) {
-        const int jj = p.idx[s[u] + l];
-        const int bb = (int)a.batch[jj];
-        gadd4(acc, __fmul_rn(p.dis[jj], di[u]), ld4(p.h2 + (int64_t)jj * H + 4 * sub),
-              ld4(p.gs + (int64_t)bb * H + 4 * sub));
-      }
-      if (valid[u]) {
-        gadd4(acc, __fmul_rn(di[u], di[u]), hs[u], ld4(p.gs + (int64_t)bi[u] * H + 4 * sub));
-        st4(p.out + i[u] * H + 4 * sub, acc);
-      }
-    }
+struct ValG2 {   // val(x) = [H2[x] > 0] * gs[batch[x]]
+  const float* h2;
+  const float* gs;
+  const int64_t* batch;
+  __device__ __forceinline__ void fetch(float* dst, int j, int sub) const {
+    cp_async_row16(dst + 4 * sub, h2 + (int64_t)j * H + 4 * sub);
   }
+  __device__ __forceinline__ int aux(int j) const { return (int)batch[j]; }
+  __device__ __forceinline__ float4 value(const float* slot, int b, int sub) const {
+    const float4 hv = ld4(slot + 4 * sub);
+    const float4 gv = ld4(gs + (int64_t)b * H + 4 * sub);
+    return make_float4(hv.x > 0.f ? gv.x : 0.f, hv.y > 0.f ? gv.y : 0.f, hv.z > 0.f ? gv.z : 0.f,
+                       hv.w > 0.f ? gv.w : 0.f);
+  }
+};
+struct PostStore {
+  float* out;
+  __device__ __forceinline__ void operator()(int i, const float4& v, int sub, unsigned, float*) const {
+    st4(out + (int64_t)i * H + 4 * sub, v);
+  }
+};
+__global__ void __launch_bounds__(256, 3) k_propagate_g2(PropG2Args a) {
+  extern __shared__ __align__(128) float sweep_smem[];
+  const PropG2Dir p = a.d[blockIdx.y];
+  csr_sweep<PROP_R, PROP_Q, false>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
+                                          ValG2{p.h2, p.gs, a.batch}, PostStore{p.out});
 }
 
 // out[f] = sum_chunk part[chunk][f]: 4 strided groups, fixed-order combine
@@ -820,9 +751,18 @@ int root_proj_launch(const RootProjArgs& a, int ndir, cudaStream_t st) {
   BIGCN_CHECK_LAUNCH("k_root_proj");
   return 0;
 }
-int prop1_mix_launch(const MixArgs& a, int ndir, cudaStream_t st) {
-  if (a.N == 0) return 0;
-  k_prop1_mix<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+int prop1_mix_launch(const MixArgs& a0, int ndir, cudaStream_t st) {
+  if (a0.N == 0) return 0;
+  constexpr int smem = SweepSmem<MIX_R, MIX_Q>::kBytes;
+  static bool attr = false;
+  if (!attr) {
+    sweep_attr(k_prop1_mix, smem);
+    attr = true;
+  }
+  MixArgs a = a0;
+  const int max_ctas = num_sms() * 3;
+  a.cb = sweep_cb(a.N, MIX_R, max_ctas);
+  k_prop1_mix<<<dim3(sweep_grid(a.N, MIX_R, a.cb, max_ctas), ndir), 256, smem, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_prop1_mix");
   return 0;
 }
@@ -843,9 +783,18 @@ int gscale_launch(const GScaleArgs& a, int ndir, cudaStream_t st) {
   BIGCN_CHECK_LAUNCH("k_gscale");
   return 0;
 }
-int propagate_g2_launch(const PropG2Args& a, int ndir, cudaStream_t st) {
-  if (a.N == 0) return 0;
-  k_propagate_g2<<<dim3(row_blocks(a.N), ndir), 256, 0, st>>>(a);
+int propagate_g2_launch(const PropG2Args& a0, int ndir, cudaStream_t st) {
+  if (a0.N == 0) return 0;
+  constexpr int smem = SweepSmem<PROP_R, PROP_Q>::kBytes;
+  static bool attr = false;
+  if (!attr) {
+    sweep_attr(k_propagate_g2, smem);
+    attr = true;
+  }
+  PropG2Args a = a0;
+  const int max_ctas = num_sms() * 3;
+  a.cb = sweep_cb(a.N, PROP_R, max_ctas);
+  k_propagate_g2<<<dim3(sweep_grid(a.N, PROP_R, a.cb, max_ctas), ndir), 256, smem, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_propagate_g2");
   return 0;
 }

@@ -213,13 +213,18 @@ class DeviceTrees:
     rootindex: torch.Tensor
 
 
-def make_device_forest(n_trees: int, nodes_per_tree: int, device, seed: int = 0) -> DeviceTrees:
+def make_device_forest(n_trees: int, nodes_per_tree: int, device, seed: int = 0, skew: float = 1.0) -> DeviceTrees:
+    """``skew`` = 1: uniform random recursive trees (parent of node i uniform in [0, i));
+    > 1 biases parents towards the early nodes (u**skew), i.e. hub-heavy reply trees whose root
+    collects O(n**(1-1/skew)) children."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     n = n_trees * nodes_per_tree
     local = torch.arange(n, device=device, dtype=torch.int64) % nodes_per_tree
     base = torch.arange(n, device=device, dtype=torch.int64) - local
     u = torch.rand(n, device=device, generator=g, dtype=torch.float64)
+    if skew != 1.0:
+        u = u ** skew
     par_local = (u * local.to(torch.float64)).to(torch.int64).clamp_(min=0)
     is_child = local > 0
     child = torch.arange(n, device=device, dtype=torch.int64)[is_child]

@@ -37,9 +37,11 @@ def _f32(t):
 
 
 # ----------------------------------------------------------------------------- graph prep
-def graph_prep(edge_indexes, num_nodes, batch=None, num_graphs=0, deg_by="target", rowsum=True):
+def graph_prep(edge_indexes, num_nodes, batch=None, num_graphs=0, deg_by="target", rowsum=True, long_rows=True):
     """gcn_norm structure for 1 or 2 edge lists.  Returns (graphs, node_ptr, flags) where each
-    graph is a dict of device tensors (see include/bigcn_b200.h: bigcn_graph_t)."""
+    graph is a dict of device tensors (see include/bigcn_b200.h: bigcn_graph_t).
+    ``long_rows=False`` leaves the hub-row lists out: propagate then walks every row
+    sequentially (exact COO' order even for rows with more than 32 in-edges)."""
     L.require_device()
     eis = [_i64(e) for e in edge_indexes]
     _need_cuda(*eis)
@@ -56,6 +58,9 @@ def graph_prep(edge_indexes, num_nodes, batch=None, num_graphs=0, deg_by="target
                  deg=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
                  dis=torch.empty(max(n, 1), dtype=torch.float32, device=dev),
                  rowsum=torch.empty(max(n, 1), dtype=torch.float32, device=dev) if rowsum else None)
+        nl = lib().bigcn_long_ws_ints(e)
+        g["in_long"] = torch.empty(nl, dtype=torch.int32, device=dev) if long_rows else None
+        g["out_long"] = torch.empty(nl, dtype=torch.int32, device=dev) if long_rows else None
         for k, v in g.items():
             setattr(structs[d], k, _p(v))
         g["E"] = e
@@ -107,9 +112,10 @@ def propagate(graph, h, bias=None, relu=False, transpose=False):
     h = _f32(h)
     n = h.shape[0]
     out = torch.empty(n, H, dtype=torch.float32, device=h.device)
-    ptr, idx = (graph["out_ptr"], graph["out_idx"]) if transpose else (graph["in_ptr"], graph["in_idx"])
-    check(lib().bigcn_propagate(_p(ptr), _p(idx), _p(graph["dis"]), n, _p(h), h.stride(0), _p(bias),
-                                int(relu), _p(out), H, _stream()), "propagate")
+    ptr, idx, lng = (graph["out_ptr"], graph["out_idx"], graph.get("out_long")) if transpose else \
+        (graph["in_ptr"], graph["in_idx"], graph.get("in_long"))
+    check(lib().bigcn_propagate(_p(ptr), _p(idx), _p(graph["dis"]), n, graph["E"], _p(lng), _p(h), h.stride(0),
+                                _p(bias), int(relu), _p(out), H, _stream()), "propagate")
     return out
 
 

@@ -96,6 +96,8 @@ typedef struct bigcn_graph {
   int32_t* deg;     /* [N]   degree incl. the unit self-loop                */
   float* dis;       /* [N]   deg^-1/2 = 1.0f / sqrtf(deg), IEEE             */
   float* rowsum;    /* [N]   sum_j A-hat[i,j] in COO' order, or NULL        */
+  int32_t* in_long; /* hub-row work list of the by-target CSR: bigcn_long_ws_ints(E) ints, or NULL */
+  int32_t* out_long;/* same for the by-source CSR                                              */
 } bigcn_graph_t;
 
 typedef struct bigcn_opts {
@@ -121,6 +123,13 @@ int bigcn_device_ok(void);
  * n_dirs = 1 or 2; edge_index[d] is [2,E[d]] int64; graphs[d] receives the
  * structure.  batch/node_ptr may be NULL (GCNConv called on its own). */
 size_t bigcn_graph_prep_workspace_bytes(int64_t N, int64_t E_max, int32_t n_dirs);
+/* Hub rows: a CSR row with more than BIGCN_LONG_ROW entries (the root of a reply tree in the
+ * child-sum direction) is summed in fixed chunks by several half-warps and combined in chunk
+ * order (deterministic, no atomics on floats).  graph prep lists those rows in in_long/out_long
+ * (device int32 buffers of this many elements for a list of E edges); NULL = every row is walked
+ * sequentially by its owner, in exact COO' order. */
+#define BIGCN_LONG_ROW 32
+size_t bigcn_long_ws_ints(int64_t E);
 int bigcn_graph_prep(int32_t n_dirs, const int64_t* const* edge_index, const int64_t* E,
                      int64_t N, const int64_t* batch, int64_t B, int32_t deg_by,
                      const bigcn_graph_t* graphs, int32_t* node_ptr /*[B+1] or NULL*/,
@@ -152,8 +161,9 @@ int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
  * out[i] = sum_{e in ptr[i]..ptr[i+1]} (dis[idx[e]]*dis[i]) * h[idx[e]]
  *          + (dis[i]*dis[i]) * h[i]  (+ bias) (relu)
  * summed in COO' order, no atomics, deterministic.  Pass in_ptr/in_idx for
- * A-hat, out_ptr/out_idx for A-hat^T (backward). */
-int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N,
+ * A-hat, out_ptr/out_idx for A-hat^T (backward).  ldh, ldo multiples of 4, 16 B aligned rows. */
+int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, int64_t N, int64_t E,
+                    int32_t* long_ws /* in_long / out_long of that CSR, or NULL */,
                     const float* h, int64_t ldh, const float* bias /*or NULL*/, int32_t relu,
                     float* out, int64_t ldo, bigcn_stream_t stream);
 

@@ -202,19 +202,33 @@ def test_xw_matches_fp32_reference(dev):
 
 
 def test_propagate_bit_exact_and_transpose(dev):
+    """Rows are summed in COO' order with separate multiply and add: bit-identical to the CPU
+    index_add_ of the oracle.  Hub rows (more than BIGCN_LONG_ROW = 32 in-edges) go through the
+    deterministic split-row path when the hub lists are present: same value to fp32 rounding
+    of a different summation order, bit-identical from run to run; without the lists
+    (long_rows=False) every row is walked sequentially and matches bit for bit."""
     from bigcn_b200 import ops
     _, cases = edge_cases()
     torch.manual_seed(1)
     for name, b in cases.items():
         n = b.x.shape[0]
         for ei in (b.edge_index, b.BU_edge_index):
-            graphs, _, _ = ops.graph_prep([ei.to(dev)], n)
             h = torch.randn(n, 64)
             bias = torch.randn(64)
             e2, w = gcn_oracle.gcn_norm(ei, n)
             want = gcn_oracle.propagate_sum(h, e2, w) + bias
-            got = ops.propagate(graphs[0], h.to(dev), bias.to(dev)).cpu()
+            g_seq, _, _ = ops.graph_prep([ei.to(dev)], n, long_rows=False)
+            got = ops.propagate(g_seq[0], h.to(dev), bias.to(dev)).cpu()
             assert (bits(got.numpy()) == bits(want.numpy())).all(), name
+            graphs, _, _ = ops.graph_prep([ei.to(dev)], n)
+            got_l = ops.propagate(graphs[0], h.to(dev), bias.to(dev)).cpu()
+            indeg = np.diff(graphs[0]["in_ptr"].cpu().numpy())
+            short = torch.from_numpy(indeg <= 32)
+            assert (bits(got_l[short].numpy()) == bits(want[short].numpy())).all(), name
+            if (~short).any():
+                assert rel_err(got_l[~short], want[~short]) < 2e-6, name
+                again = ops.propagate(graphs[0], h.to(dev), bias.to(dev)).cpu()
+                assert torch.equal(again, got_l), name            # deterministic
             # A-hat^T: linearity / adjoint property  <A h, g> == <h, A^T g>
             gq = torch.randn(n, 64)
             at_g = ops.propagate(graphs[0], gq.to(dev), transpose=True).cpu().double()
@@ -222,7 +236,40 @@ def test_propagate_bit_exact_and_transpose(dev):
             lhs, rhs = float((a_h * gq.double()).sum()), float((h.double() * at_g).sum())
             assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
             relu = ops.propagate(graphs[0], h.to(dev), bias.to(dev), relu=True).cpu()
-            assert torch.equal(relu, torch.relu(got))
+            assert torch.equal(relu, torch.relu(got_l))
+
+
+def test_propagate_hub_rows_split_path(dev):
+    """Weibo-shaped skew: one root with 20,000 children (64 chunks), mid-size hubs just above and
+    below the split threshold, many small rows around them; both CSR orientations."""
+    from bigcn_b200 import ops
+    rng = np.random.default_rng(5)
+    n = 24000
+    parent = np.zeros(n, np.int64)
+    parent[1:20001] = 0                                   # the root's 20,000 children
+    parent[20001:20034] = 1                               # 33 children: just above the threshold
+    parent[20034:20066] = 2                               # 32 children: stays on the sequential path
+    parent[20066:20400] = 3                               # 334 children
+    parent[20400:] = rng.integers(4, 20000, n - 20400)    # the rest hang off random nodes
+    child = np.arange(1, n)
+    ei = torch.from_numpy(np.stack([parent[1:], child]))
+    perm = torch.from_numpy(rng.permutation(n))           # arbitrary node numbering
+    ei = perm[ei]
+    torch.manual_seed(3)
+    h = torch.randn(n, 64)
+    for e in (ei, ei.flip(0).contiguous()):
+        graphs, _, flags = ops.graph_prep([e.to(dev)], n)
+        assert int(flags.item()) == 0
+        e2, w = gcn_oracle.gcn_norm(e, n)
+        want = gcn_oracle.propagate_sum(h.double(), e2, w.double())
+        for transpose in (False, True):
+            if transpose:
+                e2t = e2.flip(0)
+                want_t = gcn_oracle.propagate_sum(h.double(), e2t, w.double())
+            got = ops.propagate(graphs[0], h.to(dev), transpose=transpose).cpu()
+            ref = want_t if transpose else want
+            assert rel_err(got, ref) < 2e-6
+            assert torch.equal(got, ops.propagate(graphs[0], h.to(dev), transpose=transpose).cpu())
 
 
 def test_gcnconv_forward_backward(dev):
