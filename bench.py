@@ -361,7 +361,8 @@ def run_ours(args):
 
 
 def kernel_microbench(torch, L, ops, dev, hbm_peak):
-    """propagate (both CSR orientations) on a forest far larger than L2."""
+    """propagate (both CSR orientations) and readout on a forest far larger than L2
+    (16384 trees x 256 nodes = 4.2 M rows, 1.07 GB per [N,64] panel)."""
     from bigcn_b200.data import make_device_forest
     out = {}
     n_trees, per = 16384, 256
@@ -374,7 +375,7 @@ def kernel_microbench(torch, L, ops, dev, hbm_peak):
     lib = L.lib()
     st = torch.cuda.current_stream().cuda_stream
     bias = torch.zeros(64, device=dev)
-    for name, g, tr in (("propagate_td_parent_gather", graphs[0], False), ("propagate_bu_child_segment_sum", graphs[1], False)):
+    for name, g in (("propagate_td_parent_gather", graphs[0]), ("propagate_bu_child_segment_sum", graphs[1])):
         ptr, idx = g["in_ptr"], g["in_idx"]
 
         def fn(i, ptr=ptr, idx=idx, g=g):
@@ -385,8 +386,24 @@ def kernel_microbench(torch, L, ops, dev, hbm_peak):
         # N*(2*256 + 8) + 4E + 260 bytes (each source row counted once)
         byt = n * (2 * 256 + 8) + 4 * e + 260
         gbs = byt / (ms * 1e-3) / 1e9
-        out[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "ms": ms, "nodes": n, "edges": e}
+        out[name] = {"kernel": "k_propagate (CSR sweep, cp.async stage)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": gbs / hbm_peak, "frac_of_8TBs_nominal": gbs / 8000.0, "ms": ms,
+                     "nodes": n, "edges": e, "algorithmic_bytes": byt}
+    scr = torch.empty(lib.bigcn_readout_scratch_floats(n, n_trees), device=dev)
+    feat = torch.empty(n_trees, 128, device=dev)
+
+    def ro(i):
+        L.check(lib.bigcn_readout(hs[i % 2].data_ptr(), hs[(i + 1) % 2].data_ptr(), node_ptr.data_ptr(),
+                                  f.rootindex.data_ptr(), n, n_trees, feat.data_ptr(), 128, None, scr.data_ptr(),
+                                  flags.data_ptr(), st))
+    ms = time_kernel(ro, 10, torch)
+    # read N*256 (h2) + B*256 (root h1) + 4(B+1), write B*512
+    byt = n * 256 + n_trees * 256 + 4 * (n_trees + 1) + n_trees * 512
+    gbs = byt / (ms * 1e-3) / 1e9
+    out["readout_scatter_mean"] = {"kernel": "k_readout_part + k_readout_final", "bound": "hbm", "achieved": gbs,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                   "frac_of_8TBs_nominal": gbs / 8000.0, "ms": ms, "nodes": n, "trees": n_trees,
+                                   "algorithmic_bytes": byt}
     return out
 
 

@@ -71,6 +71,9 @@ _SIGS = {
     "bigcn_long_ws_ints": (C.c_size_t, [C.c_int64]),
     "bigcn_propagate": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr,
                                   C.c_int32, c_ptr, C.c_int64, c_ptr]),
+    "bigcn_readout_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "bigcn_readout": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int64, c_ptr, c_ptr,
+                                c_ptr, c_ptr]),
     "bigcn_dropout_mask": (C.c_int, [C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                      c_ptr, c_ptr]),
     "bigcn_gcnconv_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),

@@ -65,6 +65,7 @@ struct FeatWs {
   float* pos[2];            // [B][64] #{i in tree : H2[i][f] > 0}
   float* gs[2];             // [B][64] grad_feat / n_b
   float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
+  float* ro_part;           // readout slice partials
   void* prep_ws; size_t prep_bytes;
   size_t total;
 };
@@ -114,6 +115,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
+  w.ro_part = c.take<float>(readout_scratch_floats(N, B, 2));
   const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
   w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
   w.prep_ws = c.take<char>(w.prep_bytes);
@@ -237,8 +239,8 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   {
     if (dirs.n < 2) cudaMemsetAsync(feat, 0, (size_t)B * 4 * H * sizeof(float), st);
     ReadoutArgs a{};
-    a.ndir = dirs.n; a.node_ptr = w.node_ptr; a.rootindex = bt->rootindex; a.feat = feat;
-    a.N = N; a.B = B; a.flags = flags;
+    a.ndir = dirs.n; a.node_ptr = w.node_ptr; a.rootindex = bt->rootindex; a.feat = feat; a.ldfeat = 4 * H;
+    a.N = N; a.B = B; a.flags = flags; a.scratch = w.ro_part;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
       a.h2[q] = w.h2[d]; a.h1[q] = w.h1[d]; a.pos[q] = w.pos[d]; a.feat_base[q] = feat_base(d);
@@ -448,6 +450,21 @@ extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const flo
   a.N = N; a.relu = relu;
   a.d[0] = PropDir{ptr, idx, dis, h, bias, out, ldh, ldo, long_ws, E};
   return propagate_launch(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" size_t bigcn_readout_scratch_floats(int64_t N, int64_t B) { return readout_scratch_floats(N, B, 1); }
+
+extern "C" int bigcn_readout(const float* h2, const float* h1, const int32_t* node_ptr, const int64_t* rootindex,
+                             int64_t N, int64_t B, float* feat, int64_t ldfeat, float* pos, float* scratch,
+                             int32_t* flags, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(node_ptr && rootindex && feat && scratch && flags && (N == 0 || (h2 && h1)), "readout: NULL argument");
+  BIGCN_CHECK_ARG(ldfeat >= 2 * H, "readout: ldfeat must be >= 128");
+  BIGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(h2) & 15) == 0, "readout: h2 must be 16 B aligned");
+  ReadoutArgs a{};
+  a.ndir = 1; a.node_ptr = node_ptr; a.rootindex = rootindex; a.feat = feat; a.ldfeat = ldfeat;
+  a.N = N; a.B = B; a.flags = flags; a.scratch = scratch;
+  a.h2[0] = h2; a.h1[0] = h1; a.pos[0] = pos; a.feat_base[0] = 0;
+  return readout_launch(a, (cudaStream_t)stream);
 }
 
 extern "C" int bigcn_dropout_mask(uint64_t seed, int32_t stream_id, int64_t node_id_base, int64_t N,

@@ -41,8 +41,10 @@ int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
 struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; };
 struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
-struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t N, B; int32_t* flags; };
+constexpr int RO_SLICE = 512;  // rows per readout slice
+struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t ldfeat; int64_t N, B; int32_t* flags; float* scratch; int64_t nitems; };
 int readout_launch(const ReadoutArgs&, cudaStream_t);
+size_t readout_scratch_floats(int64_t N, int64_t B, int ndir);
 struct GScaleArgs { const float* grad_feat; const float* pos[2]; float* gs[2]; float* part[2]; int feat_base[2]; const int32_t* node_ptr; int64_t B; };
 int gscale_launch(const GScaleArgs&, int, cudaStream_t);
 struct PropG2Dir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h2; const float* gs; float* out; int32_t* lng; int64_t E; };

@@ -302,46 +302,90 @@ __global__ void __launch_bounds__(256, 3) k_prop1_mix(MixArgs a) {
 // feat[b, base_d + f]      = mean_{i in tree b} H2_d[i, f]           (scatter_mean, :65)
 // feat[b, base_d + 64 + f] = H1_d[rootindex[b], f]                   (:58-63; the mean of n_b
 //                            identical rows, taken as the row itself)
-// CTA per tree: 4 row-lanes x 64 features per direction, fixed-order combine.
-__global__ void __launch_bounds__(512) k_readout(ReadoutArgs a) {
-  __shared__ float part[2][4][H];
-  __shared__ int cpos[2][4][H];
-  const int64_t b = blockIdx.x;
-  const int d = threadIdx.x >> 8, g = (threadIdx.x >> 6) & 3, f = threadIdx.x & 63;
-  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
-  float acc = 0.f;
-  int npos = 0;
-  if (d < a.ndir) {
-    const float* h2 = a.h2[d];
-    int i = s + g;
-    for (; i + 12 < e; i += 16) {
-      const float v0 = h2[(int64_t)i * H + f], v1 = h2[(int64_t)(i + 4) * H + f];
-      const float v2 = h2[(int64_t)(i + 8) * H + f], v3 = h2[(int64_t)(i + 12) * H + f];
-      acc += v0; acc += v1; acc += v2; acc += v3;
-      npos += (v0 > 0.f) + (v1 > 0.f) + (v2 > 0.f) + (v3 > 0.f);
-    }
-    for (; i < e; i += 4) {
-      const float v = h2[(int64_t)i * H + f];
-      acc += v;
-      npos += v > 0.f;
-    }
-    part[d][g][f] = acc;
-    cpos[d][g][f] = npos;
+// Two launches, both with grids that depend on N and B only (no host sync on tree sizes):
+//  part : one CTA per (tree, slice of RO_SLICE global rows) pair.  Trees are contiguous and
+//         sorted, so the pair (slice g, tree b) has the unique id g + b; CTA x finds its tree by
+//         bisecting f(b) = node_ptr[b] / RO_SLICE + b.  A 59k-node Weibo tree is spread over 116
+//         CTAs, a batch of 10-node PHEME trees costs one small CTA per tree.  16 row lanes x
+//         16 float4 lanes, 8 rows in flight per thread, fixed-order combine.
+//  final: per tree, the slice partials in slice order, the divide, the positive counts the
+//         backward uses for db2, and the root row of H1.
+__global__ void __launch_bounds__(256) k_readout_part(ReadoutArgs a) {
+  __shared__ __align__(16) float part[16][H];
+  __shared__ __align__(16) float cpos[16][H];
+  const int d = blockIdx.y;
+  const int64_t x = blockIdx.x;
+  int lo = 0, hi = (int)a.B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int64_t)(a.node_ptr[mid] / RO_SLICE) + mid <= x) lo = mid;
+    else hi = mid - 1;
   }
-  __syncthreads();
-  if (d < a.ndir && g == 0) {
-    const float sum = ((part[d][0][f] + part[d][1][f]) + part[d][2][f]) + part[d][3][f];
-    if (a.pos[d]) a.pos[d][b * H + f] = (float)(cpos[d][0][f] + cpos[d][1][f] + cpos[d][2][f] + cpos[d][3][f]);
-    const int n = e - s;
-    float* fr = a.feat + b * 4 * H + a.feat_base[d];
-    fr[f] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
-    float rv = 0.f;
-    if (n > 0) {
-      const int64_t r = a.rootindex[b];
-      if (r >= 0 && r < a.N) rv = a.h1[d][r * H + f];
-      else if (f == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+  const int b = lo;
+  const int64_t g = x - b;
+  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+  const int64_t r0 = max((int64_t)s, g * RO_SLICE), r1 = min((int64_t)e, (g + 1) * RO_SLICE);
+  if (r0 >= r1) return;   // not a (tree, slice) pair: never read by the final pass
+  const int rl = threadIdx.x >> 4, sub = threadIdx.x & 15;
+  const float* h2 = a.h2[d] + 4 * sub;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), np = acc;
+  for (int64_t i = r0 + rl; i < r1; i += 16 * 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t r = i + 16 * u;
+      v[u] = r < r1 ? ld4(h2 + r * H) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    fr[H + f] = rv;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      np.x += v[u].x > 0.f ? 1.f : 0.f;
+      np.y += v[u].y > 0.f ? 1.f : 0.f;
+      np.z += v[u].z > 0.f ? 1.f : 0.f;
+      np.w += v[u].w > 0.f ? 1.f : 0.f;
+    }
+  }
+  st4(&part[rl][4 * sub], acc);
+  st4(&cpos[rl][4 * sub], np);
+  __syncthreads();
+  if (threadIdx.x < 2 * H) {
+    const int f = threadIdx.x & 63;
+    const float(*src)[H] = threadIdx.x < H ? part : cpos;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += src[r][f];
+    a.scratch[(((int64_t)d * a.nitems + x) * 2 + (threadIdx.x >> 6)) * H + f] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_readout_final(ReadoutArgs a) {
+  const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int f = threadIdx.x & 63;
+  if (b >= a.B) return;
+  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+  const int n = e - s;
+  int64_t r = -1;
+  if (n > 0) {
+    r = a.rootindex[b];
+    if (r < 0 || r >= a.N) {
+      if (f == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+      r = -1;
+    }
+  }
+  for (int d = 0; d < a.ndir; ++d) {
+    float sum = 0.f, cnt = 0.f;
+    if (n > 0) {
+      const int64_t x0 = s / RO_SLICE + b, x1 = (e - 1) / RO_SLICE + b;
+      for (int64_t x = x0; x <= x1; ++x) {
+        const float* p = a.scratch + (((int64_t)d * a.nitems + x) * 2) * H + f;
+        sum += p[0];
+        cnt += p[H];
+      }
+    }
+    if (a.pos[d]) a.pos[d][b * H + f] = cnt;
+    float* fr = a.feat + b * a.ldfeat + a.feat_base[d];
+    fr[f] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
+    fr[H + f] = r >= 0 ? a.h1[d][r * H + f] : 0.f;
   }
 }
 
@@ -766,10 +810,19 @@ int prop1_mix_launch(const MixArgs& a0, int ndir, cudaStream_t st) {
   BIGCN_CHECK_LAUNCH("k_prop1_mix");
   return 0;
 }
-int readout_launch(const ReadoutArgs& a, cudaStream_t st) {
-  if (a.B == 0) return 0;
-  k_readout<<<(int)a.B, 512, 0, st>>>(a);
-  BIGCN_CHECK_LAUNCH("k_readout");
+size_t readout_scratch_floats(int64_t N, int64_t B, int ndir) {
+  return (size_t)ndir * (size_t)(ceil_div(N > 0 ? N : 1, RO_SLICE) + B) * 2 * H;
+}
+int readout_launch(const ReadoutArgs& a0, cudaStream_t st) {
+  if (a0.B == 0) return 0;
+  ReadoutArgs a = a0;
+  a.nitems = ceil_div(a.N > 0 ? a.N : 1, RO_SLICE) + a.B;
+  if (a.N > 0) {
+    k_readout_part<<<dim3((unsigned)a.nitems, a.ndir), 256, 0, st>>>(a);
+    BIGCN_CHECK_LAUNCH("k_readout_part");
+  }
+  k_readout_final<<<(int)ceil_div(a.B, 4), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_readout_final");
   return 0;
 }
 int cs_chunks(int64_t N) { return (int)ceil_div(N > 0 ? N : 1, CS_ROWS); }

@@ -119,6 +119,21 @@ def propagate(graph, h, bias=None, relu=False, transpose=False):
     return out
 
 
+def readout(h2, h1, node_ptr, rootindex, want_pos=False):
+    """[mean over each tree of h2 | h1[rootindex]] -> [B,128] (scatter_mean + second root-extend)."""
+    L.require_device()
+    h2, h1 = _f32(h2), _f32(h1)
+    rootindex = _i64(rootindex)
+    n, b = h2.shape[0], int(rootindex.numel())
+    feat = torch.empty(b, 2 * H, dtype=torch.float32, device=h2.device)
+    pos = torch.empty(b, H, dtype=torch.float32, device=h2.device) if want_pos else None
+    scr = torch.empty(lib().bigcn_readout_scratch_floats(n, b), dtype=torch.float32, device=h2.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=h2.device)
+    check(lib().bigcn_readout(_p(h2), _p(h1), _p(node_ptr), _p(rootindex), n, b, _p(feat), 2 * H, _p(pos), _p(scr),
+                              _p(flags), _stream()), "readout")
+    return (feat, pos) if want_pos else feat
+
+
 def dropout_mask(seed, stream_id, node_id_base, n, n_cols, p, device):
     L.require_device()
     keep = torch.empty(n, n_cols, dtype=torch.uint8, device=device)

@@ -167,6 +167,19 @@ int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const float* dis, in
                     const float* h, int64_t ldh, const float* bias /*or NULL*/, int32_t relu,
                     float* out, int64_t ldo, bigcn_stream_t stream);
 
+/* ---- readout ------------------------------------------------------------
+ * Replaces the second root-extend loop + torch_scatter.scatter_mean(x, data.batch, dim=0)
+ * (BiGCN_Twitter.py:58-65) of one direction:
+ *   feat[b, f]      = mean_{i in tree b} h2[i, f]          f < 64
+ *   feat[b, 64 + f] = h1[rootindex[b], f]                  (mean of n_b copies of the root row)
+ * node_ptr[B+1] comes from graph prep; trees of any size (slices of 512 rows are summed by
+ * separate CTAs and combined in slice order: deterministic).  pos (or NULL) receives
+ * #{i in tree b : h2[i,f] > 0}, which the backward uses for db2.  feat row pitch ldfeat. */
+size_t bigcn_readout_scratch_floats(int64_t N, int64_t B);
+int bigcn_readout(const float* h2 /*[N,64]*/, const float* h1 /*[N,64]*/, const int32_t* node_ptr,
+                  const int64_t* rootindex, int64_t N, int64_t B, float* feat, int64_t ldfeat,
+                  float* pos /*[B,64] or NULL*/, float* scratch, int32_t* flags, bigcn_stream_t stream);
+
 /* ---- dropout mask spec (tests) -----------------------------------------
  * keep[i,c] (uint8) for c < n_cols of the concatenated [h1|root_extend] tensor
  * (BiGCN_Twitter.py:51-54); stream = 0 (TD) / 1 (BU). */

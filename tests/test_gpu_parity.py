@@ -272,6 +272,29 @@ def test_propagate_hub_rows_split_path(dev):
             assert torch.equal(got, ops.propagate(graphs[0], h.to(dev), transpose=transpose).cpu())
 
 
+def test_readout_matches_scatter_mean(dev):
+    """scatter_mean + second root-extend (BiGCN_Twitter.py:58-65) on ragged trees: single nodes,
+    trees inside one 512-row slice, trees straddling slices, a 70k-node Weibo-sized tree."""
+    from bigcn_b200 import ops
+    torch.manual_seed(4)
+    sizes = [1, 1, 3, 600, 5000, 2, 70000, 1, 511, 513, 1024, 7]
+    n, nb = sum(sizes), len(sizes)
+    batch = torch.repeat_interleave(torch.arange(nb), torch.tensor(sizes))
+    node_ptr = torch.zeros(nb + 1, dtype=torch.int32)
+    node_ptr[1:] = torch.cumsum(torch.tensor(sizes), 0)
+    root = torch.tensor([int(node_ptr[b]) + (sizes[b] * 7) // 11 for b in range(nb)])
+    h2 = torch.relu(torch.randn(n, 64))
+    h1 = torch.randn(n, 64)
+    feat, pos = ops.readout(h2.to(dev), h1.to(dev), node_ptr.to(dev), root.to(dev), want_pos=True)
+    want = gcn_oracle.scatter_mean(h2.double(), batch, nb)
+    assert rel_err(feat[:, :64], want) < 1e-6
+    assert torch.equal(feat[:, 64:].cpu(), h1[root])
+    want_pos = torch.zeros(nb, 64, dtype=torch.float64).index_add_(0, batch, (h2 > 0).double())
+    assert torch.equal(pos.cpu().double(), want_pos)
+    again = ops.readout(h2.to(dev), h1.to(dev), node_ptr.to(dev), root.to(dev))
+    assert torch.equal(again, feat)                                 # deterministic
+
+
 def test_gcnconv_forward_backward(dev):
     import bigcn_b200
     torch.manual_seed(2)

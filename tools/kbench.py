@@ -47,6 +47,21 @@ def main():
         bias = torch.randn(64, device=dev)
         e = int(f.edge_index.shape[1])
         byt = n * (2 * 256 + 8) + 4 * e + 260
+        # readout (scatter_mean + root rows): N*256 in, B*512 out
+        node_ptr = torch.arange(0, n + 1, per, dtype=torch.int32, device=dev)
+        scr = torch.empty(lib.bigcn_readout_scratch_floats(n, n_trees), device=dev)
+        feat = torch.empty(n_trees, 128, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def ro(i):
+            L.check(lib.bigcn_readout(hs[i % 2].data_ptr(), hs[(i + 1) % 2].data_ptr(), node_ptr.data_ptr(),
+                                      f.rootindex.data_ptr(), n, n_trees, feat.data_ptr(), 128, None, scr.data_ptr(),
+                                      flags.data_ptr(), st))
+        ms = timeit(ro)
+        rbyt = n * 256 + n_trees * 256 + 4 * (n_trees + 1) + n_trees * 512
+        gbs = rbyt / ms / 1e6
+        res[f"{fname}/readout"] = dict(ms=round(ms, 4), gbs=round(gbs, 1), frac=round(gbs / peak, 3))
+        print(f"{fname:11s} readout  {ms:8.4f} ms {gbs:8.1f} GB/s {gbs / peak:6.3f} of measured peak", flush=True)
         outs = {}
         for mode in ("split", "seq"):
             graphs, _, _ = ops.graph_prep([f.edge_index, f.BU_edge_index], n, f.batch, n_trees, rowsum=False,
