@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="bigcn_b200", choices=["bigcn_b200", "reference"])
-    ap.add_argument("--gemm-mode", default="mixed", choices=["fp32", "tf32", "tf32x3", "mixed"])
+    ap.add_argument("--gemm-mode", default="sparse", choices=["fp32", "tf32", "tf32x3", "mixed", "sparse"])
     ap.add_argument("--cpu-sample-trees", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the large-N propagate micro-benchmark")
@@ -281,55 +281,85 @@ def run_ours(args):
     w1 = torch.randn(64, K_FEATS, device=dev) * 0.02
     scr = torch.empty(lib.bigcn_xw_scratch_floats(K_FEATS, 2), device=dev)
     ys = [torch.empty(n, 128, device=dev) for n in nodes]
+    sparse = args.gemm_mode == "sparse"
+    if sparse:
+        xs_ws = [torch.empty(lib.bigcn_xsparse_workspace_bytes(n, K_FEATS), dtype=torch.uint8, device=dev) for n in nodes]
+        xs_flags = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def xw_fn(i):
         j = i % N_ROTATE
-        L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
-                             ys[j].data_ptr(), 128, L.GEMM_MODE[args.gemm_mode], scr.data_ptr(), st))
+        if sparse:      # weight re-layout + the scan that also captures the non-zeros (no CSR/CSC build)
+            L.check(lib.bigcn_xw_sparse(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
+                                        ys[j].data_ptr(), 128, 0, xs_flags.data_ptr(), xs_ws[j].data_ptr(),
+                                        xs_ws[j].numel(), st))
+        else:
+            L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
+                                 ys[j].data_ptr(), 128, L.GEMM_MODE[args.gemm_mode], scr.data_ptr(), st))
     xw_ms = time_kernel(xw_fn, 12, torch)
     mean_nodes = sum(nodes[i % N_ROTATE] for i in range(12)) / 12
     # conv1 GEMM (TD|BU fused) bytes = N*K*4 + 128*K*4 + N*128*4
     xw_bytes = mean_nodes * K_FEATS * 4 + K_FEATS * 128 * 4 + mean_nodes * 128 * 4
     xw_gbs = xw_bytes / (xw_ms * 1e-3) / 1e9
     fwd_kernel = {"fp32": "k_xw_scan<128>", "mixed": "k_xw_scan<128>", "tf32": "k_xw_tc<1> (tcgen05 kind::tf32)",
-                  "tf32x3": "k_xw_tc<2> (tcgen05 kind::tf32, W hi+lo)"}[args.gemm_mode]
+                  "tf32x3": "k_xw_tc<2> (tcgen05 kind::tf32, W hi+lo)",
+                  "sparse": "k_transpose_jobs + k_xw_scan<128, capture>"}[args.gemm_mode]
     roof_fwd = {"kernel": fwd_kernel + ": X * [W1_td;W1_bu]^T, conv1.lin of both directions in one pass over X",
                 "bound": "hbm", "achieved": xw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xw_gbs / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "ms": xw_ms, "algorithmic_bytes": xw_bytes,
                 "frac_of_8TBs_nominal": xw_gbs / 8000.0}
-    # the weight gradient dW1 = T1^T X: the second pass over X (backward)
+    # the weight gradient dW1 = T1^T X
     ts = [torch.randn(n, 128, device=dev) for n in nodes]
     dws = [torch.empty(64, K_FEATS, device=dev) for _ in range(2)]
-    wscr = torch.empty(max(lib.bigcn_xw_wgrad_scratch_floats(n, K_FEATS, 2) for n in nodes), device=dev)
+    if sparse:
+        for j in range(N_ROTATE):    # build the column-sorted copies once (in a step: on the side stream)
+            L.check(lib.bigcn_xw_sparse(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
+                                        ys[j].data_ptr(), 128, 1, xs_flags.data_ptr(), xs_ws[j].data_ptr(),
+                                        xs_ws[j].numel(), st))
 
-    def dw_fn(i):
-        j = i % N_ROTATE
-        L.check(lib.bigcn_xw_wgrad(resident[j].x.data_ptr(), nodes[j], K_FEATS, ts[j].data_ptr(), 2, dws[0].data_ptr(),
-                                   dws[1].data_ptr(), K_FEATS, L.GEMM_MODE[args.gemm_mode], wscr.data_ptr(), st))
+        def dw_fn(i):
+            j = i % N_ROTATE
+            L.check(lib.bigcn_xw_wgrad_sparse(nodes[j], K_FEATS, ts[j].data_ptr(), 2, dws[0].data_ptr(), dws[1].data_ptr(),
+                                              K_FEATS, xs_ws[j].data_ptr(), xs_ws[j].numel(), st))
+    else:
+        wscr = torch.empty(max(lib.bigcn_xw_wgrad_scratch_floats(n, K_FEATS, 2) for n in nodes), device=dev)
+
+        def dw_fn(i):
+            j = i % N_ROTATE
+            L.check(lib.bigcn_xw_wgrad(resident[j].x.data_ptr(), nodes[j], K_FEATS, ts[j].data_ptr(), 2, dws[0].data_ptr(),
+                                       dws[1].data_ptr(), K_FEATS, L.GEMM_MODE[args.gemm_mode], wscr.data_ptr(), st))
     dw_ms = time_kernel(dw_fn, 12, torch)
     # same algorithmic bytes: X once, T [N,128] once, dW [128,K] once
     dw_gbs = xw_bytes / (dw_ms * 1e-3) / 1e9
     bwd_kernel = {"fp32": "k_dw_slab<128> + k_dw_reduce", "tf32": "k_dw_tc<1> (tcgen05 kind::tf32, MN-major) + k_dw_reduce",
                   "tf32x3": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce",
-                  "mixed": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce"}[args.gemm_mode]
-    roof_bwd = {"kernel": bwd_kernel + ": dW1 = T1^T X for both directions, second pass over X",
+                  "mixed": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce",
+                  "sparse": "k_dw_sweep (CSR sweep over the column-sorted non-zeros of X)"}[args.gemm_mode]
+    roof_bwd = {"kernel": bwd_kernel + ": dW1 = T1^T X for both directions" + ("" if sparse else ", second pass over X"),
                 "bound": "hbm", "achieved": dw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dw_gbs / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "ms": dw_ms, "algorithmic_bytes": xw_bytes,
                 "frac_of_8TBs_nominal": dw_gbs / 8000.0,
                 "note": "ms covers the split-K reduce (and the T split) launched with the GEMM"}
+    if sparse:
+        nnz = int((resident[0].x != 0).sum().item())
+        sw_bytes = nnz * (8 + 512) + K_FEATS * 128 * 4 + (K_FEATS + 1) * 4     # entries + gathered T rows + dW
+        roof_bwd.update({"bound": "l2 (gathers of L2-resident T1 rows; X is not read again)",
+                         "achieved": sw_bytes / (dw_ms * 1e-3) / 1e9, "frac": None, "peak": None,
+                         "algorithmic_bytes": sw_bytes, "nnz": nnz, "frac_of_8TBs_nominal": None,
+                         "note": "the dense-mode second pass over X (%.0f MB) is gone" % (nodes[0] * K_FEATS * 4 / 1e6)})
     # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if args.gemm_mode in ("fp32", "mixed"):
-            roof_fwd["traffic"] = tr["k_xw_scan"]["bytes"]
-            roof_fwd["traffic_note"] = f"ncu capture at N = {tr['k_xw_scan']['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
+        if args.gemm_mode in ("fp32", "mixed", "sparse"):
+            key = "k_xw_scan_capture" if sparse and "k_xw_scan_capture" in tr else "k_xw_scan"
+            roof_fwd["traffic"] = tr[key]["bytes"]
+            roof_fwd["traffic_note"] = f"ncu capture of {key} at N = {tr[key]['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
         if args.gemm_mode in ("tf32x3", "mixed"):
             roof_bwd["traffic"] = tr["k_dw_tc"]["bytes"]
             roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {tr['k_dw_tc']['nodes']} nodes"
     except Exception:  # noqa: BLE001
         pass
-    roof, other_gemm = (roof_bwd, roof_fwd) if dw_ms >= xw_ms else (roof_fwd, roof_bwd)
-    others = {"other_x_stream": other_gemm}
+    roof, other_gemm = (roof_bwd, roof_fwd) if (dw_ms >= xw_ms and not sparse) else (roof_fwd, roof_bwd)
+    others = {"weight_gradient_dW1" if sparse else "other_x_stream": other_gemm}
     if not args.no_kernels:
         others.update(kernel_microbench(torch, L, ops, dev, hbm_peak))
 

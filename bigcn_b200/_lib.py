@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libbigcn_b200.so")
 H = 64
 FLAG_EDGE_RANGE, FLAG_BATCH_ORDER, FLAG_ROOT_RANGE = 1, 2, 4
 DEG_BY = {"target": 0, "source": 1}
-GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3}
+GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3, "sparse": 4}
+FLAG_X_NOT_SPARSE = 8
 DIR_TD, DIR_BU = 1, 2
 
 c_f32p = C.c_void_p  # device pointers travel as integers
@@ -45,7 +46,7 @@ class Graph(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("training", C.c_int32), ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32),
-                ("bwd_phase", C.c_int32)]
+                ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32)]
 
 
 class BigcnError(RuntimeError):
@@ -55,6 +56,8 @@ class BigcnError(RuntimeError):
 _SIGS = {
     "bigcn_last_error": (C.c_char_p, []),
     "bigcn_version": (C.c_int, []),
+    "bigcn_join_internal_streams": (C.c_int, [c_ptr]),
+    "bigcn_internal_stream": (c_ptr, []),
     "bigcn_device_ok": (C.c_int, []),
     "bigcn_graph_prep_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "bigcn_graph_prep": (C.c_int, [C.c_int32, C.POINTER(c_ptr), C.POINTER(C.c_int64), C.c_int64, c_ptr,
@@ -66,6 +69,12 @@ _SIGS = {
     "bigcn_xw_wgrad_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "bigcn_xw_wgrad": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, C.c_int64, C.c_int32,
                                  c_ptr, c_ptr]),
+    "bigcn_xsparse_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "bigcn_xw_sparse": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int32,
+                                  c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_xw_wgrad_sparse": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, C.c_int64, c_ptr,
+                                        C.c_size_t, c_ptr]),
+    "bigcn_xsparse_view": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_size_t] + [C.POINTER(c_ptr)] * 7),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
     "bigcn_long_ws_ints": (C.c_size_t, [C.c_int64]),

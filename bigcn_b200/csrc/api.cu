@@ -2,6 +2,7 @@
 // own, and the small exported helpers.  Every function only enqueues kernels on the caller's
 // stream; the workspace carved here carries what backward needs.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -26,12 +27,47 @@ int num_sms() {
   return n;
 }
 
+// ---- side stream: short independent kernels run beside the long X stream -------------------
+// One high-priority non-blocking stream and a few events per device, created on first use.
+// Every entry point that forks onto it joins again before it returns, so at return all of its
+// work is ordered on the caller's stream (and a CUDA-graph capture sees a fork/join diamond).
+struct SideCtx {
+  SideStream s;        // high priority: work the main stream will wait for soon (graph prep)
+  cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
+  cudaEvent_t ev[4];
+  bool ok;
+};
+static SideCtx* side_ctx() {
+  static SideCtx ctx[64];
+  static bool init[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!init[dev]) {
+    init[dev] = true;
+    SideCtx& c = ctx[dev];
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 4 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    const char* e = getenv("BIGCN_NO_SIDE_STREAM");
+    if (e && e[0] == '1') c.ok = false;
+  }
+  return ctx[dev].ok ? &ctx[dev] : nullptr;
+}
+// `to` waits for everything queued on `from` so far
+static void stream_after(SideCtx* c, int ev, cudaStream_t from, cudaStream_t to) {
+  cudaEventRecord(c->ev[ev], from);
+  cudaStreamWaitEvent(to, c->ev[ev], 0);
+}
+
 // w[0..n_w): PyG [64, K] weights (row pitch ldw).  scratch: 2 * 64 * n_w * K floats -- the
 // transposed copy the fp32 scan streams, or the TF32 hi/lo split of the tensor-core modes.
 int xw_dispatch(const float* x, int64_t N, int64_t K, const float* const* w, int n_w, int64_t ldw,
                 float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st) {
   BIGCN_CHECK_ARG(n_w == 1 || n_w == 2, "xw: one or two weight matrices");
   const int n_out = H * n_w;
+  if (mode == BIGCN_GEMM_SPARSE) mode = BIGCN_GEMM_FP32;   // on its own the product is the exact scan
   if (mode == BIGCN_GEMM_FP32 || mode == BIGCN_GEMM_MIXED) {
     TransposeJobs js{};
     for (int q = 0; q < n_w; ++q) js.job[js.n++] = TransposeJob{w[q], ldw, 0, K, scratch, n_out, q * H};
@@ -66,6 +102,7 @@ struct FeatWs {
   float* gs[2];             // [B][64] grad_feat / n_b
   float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
   float* ro_part;           // readout slice partials
+  XSparse xs;               // row-sparse view of X (gemm_mode SPARSE)
   void* prep_ws; size_t prep_bytes;
   size_t total;
 };
@@ -116,6 +153,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
   w.ro_part = c.take<float>(readout_scratch_floats(N, B, 2));
+  w.xs = xs_carve(c, N, K);
   const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
   w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
   w.prep_ws = c.take<char>(w.prep_bytes);
@@ -163,49 +201,68 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
                   ws_bytes, w.total);
   const int64_t N = dm->N, B = dm->B, K = dm->K;
   const Dirs dirs = active_dirs(o->dir_mask);
-  // 1. structure of both directions, node_ptr
-  {
-    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
-    const int64_t E[2] = {dm->E_td, dm->E_bu};
-    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
-                                 w.prep_bytes, st))
-      return rc;
-  }
-  // 2. weights in the layouts the kernels stream
+  const bool scan_mode = o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED ||
+                         o->gemm_mode == BIGCN_GEMM_SPARSE;
+  const bool sparse = o->gemm_mode == BIGCN_GEMM_SPARSE;
+  const bool dropping = o->training && o->p_drop > 0.f;
+  // 1. weights in the layouts the kernels stream
   const int n_out = dirs.n == 2 ? 128 : 64;
   {
     TransposeJobs js{};
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      if (o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED)
-        js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
+      if (scan_mode) js.job[js.n++] = TransposeJob{dir_w1(pr, d), K, 0, K, w.w1T, n_out, q * H};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, 0, H, w.w2aT[d], H, 0};
       js.job[js.n++] = TransposeJob{dir_w2(pr, d), H + K, H, K, w.w2bT[d], H, 0};
     }
     if (int rc = transpose_jobs_launch(js, st)) return rc;
   }
-  // 3. X W1^T for all active directions in one pass over X
-  if (o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED) {
+  // 2. side stream (beside the X stream): structure of both directions, node_ptr, root columns
+  //    and, without dropout, the per-tree root projection
+  SideCtx* sc = side_ctx();
+  cudaStream_t ss = sc ? sc->s.side : st;
+  if (sc) stream_after(sc, 0, st, ss);
+  {
+    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
+    const int64_t E[2] = {dm->E_td, dm->E_bu};
+    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
+                                 w.prep_bytes, ss))
+      return rc;
+    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
+                 w.slot, w.overflow, DW2B_CAP};
+    if (int rc = root_nz_launch(a, ss)) return rc;
+    if (!dropping) {
+      RootProjArgs pa{};
+      pa.cnt = w.rnz_cnt; pa.col = w.rnz_col; pa.val = w.rnz_val; pa.B = B; pa.K = K;
+      for (int q = 0; q < dirs.n; ++q) {
+        pa.w2bT[q] = w.w2bT[dirs.id[q]];
+        pa.P[q] = w.P[dirs.id[q]];
+      }
+      if (int rc = root_proj_launch(pa, dirs.n, ss)) return rc;
+    }
+  }
+  // 3. X W1^T for all active directions in one pass over X (main stream)
+  if (sparse) {
+    if (int rc = xw_fp32_capture(bt->x, N, K, w.w1T, n_out, w.xw, n_out, w.xs, st)) return rc;
+  } else if (scan_mode) {
     if (int rc = xw_fp32(bt->x, N, K, w.w1T, n_out, w.xw, n_out, st)) return rc;
   } else {
     const float* ws[2] = {dir_w1(pr, dirs.id[0]), dirs.n == 2 ? dir_w1(pr, dirs.id[1]) : nullptr};
     if (int rc = xw_tc_weights(bt->x, N, K, ws, K, n_out, w.w1T, w.xw, n_out, o->gemm_mode, st)) return rc;
   }
-  // 4. root columns (and, without dropout, the per-tree projection)
-  {
-    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
-                 w.slot, w.overflow, DW2B_CAP};
-    if (int rc = root_nz_launch(a, st)) return rc;
-  }
-  const bool dropping = o->training && o->p_drop > 0.f;
-  if (!dropping) {
-    RootProjArgs a{};
-    a.cnt = w.rnz_cnt; a.col = w.rnz_col; a.val = w.rnz_val; a.B = B; a.K = K;
-    for (int q = 0; q < dirs.n; ++q) {
-      a.w2bT[q] = w.w2bT[dirs.id[q]];
-      a.P[q] = w.P[dirs.id[q]];
+  // 4. the structure is needed from here on; the side stream goes on to sort the captured
+  //    non-zeros of X by column for the weight gradient while the rest of the forward runs
+  if (sc) stream_after(sc, 1, ss, st);
+  bool side_busy = false;
+  if (sparse) {
+    if (o->skip_wgrad_prep || N == 0) {
+      cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), st);
+    } else {
+      if (sc) stream_after(sc, 2, st, sc->low);
+      w.xs.flags = flags;
+      if (int rc = xs_build_csc(w.xs, bt->x, true, sc ? sc->low : st)) return rc;
+      side_busy = sc != nullptr;
     }
-    if (int rc = root_proj_launch(a, dirs.n, st)) return rc;
   }
   // 5. conv1 propagate + relu/dropout + conv2 lin
   {
@@ -247,6 +304,9 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     }
     if (int rc = readout_launch(a, st)) return rc;
   }
+  // the column sort keeps running on the low-priority stream: features_backward waits for it
+  // right before the sweep that needs it (event 3)
+  if (side_busy) cudaEventRecord(sc->ev[3], sc->low);
   return 0;
 }
 
@@ -267,6 +327,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   // bwd_phase: 0 = everything, 1 = all but dW1, 2 = dW1 only (lets the caller all-reduce the
   // other gradients while the second X stream runs)
   const int phase = o->bwd_phase;
+  SideCtx* sc = side_ctx();
+  cudaStream_t ss = sc ? sc->s.side : st;
   if (phase == 2) goto dw1_only;
   // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
@@ -293,7 +355,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_g2_launch(a, dirs.n, st)) return rc;
   }
-  // 3. dW2a = T2^T A1
+  // 3./4. on the side stream, beside the G1 -> T1 -> dW1 chain: dW2a = T2^T A1 and dW2b
+  if (sc) stream_after(sc, 0, st, ss);
   {
     OuterArgs a{};
     OuterReduceArgs r{};
@@ -303,18 +366,17 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       a.u[q] = t2[d]; a.v[q] = w.a1[d]; a.part[q] = w.op_part[d];
       r.part[q] = w.op_part[d]; r.dst[q] = gdir_w2(gr, d);
     }
-    if (int rc = outer64_launch(a, r, dirs.n, st)) return rc;
+    if (int rc = outer64_launch(a, r, dirs.n, ss)) return rc;
   }
-  // 4. dW2b (root part of conv2.lin)
   {
     if (!dropping) {
-      SegSumArgs s{};
-      s.node_ptr = w.node_ptr;
+      SegSumArgs sg{};
+      sg.node_ptr = w.node_ptr;
       for (int q = 0; q < dirs.n; ++q) {
-        s.t[q] = t2[dirs.id[q]];
-        s.out[q] = w.dP[dirs.id[q]];
+        sg.t[q] = t2[dirs.id[q]];
+        sg.out[q] = w.dP[dirs.id[q]];
       }
-      if (int rc = segsum_launch(s, B, dirs.n, st)) return rc;
+      if (int rc = segsum_launch(sg, B, dirs.n, ss)) return rc;
     }
     Dw2bArgs a{};
     a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr; a.batch = bt->batch;
@@ -325,7 +387,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       const int d = dirs.id[q];
       a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d)};
     }
-    if (int rc = dw2b_launch(a, dirs.n, dropping, st)) return rc;
+    if (int rc = dw2b_launch(a, dirs.n, dropping, ss)) return rc;
   }
   // 5. G1 = (T2 W2a) * mask * [H1 > 0]; db1
   {
@@ -352,13 +414,18 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
+  // the dense dW1 paths reuse T2's buffer, which the side stream reads: join first
+  if (sc) stream_after(sc, 1, ss, st);
   if (phase == 1) return 0;
 dw1_only:
-  // 7. dW1 = T1^T X, one more pass over X
+  // 7. dW1 = T1^T X: a sweep over the column-sorted non-zeros (SPARSE) or one more pass over X
   {
     float* da = gdir_w1(gr, dirs.id[0]);
     float* db = dirs.n == 2 ? gdir_w1(gr, dirs.id[1]) : nullptr;
-    if (o->gemm_mode == BIGCN_GEMM_FP32) {
+    if (o->gemm_mode == BIGCN_GEMM_SPARSE) {
+      if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);   // column-sorted X of the forward (no-op if none pending)
+      if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
+    } else if (o->gemm_mode == BIGCN_GEMM_FP32) {
       if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
     } else {   // G1 (w.z) and T2 (w.xw) are dead here: they hold the TF32 hi / lo split of T1
       if (int rc = dw_tc(bt->x, N, K, t1cat, n_out, n_out, w.z[0], w.xw, w.dw_part, da, K, 0, db, K, 0,
@@ -422,6 +489,22 @@ __global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ g
 using namespace bigcn;
 
 extern "C" const char* bigcn_last_error(void) { return g_err; }
+// `stream` waits for everything the library still has in flight on its internal streams
+extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {
+  SideCtx* sc = side_ctx();
+  if (!sc) return 0;
+  cudaEventRecord(sc->ev[1], sc->s.side);
+  cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[1], 0);
+  cudaEventRecord(sc->ev[2], sc->low);
+  cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[2], 0);
+  return 0;
+}
+// the internal low-priority stream (cudaStream_t) or NULL: lets a caching allocator be told that
+// a workspace is in use there (torch: Tensor.record_stream(ExternalStream(handle)))
+extern "C" void* bigcn_internal_stream(void) {
+  SideCtx* sc = side_ctx();
+  return sc ? (void*)sc->low : nullptr;
+}
 extern "C" int bigcn_version(void) { return 100; }
 extern "C" int bigcn_device_ok(void) {
   int dev = 0, major = 0;
@@ -540,6 +623,7 @@ extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int6
   ColsumArgs c{};
   c.nchunk = nchunk; c.part[0] = cw.cs_part; c.out[0] = db;
   if (int rc = colsum_reduce_launch(c, 1, st)) return rc;
+  if (gemm_mode == BIGCN_GEMM_SPARSE) gemm_mode = BIGCN_GEMM_FP32;
   // T = A-hat^T grad_out
   PropArgs a{};
   a.N = N; a.relu = 0;
@@ -549,6 +633,66 @@ extern "C" int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int6
   if (gemm_mode == BIGCN_GEMM_FP32) return dw_fp32(x, N, K, cw.xw, H, 64, cw.dw_part, dw, K, 0, nullptr, 0, 0, st);
   return dw_tc(x, N, K, cw.xw, H, 64, cw.split, cw.split + (size_t)(N > 0 ? N : 1) * H, cw.dw_part, dw, K, 0,
                nullptr, 0, 0, gemm_mode, st);
+}
+
+// ---- X * W^T with the row-sparse capture, and its weight gradient, on their own -------------
+struct XsWs {
+  XSparse xs;
+  float* wT;
+  size_t total;
+};
+static XsWs carve_xs(int64_t N, int64_t K, void* ws, size_t bytes) {
+  XsWs w{};
+  Carver c(ws, bytes);
+  w.xs = xs_carve(c, N, K);
+  w.wT = c.take<float>((size_t)K * 128);
+  w.total = align_up(c.off, 256);
+  return w;
+}
+extern "C" size_t bigcn_xsparse_workspace_bytes(int64_t N, int64_t K) { return carve_xs(N, K, nullptr, 0).total; }
+
+extern "C" int bigcn_xw_sparse(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
+                               float* y, int64_t ldy, int32_t build_csc, int32_t* flags, void* workspace,
+                               size_t workspace_bytes, bigcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BIGCN_CHECK_ARG(N >= 0 && K > 0 && w0 && flags && (N == 0 || (x && y)), "xw_sparse: bad arguments");
+  XsWs w = carve_xs(N, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= w.total, "xw_sparse: workspace too small");
+  if (N == 0) {
+    cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), st);
+    return 0;
+  }
+  const int n_w = w1 ? 2 : 1;
+  TransposeJobs js{};
+  js.job[js.n++] = TransposeJob{w0, ldw, 0, K, w.wT, H * n_w, 0};
+  if (w1) js.job[js.n++] = TransposeJob{w1, ldw, 0, K, w.wT, H * n_w, H};
+  if (int rc = transpose_jobs_launch(js, st)) return rc;
+  if (int rc = xw_fp32_capture(x, N, K, w.wT, H * n_w, y, ldy, w.xs, st)) return rc;
+  if (!build_csc) {
+    cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), st);
+    return 0;
+  }
+  w.xs.flags = flags;
+  return xs_build_csc(w.xs, x, true, st);
+}
+
+extern "C" int bigcn_xw_wgrad_sparse(int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0, float* dw1,
+                                     int64_t ldw, void* workspace, size_t workspace_bytes, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(t && dw0 && (n_w == 1 || (n_w == 2 && dw1)), "xw_wgrad_sparse: bad arguments");
+  XsWs w = carve_xs(N, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= w.total, "xw_wgrad_sparse: workspace too small");
+  return dw_sparse(w.xs, t, H * n_w, H * n_w, dw0, dw1, ldw, (cudaStream_t)stream);
+}
+
+// device pointers of the CSR / CSC built in a bigcn_xw_sparse workspace (tests, sparse loaders)
+extern "C" int bigcn_xsparse_view(int64_t N, int64_t K, void* workspace, size_t workspace_bytes, int32_t** state,
+                                  int32_t** ptr, int32_t** col, float** val, int32_t** cptr, int32_t** crow,
+                                  float** cval) {
+  XsWs w = carve_xs(N, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= w.total, "xsparse_view: workspace too small");
+  *state = w.xs.state; *ptr = w.xs.ptr; *col = w.xs.col; *val = w.xs.val;
+  *cptr = w.xs.cptr; *crow = w.xs.crow; *cval = w.xs.cval;
+  return 0;
 }
 
 // ---- weight gradient of X * W^T on its own (the autograd transpose of GCNConv.lin) -------
@@ -566,7 +710,7 @@ extern "C" int bigcn_xw_wgrad(const float* x, int64_t N, int64_t K, const float*
   float* partial = scratch;
   float* hi = scratch + dw_partial_floats(N, K, n_out);
   float* lo = hi + (size_t)(N > 0 ? N : 1) * n_out;
-  if (gemm_mode == BIGCN_GEMM_FP32)
+  if (gemm_mode == BIGCN_GEMM_FP32 || gemm_mode == BIGCN_GEMM_SPARSE)
     return dw_fp32(x, N, K, t, n_out, n_out, partial, dw0, ldw, 0, dw1, ldw, 0, st);
   return dw_tc(x, N, K, t, n_out, n_out, hi, lo, partial, dw0, ldw, 0, dw1, ldw, 0, gemm_mode, st);
 }

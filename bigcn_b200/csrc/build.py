@@ -6,8 +6,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "graph_prep.cu", "xw.cu", "gemm_tc.cu", "propagate.cu", "head.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "bigcn_b200.h")]
+SOURCES = ["api.cu", "graph_prep.cu", "xw.cu", "xsparse.cu", "gemm_tc.cu", "propagate.cu", "head.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "gather.cuh", os.path.join("..", "..", "include", "bigcn_b200.h")]
 LIB = os.path.join(HERE, "..", "libbigcn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -100,9 +100,23 @@ __host__ __device__ inline void long_chunking(int len, int& lch, int& nch) {
 struct Csr {
   const int32_t* ptr;
   const int32_t* idx;
-  const float* dis;
   int32_t* lng;   // hub-row list of this CSR or nullptr (rows are then walked by their owner)
-  int64_t E;
+  int64_t E;      // edge capacity the hub-row list was laid out for
+};
+
+// edge weights.  GCN: w(e: j -> i) = dis[j] * dis[i], plus the self-loop dis[i]^2.
+struct WtGcn {
+  const float* dis;
+  static constexpr bool kSelf = true;
+  __device__ __forceinline__ float row(int i) const { return dis[i]; }
+  __device__ __forceinline__ float edge(int, int j, float drow) const { return __fmul_rn(dis[j], drow); }
+};
+// explicit per-entry weights, no self term (column-sorted X for the weight gradient)
+struct WtVal {
+  const float* val;
+  static constexpr bool kSelf = false;
+  __device__ __forceinline__ float row(int) const { return 0.f; }
+  __device__ __forceinline__ float edge(int e, int, float) const { return val[e]; }
 };
 
 // plain feature rows: val(j) = h[j, :]
@@ -142,8 +156,8 @@ static inline int sweep_grid(int64_t N, int R, int cb, int max_ctas) {
   return (int)blocks;
 }
 
-template <int R, int Q, bool EXACT, class Val, class Post>
-__device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb, float* smem_dyn,
+template <int R, int Q, bool EXACT, class Wt, class Val, class Post>
+__device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n, const int cb, float* smem_dyn,
                                           const Val val, const Post post) {
   static_assert(R <= 15 && Q <= 16, "one lane per row pointer / staged edge");
   const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
@@ -175,12 +189,14 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
     // row pointers, dis and aux of the block: one lane per row
     if (sub <= nrows && nrows > 0) sp[sub] = g.ptr[i0 + sub];
     if (sub < nrows) {
-      sd[sub] = g.dis[i0 + sub];
-      sa[Q + sub] = val.aux(i0 + sub);
+      sd[sub] = wt.row(i0 + sub);
+      if (Wt::kSelf) sa[Q + sub] = val.aux(i0 + sub);
     }
+    if (Wt::kSelf) {
 #pragma unroll
-    for (int u = 0; u < R; ++u)
-      if (u < nrows) val.fetch(st + u * H, i0 + u, sub);
+      for (int u = 0; u < R; ++u)
+        if (u < nrows) val.fetch(st + u * H, i0 + u, sub);
+    }
     __syncwarp();
     // offsets of the rows in the block's edge stream; hub rows are left to the split path
     unsigned longmask = 0;
@@ -204,8 +220,10 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
     unsigned flushed = 0;      // rows whose finished sum sits in their stage slot
     // finished row: add the self-loop term and park the sum in the row's own stage slot
     auto flush = [&](int u) {
-      const float d = sd[u];
-      acc_add<EXACT>(acc, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
+      if (Wt::kSelf) {
+        const float d = sd[u];
+        acc_add<EXACT>(acc, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
+      }
       st4(st + u * H + 4 * sub, acc);
       flushed |= 1u << u;
     };
@@ -218,8 +236,9 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
         int u = 0;
 #pragma unroll
         for (int k = 1; k < R; ++k) u += (s >= sq[k]) ? 1 : 0;   // sq is non-decreasing
-        j = g.idx[sp[u] + (s - sq[u])];
-        sw[sub] = __fmul_rn(g.dis[j], sd[u]);
+        const int e = sp[u] + (s - sq[u]);
+        j = g.idx[e];
+        sw[sub] = wt.edge(e, j, sd[u]);
         su[sub] = u;
         sa[sub] = val.aux(j);
       }
@@ -255,8 +274,10 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
         v = ld4(st + u * H + 4 * sub);   // a lane re-reads only what it wrote itself
       } else {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float d = sd[u];
-        acc_add<EXACT>(v, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
+        if (Wt::kSelf) {
+          const float d = sd[u];
+          acc_add<EXACT>(v, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
+        }
       }
       post(i0 + u, v, sub, hm, st + (R + (u & (Q - 1))) * H);
     }
@@ -273,14 +294,14 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
     int lch, nch;
     long_chunking(len, lch, nch);
     const int s = rs + (t - item0) * lch, e = min(rs + len, s + lch);
-    const float d = g.dis[row];
+    const float d = wt.row(row);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e0 = s; e0 < e; e0 += Q) {
       const int nb = min(Q, e - e0);
       int j = 0;
       if (sub < nb) {
         j = g.idx[e0 + sub];
-        sw[sub] = __fmul_rn(g.dis[j], d);
+        sw[sub] = wt.edge(e0 + sub, j, d);
         sa[sub] = val.aux(j);
       }
 #pragma unroll
@@ -301,8 +322,10 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
     old = __shfl_sync(hm, old, 0, 16);
     if (old == nch - 1) {   // last chunk in: ordered combine, self-loop, epilogue
       __threadfence();
-      val.fetch(st, row, sub);
-      if (sub == 0) sa[Q] = val.aux(row);
+      if (Wt::kSelf) {
+        val.fetch(st, row, sub);
+        if (sub == 0) sa[Q] = val.aux(row);
+      }
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* p0 = L.partial + (size_t)item0 * H + 4 * sub;
       for (int c = 0; c < nch; ++c) {
@@ -314,7 +337,7 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const int n, const int cb
       }
       cp_async_commit_wait_all();
       __syncwarp(hm);
-      acc_add<EXACT>(tot, __fmul_rn(d, d), val.value(st, sa[Q], sub));
+      if (Wt::kSelf) acc_add<EXACT>(tot, __fmul_rn(d, d), val.value(st, sa[Q], sub));
       if (sub == 0) L.done[slot] = 0;   // ready for the next launch over this CSR
       post(row, tot, sub, hm, st + R * H);
     }

@@ -73,5 +73,45 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
                   float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st);
 bool xw_tc_available();
 
+// ---- row-sparse view of X (xsparse.cu) -------------------------------------------------------
+constexpr int XS_ELL = 32;           // non-zeros per row the forward scan captures in place
+constexpr int XS_CAP_PER_ROW = 48;   // the CSR / CSC buffers hold N * min(K, 48) entries
+struct XSparse {
+  int64_t N, K, cap;
+  int32_t* state;     // [0] nnz the sort / sweep work on, [1] 1 = more non-zeros than cap
+  int32_t* cnt;       // [N]    non-zeros per row (exact)
+  int32_t* ell_col;   // [N][XS_ELL]
+  float* ell_val;     // [N][XS_ELL]
+  int32_t* ptr;       // [N+1]  CSR
+  int32_t* col;       // [cap]
+  int32_t* row;       // [cap]
+  float* val;         // [cap]
+  int32_t* keys[2];   // radix ping-pong
+  int32_t* perm[2];
+  int32_t* hist;
+  int32_t* bsum;
+  int32_t* cptr;      // [K+1]  CSC
+  int32_t* crow;      // [cap]
+  float* cval;        // [cap]
+  int32_t* clong[2];  // hub-column lists, one per 64-output half (each owns its partials / arrival counters)
+  int32_t* flags;     // caller's violation word (BIGCN_FLAG_X_NOT_SPARSE)
+};
+int64_t xs_capacity(int64_t N, int64_t K);
+XSparse xs_carve(Carver& c, int64_t N, int64_t K);
+int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st);
+int dw_sparse(const XSparse& x, const float* t, int64_t ldt, int n_out, float* dw_a, float* dw_b, int64_t ldw,
+              cudaStream_t st);
+int xw_fp32_capture(const float*, int64_t, int64_t, const float*, int, float*, int64_t, const XSparse&, cudaStream_t);
+int xw_csr(const XSparse& x, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st);
+
+// fork / join onto the library's side stream (independent short kernels run beside the X stream)
+struct SideStream {
+  cudaStream_t side;
+  cudaEvent_t fork_ev, join_ev;
+};
+SideStream* side_stream();
+int side_fork(cudaStream_t main_st, SideStream** out);   // side waits for everything queued on main so far
+int side_join(cudaStream_t main_st, SideStream* s);      // main waits for everything queued on side
+
 
 }  // namespace bigcn

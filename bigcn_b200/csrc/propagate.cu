@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256, 3) k_propagate(PropArgs a) {
   const int sub = threadIdx.x & 15;
   PostBiasRelu post{p.bias, p.out, p.ldo, a.relu, make_float4(0.f, 0.f, 0.f, 0.f)};
   if (p.bias) post.b = ld4(p.bias + 4 * sub);
-  csr_sweep<PROP_R, PROP_Q, true>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
-                                         ValRow{p.h, p.ldh}, post);
+  csr_sweep<PROP_R, PROP_Q, true>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
+                                  ValRow{p.h, p.ldh}, post);
 }
 
 template <class K>
@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(256, 3) k_prop1_mix(MixArgs a) {
   // csr_sweep starts with a __syncthreads()
   const int sub = threadIdx.x & 15;
   PostMix post{p, sW, a.batch, a.rnz_cnt, a.rnz_col, a.rnz_val, a.K, a.node_id_base, ld4(p.b1 + 4 * sub)};
-  csr_sweep<MIX_R, MIX_Q, true>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
-                                      ValRow{p.xw, a.ldxw}, post);
+  csr_sweep<MIX_R, MIX_Q, true>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
+                                ValRow{p.xw, a.ldxw}, post);
 }
 
 
@@ -438,8 +438,8 @@ struct PostStore {
 __global__ void __launch_bounds__(256, 3) k_propagate_g2(PropG2Args a) {
   extern __shared__ __align__(128) float sweep_smem[];
   const PropG2Dir p = a.d[blockIdx.y];
-  csr_sweep<PROP_R, PROP_Q, false>(Csr{p.ptr, p.idx, p.dis, p.lng, p.E}, (int)a.N, a.cb, sweep_smem,
-                                          ValG2{p.h2, p.gs, a.batch}, PostStore{p.out});
+  csr_sweep<PROP_R, PROP_Q, false>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
+                                   ValG2{p.h2, p.gs, a.batch}, PostStore{p.out});
 }
 
 // out[f] = sum_chunk part[chunk][f]: 4 strided groups, fixed-order combine

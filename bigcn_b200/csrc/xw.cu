@@ -18,10 +18,14 @@ namespace bigcn {
 // L1/L2 resident) into n_out/32 registers per lane.
 constexpr int XW_U = 8;
 
-template <int NOUT, bool VEC4>
+// CAPTURE: lane 0 also records every non-zero (column, value) in the row's ELL slots and the
+// exact count (xsparse.cu turns that into the CSR / CSC the sparse weight gradient sweeps).
+template <int NOUT, bool VEC4, bool CAPTURE>
 __global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, int64_t N, int64_t K,
                                                  const float* __restrict__ wt,
-                                                 float* __restrict__ y, int64_t ldy) {
+                                                 float* __restrict__ y, int64_t ldy,
+                                                 int32_t* __restrict__ xs_cnt, int32_t* __restrict__ xs_col,
+                                                 float* __restrict__ xs_val) {
   constexpr int V = NOUT / 32;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -31,6 +35,7 @@ __global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, in
     float acc[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    int nz = 0;
     for (int64_t k0 = 0; k0 < K; k0 += 128 * XW_U) {
       float4 v[XW_U];
 #pragma unroll
@@ -58,6 +63,13 @@ __global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, in
             m &= m - 1;
             const float val = __shfl_sync(FULL_MASK, comp, sl);
             const int64_t k = k0 + u * 128 + sl * 4 + c;
+            if (CAPTURE) {
+              if (lane == 0 && nz < XS_ELL) {
+                xs_col[row * XS_ELL + nz] = (int32_t)k;
+                xs_val[row * XS_ELL + nz] = val;
+              }
+              ++nz;
+            }
             const float* wr = wt + k * NOUT + lane * V;
             if (V == 4) {
               const float4 w = *reinterpret_cast<const float4*>(wr);
@@ -79,24 +91,97 @@ __global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, in
       *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     else
       *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+    if (CAPTURE && lane == 0) xs_cnt[row] = nz;
   }
+}
+
+template <bool CAPTURE>
+static int xw_scan_launch(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
+                          int32_t* xs_cnt, int32_t* xs_col, float* xs_val, int ctas_per_sm, cudaStream_t st) {
+  if (N == 0) return 0;
+  const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int blocks = (int)ceil_div(N, 8);
+  const int cap = num_sms() * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (n_out == 128) {
+    if (vec4) k_xw_scan<128, true, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    else k_xw_scan<128, false, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+  } else {
+    if (vec4) k_xw_scan<64, true, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    else k_xw_scan<64, false, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+  }
+  BIGCN_CHECK_LAUNCH("k_xw_scan");
+  return 0;
 }
 
 int xw_fp32(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
             cudaStream_t st) {
-  if (N == 0) return 0;
-  const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  int blocks = (int)ceil_div(N, 8);
+  return xw_scan_launch<false>(x, N, K, wt, n_out, y, ldy, nullptr, nullptr, nullptr, 8, st);
+}
+// 6 CTAs per SM (the stream is HBM-bound with ~200 KB in flight per SM either way): leaves room
+// for the short kernels of the side stream to run beside it
+int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
+                    const XSparse& xs, cudaStream_t st) {
+  return xw_scan_launch<true>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
+}
+
+// y = x * wt from the CSR of x (sparse input: the dense matrix never reaches the device).
+// Warp per row; the row's (col, val) pairs are fetched 32 at a time, then one fma chain per
+// output in CSR order (ascending columns).
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restrict__ wt, float* __restrict__ y,
+                                                int64_t ldy) {
+  constexpr int V = NOUT / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < xs.N; row += nwarp) {
+    const int s = xs.ptr[row], e = xs.ptr[row + 1];
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int p0 = s; p0 < e; p0 += 32) {
+      const int p = p0 + lane;
+      int k = 0;
+      float v = 0.f;
+      if (p < e) {
+        k = xs.col[p];
+        v = xs.val[p];
+      }
+      const int m = min(32, e - p0);
+      for (int l = 0; l < m; ++l) {
+        const int kk = __shfl_sync(FULL_MASK, k, l);
+        const float vv = __shfl_sync(FULL_MASK, v, l);
+        const float* wr = wt + (int64_t)kk * NOUT + lane * V;
+        if (V == 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wr);
+          acc[0] = fmaf(vv, w.x, acc[0]);
+          acc[1] = fmaf(vv, w.y, acc[1]);
+          acc[2] = fmaf(vv, w.z, acc[2]);
+          acc[3] = fmaf(vv, w.w, acc[3]);
+        } else {
+          const float2 w = *reinterpret_cast<const float2*>(wr);
+          acc[0] = fmaf(vv, w.x, acc[0]);
+          acc[1] = fmaf(vv, w.y, acc[1]);
+        }
+      }
+    }
+    float* yr = y + row * ldy + lane * V;
+    if (V == 4)
+      *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+      *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+  }
+}
+
+int xw_csr(const XSparse& xs, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st) {
+  if (xs.N == 0) return 0;
+  int blocks = (int)ceil_div(xs.N, 8);
   const int cap = num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (n_out == 128) {
-    if (vec4) k_xw_scan<128, true><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
-    else k_xw_scan<128, false><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
-  } else {
-    if (vec4) k_xw_scan<64, true><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
-    else k_xw_scan<64, false><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy);
-  }
-  BIGCN_CHECK_LAUNCH("k_xw_scan");
+  if (n_out == 128) k_xw_csr<128><<<blocks, 256, 0, st>>>(xs, wt, y, ldy);
+  else k_xw_csr<64><<<blocks, 256, 0, st>>>(xs, wt, y, ldy);
+  BIGCN_CHECK_LAUNCH("k_xw_csr");
   return 0;
 }
 

@@ -106,6 +106,57 @@ def xw(x, weights, gemm_mode="fp32"):
     return y
 
 
+class XSparseProduct:
+    """y = x @ cat(weights).T through the exact scan that also captures the non-zeros of x
+    (``gemm_mode='sparse'`` on its own).  ``wgrad(t)`` returns the weight gradients from the
+    column-sorted copy; ``csr()`` / ``csc()`` expose the structures built on the device."""
+
+    def __init__(self, x, weights):
+        L.require_device()
+        x = _f32(x)
+        ws_ = [_f32(w) for w in weights]
+        _need_cuda(x, *ws_)
+        self.n, self.k, self.n_w = x.shape[0], x.shape[1], len(ws_)
+        self.ws = torch.empty(lib().bigcn_xsparse_workspace_bytes(self.n, self.k), dtype=torch.uint8, device=x.device)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        self.y = torch.empty(self.n, H * self.n_w, dtype=torch.float32, device=x.device)
+        check(lib().bigcn_xw_sparse(_p(x), self.n, self.k, _p(ws_[0]), _p(ws_[1]) if self.n_w == 2 else None,
+                                    ws_[0].stride(0), _p(self.y), H * self.n_w, 1, _p(self.flags), _p(self.ws),
+                                    self.ws.numel(), _stream()), "xw_sparse")
+
+    def wgrad(self, t):
+        t = _f32(t)
+        dev = t.device
+        dws = [torch.empty(H, self.k, dtype=torch.float32, device=dev) for _ in range(self.n_w)]
+        check(lib().bigcn_xw_wgrad_sparse(self.n, self.k, _p(t), self.n_w, _p(dws[0]),
+                                          _p(dws[1]) if self.n_w == 2 else None, self.k, _p(self.ws),
+                                          self.ws.numel(), _stream()), "xw_wgrad_sparse")
+        return dws
+
+    def _view(self):
+        ptrs = [C.c_void_p() for _ in range(7)]
+        check(lib().bigcn_xsparse_view(self.n, self.k, _p(self.ws), self.ws.numel(), *[C.byref(p) for p in ptrs]),
+              "xsparse_view")
+        base = self.ws.data_ptr()
+
+        def arr(p, count, dtype):
+            off = p.value - base
+            return self.ws[off:off + count * 4].view(dtype)
+        state = arr(ptrs[0], 4, torch.int32)
+        nnz = int(state[0].item())
+        return dict(state=state, nnz=nnz, ptr=arr(ptrs[1], self.n + 1, torch.int32), col=arr(ptrs[2], nnz, torch.int32),
+                    val=arr(ptrs[3], nnz, torch.float32), cptr=arr(ptrs[4], self.k + 1, torch.int32),
+                    crow=arr(ptrs[5], nnz, torch.int32), cval=arr(ptrs[6], nnz, torch.float32))
+
+    def csr(self):
+        v = self._view()
+        return v["ptr"], v["col"], v["val"]
+
+    def csc(self):
+        v = self._view()
+        return v["cptr"], v["crow"], v["cval"]
+
+
 def propagate(graph, h, bias=None, relu=False, transpose=False):
     """out = A-hat h (+bias)(relu), or A-hat^T h with transpose=True."""
     L.require_device()
@@ -154,6 +205,9 @@ def raise_on_flags(flags: torch.Tensor):
         msgs.append("data.batch is not sorted ascending within [0, B)")
     if v & L.FLAG_ROOT_RANGE:
         msgs.append("data.rootindex has an entry outside [0, N)")
+    if v & L.FLAG_X_NOT_SPARSE:
+        msgs.append("gemm_mode='sparse' needs at most N*min(K,48) non-zeros in data.x (the conv1 weight "
+                    "gradient of this batch is NaN): use 'mixed' / 'tf32x3' / 'fp32' for dense features")
     raise IndexError("bigcn_b200: invalid graph input: " + "; ".join(msgs))
 
 
@@ -233,7 +287,8 @@ class FeaturesFunction(torch.autograd.Function):
         dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, opts["node_id_base"])
         o = Opts(training=int(opts["training"]), p_drop=float(opts["p"]), seed=int(opts["seed"]),
                  deg_by=L.DEG_BY[opts["deg_by"]], gemm_mode=L.GEMM_MODE[opts["gemm_mode"]],
-                 dir_mask=int(opts["dir_mask"]))
+                 dir_mask=int(opts["dir_mask"]),
+                 skip_wgrad_prep=int(not any(ctx.needs_input_grad)))   # inference: no column sort of x
         ws_bytes = lib().bigcn_features_workspace_bytes(C.byref(dims))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         flags = opts.get("flags")
@@ -242,6 +297,14 @@ class FeaturesFunction(torch.autograd.Function):
         feat = torch.empty(dims.B, 4 * H, dtype=torch.float32, device=x.device)
         check(lib().bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(pr), C.byref(o), _p(feat),
                                            _p(flags), _p(ws), ws_bytes, _stream()), "features_forward")
+        if o.gemm_mode == L.GEMM_MODE["sparse"] and not o.skip_wgrad_prep:
+            # the column sort of x is still running on the library's low-priority stream: keep the
+            # caching allocator from recycling the workspace (or x) under it
+            h = lib().bigcn_internal_stream()
+            if h:
+                side = torch.cuda.ExternalStream(h, device=x.device)
+                ws.record_stream(side)
+                x.record_stream(side)
         ctx.save_for_backward(x, ei, bu_ei, batch, rootindex, ws, *[p for p in params if p is not None])
         ctx.present = [p is not None for p in params]
         ctx.o = o

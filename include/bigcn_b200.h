@@ -5,9 +5,16 @@
  * (passed as void*, i.e. cudaStream_t).  Nothing here depends on torch.
  * Buffers are borrowed: the caller allocates inputs, outputs and workspaces
  * (sizes come from the *_bytes queries) and keeps them alive until the stream
- * has drained.  No entry point synchronises the host, allocates device memory
- * or touches any stream but the one given, so all of them can be captured in a
- * CUDA graph.  Return value: 0 = ok, non-zero = error (bigcn_last_error()).
+ * has drained.  No entry point synchronises the host or allocates device memory.
+ * bigcn_features_forward / _backward fork short independent kernels onto internal
+ * streams (created on first use, per device) and join them again before they return:
+ * at return all work is ordered on the caller's stream.  One exception: in
+ * BIGCN_GEMM_SPARSE training the forward leaves the column sort of x running on a
+ * low-priority stream and bigcn_features_backward waits for it where it needs it; the
+ * workspace must outlive that (bigcn_join_internal_streams(stream) makes `stream` wait
+ * for everything in flight; bigcn_internal_stream() is that stream's handle for
+ * allocators that track per-stream use).  Calls are not re-entrant per device.
+ * Return value: 0 = ok, non-zero = error (bigcn_last_error()).
  * Data-dependent input violations (edge endpoint >= N, unsorted batch, root
  * outside its tree) never produce a silent wrong answer: they raise bits in the
  * caller's device-side `flags` word, which the host reads at its next sync.
@@ -38,6 +45,8 @@ extern "C" {
 #define BIGCN_FLAG_EDGE_RANGE 1   /* an edge endpoint is < 0 or >= N            */
 #define BIGCN_FLAG_BATCH_ORDER 2  /* batch[] not sorted ascending / out of [0,B) */
 #define BIGCN_FLAG_ROOT_RANGE 4   /* rootindex[b] outside [0,N)                 */
+#define BIGCN_FLAG_X_NOT_SPARSE 8 /* BIGCN_GEMM_SPARSE on a batch with more non-zeros than N*min(K,48):
+                                     the conv1 weight gradient is NaN, use a dense gemm_mode          */
 
 /* degree convention of gcn_norm: PyG 2.x sums at the target (col); the
  * readme-pinned 1.3.2 summed at the source (row). */
@@ -50,6 +59,9 @@ extern "C" {
 #define BIGCN_GEMM_TF32X3 2
 /* exact fp32 scan for X*W (forward), tcgen05 hi/lo-split GEMM for the weight gradient */
 #define BIGCN_GEMM_MIXED 3
+/* exact fp32 scan forward that also captures the non-zeros of x; the weight gradient is a sweep
+ * over the column-sorted non-zeros (no second pass over x).  For bag-of-words inputs. */
+#define BIGCN_GEMM_SPARSE 4
 
 /* direction bits */
 #define BIGCN_DIR_TD 1
@@ -108,9 +120,14 @@ typedef struct bigcn_opts {
   int32_t gemm_mode;  /* BIGCN_GEMM_*                                               */
   int32_t dir_mask;   /* BIGCN_DIR_TD | BIGCN_DIR_BU                                */
   int32_t bwd_phase;  /* features_backward: 0 all, 1 all but dW1, 2 dW1 only        */
+  int32_t skip_wgrad_prep; /* BIGCN_GEMM_SPARSE forward: 1 = inference, do not sort the
+                              non-zeros of x by column (features_backward would then
+                              return NaN for the conv1 weight gradient)              */
 } bigcn_opts_t;
 
 const char* bigcn_last_error(void);
+int bigcn_join_internal_streams(bigcn_stream_t stream);
+void* bigcn_internal_stream(void);
 int bigcn_version(void);
 /* 1 if the library carries sm_100a code and the current device is cc 10.x */
 int bigcn_device_ok(void);
@@ -151,6 +168,22 @@ int bigcn_xw(const float* x, int64_t N, int64_t K, const float* w0, const float*
 size_t bigcn_xw_wgrad_scratch_floats(int64_t N, int64_t K, int32_t n_w);
 int bigcn_xw_wgrad(const float* x, int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0,
                    float* dw1, int64_t ldw, int32_t gemm_mode, float* scratch, bigcn_stream_t stream);
+/* The same product and gradient through the row-sparse view of x (BIGCN_GEMM_SPARSE, for
+ * bag-of-words inputs: Process/getTwittergraph.py:16-24 densifies `index:count` pairs).
+ * bigcn_xw_sparse: exact fp32 scan that also records the non-zeros of x, then CSR
+ * (ptr,col,val) and, through a stable radix sort, the column-sorted CSC (cptr,crow,cval) in
+ * the workspace.  bigcn_xw_wgrad_sparse: dw_d[o,k] = sum over column k of x (rows ascending) of
+ * x[i,k] * t[i, 64 d + o] -- no second pass over x; NaN (and BIGCN_FLAG_X_NOT_SPARSE raised by
+ * the forward) when x holds more than N*min(K,48) non-zeros.  state[0] = nnz. */
+size_t bigcn_xsparse_workspace_bytes(int64_t N, int64_t K);
+int bigcn_xw_sparse(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
+                    float* y, int64_t ldy, int32_t build_csc /* 0: product only (inference) */,
+                    int32_t* flags, void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+int bigcn_xw_wgrad_sparse(int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0, float* dw1,
+                          int64_t ldw, void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+int bigcn_xsparse_view(int64_t N, int64_t K, void* workspace, size_t workspace_bytes, int32_t** state,
+                       int32_t** ptr, int32_t** col, float** val, int32_t** cptr, int32_t** crow,
+                       float** cval);
 /* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
 int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
                            float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);
