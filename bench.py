@@ -206,6 +206,7 @@ def run_ours(args):
                              validate="off").to(dev).train()
     tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world)
     b_global = TREES_PER_GPU * world
+    sparse_ok = args.gemm_mode == "sparse"
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,33 +239,91 @@ def run_ours(args):
     final_loss = float(loss.item())
 
     # ---- end to end: host buffers in, loss out ---------------------------------------
+    # Every step starts from the PINNED HOST tensors of a batch (the dense fp32 data.x the
+    # reference's loader produces, edge lists, batch vector, labels) and ends with the loss on
+    # the host.  Two routes for the dense matrix, both through the public API:
+    #   "dense_h2d"    : copy the dense [N,5000] matrix to the device (644 MB over PCIe)
+    #   "host_compact" : bigcn_b200.host_dense_to_csr -- one threaded pass over the host
+    #                    matrix keeps the non-zero entries -- then copy the CSR (a few MB)
+    # and, separately, the loader-native sparse route ("e2e_sparse_loader": the batch is already
+    # CSR on the host, as a loader that keeps the reference's index:count pairs would hand it).
+    small_keys = [k for k in Batch._tensor_keys if k != "x"]
     stage = [Batch(**{k: torch.empty_like(getattr(b, k), device=dev) for k in Batch._tensor_keys}) for b in host[:2]]
 
-    def e2e_step(i):
-        src, dst = host[i % N_ROTATE], stage[i % 2]
-        for k in Batch._tensor_keys:
+    def copy_small(src, dst):
+        for k in small_keys:
             s, d = getattr(src, k), getattr(dst, k)
             if d.shape != s.shape:
                 d = torch.empty_like(s, device=dev)
                 setattr(dst, k, d)
             d.copy_(s, non_blocking=True)
-        l = tr.step(dst, b_global=b_global)
-        return float(l.item())           # device -> host read of the step's result
 
-    for i in range(max(1, min(args.warmup, 3))):
-        e2e_step(i)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 12))
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    g1.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), 0.0))
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_value = TREES_PER_GPU * world * e2e_steps / (e2e_ms * 1e-3)
+    def e2e_dense(i):
+        src, dst = host[i % N_ROTATE], stage[i % 2]
+        copy_small(src, dst)
+        if not isinstance(dst.x, torch.Tensor) or dst.x.shape != src.x.shape:
+            dst.x = torch.empty_like(src.x, device=dev)
+        dst.x.copy_(src.x, non_blocking=True)
+        return float(tr.step(dst, b_global=b_global).item())      # device -> host read of the step's result
+
+    host_csr = [None, None]
+    cap = max(nodes) * 48
+    dev_csr = [ops.SparseX(torch.empty(max(nodes) + 1, dtype=torch.int32, device=dev),
+                           torch.empty(cap, dtype=torch.int32, device=dev),
+                           torch.empty(cap, dtype=torch.float32, device=dev), (0, K_FEATS)) for _ in range(2)]
+
+    def ship_csr(sx, slot):
+        d = dev_csr[slot]
+        n, nnz = sx.shape[0], int(sx.col.numel())
+        d.ptr[:n + 1].copy_(sx.ptr, non_blocking=True)
+        d.col[:nnz].copy_(sx.col, non_blocking=True)
+        d.val[:nnz].copy_(sx.val, non_blocking=True)
+        return ops.SparseX(d.ptr[:n + 1], d.col[:nnz], d.val[:nnz], sx.shape)
+
+    def e2e_compact(i):
+        src, dst = host[i % N_ROTATE], stage[i % 2]
+        host_csr[i % 2] = bigcn_b200.host_dense_to_csr(src.x, out=host_csr[i % 2], cap=cap)   # threaded pass over the dense host x
+        copy_small(src, dst)
+        dst.x = ship_csr(host_csr[i % 2], i % 2)
+        return float(tr.step(dst, b_global=b_global).item())
+
+    loader_csr = [bigcn_b200.host_dense_to_csr(b.x, cap=cap) for b in host] if sparse_ok else None
+
+    def e2e_loader(i):
+        src, dst = host[i % N_ROTATE], stage[i % 2]
+        copy_small(src, dst)
+        dst.x = ship_csr(loader_csr[i % N_ROTATE], i % 2)
+        return float(tr.step(dst, b_global=b_global).item())
+
+    def time_e2e(fn):
+        for i in range(max(1, min(args.warmup, 3))):
+            fn(i)
+        barrier()
+        n_steps = max(3, min(args.steps, 12))
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            fn(i)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ms = max_over_ranks(wall)           # host work is part of this path: wall clock, max over ranks
+        return TREES_PER_GPU * world * n_steps / (ms * 1e-3), ms / n_steps, n_steps
+
+    small_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in small_keys)
+    routes = {}
+    v, ms_, n_ = time_e2e(e2e_dense)
+    routes["dense_h2d"] = {"value": v, "ms_per_step": ms_, "h2d_bytes_per_step": h2d_bytes}
+    if sparse_ok:
+        v, ms_, n_ = time_e2e(e2e_compact)
+        routes["host_compact"] = {"value": v, "ms_per_step": ms_,
+                                  "h2d_bytes_per_step": small_bytes + host_csr[0].nbytes(),
+                                  "host_threads": os.cpu_count()}
+        v, ms_, n_ = time_e2e(e2e_loader)
+        routes["sparse_loader"] = {"value": v, "ms_per_step": ms_,
+                                   "h2d_bytes_per_step": small_bytes + loader_csr[0].nbytes()}
+    best = max((k for k in routes if k != "sparse_loader"), key=lambda k: routes[k]["value"])
+    e2e_value, e2e_ms, e2e_steps = routes[best]["value"], routes[best]["ms_per_step"], n_
+    e2e_h2d = routes[best]["h2d_bytes_per_step"]
 
     if rank != 0:
         if world > 1:
@@ -377,10 +436,18 @@ def run_ours(args):
                        "l2": f"{N_ROTATE} batches in rotation, {nodes[0] * K_FEATS * 4 / 1e6:.0f} MB of features each (> 126 MB L2)",
                        "parallelism": f"dp{world} (trees sharded, one NCCL all-reduce of the flat gradient)" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms, "route": best,
+                    "note": "dense fp32 data.x in pinned host memory -> loss on the host, wall clock; routes timed: "
+                            "dense_h2d = the matrix crosses PCIe as is, host_compact = host_dense_to_csr keeps the "
+                            "non-zeros on the host and the CSR crosses PCIe; the faster one is reported",
+                    "routes": {k: v for k, v in routes.items() if k != "sparse_loader"}},
             "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode),
             "roofline": roof, "final_loss": final_loss}
+    if "sparse_loader" in routes:
+        line["e2e_sparse_loader"] = dict(routes["sparse_loader"], unit="trees/s", d2h_bytes_per_step=4,
+                                         note="data.x already CSR on the host (a loader that keeps the reference's "
+                                              "index:count pairs): SURVEY 8f N1, an API extension, not the dense contract")
     if others:
         line["roofline_others"] = others
     if cpu is not None:

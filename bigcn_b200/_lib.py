@@ -17,6 +17,7 @@ FLAG_EDGE_RANGE, FLAG_BATCH_ORDER, FLAG_ROOT_RANGE = 1, 2, 4
 DEG_BY = {"target": 0, "source": 1}
 GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3, "sparse": 4}
 FLAG_X_NOT_SPARSE = 8
+FLAG_X_CSR_RANGE = 16
 DIR_TD, DIR_BU = 1, 2
 
 c_f32p = C.c_void_p  # device pointers travel as integers
@@ -30,7 +31,8 @@ class Dims(C.Structure):
 
 class BatchPtrs(C.Structure):
     _fields_ = [("x", c_ptr), ("edge_index", c_ptr), ("bu_edge_index", c_ptr), ("batch", c_ptr),
-                ("rootindex", c_ptr), ("node_id_base", C.c_int64)]
+                ("rootindex", c_ptr), ("node_id_base", C.c_int64),
+                ("x_ptr", c_ptr), ("x_col", c_ptr), ("x_val", c_ptr)]
 
 
 class Params(C.Structure):
@@ -75,6 +77,7 @@ _SIGS = {
     "bigcn_xw_wgrad_sparse": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, C.c_int64, c_ptr,
                                         C.c_size_t, c_ptr]),
     "bigcn_xsparse_view": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_size_t] + [C.POINTER(c_ptr)] * 7),
+    "bigcn_host_dense_to_csr": (C.c_int64, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int32]),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
     "bigcn_long_ws_ints": (C.c_size_t, [C.c_int64]),

@@ -205,6 +205,14 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
                          o->gemm_mode == BIGCN_GEMM_SPARSE;
   const bool sparse = o->gemm_mode == BIGCN_GEMM_SPARSE;
   const bool dropping = o->training && o->p_drop > 0.f;
+  const bool csr_in = bt->x == nullptr && N > 0;
+  BIGCN_CHECK_ARG(!csr_in || (sparse && bt->x_ptr && bt->x_col && bt->x_val),
+                  "features_forward: x == NULL needs gemm_mode SPARSE and x_ptr / x_col / x_val");
+  if (csr_in) {
+    w.xs.ptr = const_cast<int32_t*>(bt->x_ptr);
+    w.xs.col = const_cast<int32_t*>(bt->x_col);
+    w.xs.val = const_cast<float*>(bt->x_val);
+  }
   // 1. weights in the layouts the kernels stream
   const int n_out = dirs.n == 2 ? 128 : 64;
   {
@@ -230,7 +238,11 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       return rc;
     RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
                  w.slot, w.overflow, DW2B_CAP};
-    if (int rc = root_nz_launch(a, ss)) return rc;
+    if (csr_in) {
+      if (int rc = root_nz_csr_launch(a, bt->x_ptr, bt->x_col, bt->x_val, ss)) return rc;
+    } else {
+      if (int rc = root_nz_launch(a, ss)) return rc;
+    }
     if (!dropping) {
       RootProjArgs pa{};
       pa.cnt = w.rnz_cnt; pa.col = w.rnz_col; pa.val = w.rnz_val; pa.B = B; pa.K = K;
@@ -242,7 +254,9 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     }
   }
   // 3. X W1^T for all active directions in one pass over X (main stream)
-  if (sparse) {
+  if (csr_in) {
+    if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st)) return rc;
+  } else if (sparse) {
     if (int rc = xw_fp32_capture(bt->x, N, K, w.w1T, n_out, w.xw, n_out, w.xs, st)) return rc;
   } else if (scan_mode) {
     if (int rc = xw_fp32(bt->x, N, K, w.w1T, n_out, w.xw, n_out, st)) return rc;
@@ -260,7 +274,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     } else {
       if (sc) stream_after(sc, 2, st, sc->low);
       w.xs.flags = flags;
-      if (int rc = xs_build_csc(w.xs, bt->x, true, sc ? sc->low : st)) return rc;
+      if (int rc = xs_build_csc(w.xs, bt->x, !csr_in, sc ? sc->low : st)) return rc;
       side_busy = sc != nullptr;
     }
   }

@@ -7,6 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "graph_prep.cu", "xw.cu", "xsparse.cu", "gemm_tc.cu", "propagate.cu", "head.cu"]
+HOST_SOURCES = ["host_compact.cpp"]      # host-only C++ (g++), linked into the same library
 HEADERS = ["common.cuh", "kernels.cuh", "gather.cuh", os.path.join("..", "..", "include", "bigcn_b200.h")]
 LIB = os.path.join(HERE, "..", "libbigcn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -19,7 +20,7 @@ def _stale() -> bool:
     if not os.path.exists(lib):
         return True
     t = os.path.getmtime(lib)
-    deps = [os.path.join(HERE, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(HERE, f) for f in SOURCES + HOST_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -36,6 +37,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
+    for s in HOST_SOURCES:
+        o = os.path.join(HERE, s.replace(".cpp", ".o"))
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(HERE, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
     failed = False
     for s, p in procs:
         out, _ = p.communicate()
@@ -46,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    subprocess.check_call([NVCC, "-shared", *FLAGS[:2], "-cudart", "static", "-o", lib, *objs])
+    subprocess.check_call([NVCC, "-shared", *FLAGS[:2], "-cudart", "static", "-Xcompiler", "-pthread", "-o", lib, *objs])
     return lib
 
 

@@ -36,6 +36,7 @@ struct PropArgs { PropDir d[2]; int64_t N; int32_t relu; int32_t cb; };
 int propagate_launch(const PropArgs&, int, cudaStream_t);
 struct RootNzArgs { const float* x; const int64_t* rootindex; int64_t N, B, K; int32_t* cnt; int32_t* col; float* val; int32_t* flags; int32_t* slot; int32_t* overflow; int32_t cap; };
 int root_nz_launch(const RootNzArgs&, cudaStream_t);
+int root_nz_csr_launch(const RootNzArgs&, const int32_t*, const int32_t*, const float*, cudaStream_t);
 struct RootProjArgs { const int32_t* cnt; const int32_t* col; const float* val; const float* w2bT[2]; float* P[2]; int64_t B, K; };
 int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
 struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; };

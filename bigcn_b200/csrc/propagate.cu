@@ -132,6 +132,43 @@ __global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
   }
 }
 
+// the same from a CSR of x (sparse input): the root row's positive entries in CSR order
+__global__ void __launch_bounds__(256) k_root_nz_csr(RootNzArgs a, const int32_t* __restrict__ xptr,
+                                                     const int32_t* __restrict__ xcol, const float* __restrict__ xval) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  for (int64_t k = threadIdx.x; k < a.K; k += blockDim.x) a.slot[b * a.K + k] = -1;
+  __syncthreads();
+  if (w != 0) return;
+  const int64_t r = a.rootindex[b];
+  const bool ok = r >= 0 && r < a.N;
+  if (!ok && lane == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+  const int s = ok ? xptr[r] : 0, e = ok ? xptr[r + 1] : 0;
+  int n = 0;
+  for (int p0 = s; p0 < e; p0 += 32) {
+    const int p = p0 + lane;
+    int k = 0;
+    float v = 0.f;
+    if (p < e) {
+      k = xcol[p];
+      v = xval[p];
+    }
+    const bool pos_ok = v > 0.f && k >= 0 && k < a.K;
+    const unsigned m = __ballot_sync(FULL_MASK, pos_ok);
+    if (pos_ok) {
+      const int pos = n + __popc(m & ((1u << lane) - 1u));
+      a.col[b * a.K + pos] = k;
+      a.val[b * a.K + pos] = v;
+      a.slot[b * a.K + k] = pos;
+    }
+    n += __popc(m);
+  }
+  if (lane == 0) {
+    a.cnt[b] = n;
+    if (n > a.cap) atomicOr(a.overflow, 1);
+  }
+}
+
 // eval mode: P[d][b][:] = relu(x_root[b]) * W2b_d^T, once per tree
 __global__ void __launch_bounds__(256) k_root_proj(RootProjArgs a) {
   const int d = blockIdx.y;
@@ -591,9 +628,9 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
       for (int q = 0; q < 4; ++q) {
         const int64_t b = b0 + q * 32 + lane;
         float v = 0.f;
-        if (b < a.B) {
-          const int64_t r = a.rootindex[b];
-          if (r >= 0 && r < a.N) v = a.x[r * a.K + k];
+        if (b < a.B) {   // relu(x_root[b][k]) through the slot map (no dense x needed)
+          const int t = a.slot[b * a.K + k];
+          if (t >= 0) v = a.rnz_val[b * a.K + t];
         }
         const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
         if (v > 0.f) {
@@ -780,6 +817,14 @@ __global__ void k_dropout_mask(DropSpec ds, int64_t node_id_base, int64_t N, int
 }
 
 // ---------------------------------------------------------------- host-side launchers
+int root_nz_csr_launch(const RootNzArgs& a, const int32_t* xptr, const int32_t* xcol, const float* xval,
+                       cudaStream_t st) {
+  cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st);
+  if (a.B == 0) return 0;
+  k_root_nz_csr<<<(int)a.B, 256, 0, st>>>(a, xptr, xcol, xval);
+  BIGCN_CHECK_LAUNCH("k_root_nz_csr");
+  return 0;
+}
 int root_nz_launch(const RootNzArgs& a, cudaStream_t st) {
   cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st);
   if (a.B == 0) return 0;

@@ -197,7 +197,12 @@ __global__ void __launch_bounds__(256) k_xs_from_csr(XSparse x) {
   for (int64_t i = w0; i < x.N; i += nw) {
     const int s = x.ptr[i], e = x.ptr[i + 1];
     for (int p = s + lane; p < e; p += 32) {
-      x.keys[0][p] = x.col[p];
+      int k = x.col[p];
+      if (k < 0 || k >= x.K) {   // ignored by the forward product too (xw.cu)
+        if (x.flags) atomicOr(x.flags, BIGCN_FLAG_X_CSR_RANGE);
+        k = 0;
+      }
+      x.keys[0][p] = k;
       x.perm[0][p] = p;
       x.row[p] = (int32_t)i;
     }
@@ -295,7 +300,8 @@ __global__ void __launch_bounds__(256) k_xs_finish(XSparse x, int src) {
   for (int64_t q = t0; q < n; q += stride) {
     const int p = perm[q];
     x.crow[q] = x.row[p];
-    x.cval[q] = x.val[p];
+    const int kc = x.col[p];
+    x.cval[q] = (kc >= 0 && kc < x.K) ? x.val[p] : 0.f;
     const int cur = keys[q];
     const int prev = q > 0 ? keys[q - 1] : -1;
     for (int k = prev + 1; k <= cur; ++k) x.cptr[k] = (int32_t)q;

@@ -147,6 +147,10 @@ __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restr
       if (p < e) {
         k = xs.col[p];
         v = xs.val[p];
+        if (k < 0 || k >= xs.K) {   // flagged by k_xs_from_csr / k_root_nz_csr; contributes nothing
+          k = 0;
+          v = 0.f;
+        }
       }
       const int m = min(32, e - p0);
       for (int l = 0; l < m; ++l) {

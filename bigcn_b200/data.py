@@ -50,14 +50,14 @@ class Batch(Data):
     def to(self, device, non_blocking=False):
         for k in self._tensor_keys:
             v = getattr(self, k, None)
-            if isinstance(v, torch.Tensor):
+            if isinstance(v, torch.Tensor) or hasattr(v, "ptr"):      # tensors and ops.SparseX
                 setattr(self, k, v.to(device, non_blocking=non_blocking))
         return self
 
     def pin_memory(self):
         for k in self._tensor_keys:
             v = getattr(self, k, None)
-            if isinstance(v, torch.Tensor):
+            if isinstance(v, torch.Tensor) or hasattr(v, "ptr"):
                 setattr(self, k, v.pin_memory())
         return self
 

@@ -36,6 +36,85 @@ def _f32(t):
     return t.contiguous()
 
 
+# ----------------------------------------------------------------------------- sparse data.x
+class SparseX:
+    """``data.x`` as CSR (int32 ``ptr [N+1]``, int32 ``col``, fp32 ``val``): what the
+    ``gemm_mode='sparse'`` path consumes when the dense [N, K] matrix is never shipped to the
+    device (a loader that keeps the reference's ``index:count`` pairs,
+    Process/getTwittergraph.py:16-24, or :func:`host_dense_to_csr` on a dense host matrix).
+    Quacks enough like a tensor for ``forward(data)``: ``shape``, ``device``, ``to``."""
+
+    def __init__(self, ptr, col, val, shape):
+        self.ptr, self.col, self.val = ptr, col, val
+        self.shape = (int(shape[0]), int(shape[1]))
+
+    @property
+    def device(self):
+        return self.val.device
+
+    @property
+    def is_cuda(self):
+        return self.val.is_cuda
+
+    def to(self, device, non_blocking=False):
+        return SparseX(self.ptr.to(device, non_blocking=non_blocking), self.col.to(device, non_blocking=non_blocking),
+                       self.val.to(device, non_blocking=non_blocking), self.shape)
+
+    def pin_memory(self):
+        return SparseX(self.ptr.pin_memory(), self.col.pin_memory(), self.val.pin_memory(), self.shape)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.ptr, self.col, self.val))
+
+    @staticmethod
+    def from_torch_csr(t):
+        t = t.coalesce() if t.layout == torch.sparse_coo else t
+        if t.layout != torch.sparse_csr:
+            t = t.to_sparse_csr()
+        return SparseX(t.crow_indices().to(torch.int32), t.col_indices().to(torch.int32),
+                       t.values().to(torch.float32), t.shape)
+
+    def to_dense(self):
+        n, k = self.shape
+        rows = torch.repeat_interleave(torch.arange(n, device=self.ptr.device),
+                                       (self.ptr[1:] - self.ptr[:-1]).long())
+        out = torch.zeros(n, k, dtype=torch.float32, device=self.val.device)
+        out[rows, self.col.long()] = self.val
+        return out
+
+
+def host_dense_to_csr(x, n_threads=0, out=None, cap=None):
+    """One threaded pass over a dense HOST matrix -> :class:`SparseX` in (pinned) host memory
+    (bigcn_host_dense_to_csr, csrc/host_compact.cpp: data movement only).  ``out`` may be a
+    SparseX whose buffers are reused when large enough."""
+    if x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise L.BigcnError("host_dense_to_csr: expects a contiguous fp32 CPU tensor")
+    n, k = x.shape
+    cap = int(cap if cap is not None else n * min(k, 48))
+    if out is not None and out.ptr.numel() >= n + 1 and out.col.numel() >= cap:
+        ptr, col, val = out.ptr, out.col, out.val
+    else:
+        pin = torch.cuda.is_available()
+        ptr = torch.empty(n + 1, dtype=torch.int32, pin_memory=pin)
+        col = torch.empty(cap, dtype=torch.int32, pin_memory=pin)
+        val = torch.empty(cap, dtype=torch.float32, pin_memory=pin)
+    nnz = lib().bigcn_host_dense_to_csr(x.data_ptr(), n, k, ptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                        col.numel(), int(n_threads))
+    if nnz < 0:
+        raise L.BigcnError(f"host_dense_to_csr: {-nnz} non-zeros do not fit the sparse layout (capacity {col.numel()}): "
+                           "the features are not row-sparse, ship them dense")
+    return SparseX(ptr[:n + 1], col[:nnz], val[:nnz], (n, k))
+
+
+def _as_x(x):
+    """dense fp32 tensor | SparseX | torch sparse tensor -> (dense or None, SparseX or None)"""
+    if isinstance(x, SparseX):
+        return None, x
+    if isinstance(x, torch.Tensor) and x.layout != torch.strided:
+        return None, SparseX.from_torch_csr(x)
+    return _f32(x), None
+
+
 # ----------------------------------------------------------------------------- graph prep
 def graph_prep(edge_indexes, num_nodes, batch=None, num_graphs=0, deg_by="target", rowsum=True, long_rows=True):
     """gcn_norm structure for 1 or 2 edge lists.  Returns (graphs, node_ptr, flags) where each
@@ -205,6 +284,8 @@ def raise_on_flags(flags: torch.Tensor):
         msgs.append("data.batch is not sorted ascending within [0, B)")
     if v & L.FLAG_ROOT_RANGE:
         msgs.append("data.rootindex has an entry outside [0, N)")
+    if v & L.FLAG_X_CSR_RANGE:
+        msgs.append("sparse data.x has a column index outside [0, in_feats)")
     if v & L.FLAG_X_NOT_SPARSE:
         msgs.append("gemm_mode='sparse' needs at most N*min(K,48) non-zeros in data.x (the conv1 weight "
                     "gradient of this batch is NaN): use 'mixed' / 'tf32x3' / 'fp32' for dense features")
@@ -254,12 +335,14 @@ class GCNConvFunction(torch.autograd.Function):
 _PNAMES = ("td_w1", "td_b1", "td_w2", "td_b2", "bu_w1", "bu_b1", "bu_w2", "bu_b2")
 
 
-def _make_structs(x, ei, bu_ei, batch, rootindex, params, num_classes, node_id_base):
-    n, k = x.shape
+def _make_structs(x, ei, bu_ei, batch, rootindex, params, num_classes, node_id_base, xs=None):
+    n, k = xs.shape if xs is not None else x.shape
     dims = Dims(N=n, B=int(rootindex.numel()), K=k, C=num_classes, E_td=int(ei.shape[1]),
                 E_bu=int(bu_ei.shape[1]))
     bt = BatchPtrs(x=_p(x), edge_index=_p(ei), bu_edge_index=_p(bu_ei), batch=_p(batch),
                    rootindex=_p(rootindex), node_id_base=int(node_id_base))
+    if xs is not None:
+        bt.x_ptr, bt.x_col, bt.x_val = _p(xs.ptr), _p(xs.col), _p(xs.val)
     pr = Params()
     for name, t in zip(_PNAMES, params):
         setattr(pr, name, _p(t))
@@ -273,28 +356,33 @@ class FeaturesFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ei, bu_ei, batch, rootindex, opts, *params):
         L.require_device()
-        x = _f32(x)
+        x, xs = _as_x(x)
+        if xs is not None and opts["gemm_mode"] != "sparse":
+            raise L.BigcnError("a sparse data.x needs gemm_mode='sparse'")
         ei, bu_ei, batch, rootindex = _i64(ei), _i64(bu_ei), _i64(batch), _i64(rootindex)
         params = tuple(None if p is None else _f32(p) for p in params)
         _need_cuda(x, ei, bu_ei, batch, rootindex, *params)
-        k = x.shape[1]
+        if xs is not None:
+            _need_cuda(xs.ptr, xs.col, xs.val)
+        k = xs.shape[1] if xs is not None else x.shape[1]
+        dev = xs.device if xs is not None else x.device
         for name, p in zip(_PNAMES, params):
             if p is None:
                 continue
             want = {"w1": (H, k), "b1": (H,), "w2": (H, H + k), "b2": (H,)}[name[3:]]
             if tuple(p.shape) != want:
                 raise L.BigcnError(f"{name}: expected shape {want} (hid_feats = out_feats = 64), got {tuple(p.shape)}")
-        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, opts["node_id_base"])
+        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, opts["node_id_base"], xs)
         o = Opts(training=int(opts["training"]), p_drop=float(opts["p"]), seed=int(opts["seed"]),
                  deg_by=L.DEG_BY[opts["deg_by"]], gemm_mode=L.GEMM_MODE[opts["gemm_mode"]],
                  dir_mask=int(opts["dir_mask"]),
                  skip_wgrad_prep=int(not any(ctx.needs_input_grad)))   # inference: no column sort of x
         ws_bytes = lib().bigcn_features_workspace_bytes(C.byref(dims))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         flags = opts.get("flags")
         if flags is None:
-            flags = torch.zeros(1, dtype=torch.int32, device=x.device)
-        feat = torch.empty(dims.B, 4 * H, dtype=torch.float32, device=x.device)
+            flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        feat = torch.empty(dims.B, 4 * H, dtype=torch.float32, device=dev)
         check(lib().bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(pr), C.byref(o), _p(feat),
                                            _p(flags), _p(ws), ws_bytes, _stream()), "features_forward")
         if o.gemm_mode == L.GEMM_MODE["sparse"] and not o.skip_wgrad_prep:
@@ -302,10 +390,12 @@ class FeaturesFunction(torch.autograd.Function):
             # caching allocator from recycling the workspace (or x) under it
             h = lib().bigcn_internal_stream()
             if h:
-                side = torch.cuda.ExternalStream(h, device=x.device)
-                ws.record_stream(side)
-                x.record_stream(side)
-        ctx.save_for_backward(x, ei, bu_ei, batch, rootindex, ws, *[p for p in params if p is not None])
+                side = torch.cuda.ExternalStream(h, device=dev)
+                for t in (ws, x) if xs is None else (ws, xs.ptr, xs.col, xs.val):
+                    t.record_stream(side)
+        xt = (x,) if xs is None else (xs.ptr, xs.col, xs.val)
+        ctx.x_sparse_shape = None if xs is None else xs.shape
+        ctx.save_for_backward(*xt, ei, bu_ei, batch, rootindex, ws, *[p for p in params if p is not None])
         ctx.present = [p is not None for p in params]
         ctx.o = o
         ctx.node_id_base = opts["node_id_base"]
@@ -315,10 +405,14 @@ class FeaturesFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_feat):
         saved = ctx.saved_tensors
-        x, ei, bu_ei, batch, rootindex, ws = saved[:6]
+        x, xs = saved[0], None
+        if ctx.x_sparse_shape is not None:
+            x, xs = None, SparseX(saved[0], saved[1], saved[2], ctx.x_sparse_shape)
+            saved = saved[2:]
+        ei, bu_ei, batch, rootindex, ws = saved[1:6]
         it = iter(saved[6:])
         params = tuple(next(it) if pres else None for pres in ctx.present)
-        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, ctx.node_id_base)
+        dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, ctx.node_id_base, xs)
         grads = tuple(None if p is None else torch.empty_like(p) for p in params)
         gs = Params()
         for name, t in zip(_PNAMES, grads):

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as L
 from ._lib import H, Opts, Params, check, lib
-from .ops import _make_structs, _p, _stream, _i64, _f32, raise_on_flags
+from .ops import _make_structs, _p, _stream, _i64, _f32, _as_x, raise_on_flags
 
 # flat layout: the two conv1 weights (the gradients the second X stream produces LAST) first, so
 # the gradient splits into two contiguous all-reduce buckets: [W1_td | W1_bu] and [everything else]
@@ -86,21 +86,21 @@ class FusedTrainer:
     def step(self, data, b_global=None, node_id_base=0, seed=None):
         """One optimisation step on a device-resident batch; returns the loss (device scalar)."""
         m = self.model
-        x = _f32(data.x)
+        x, xs = _as_x(data.x)
         ei, bu, batch, root = _i64(data.edge_index), _i64(data.BU_edge_index), _i64(data.batch), \
             _i64(data.rootindex)
         y = _i64(data.y)
         td = m.TDrumorGCN
         c = m.fc.weight.shape[0]
-        dims, bt, _ = _make_structs(x, ei, bu, batch, root, (None,) * 8, c, node_id_base)
+        dims, bt, _ = _make_structs(x, ei, bu, batch, root, (None,) * 8, c, node_id_base, xs)
         if seed is None:
             seed = (td.seed + self._calls) & ((1 << 64) - 1)
         self._calls += 1
         o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(seed), deg_by=L.DEG_BY[td.deg_by],
                  gemm_mode=L.GEMM_MODE[td.gemm_mode], dir_mask=L.DIR_TD | L.DIR_BU)
-        ws = self._workspace(dims, x.device)
+        dev = xs.device if xs is not None else x.device
+        ws = self._workspace(dims, dev)
         b = dims.B
-        dev = x.device
         feat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
         logp = torch.empty(b, c, dtype=torch.float32, device=dev)
         glogp = torch.empty(b, c, dtype=torch.float32, device=dev)

@@ -48,6 +48,8 @@ extern "C" {
 #define BIGCN_FLAG_X_NOT_SPARSE 8 /* BIGCN_GEMM_SPARSE on a batch with more non-zeros than N*min(K,48):
                                      the conv1 weight gradient is NaN, use a dense gemm_mode          */
 
+#define BIGCN_FLAG_X_CSR_RANGE 16  /* sparse input: a column index of x is outside [0,K) (entry ignored) */
+
 /* degree convention of gcn_norm: PyG 2.x sums at the target (col); the
  * readme-pinned 1.3.2 summed at the source (row). */
 #define BIGCN_DEG_BY_TARGET 0
@@ -87,6 +89,12 @@ typedef struct bigcn_batch {
   const int64_t* rootindex;     /* [B]      data.rootindex (global ids)  */
   int64_t node_id_base;         /* global id of local node 0: dropout masks are keyed on
                                    global ids so they do not depend on the world size */
+  /* Sparse input (BIGCN_GEMM_SPARSE only, x == NULL): data.x as CSR, e.g. from a loader that
+   * keeps the `index:count` pairs of Process/getTwittergraph.py:16-24 or from
+   * bigcn_host_dense_to_csr.  Columns of a row must be distinct. */
+  const int32_t* x_ptr;         /* [N+1]                                   */
+  const int32_t* x_col;         /* [x_ptr[N]]                              */
+  const float* x_val;           /* [x_ptr[N]]                              */
 } bigcn_batch_t;
 
 /* Parameters in PyG-2.x state_dict layout:
@@ -184,6 +192,13 @@ int bigcn_xw_wgrad_sparse(int64_t N, int64_t K, const float* t, int32_t n_w, flo
 int bigcn_xsparse_view(int64_t N, int64_t K, void* workspace, size_t workspace_bytes, int32_t** state,
                        int32_t** ptr, int32_t** col, float** val, int32_t** cptr, int32_t** crow,
                        float** cval);
+/* HOST function: one pass over a dense row-major host matrix (pinned or pageable) with
+ * n_threads host threads (0 = all cores) that keeps the non-zero entries as CSR in host
+ * buffers, columns ascending in every row -- 8 bytes per non-zero cross PCIe instead of
+ * 4*K bytes per row.  No arithmetic.  Returns nnz, or -(needed nnz) when cap is too small. */
+int64_t bigcn_host_dense_to_csr(const float* x, int64_t N, int64_t K, int32_t* ptr /*[N+1]*/,
+                                int32_t* col /*[cap]*/, float* val /*[cap]*/, int64_t cap,
+                                int32_t n_threads);
 /* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
 int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
                            float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);

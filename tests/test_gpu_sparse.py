@@ -133,3 +133,67 @@ def test_sparse_mode_rejects_dense_features(dev):
     assert torch.isnan(m.TDrumorGCN.conv1.lin.weight.grad).all()
     with pytest.raises(IndexError):
         m.check_inputs()
+
+
+def test_sparse_input_x_never_dense_on_device(dev):
+    """data.x handed over as CSR (ops.SparseX from the host compaction, or a torch sparse
+    tensor): forward through the CSR product, root rows and weight gradient from the same CSR.
+    Same bars against the oracle run on the dense matrix."""
+    from bigcn_b200 import ops
+    b = make_batch("twitter15", 9, seed=12, train=True, in_feats=2000)
+    x = b.x.numpy().copy()
+    x[:, 11] = 2.0                                   # hub column
+    x[5, :100] = np.linspace(-1, 1, 100)             # a 100-entry row
+    b.x = torch.from_numpy(x)
+    K, n = 2000, b.x.shape[0]
+    ref, m = pair(K, 4, dev, 21)
+    ref.train(); m.train()
+    sx = ops.host_dense_to_csr(b.x, n_threads=2, cap=n * 64)
+    bd = to_dev(b, dev)
+    bd.x = sx.to(dev)
+    got = m(bd)
+    m.check_inputs()
+    s = m.TDrumorGCN.last_seed
+    ktd = torch.from_numpy(gcn_oracle.dropout_keep_mask(s, 0, np.arange(n), 64 + K, 0.5))
+    kbu = torch.from_numpy(gcn_oracle.dropout_keep_mask(s, 1, np.arange(n), 64 + K, 0.5))
+    want = ref(b, keep_td=ktd, keep_bu=kbu)
+    assert rel_err(got, want) < 1e-5
+    torch.nn.functional.nll_loss(want, b.y).backward()
+    torch.nn.functional.nll_loss(got, b.y.to(dev)).backward()
+    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 1e-4, name
+    # torch sparse tensor as data.x, eval mode
+    m.eval(); ref.eval()
+    bd.x = b.x.to_sparse_csr().to(dev)
+    assert rel_err(m(bd), ref(b)) < 1e-5
+    # a column index outside [0, K) is reported, not read out of bounds
+    bad = ops.SparseX(sx.ptr.clone(), sx.col.clone(), sx.val.clone(), sx.shape)
+    bad.col[3] = K + 5
+    bd.x = bad.to(dev)
+    m.train()
+    m.validate = "off"
+    out = m(bd)
+    out.sum().backward()
+    with pytest.raises(IndexError):
+        m.check_inputs()
+
+
+def test_fused_trainer_sparse_input_matches_dense_input(dev):
+    """FusedTrainer steps fed with SparseX batches track the same steps fed with dense x."""
+    import bigcn_b200
+    from bigcn_b200 import ops
+    b = make_batch("twitter16", 8, seed=13, train=True, in_feats=1500)
+    losses = []
+    for sparse_in in (False, True):
+        torch.manual_seed(5)
+        m = bigcn_b200.BiGCN(1500, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
+        tr = bigcn_b200.FusedTrainer(m, lr=5e-4, weight_decay=1e-4)
+        bd = to_dev(b, dev)
+        if sparse_in:
+            bd.x = ops.host_dense_to_csr(b.x).to(dev)
+        ls = [float(tr.step(bd, seed=100 + i).item()) for i in range(4)]
+        tr.check_inputs()
+        losses.append(ls)
+    for a, c in zip(*losses):
+        assert abs(a - c) < 2e-6 * max(1.0, abs(a))
+    assert losses[0][-1] < losses[0][0]
