@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="bigcn_b200", choices=["bigcn_b200", "reference"])
     ap.add_argument("--gemm-mode", default="sparse", choices=["fp32", "tf32", "tf32x3", "mixed", "sparse"])
+    ap.add_argument("--comm", default="auto", choices=["auto", "symm", "nccl"],
+                    help="N > 1: fused peer-memory optimiser step (symm) or NCCL all-reduce + Adam")
     ap.add_argument("--cpu-sample-trees", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the large-N propagate micro-benchmark")
@@ -204,9 +206,11 @@ def run_ours(args):
     torch.manual_seed(0)
     model = bigcn_b200.BiGCN(K_FEATS, 64, 64, dev, num_classes=N_CLASSES, gemm_mode=args.gemm_mode,
                              validate="off").to(dev).train()
-    tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world)
+    tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world,
+                                 comm=args.comm)
     b_global = TREES_PER_GPU * world
     sparse_ok = args.gemm_mode == "sparse"
+    tr_comm, tr_comm_note = tr.comm, tr.comm_note
 
     def barrier():
         torch.cuda.synchronize()
@@ -282,11 +286,13 @@ def run_ours(args):
 
     def e2e_compact(i):
         src, dst = host[i % N_ROTATE], stage[i % 2]
-        host_csr[i % 2] = bigcn_b200.host_dense_to_csr(src.x, out=host_csr[i % 2], cap=cap)   # threaded pass over the dense host x
+        host_csr[i % 2] = bigcn_b200.host_dense_to_csr(src.x, out=host_csr[i % 2], cap=cap,
+                                                       n_threads=host_threads)   # threaded pass over the dense host x
         copy_small(src, dst)
         dst.x = ship_csr(host_csr[i % 2], i % 2)
         return float(tr.step(dst, b_global=b_global).item())
 
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     loader_csr = [bigcn_b200.host_dense_to_csr(b.x, cap=cap) for b in host] if sparse_ok else None
 
     def e2e_loader(i):
@@ -317,7 +323,7 @@ def run_ours(args):
         v, ms_, n_ = time_e2e(e2e_compact)
         routes["host_compact"] = {"value": v, "ms_per_step": ms_,
                                   "h2d_bytes_per_step": small_bytes + host_csr[0].nbytes(),
-                                  "host_threads": os.cpu_count()}
+                                  "host_threads": host_threads}
         v, ms_, n_ = time_e2e(e2e_loader)
         routes["sparse_loader"] = {"value": v, "ms_per_step": ms_,
                                    "h2d_bytes_per_step": small_bytes + loader_csr[0].nbytes()}
@@ -434,7 +440,10 @@ def run_ours(args):
                                    f"{TREES_PER_GPU} trees/GPU, K={K_FEATS}, C={N_CLASSES}, DropEdge 0.2/0.2, dropout 0.5",
                        "trees_per_gpu": TREES_PER_GPU, "nodes_per_batch": nodes, "gemm_mode": args.gemm_mode,
                        "l2": f"{N_ROTATE} batches in rotation, {nodes[0] * K_FEATS * 4 / 1e6:.0f} MB of features each (> 126 MB L2)",
-                       "parallelism": f"dp{world} (trees sharded, one NCCL all-reduce of the flat gradient)" if world > 1 else "single GPU"},
+                       "parallelism": (f"dp{world} (trees sharded; " + (
+                           "gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory"
+                           if tr_comm == "symm" else "two bucketed NCCL all-reduces of the flat gradient + Adam on every rank")
+                           + ")") if world > 1 else "single GPU", "comm": tr_comm, "comm_note": tr_comm_note},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms, "route": best,

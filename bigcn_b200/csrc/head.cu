@@ -164,6 +164,97 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
 }
 __global__ void k_step_inc(int64_t* step_count) { *step_count += 1; }
 
+// ---- data-parallel optimiser step over peer memory (NVLink 5 / NVSwitch) ---------------------
+// Replaces "all-reduce the flat gradient, then Adam on every rank" (the reference trains on one
+// GPU; SURVEY.md 8e adds the tree-sharded data parallelism).  Every rank's flat gradient and
+// parameter buffers are mapped into every process (symmetric memory).  Rank r owns the slice
+// [lo, hi) of the flat vector: it loads that slice of ALL ranks' gradients through peer
+// addresses, adds them in rank order (the same sum on any world size ordering, bit-identical
+// parameters on all ranks), runs Adam on its shard of the optimiser state and stores the new
+// parameter values straight into every rank's parameter buffer -- reduce-scatter, optimiser and
+// all-gather in one kernel, 2/world of the all-reduce traffic per link direction, 1/world of the
+// Adam work.  The caller brackets it with cross-rank barriers.
+constexpr int DP_MAX_WORLD = 16;
+struct DpArgs {
+  const float* grads[DP_MAX_WORLD];
+  float* params[DP_MAX_WORLD];
+  int world, rank;
+  float* m;
+  float* v;
+  int64_t lo, hi;    // multiples of 4 (except hi == n)
+  const int64_t* seg_end;
+  const float* seg_lr;
+  int n_seg;
+  double beta1, beta2;
+  float eps, wd, gscale;
+  const int64_t* step_count;
+};
+__global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double step = (double)(*a.step_count + 1);
+    s_bc[0] = (float)(1.0 - pow(a.beta1, step));
+    s_bc[1] = (float)sqrt(1.0 - pow(a.beta2, step));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2s = s_bc[1];
+  const float beta2 = (float)a.beta2;
+  const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+  auto lr_of = [&](int64_t i) {
+    float lr = a.seg_lr[a.n_seg - 1];
+    for (int s = 0; s < a.n_seg; ++s)
+      if (i < a.seg_end[s]) {
+        lr = a.seg_lr[s];
+        break;
+      }
+    return lr;
+  };
+  auto upd = [&](float pv, float gv, float& mi, float& vi, float lr) {
+    const float gr = fmaf(a.wd, pv, gv * a.gscale);
+    mi = mi + (gr - mi) * omb1;
+    vi = vi * beta2 + omb2 * (gr * gr);
+    const float denom = sqrtf(vi) / bc2s + a.eps;
+    return pv - (lr / bc1) * (mi / denom);
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (a.hi - a.lo) / 4;
+  for (int64_t q = tid; q < n4; q += nth) {
+    const int64_t i = a.lo + 4 * q;
+    float4 gq[DP_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r)
+      if (r < a.world) gq[r] = *reinterpret_cast<const float4*>(a.grads[r] + i);   // peer loads, all in flight
+    float4 g = gq[0];
+#pragma unroll
+    for (int r = 1; r < DP_MAX_WORLD; ++r)
+      if (r < a.world) {
+        g.x += gq[r].x; g.y += gq[r].y; g.z += gq[r].z; g.w += gq[r].w;
+      }
+    float4 pv = *reinterpret_cast<const float4*>(a.params[a.rank] + i);
+    float4 mv = *reinterpret_cast<float4*>(a.m + i);
+    float4 vv = *reinterpret_cast<float4*>(a.v + i);
+    pv.x = upd(pv.x, g.x, mv.x, vv.x, lr_of(i + 0));
+    pv.y = upd(pv.y, g.y, mv.y, vv.y, lr_of(i + 1));
+    pv.z = upd(pv.z, g.z, mv.z, vv.z, lr_of(i + 2));
+    pv.w = upd(pv.w, g.w, mv.w, vv.w, lr_of(i + 3));
+    *reinterpret_cast<float4*>(a.m + i) = mv;
+    *reinterpret_cast<float4*>(a.v + i) = vv;
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r)
+      if (r < a.world) *reinterpret_cast<float4*>(a.params[r] + i) = pv;          // peer stores
+  }
+  for (int64_t i = a.lo + 4 * n4 + tid; i < a.hi; i += nth) {   // tail of the last rank's slice
+    float g = 0.f;
+    for (int r = 0; r < a.world; ++r) g += a.grads[r][i];
+    float mi = a.m[i], vi = a.v[i];
+    const float pn = upd(a.params[a.rank][i], g, mi, vi, lr_of(i));
+    a.m[i] = mi;
+    a.v[i] = vi;
+    for (int r = 0; r < a.world; ++r) a.params[r][i] = pn;
+  }
+}
+
 }  // namespace bigcn
 
 using namespace bigcn;
@@ -213,6 +304,48 @@ extern "C" int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, in
   BIGCN_CHECK_ARG(B_global > 0, "nll_loss: B_global must be positive");
   k_nll<<<1, 256, 0, (cudaStream_t)stream>>>(logp, y, B, (int)C, 1.0f / (float)B_global, loss, grad_logp);
   BIGCN_CHECK_LAUNCH("k_nll");
+  return 0;
+}
+
+extern "C" int bigcn_dp_slice(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi) {
+  BIGCN_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && lo && hi, "dp_slice: bad arguments");
+  const int64_t chunk = ceil_div(ceil_div(n, 4), world) * 4;
+  *lo = chunk * rank < n ? chunk * rank : n;
+  *hi = *lo + chunk < n ? *lo + chunk : n;
+  return 0;
+}
+
+extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* params, int32_t world, int32_t rank,
+                                    float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
+                                    const float* seg_lr, int32_t n_seg, double beta1, double beta2, double eps,
+                                    double weight_decay, double grad_scale, int64_t* step_count,
+                                    bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(grads && params && world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world,
+                  "dp_reduce_adam: world must be 1..%d", DP_MAX_WORLD);
+  BIGCN_CHECK_ARG(n_seg >= 1, "dp_reduce_adam: need at least one lr segment");
+  cudaStream_t st = (cudaStream_t)stream;
+  DpArgs a{};
+  for (int r = 0; r < world; ++r) {
+    BIGCN_CHECK_ARG(grads[r] && params[r], "dp_reduce_adam: NULL peer buffer");
+    BIGCN_CHECK_ARG(((reinterpret_cast<uintptr_t>(grads[r]) | reinterpret_cast<uintptr_t>(params[r])) & 15) == 0,
+                    "dp_reduce_adam: peer buffers must be 16 B aligned");
+    a.grads[r] = grads[r];
+    a.params[r] = params[r];
+  }
+  a.world = world; a.rank = rank; a.m = exp_avg; a.v = exp_avg_sq;
+  bigcn_dp_slice(n, world, rank, &a.lo, &a.hi);
+  a.seg_end = seg_end; a.seg_lr = seg_lr; a.n_seg = n_seg;
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = (float)eps; a.wd = (float)weight_decay; a.gscale = (float)grad_scale;
+  a.step_count = step_count;
+  if (a.hi > a.lo) {
+    int blocks = (int)ceil_div((a.hi - a.lo + 3) / 4, 256);
+    const int cap = num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    k_dp_reduce_adam<<<blocks, 256, 0, st>>>(a);
+    BIGCN_CHECK_LAUNCH("k_dp_reduce_adam");
+  }
+  k_step_inc<<<1, 1, 0, st>>>(step_count);
+  BIGCN_CHECK_LAUNCH("k_step_inc");
   return 0;
 }
 

@@ -33,12 +33,18 @@ class FusedTrainer:
     """Adam(lr, weight_decay) with BU conv1/conv2 at lr/5 over a flat parameter buffer."""
 
     def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=1, validate=False):
+                 process_group=None, world_size=1, validate=False, comm="auto"):
+        """``comm`` (world_size > 1): "symm" = one fused kernel over NVLink peer memory
+        (reduce-scatter of the gradients in rank order + Adam on the owned shard + all-gather of
+        the parameters, bigcn_dp_reduce_adam) between two symmetric-memory barriers; "nccl" = two
+        bucketed NCCL all-reduces overlapping the last backward kernels + Adam on every rank;
+        "auto" = symm when the symmetric-memory rendezvous succeeds, else nccl."""
         L.require_device()
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg, self.world = process_group, world_size
         self.validate = validate
+        self.comm, self.comm_note = "single", ""
         named = dict(model.named_parameters())
         dev = named[_ORDER[0]].device
         if dev.type != "cuda":
@@ -48,8 +54,20 @@ class FusedTrainer:
         for s in sizes:
             offs.append(offs[-1] + (s + 3) // 4 * 4)   # keep every tensor 16 B aligned
         self.n = offs[-1]
-        self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat = self.grad = None
+        if world_size > 1:
+            self.comm = "nccl"
+            if comm in ("auto", "symm"):
+                try:
+                    self._setup_symm(dev)
+                    self.comm = "symm"
+                except Exception as e:  # noqa: BLE001
+                    if comm == "symm":
+                        raise
+                    self.comm_note = f"symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-reduce"
+        if self.flat is None:
+            self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.views, self.gviews = {}, {}
@@ -61,6 +79,8 @@ class FusedTrainer:
                 p.data = v                         # the module now reads the flat buffer
                 self.views[name] = v
                 self.gviews[name] = self.grad[o:o + s].view(p.shape)
+        if self.world > 1:                         # identical start on every rank
+            torch.distributed.broadcast(self.flat, src=0, group=self.pg)
         # lr groups: TD convs + fc at lr, BU convs at lr/5  (BiGCN_Twitter.py:146-153)
         self.seg_end = torch.tensor(offs[1:], dtype=torch.int64, device=dev)
         self.seg_lr = torch.tensor([lr / d for d in _LR_DIV], dtype=torch.float32, device=dev)
@@ -77,6 +97,29 @@ class FusedTrainer:
         self.launches_per_step = None
 
     # -------------------------------------------------------------------------------
+    def _setup_symm(self, dev):
+        """Flat parameter / gradient buffers in symmetric memory: every rank's buffers mapped into
+        every process over NVLink (torch.distributed._symmetric_memory: allocation, rendezvous and
+        the cross-rank barrier; the data path is this library's kernel)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001  (not needed / deprecated on recent torch)
+            pass
+        flat = symm.empty(self.n, dtype=torch.float32, device=dev)
+        grad = symm.empty(self.n, dtype=torch.float32, device=dev)
+        hf, hg = symm.rendezvous(flat, group), symm.rendezvous(grad, group)
+        if hf.world_size != self.world or len(hg.buffer_ptrs) != self.world:
+            raise RuntimeError("symmetric memory world size mismatch")
+        flat.zero_()
+        grad.zero_()
+        self.flat, self.grad, self._hf, self._hg = flat, grad, hf, hg
+        self._rank = hf.rank
+        self._pptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in hg.buffer_ptrs])
+
     def _workspace(self, dims, dev):
         need = lib().bigcn_features_workspace_bytes(C.byref(dims))
         if self._ws is None or self._ws.numel() < need:
@@ -116,6 +159,19 @@ class FusedTrainer:
         scr = torch.empty(nscr, dtype=torch.float32, device=dev)
         check(l.bigcn_head_backward(_p(glogp), _p(logp), _p(feat), b, c, self._pr.fc_w, _p(gfeat),
                                     self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_backward")
+        if self.comm == "symm":
+            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+            self._hg.barrier(channel=0)        # every rank's gradient is complete
+            check(l.bigcn_dp_reduce_adam(self._gptrs, self._pptrs, self.world, self._rank, _p(self.exp_avg),
+                                         _p(self.exp_avg_sq), self.n, _p(self.seg_end), _p(self.seg_lr), self.n_seg,
+                                         self.betas[0], self.betas[1], self.eps, self.wd, 1.0, _p(self.step_count),
+                                         st), "dp_reduce_adam")
+            self._hf.barrier(channel=1)        # every rank's parameters are written; gradients are free again
+            self.last_logp = logp
+            if self.validate:
+                raise_on_flags(self.flags)
+            return loss
         if self.world > 1:
             # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
             o.bwd_phase = 1

@@ -463,6 +463,47 @@ def test_single_direction_modules(dev):
         compare_grads(m, ref)
 
 
+def test_dp_reduce_adam_two_ranks_emulated_on_one_device(dev):
+    """bigcn_dp_reduce_adam (reduce-scatter in rank order + Adam on the owned shard + parameter
+    all-gather through peer pointers) with both ranks' buffers on this device: after each rank
+    ran its slice, both parameter copies equal torch.optim.Adam on the summed gradient."""
+    import ctypes as C
+    from bigcn_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(11)
+    n, world = 10007, 3                      # n not a multiple of 4: the last slice has a scalar tail
+    p0 = torch.randn(n)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-4)
+    params = [p0.clone().to(dev) for _ in range(world)]
+    ms = [torch.zeros(n, device=dev) for _ in range(world)]
+    vs = [torch.zeros(n, device=dev) for _ in range(world)]
+    steps = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    seg_end = torch.tensor([n], dtype=torch.int64, device=dev)
+    seg_lr = torch.tensor([1e-3], dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for it in range(3):
+        grads = [torch.randn(n) for _ in range(world)]
+        ref.grad = sum(g.double() for g in grads).float()
+        opt.step()
+        gd = [g.to(dev) for g in grads]
+        gp = (C.c_void_p * world)(*[g.data_ptr() for g in gd])
+        pp = (C.c_void_p * world)(*[p.data_ptr() for p in params])
+        for r in range(world):
+            L.check(lib.bigcn_dp_reduce_adam(gp, pp, world, r, ms[r].data_ptr(), vs[r].data_ptr(), n,
+                                             seg_end.data_ptr(), seg_lr.data_ptr(), 1, 0.9, 0.999, 1e-8, 1e-4, 1.0,
+                                             steps[r].data_ptr(), st))
+        for r in range(1, world):
+            assert torch.equal(params[r], params[0])           # every copy got the owner's value
+        assert rel_err(params[0], ref.data) < 2e-6
+    lo, hi = C.c_int64(), C.c_int64()
+    cover = []
+    for r in range(world):
+        lib.bigcn_dp_slice(n, world, r, C.byref(lo), C.byref(hi))
+        cover.append((lo.value, hi.value))
+    assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
 def test_determinism_run_to_run(dev):
     b = make_batch("twitter15", 10, seed=8, train=True, in_feats=300)
     _, m = make_pair(300, 4, dev, seed=6)
