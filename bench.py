@@ -182,7 +182,7 @@ def run_ours(args):
     import torch
     import bigcn_b200
     from bigcn_b200 import _lib as L, ops
-    from bigcn_b200.data import make_batch, Batch
+    from bigcn_b200.data import make_batch, make_batch_shard, Batch
     from bigcn_b200.trainer import launches_per_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,8 +197,12 @@ def run_ours(args):
         pg = dist.group.WORLD
     L.require_device()
 
-    # ---- data: N_ROTATE distinct batches per rank, pinned on the host and resident in HBM
-    host = [make_batch(SHAPE, TREES_PER_GPU, seed=1000 * rank + i, train=True).pin_memory() for i in range(N_ROTATE)]
+    # ---- data: N_ROTATE distinct GLOBAL batches of 128 trees per GPU; every rank builds its
+    # contiguous, node-balanced range of trees, pinned on the host and resident in HBM
+    shards = [make_batch_shard(SHAPE, TREES_PER_GPU * world, seed=1000 + i, rank=rank, world=world, train=True)
+              for i in range(N_ROTATE)]
+    host = [sh[0].pin_memory() for sh in shards]
+    id_base = [sh[1] for sh in shards]
     resident = [Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys}) for b in host]
     nodes = [int(b.x.shape[0]) for b in host]
     h2d_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in Batch._tensor_keys)
@@ -227,18 +231,29 @@ def run_ours(args):
 
     # ---- device-resident timing ------------------------------------------------------
     for i in range(args.warmup):
-        tr.step(resident[i % N_ROTATE], b_global=b_global)
+        tr.step(resident[i % N_ROTATE], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
     tr.check_inputs()
     barrier()
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
+        t_cpu0 = time.perf_counter()
         e0.record()
         for i in range(args.steps):
-            loss = tr.step(resident[i % N_ROTATE], b_global=b_global)
+            loss = tr.step(resident[i % N_ROTATE], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
         e1.record()
+        cpu_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / args.steps
         barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    my_ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(my_ms)
+    per_rank = [my_ms / args.steps]
+    per_rank_cpu = [cpu_enqueue_ms]
+    if world > 1:
+        t = torch.tensor([my_ms / args.steps, cpu_enqueue_ms], dtype=torch.float64, device=dev)
+        g = [torch.empty_like(t) for _ in range(world)]
+        torch.distributed.all_gather(g, t)
+        per_rank = [float(x[0]) for x in g]
+        per_rank_cpu = [float(x[1]) for x in g]
     value = TREES_PER_GPU * world * args.steps / (ms * 1e-3)
     final_loss = float(loss.item())
 
@@ -268,7 +283,7 @@ def run_ours(args):
         if not isinstance(dst.x, torch.Tensor) or dst.x.shape != src.x.shape:
             dst.x = torch.empty_like(src.x, device=dev)
         dst.x.copy_(src.x, non_blocking=True)
-        return float(tr.step(dst, b_global=b_global).item())      # device -> host read of the step's result
+        return float(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]).item())   # device -> host read of the step's result
 
     host_csr = [None, None]
     cap = max(nodes) * 48
@@ -290,7 +305,7 @@ def run_ours(args):
                                                        n_threads=host_threads)   # threaded pass over the dense host x
         copy_small(src, dst)
         dst.x = ship_csr(host_csr[i % 2], i % 2)
-        return float(tr.step(dst, b_global=b_global).item())
+        return float(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]).item())
 
     host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     loader_csr = [bigcn_b200.host_dense_to_csr(b.x, cap=cap) for b in host] if sparse_ok else None
@@ -299,7 +314,7 @@ def run_ours(args):
         src, dst = host[i % N_ROTATE], stage[i % 2]
         copy_small(src, dst)
         dst.x = ship_csr(loader_csr[i % N_ROTATE], i % 2)
-        return float(tr.step(dst, b_global=b_global).item())
+        return float(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]).item())
 
     def time_e2e(fn):
         for i in range(max(1, min(args.warmup, 3))):
@@ -439,6 +454,7 @@ def run_ours(args):
             "config": {"workload": f"{SHAPE}-shaped BiGCN training step (graph prep+fwd+nll+bwd+Adam), "
                                    f"{TREES_PER_GPU} trees/GPU, K={K_FEATS}, C={N_CLASSES}, DropEdge 0.2/0.2, dropout 0.5",
                        "trees_per_gpu": TREES_PER_GPU, "nodes_per_batch": nodes, "gemm_mode": args.gemm_mode,
+                       "sharding": "global batch of 128 trees per GPU, contiguous tree ranges balanced by node count",
                        "l2": f"{N_ROTATE} batches in rotation, {nodes[0] * K_FEATS * 4 / 1e6:.0f} MB of features each (> 126 MB L2)",
                        "parallelism": (f"dp{world} (trees sharded; " + (
                            "gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory"
@@ -451,8 +467,11 @@ def run_ours(args):
                             "dense_h2d = the matrix crosses PCIe as is, host_compact = host_dense_to_csr keeps the "
                             "non-zeros on the host and the CSR crosses PCIe; the faster one is reported",
                     "routes": {k: v for k, v in routes.items() if k != "sparse_loader"}},
-            "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode),
-            "roofline": roof, "final_loss": final_loss}
+            "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode, K_FEATS),
+            "roofline": roof, "final_loss": final_loss,
+            "per_rank": {"gpu_ms_per_step": [round(v, 4) for v in per_rank],
+                         "cpu_enqueue_ms_per_step": [round(v, 4) for v in per_rank_cpu],
+                         "nodes_per_step_mean": sum(nodes) / len(nodes)}}
     if "sparse_loader" in routes:
         line["e2e_sparse_loader"] = dict(routes["sparse_loader"], unit="trees/s", d2h_bytes_per_step=4,
                                          note="data.x already CSR on the host (a loader that keeps the reference's "

@@ -34,7 +34,7 @@ int num_sms() {
 struct SideCtx {
   SideStream s;        // high priority: work the main stream will wait for soon (graph prep)
   cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
-  cudaEvent_t ev[4];
+  cudaEvent_t ev[8];
   bool ok;
 };
 static SideCtx* side_ctx() {
@@ -49,7 +49,7 @@ static SideCtx* side_ctx() {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess;
-    for (int i = 0; i < 4 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 8 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
     if (e && e[0] == '1') c.ok = false;
   }
@@ -59,6 +59,18 @@ static SideCtx* side_ctx() {
 static void stream_after(SideCtx* c, int ev, cudaStream_t from, cudaStream_t to) {
   cudaEventRecord(c->ev[ev], from);
   cudaStreamWaitEvent(to, c->ev[ev], 0);
+}
+
+// for the other translation units (head.cu): run something beside the caller's stream
+cudaStream_t side_fork(cudaStream_t main_st) {
+  SideCtx* c = side_ctx();
+  if (!c) return main_st;
+  stream_after(c, 4, main_st, c->s.side);
+  return c->s.side;
+}
+void side_join(cudaStream_t main_st) {   // main waits for everything queued on the side stream
+  SideCtx* c = side_ctx();
+  if (c) stream_after(c, 5, c->s.side, main_st);
 }
 
 // w[0..n_w): PyG [64, K] weights (row pitch ldw).  scratch: 2 * 64 * n_w * K floats -- the
@@ -97,7 +109,8 @@ struct FeatWs {
   float* dw_part;           // dW1 slab partials
   float* dP[2];             // [B][64]
   int32_t* slot;            // [B][K] slot of column k in tree b's root list, or -1
-  int32_t* overflow;        // [1] some root row has more than DW2B_CAP positive columns
+  int32_t* overflow;        // [0] some root row has more than DW2B_CAP positive columns; [1 + k] column k is
+                            // positive in some root row
   float* pos[2];            // [B][64] #{i in tree : H2[i][f] > 0}
   float* gs[2];             // [B][64] grad_feat / n_b
   float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
@@ -148,7 +161,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
   for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   w.slot = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
-  w.overflow = c.take<int32_t>(1);
+  w.overflow = c.take<int32_t>(1 + K);
   for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
@@ -341,6 +354,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   // bwd_phase: 0 = everything, 1 = all but dW1, 2 = dW1 only (lets the caller all-reduce the
   // other gradients while the second X stream runs)
   const int phase = o->bwd_phase;
+  ColsumArgs db2_reduce{};
   SideCtx* sc = side_ctx();
   cudaStream_t ss = sc ? sc->s.side : st;
   if (phase == 2) goto dw1_only;
@@ -356,7 +370,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       c.part[q] = w.cs_part[d]; c.out[q] = gdir_b2(gr, d);
     }
     if (int rc = gscale_launch(a, dirs.n, st)) return rc;
-    if (int rc = colsum_reduce_launch(c, dirs.n, st)) return rc;
+    db2_reduce = c;   // summed on the side stream (below)
   }
   // 2. T2 = A-hat^T G2 with G2 = [H2 > 0] * gs[batch] formed inside the gather
   {
@@ -369,8 +383,9 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_g2_launch(a, dirs.n, st)) return rc;
   }
-  // 3./4. on the side stream, beside the G1 -> T1 -> dW1 chain: dW2a = T2^T A1 and dW2b
+  // 3./4. on the side stream, beside the G1 -> T1 -> dW1 chain: db2, dW2a = T2^T A1 and dW2b
   if (sc) stream_after(sc, 0, st, ss);
+  if (int rc = colsum_reduce_launch(db2_reduce, dirs.n, ss)) return rc;
   {
     OuterArgs a{};
     OuterReduceArgs r{};
@@ -415,7 +430,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       c.part[q] = w.cs_part[d]; c.out[q] = gdir_b1(gr, d);
     }
     if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;
-    if (int rc = colsum_reduce_launch(c, dirs.n, st)) return rc;
+    if (sc) stream_after(sc, 2, st, ss);           // db1: ordered sum of the partials, beside T1
+    if (int rc = colsum_reduce_launch(c, dirs.n, ss)) return rc;
   }
   // 6. T1 = A-hat^T G1, both directions side by side in one [N][n_out] matrix
   {

@@ -1,7 +1,7 @@
 // Head (fc + log_softmax), nll loss and Adam: the small fp32 pieces around the path.
 // Replaces BiGCN_Twitter.py:129-130 (fc, log_softmax), :184 (F.nll_loss) and the
 // torch.optim.Adam step configured at :146-153.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace bigcn {
 
@@ -60,6 +60,70 @@ __global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__
   for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
 }
 
+// Training head in one launch: fc + log_softmax (:129-130), F.nll_loss's gradient (:184) and the
+// log_softmax / fc backward towards the features.  Warp per tree, lane c holds class c.
+//   logp = log_softmax(feat W^T + b);  g = -[c == y] / B_global;  dl = g - exp(logp) * sum(g)
+//   grad_feat = dl W;  lossvec[b] = -logp[b][y_b]   (summed in tree order by k_loss_sum)
+__global__ void __launch_bounds__(256) k_head_train(const float* __restrict__ feat, const int64_t* __restrict__ y,
+                                                    int64_t B, int C, float inv_bg, const float* __restrict__ W,
+                                                    const float* __restrict__ bias, float* __restrict__ logp,
+                                                    float* __restrict__ dl_out, float* __restrict__ gfeat,
+                                                    float* __restrict__ lossvec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float fv[FEAT / 32];
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) fv[j] = feat[b * FEAT + j * 32 + lane];
+  float mine = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    float p = 0.f;
+#pragma unroll
+    for (int j = 0; j < FEAT / 32; ++j) p = fmaf(fv[j], W[c * FEAT + j * 32 + lane], p);
+    p = warp_sum(p) + bias[c];
+    if (lane == c) mine = p;
+  }
+  float m = mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+  const float ex = lane < C ? expf(mine - m) : 0.f;
+  const float se = warp_sum(ex);
+  const float lp = (mine - m) - logf(se);
+  if (lane < C) logp[b * C + lane] = lp;
+  const int64_t t = y[b];
+  const bool hit = t >= 0 && t < C;
+  const float gv = (lane < C && hit && lane == (int)t) ? -inv_bg : 0.f;
+  const float sg = warp_sum(gv);
+  const float dl = lane < C ? gv - expf(lp) * sg : 0.f;
+  if (lane < C) dl_out[b * C + lane] = dl;
+  const float mylp = __shfl_sync(FULL_MASK, lp, hit ? (int)t : 0);
+  if (lane == 0) lossvec[b] = hit ? -mylp : 0.f;
+  float out[FEAT / 32];
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) out[j] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = __shfl_sync(FULL_MASK, dl, c);
+#pragma unroll
+    for (int j = 0; j < FEAT / 32; ++j) out[j] = fmaf(d, W[c * FEAT + j * 32 + lane], out[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
+}
+// loss = (1/Bg) * sum_b lossvec[b], same strided order as k_nll
+__global__ void __launch_bounds__(256) k_loss_sum(const float* __restrict__ lossvec, int64_t B, float inv_bg,
+                                                  float* __restrict__ loss) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += 256) acc += lossvec[b];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0] * inv_bg;
+}
+
 // dW[c][f] = sum_b dl[b][c] feat[b][f] (+ bias column f == 256): thread per (c, f), a chunk
 // of HB_TREES trees per blockIdx.y, trees in order; chunks are summed in order by k_head_bwd_red.
 constexpr int HB_TREES = 32;
@@ -109,10 +173,10 @@ __global__ void __launch_bounds__(256) k_nll(const float* __restrict__ logp,
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, int64_t n, const int64_t* __restrict__ seg_end,
                        const float* __restrict__ seg_lr, int n_seg, double beta1d, double beta2d,
-                       float eps, float wd, float gscale, const int64_t* step_count) {
+                       float eps, float wd, float gscale, int64_t* step_count) {
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {   // the double-precision pow() runs once per block, not per thread
-    const double step = (double)(*step_count + 1);
+    const double step = (double)(*(volatile int64_t*)step_count + 1);
     s_bc[0] = (float)(1.0 - pow(beta1d, step));
     s_bc[1] = (float)sqrt(1.0 - pow(beta2d, step));
   }
@@ -161,6 +225,17 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     m[i] = mi;
     v[i] = vi;
   }
+  // the last block to finish advances the step (every block read it at its start) and resets
+  // the arrival counter kept in step_count[1]
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* arrive = reinterpret_cast<unsigned long long*>(step_count + 1);
+    __threadfence();
+    if (atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1) {
+      *arrive = 0ull;
+      *step_count += 1;
+    }
+  }
 }
 __global__ void k_step_inc(int64_t* step_count) { *step_count += 1; }
 
@@ -187,12 +262,12 @@ struct DpArgs {
   int n_seg;
   double beta1, beta2;
   float eps, wd, gscale;
-  const int64_t* step_count;
+  int64_t* step_count;
 };
 __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {
-    const double step = (double)(*a.step_count + 1);
+    const double step = (double)(*(volatile int64_t*)a.step_count + 1);
     s_bc[0] = (float)(1.0 - pow(a.beta1, step));
     s_bc[1] = (float)sqrt(1.0 - pow(a.beta2, step));
   }
@@ -253,6 +328,15 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     a.v[i] = vi;
     for (int r = 0; r < a.world; ++r) a.params[r][i] = pn;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // last block: advance the step, reset the arrival counter (step_count[1])
+    unsigned long long* arrive = reinterpret_cast<unsigned long long*>(a.step_count + 1);
+    __threadfence();
+    if (atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1) {
+      *arrive = 0ull;
+      *a.step_count += 1;
+    }
+  }
 }
 
 }  // namespace bigcn
@@ -298,6 +382,44 @@ extern "C" int bigcn_head_backward(const float* grad_logp, const float* logp, co
   return 0;
 }
 
+extern "C" size_t bigcn_head_train_scratch_floats(int64_t B, int64_t C) {
+  return bigcn_head_backward_scratch_floats(B, C) + (size_t)(B > 0 ? B : 1);
+}
+
+// fc + log_softmax + nll_loss and their backward in one call (the training step's head):
+// one launch on the caller's stream for what the features' backward waits for (grad_feat); the
+// fc gradients and the loss scalar are formed on the side stream and joined by the next
+// bigcn_features_backward / bigcn_adam_step / bigcn_dp_reduce_adam on this stream.
+extern "C" int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
+                                const float* fc_w, const float* fc_b, float* logp, float* loss, float* grad_feat,
+                                float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
+                                bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(C >= 1 && C <= 32, "head_train: C must be in [1,32]");
+  BIGCN_CHECK_ARG(B_global > 0, "head_train: B_global must be positive");
+  BIGCN_CHECK_ARG(feat && y && fc_w && fc_b && logp && loss && grad_feat && d_fc_w && d_fc_b, "head_train: NULL argument");
+  BIGCN_CHECK_ARG(scratch && scratch_floats >= bigcn_head_train_scratch_floats(B, C), "head_train: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dl = scratch;
+  float* part = scratch + B * C;
+  const int nchunk = B > 0 ? (int)ceil_div(B, HB_TREES) : 1;
+  float* lossvec = part + (size_t)nchunk * C * (FEAT + 1);
+  const float inv_bg = 1.0f / (float)B_global;
+  if (B > 0) {
+    k_head_train<<<(int)ceil_div(B, 8), 256, 0, st>>>(feat, y, B, (int)C, inv_bg, fc_w, fc_b, logp, dl, grad_feat,
+                                                      lossvec);
+    BIGCN_CHECK_LAUNCH("k_head_train");
+  }
+  cudaStream_t ss = side_fork(st);
+  const int tot = (int)C * (FEAT + 1);
+  k_head_bwd_w<<<dim3((tot + 127) / 128, nchunk), 128, 0, ss>>>(dl, feat, B, (int)C, part);
+  BIGCN_CHECK_LAUNCH("k_head_bwd_w");
+  k_head_bwd_red<<<(tot + 127) / 128, 128, 0, ss>>>(part, nchunk, (int)C, d_fc_w, d_fc_b);
+  BIGCN_CHECK_LAUNCH("k_head_bwd_red");
+  k_loss_sum<<<1, 256, 0, ss>>>(lossvec, B, inv_bg, loss);
+  BIGCN_CHECK_LAUNCH("k_loss_sum");
+  return 0;
+}
+
 extern "C" int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C,
                               int64_t B_global, float* loss, float* grad_logp,
                               bigcn_stream_t stream) {
@@ -324,6 +446,7 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
                   "dp_reduce_adam: world must be 1..%d", DP_MAX_WORLD);
   BIGCN_CHECK_ARG(n_seg >= 1, "dp_reduce_adam: need at least one lr segment");
   cudaStream_t st = (cudaStream_t)stream;
+  side_join(st);   // fc gradients / loss of bigcn_head_train
   DpArgs a{};
   for (int r = 0; r < world; ++r) {
     BIGCN_CHECK_ARG(grads[r] && params[r], "dp_reduce_adam: NULL peer buffer");
@@ -343,9 +466,10 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
     if (blocks > cap) blocks = cap;
     k_dp_reduce_adam<<<blocks, 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_dp_reduce_adam");
+  } else {
+    k_step_inc<<<1, 1, 0, st>>>(step_count);
+    BIGCN_CHECK_LAUNCH("k_step_inc");
   }
-  k_step_inc<<<1, 1, 0, st>>>(step_count);
-  BIGCN_CHECK_LAUNCH("k_step_inc");
   return 0;
 }
 
@@ -355,6 +479,7 @@ extern "C" int bigcn_adam_step(float* param, const float* grad, float* exp_avg, 
                                double grad_scale, int64_t* step_count, bigcn_stream_t stream) {
   BIGCN_CHECK_ARG(n_seg >= 1, "adam_step: need at least one lr segment");
   cudaStream_t st = (cudaStream_t)stream;
+  side_join(st);   // fc gradients / loss of bigcn_head_train
   if (n > 0) {
     int blocks = (int)ceil_div(n, 256);
     const int cap = num_sms() * 8;
@@ -362,8 +487,9 @@ extern "C" int bigcn_adam_step(float* param, const float* grad, float* exp_avg, 
     k_adam<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, seg_end, seg_lr, n_seg, beta1,
                                    beta2, (float)eps, (float)weight_decay, (float)grad_scale, step_count);
     BIGCN_CHECK_LAUNCH("k_adam");
+  } else {
+    k_step_inc<<<1, 1, 0, st>>>(step_count);
+    BIGCN_CHECK_LAUNCH("k_step_inc");
   }
-  k_step_inc<<<1, 1, 0, st>>>(step_count);
-  BIGCN_CHECK_LAUNCH("k_step_inc");
   return 0;
 }

@@ -105,14 +105,12 @@ int dw_sparse(const XSparse& x, const float* t, int64_t ldt, int n_out, float* d
 int xw_fp32_capture(const float*, int64_t, int64_t, const float*, int, float*, int64_t, const XSparse&, cudaStream_t);
 int xw_csr(const XSparse& x, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st);
 
-// fork / join onto the library's side stream (independent short kernels run beside the X stream)
+// fork / join onto the library's side stream (independent short kernels run beside the main chain)
 struct SideStream {
   cudaStream_t side;
-  cudaEvent_t fork_ev, join_ev;
 };
-SideStream* side_stream();
-int side_fork(cudaStream_t main_st, SideStream** out);   // side waits for everything queued on main so far
-int side_join(cudaStream_t main_st, SideStream* s);      // main waits for everything queued on side
+cudaStream_t side_fork(cudaStream_t main_st);   // the side stream, ordered after everything queued on main so far
+void side_join(cudaStream_t main_st);           // main waits for everything queued on the side stream
 
 
 }  // namespace bigcn

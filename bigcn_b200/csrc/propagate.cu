@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
     if (v > 0.f) {
       a.col[b * a.K + pos] = (int32_t)k;
       a.val[b * a.K + pos] = v;
+      a.overflow[1 + k] = 1;   // column k is positive in some root row (same value from every writer)
     }
     if (k < a.K) a.slot[b * a.K + k] = v > 0.f ? pos : -1;
   }
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) k_root_nz_csr(RootNzArgs a, const int32_t
       a.col[b * a.K + pos] = k;
       a.val[b * a.K + pos] = v;
       a.slot[b * a.K + k] = pos;
+      a.overflow[1 + k] = 1;
     }
     n += __popc(m);
   }
@@ -575,20 +577,27 @@ __global__ void __launch_bounds__(256) k_outer64(OuterArgs a) {
     *reinterpret_cast<float4*>(out + (ty * 4 + i) * H + tx * 4) =
         make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
-// dst[o*ld + k] = sum_chunk part[chunk][o*64 + k]
-__global__ void k_outer_reduce(OuterReduceArgs a) {
+// dst[o*ld + k] = sum_chunk part[chunk][o*64 + k]: CTA = 64 outputs x 4 chains (chain g takes
+// the chunks c = g mod 4 in order, 8 loads in flight), combined as (s0 + s1) + (s2 + s3)
+__global__ void __launch_bounds__(256) k_outer_reduce(OuterReduceArgs a) {
+  __shared__ float red[4][64];
   const int d = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 0..4095
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains, fixed combine order
-  int c = 0;
-  for (; c + 4 <= a.nchunk; c += 4) {
-    s0 += a.part[d][(int64_t)(c + 0) * H * H + idx];
-    s1 += a.part[d][(int64_t)(c + 1) * H * H + idx];
-    s2 += a.part[d][(int64_t)(c + 2) * H * H + idx];
-    s3 += a.part[d][(int64_t)(c + 3) * H * H + idx];
+  const int g = threadIdx.x >> 6, l = threadIdx.x & 63;
+  const int idx = blockIdx.x * 64 + l;  // 0..4095
+  const float* __restrict__ p = a.part[d] + idx;
+  float s = 0.f;
+  int c = g;
+  for (; c + 28 < a.nchunk; c += 32) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(c + 4 * u) * H * H];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
   }
-  for (; c < a.nchunk; ++c) s0 += a.part[d][(int64_t)c * H * H + idx];
-  a.dst[d][(int64_t)(idx >> 6) * a.ld + (idx & 63)] = (s0 + s1) + (s2 + s3);
+  for (; c < a.nchunk; c += 4) s += p[(int64_t)c * H * H];
+  red[g][l] = s;
+  __syncthreads();
+  if (g == 0) a.dst[d][(int64_t)(idx >> 6) * a.ld + (idx & 63)] = (red[0][l] + red[1][l]) + (red[2][l] + red[3][l]);
 }
 
 // per-tree segment sum: dP[d][b][f] = sum_{i in b} T2_d[i][f]   (eval-mode dW2b)
@@ -747,7 +756,8 @@ __global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
   const int cg = w >> 2, g = w & 3;
   const int64_t k = (int64_t)blockIdx.x * 2 + cg;
   float2 acc = make_float2(0.f, 0.f);
-  if (k < a.K) {
+  // most columns are positive in no root row of the batch: nothing to look up for them
+  if (k < a.K && a.overflow[1 + k] != 0) {
     for (int64_t b0 = (int64_t)g * 32; b0 < a.B; b0 += 128) {
       const int64_t b = b0 + lane;
       const int t = b < a.B ? a.slot[b * a.K + k] : -1;
@@ -819,14 +829,14 @@ __global__ void k_dropout_mask(DropSpec ds, int64_t node_id_base, int64_t N, int
 // ---------------------------------------------------------------- host-side launchers
 int root_nz_csr_launch(const RootNzArgs& a, const int32_t* xptr, const int32_t* xcol, const float* xval,
                        cudaStream_t st) {
-  cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st);
+  cudaMemsetAsync(a.overflow, 0, (size_t)(1 + a.K) * sizeof(int32_t), st);
   if (a.B == 0) return 0;
   k_root_nz_csr<<<(int)a.B, 256, 0, st>>>(a, xptr, xcol, xval);
   BIGCN_CHECK_LAUNCH("k_root_nz_csr");
   return 0;
 }
 int root_nz_launch(const RootNzArgs& a, cudaStream_t st) {
-  cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st);
+  cudaMemsetAsync(a.overflow, 0, (size_t)(1 + a.K) * sizeof(int32_t), st);
   if (a.B == 0) return 0;
   const size_t smem = (size_t)((a.K + 31) / 32) * sizeof(int);
   BIGCN_CHECK_ARG(smem <= 48 * 1024, "root_nz: in_feats too large (%lld)", (long long)a.K);
@@ -912,7 +922,7 @@ int outer64_launch(const OuterArgs& a, const OuterReduceArgs& r, int ndir, cudaS
     k_outer64<<<dim3(op_chunks(a.N), ndir), 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_outer64");
   }
-  k_outer_reduce<<<dim3(H * H / 256, ndir), 256, 0, st>>>(r);
+  k_outer_reduce<<<dim3(H * H / 64, ndir), 256, 0, st>>>(r);
   BIGCN_CHECK_LAUNCH("k_outer_reduce");
   return 0;
 }

@@ -203,6 +203,27 @@ def make_batch(shape: str, n_trees: int, seed: int = 0, train: bool = True,
     return collate(trees)
 
 
+def make_batch_shard(shape: str, n_trees_global: int, seed: int, rank: int = 0, world: int = 1,
+                     train: bool = True, in_feats: int | None = None, num_classes: int | None = None):
+    """Rank `rank`'s share of a GLOBAL batch of n_trees_global trees: tree sizes
+    come from one generator every rank replays, trees are assigned as contiguous ranges balanced
+    by NODE count (dist.shard_trees) and each tree is generated from its own (seed, tree index)
+    stream, so any rank can build any tree and the global batch does not depend on the world
+    size.  Returns (Batch, node_id_base, (lo, hi))."""
+    from .dist import shard_trees, node_id_base
+    sizes = tree_sizes(shape, n_trees_global, np.random.default_rng(seed))
+    lo, hi = shard_trees(sizes, world)[rank]
+    rate = SHAPES[shape]["droprate"] if train else 0.0
+    trees = []
+    for t in range(lo, hi):
+        rng = np.random.default_rng([seed, t])
+        tr = make_tree(shape, int(sizes[t]), rng, in_feats, num_classes)
+        if rate > 0:
+            tr = drop_edge(tr, rate, rate, rng)
+        trees.append(tr)
+    return collate(trees), node_id_base(sizes, lo), (lo, hi)
+
+
 @dataclass
 class DeviceTrees:
     """Large synthetic forest built directly on the device (kernel micro-benchmarks

@@ -86,7 +86,7 @@ class FusedTrainer:
         self.seg_lr = torch.tensor([lr / d for d in _LR_DIV], dtype=torch.float32, device=dev)
         self.n_seg = len(_LR_DIV)
         self.w1_end = offs[2]                    # [0, w1_end) = the two conv1 weight gradients
-        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)   # [step, arrival counter]
         self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pr, self._gr = Params(), Params()
         for name in _ORDER:
@@ -146,19 +146,16 @@ class FusedTrainer:
         b = dims.B
         feat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
         logp = torch.empty(b, c, dtype=torch.float32, device=dev)
-        glogp = torch.empty(b, c, dtype=torch.float32, device=dev)
         gfeat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         st = _stream()
         l = lib()
         check(l.bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(feat),
                                        _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
-        check(l.bigcn_head_forward(_p(feat), b, c, self._pr.fc_w, self._pr.fc_b, _p(logp), st), "head_forward")
-        check(l.bigcn_nll_loss(_p(logp), _p(y), b, c, int(b_global or b), _p(loss), _p(glogp), st), "nll_loss")
-        nscr = l.bigcn_head_backward_scratch_floats(b, c)
+        nscr = l.bigcn_head_train_scratch_floats(b, c)
         scr = torch.empty(nscr, dtype=torch.float32, device=dev)
-        check(l.bigcn_head_backward(_p(glogp), _p(logp), _p(feat), b, c, self._pr.fc_w, _p(gfeat),
-                                    self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_backward")
+        check(l.bigcn_head_train(_p(feat), _p(y), b, c, int(b_global or b), self._pr.fc_w, self._pr.fc_b, _p(logp),
+                                 _p(loss), _p(gfeat), self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_train")
         if self.comm == "symm":
             check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                             C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
@@ -199,20 +196,33 @@ class FusedTrainer:
         raise_on_flags(self.flags)
 
 
-def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm_mode: str = "fp32") -> int:
+def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm_mode: str = "fp32",
+                      in_feats: int = 5000, comm: str = "single", sparse_input: bool = False) -> int:
     """How many kernels of this library one FusedTrainer.step enqueues (for bench.py's
-    gpu_launches claim); mirrors the launch sequence in csrc/api.cu + graph_prep.cu."""
-    bits = 1
-    while (1 << bits) <= n_nodes:
-        bits += 1
-    passes = (bits + 7) // 8
-    prep = 1 + 2 + 3 * passes + 1            # count, scan x2, radix passes, deg  (memset not counted)
+    gpu_launches claim); mirrors the launch sequence in csrc/api.cu, graph_prep.cu, xsparse.cu
+    (checked against the ncu launch list in profiles/)."""
+    def radix_passes(n):
+        bits = 1
+        while (1 << bits) <= n:
+            bits += 1
+        return (bits + 7) // 8
+    prep = 1 + 2 + 3 * radix_passes(n_nodes) + 1 + 1   # count, scan x2, radix passes, deg, hub lists
+    sparse = gemm_mode == "sparse"
     xw = 1 + (n_dirs if gemm_mode == "tf32x3" else 0)     # [W hi/lo split per direction], X*W
-    fwd = prep + 1 + xw + 1 + (0 if training else 1) + 1 + 1 + 1   # transposes, xw, root_nz, [proj], mix, prop2, readout
+    csc = 0
+    if sparse:      # row scan x2 + compaction (or CSR ingest), radix passes over the column keys, finish, hub columns
+        kbits = max(1, (in_feats - 1).bit_length())
+        csc = (1 if sparse_input else 3) + 3 * ((kbits + 7) // 8) + 2
+    # transposes, prep, root_nz, [root_proj], xw, [csc build], mix, prop2, readout x2
+    fwd = 1 + prep + 1 + (0 if training else 1) + xw + csc + 1 + 1 + 2
     head = 1 + 1 + 3                           # head fwd, nll, head bwd (feat, w partial, w reduce)
-    dw = 1 + (1 if gemm_mode in ("tf32x3", "mixed") else 0) + n_dirs   # [T hi/lo split], dW GEMM/scan, reduce x dirs
+    if sparse:
+        dw = 1                                 # sweep over the column-sorted non-zeros
+    else:
+        dw = 1 + (1 if gemm_mode in ("tf32x3", "mixed") else 0) + n_dirs   # [T hi/lo split], dW GEMM/scan, reduce x dirs
     # gscale+colsum, propT(g2), outer x2, [segsum | dw2b part], dw2b reduce + dense fallback,
     # bwdmix+colsum, propT, dW
     bwd = 2 + 1 + 2 + 1 + 2 + 2 + 1 + dw
-    adam = 2
+    head = 1 + 3                               # fused head (fwd + nll + grad_feat), then dW / db / loss sum
+    adam = 1                                   # Adam (or the fused peer-memory reduce + Adam) incl. the step counter
     return fwd + head + bwd + adam

@@ -275,12 +275,23 @@ int bigcn_head_backward(const float* grad_logp, const float* logp, const float* 
                         float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
                         bigcn_stream_t stream);
 
+/* The training step's head in one call: bigcn_head_forward + bigcn_nll_loss + bigcn_head_backward
+ * (same arithmetic).  One launch on `stream` produces logp and grad_feat; d_fc_w, d_fc_b and the
+ * loss scalar are finished on the library's side stream and are ordered before whatever
+ * bigcn_features_backward / bigcn_adam_step / bigcn_dp_reduce_adam later do on `stream`. */
+size_t bigcn_head_train_scratch_floats(int64_t B, int64_t C);
+int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
+                     const float* fc_w, const float* fc_b, float* logp, float* loss, float* grad_feat,
+                     float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
+                     bigcn_stream_t stream);
+
 /* ---- loss and optimiser (the step around the path, :184-189, :146-153) --
  * loss = -(1/B_global) sum_b logp[b,y[b]] (F.nll_loss, mean); grad_logp = dloss/dlogp. */
 int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
                    float* loss /*[1]*/, float* grad_logp /*[B,C] or NULL*/, bigcn_stream_t stream);
 /* torch.optim.Adam (coupled L2) over one flat buffer; lr_of_segment: n_seg pairs
- * (end_offset, lr) on the DEVICE; step_count: device int64, incremented here. */
+ * (end_offset, lr) on the DEVICE; step_count: device int64[2], zero-initialised by the caller:
+ * [0] the step, advanced here by the last block of the update kernel, [1] its arrival counter. */
 int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                     int64_t n, const int64_t* seg_end, const float* seg_lr, int32_t n_seg,
                     double beta1, double beta2, double eps, double weight_decay,

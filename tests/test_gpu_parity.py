@@ -478,7 +478,7 @@ def test_dp_reduce_adam_two_ranks_emulated_on_one_device(dev):
     params = [p0.clone().to(dev) for _ in range(world)]
     ms = [torch.zeros(n, device=dev) for _ in range(world)]
     vs = [torch.zeros(n, device=dev) for _ in range(world)]
-    steps = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    steps = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
     seg_end = torch.tensor([n], dtype=torch.int64, device=dev)
     seg_lr = torch.tensor([1e-3], dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -539,4 +539,4 @@ def test_fused_trainer_matches_reference_adam(dev):
         assert abs(float(loss.item()) - float(loss_ref)) < 1e-5 * max(1.0, abs(float(loss_ref)))
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         assert rel_err(p, q) < 2e-5, name
-    assert int(tr.step_count.item()) == 3
+    assert int(tr.step_count[0].item()) == 3
