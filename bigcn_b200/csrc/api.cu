@@ -355,6 +355,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   // other gradients while the second X stream runs)
   const int phase = o->bwd_phase;
   ColsumArgs db2_reduce{};
+  const bool join_late = o->gemm_mode == BIGCN_GEMM_SPARSE && phase == 0;
   SideCtx* sc = side_ctx();
   cudaStream_t ss = sc ? sc->s.side : st;
   if (phase == 2) goto dw1_only;
@@ -444,8 +445,9 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
-  // the dense dW1 paths reuse T2's buffer, which the side stream reads: join first
-  if (sc) stream_after(sc, 1, ss, st);
+  // the dense dW1 paths reuse T2's buffer, which the side stream reads: join first.  The sparse
+  // sweep touches none of the side stream's buffers and joins after it.
+  if (sc && !join_late) stream_after(sc, 1, ss, st);
   if (phase == 1) return 0;
 dw1_only:
   // 7. dW1 = T1^T X: a sweep over the column-sorted non-zeros (SPARSE) or one more pass over X
@@ -455,6 +457,7 @@ dw1_only:
     if (o->gemm_mode == BIGCN_GEMM_SPARSE) {
       if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);   // column-sorted X of the forward (no-op if none pending)
       if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
+      if (sc && join_late) stream_after(sc, 1, ss, st);
     } else if (o->gemm_mode == BIGCN_GEMM_FP32) {
       if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
     } else {   // G1 (w.z) and T2 (w.xw) are dead here: they hold the TF32 hi / lo split of T1
@@ -518,6 +521,14 @@ __global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ g
 
 using namespace bigcn;
 
+// tuning knobs for tools/stepbench.py (0 = the shipped configuration); not part of the documented ABI
+namespace bigcn {
+static int g_knob[16];
+int debug_knob(int key) { return key >= 0 && key < 16 ? g_knob[key] : 0; }
+}  // namespace bigcn
+extern "C" void bigcn_debug_set(int key, int value) {
+  if (key >= 0 && key < 16) bigcn::g_knob[key] = value;
+}
 extern "C" const char* bigcn_last_error(void) { return g_err; }
 // `stream` waits for everything the library still has in flight on its internal streams
 extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {

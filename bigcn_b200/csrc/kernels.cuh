@@ -97,6 +97,7 @@ struct XSparse {
   int32_t* clong[2];  // hub-column lists, one per 64-output half (each owns its partials / arrival counters)
   int32_t* flags;     // caller's violation word (BIGCN_FLAG_X_NOT_SPARSE)
 };
+int debug_knob(int key);
 int64_t xs_capacity(int64_t N, int64_t K);
 XSparse xs_carve(Carver& c, int64_t N, int64_t K);
 int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st);

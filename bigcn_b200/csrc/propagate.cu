@@ -15,7 +15,8 @@ namespace bigcn {
 // ---------------------------------------------------------------- A-hat / A-hat^T propagate
 // out = A-hat h (+ bias)(relu): the CSR sweep of gather.cuh with a bias / relu / store epilogue.
 constexpr int PROP_R = 8, PROP_Q = 8;     // 64 KB stage per CTA, 3 CTAs per SM
-constexpr int MIX_R = 4, MIX_Q = 8;       // 48 KB stage + 16 KB W2a per CTA, 3 CTAs per SM
+constexpr int MIX_R = 2, MIX_Q = 4;       // 24 KB stage + 16 KB W2a per CTA, 4 CTAs per SM (64 registers): the
+                                          // heavy per-row epilogue wants warps in flight more than a deep stage
 
 struct PostBiasRelu {
   const float* bias;
@@ -324,7 +325,8 @@ struct PostMix {
   }
 };
 
-__global__ void __launch_bounds__(256, 3) k_prop1_mix(MixArgs a) {
+template <int R, int Q, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_prop1_mix(MixArgs a) {
   extern __shared__ __align__(128) float sweep_smem[];
   __shared__ __align__(16) float sW[H * H];
   const MixDir p = a.d[blockIdx.y];
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(256, 3) k_prop1_mix(MixArgs a) {
   // csr_sweep starts with a __syncthreads()
   const int sub = threadIdx.x & 15;
   PostMix post{p, sW, a.batch, a.rnz_cnt, a.rnz_col, a.rnz_val, a.K, a.node_id_base, ld4(p.b1 + 4 * sub)};
-  csr_sweep<MIX_R, MIX_Q, true>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
-                                ValRow{p.xw, a.ldxw}, post);
+  csr_sweep<R, Q, true>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
+                        ValRow{p.xw, a.ldxw}, post);
 }
 
 
@@ -754,7 +756,8 @@ __global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
   const Dw2bDir& p = a.d[blockIdx.y];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cg = w >> 2, g = w & 3;
-  const int64_t k = (int64_t)blockIdx.x * 2 + cg;
+  for (int64_t kp = blockIdx.x; kp * 2 < a.K; kp += gridDim.x) {   // column pairs (CTA launch rate, not work, bound this)
+  const int64_t k = kp * 2 + cg;
   float2 acc = make_float2(0.f, 0.f);
   // most columns are positive in no root row of the batch: nothing to look up for them
   if (k < a.K && a.overflow[1 + k] != 0) {
@@ -807,6 +810,8 @@ __global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
       p.dw2[(int64_t)o * a.ld + H + k] = tot * sc;
     }
   }
+  __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------- dropout mask materialisation (tests)
@@ -850,20 +855,31 @@ int root_proj_launch(const RootProjArgs& a, int ndir, cudaStream_t st) {
   BIGCN_CHECK_LAUNCH("k_root_proj");
   return 0;
 }
-int prop1_mix_launch(const MixArgs& a0, int ndir, cudaStream_t st) {
-  if (a0.N == 0) return 0;
-  constexpr int smem = SweepSmem<MIX_R, MIX_Q>::kBytes;
+template <int R, int Q, int MINB>
+static int mix_launch(const MixArgs& a0, int ndir, cudaStream_t st) {
+  constexpr int smem = SweepSmem<R, Q>::kBytes;
   static bool attr = false;
   if (!attr) {
-    sweep_attr(k_prop1_mix, smem);
+    sweep_attr(k_prop1_mix<R, Q, MINB>, smem);
     attr = true;
   }
   MixArgs a = a0;
-  const int max_ctas = num_sms() * 3;
-  a.cb = sweep_cb(a.N, MIX_R, max_ctas);
-  k_prop1_mix<<<dim3(sweep_grid(a.N, MIX_R, a.cb, max_ctas), ndir), 256, smem, st>>>(a);
+  const int max_ctas = num_sms() * MINB;
+  a.cb = sweep_cb(a.N, R, max_ctas);
+  k_prop1_mix<R, Q, MINB><<<dim3(sweep_grid(a.N, R, a.cb, max_ctas), ndir), 256, smem, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_prop1_mix");
   return 0;
+}
+int prop1_mix_launch(const MixArgs& a, int ndir, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  switch (debug_knob(2)) {
+    case 1: return mix_launch<4, 4, 4>(a, ndir, st);
+    case 2: return mix_launch<2, 8, 4>(a, ndir, st);
+    case 3: return mix_launch<2, 4, 5>(a, ndir, st);
+    case 4: return mix_launch<8, 8, 2>(a, ndir, st);
+    case 5: return mix_launch<4, 8, 3>(a, ndir, st);
+    default: return mix_launch<MIX_R, MIX_Q, 4>(a, ndir, st);
+  }
 }
 size_t readout_scratch_floats(int64_t N, int64_t B, int ndir) {
   return (size_t)ndir * (size_t)(ceil_div(N > 0 ? N : 1, RO_SLICE) + B) * 2 * H;
@@ -938,7 +954,12 @@ int dw2b_launch(const Dw2bArgs& a, int ndir, bool dropping, cudaStream_t st) {
     k_dw2b_part<<<dim3(dw2b_blocks(a.N), ndir), 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_dw2b_part");
   }
-  k_dw2b_reduce<<<dim3((int)ceil_div(a.K, 2), ndir), 256, 0, st>>>(a);
+  {
+    int64_t g = ceil_div(a.K, 2);
+    const int64_t cap = (int64_t)num_sms() * 4;
+    if (g > cap) g = cap;
+    k_dw2b_reduce<<<dim3((int)g, ndir), 256, 0, st>>>(a);
+  }
   BIGCN_CHECK_LAUNCH("k_dw2b_reduce");
   k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);   // dense-root fallback, returns at once otherwise
   BIGCN_CHECK_LAUNCH("k_dw2b");

@@ -401,35 +401,49 @@ struct DwSweepArgs {
   int32_t cb;
 };
 
-__global__ void __launch_bounds__(256, 3) k_dw_sweep(DwSweepArgs a) {
+template <int R, int Q, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_dw_sweep(DwSweepArgs a) {
   extern __shared__ __align__(128) float sweep_smem[];
   const int d = blockIdx.y;
-  csr_sweep<DW_R, DW_Q, false>(Csr{a.x.cptr, a.x.crow, a.x.clong[d], a.x.cap}, WtVal{a.x.cval}, (int)a.x.K, a.cb, sweep_smem,
+  csr_sweep<R, Q, false>(Csr{a.x.cptr, a.x.crow, a.x.clong[d], a.x.cap}, WtVal{a.x.cval}, (int)a.x.K, a.cb, sweep_smem,
                          ValRow{a.t + d * H, a.ldt}, PostDw{a.dw[d], a.ldw, a.x.state});
+}
+
+template <int R, int Q, int MINB>
+static int dw_sweep_launch(DwSweepArgs& a, int n_out, cudaStream_t st) {
+  constexpr int smem = SweepSmem<R, Q>::kBytes;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_dw_sweep<R, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  // the work is in the hub columns (a bag-of-words matrix is Zipf-skewed: most non-zeros sit in
+  // columns with more than LONG_ROW entries), i.e. in the (column, chunk) items every half-warp of
+  // the grid picks up after the short columns: fill the machine whatever K is
+  const int max_ctas = num_sms() * MINB;
+  a.cb = 8;
+  int grid = sweep_grid(a.x.K, R, a.cb, max_ctas);
+  const int64_t by_items = ceil_div(a.x.cap / LONG_ROW, 16);
+  if (grid < max_ctas) grid = (int)(by_items < max_ctas ? (by_items > grid ? by_items : grid) : max_ctas);
+  k_dw_sweep<R, Q, MINB><<<dim3(grid, n_out / H), 256, smem, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_dw_sweep");
+  return 0;
 }
 
 int dw_sparse(const XSparse& x, const float* t, int64_t ldt, int n_out, float* dw_a, float* dw_b, int64_t ldw,
               cudaStream_t st) {
   if (x.K == 0) return 0;
-  constexpr int smem = SweepSmem<DW_R, DW_Q>::kBytes;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_dw_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
   DwSweepArgs a{};
   a.x = x; a.t = t; a.ldt = ldt; a.dw[0] = dw_a; a.dw[1] = dw_b; a.ldw = ldw;
-  // the work is in the hub columns (a bag-of-words matrix is Zipf-skewed: most non-zeros sit in
-  // columns with more than LONG_ROW entries), i.e. in the (column, chunk) items every half-warp of
-  // the grid picks up after the short columns: fill the machine whatever K is
-  const int max_ctas = num_sms() * 3;
-  a.cb = 8;
-  int grid = sweep_grid(x.K, DW_R, a.cb, max_ctas);
-  const int64_t by_items = ceil_div(x.cap / LONG_ROW, 16);
-  if (grid < max_ctas) grid = (int)(by_items < max_ctas ? (by_items > grid ? by_items : grid) : max_ctas);
-  k_dw_sweep<<<dim3(grid, n_out / H), 256, smem, st>>>(a);
-  BIGCN_CHECK_LAUNCH("k_dw_sweep");
-  return 0;
+  switch (debug_knob(1)) {
+    case 1: return dw_sweep_launch<2, 8, 4>(a, n_out, st);
+    case 2: return dw_sweep_launch<1, 8, 4>(a, n_out, st);
+    case 3: return dw_sweep_launch<4, 8, 3>(a, n_out, st);
+    case 4: return dw_sweep_launch<2, 8, 5>(a, n_out, st);
+    case 5: return dw_sweep_launch<1, 16, 3>(a, n_out, st);
+    case 6: return dw_sweep_launch<1, 4, 6>(a, n_out, st);
+    default: return dw_sweep_launch<DW_R, DW_Q, 3>(a, n_out, st);
+  }
 }
 
 }  // namespace bigcn

@@ -20,8 +20,8 @@ constexpr int XW_U = 8;
 
 // CAPTURE: lane 0 also records every non-zero (column, value) in the row's ELL slots and the
 // exact count (xsparse.cu turns that into the CSR / CSC the sparse weight gradient sweeps).
-template <int NOUT, bool VEC4, bool CAPTURE>
-__global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, int64_t N, int64_t K,
+template <int NOUT, bool VEC4, bool CAPTURE, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__ x, int64_t N, int64_t K,
                                                  const float* __restrict__ wt,
                                                  float* __restrict__ y, int64_t ldy,
                                                  int32_t* __restrict__ xs_cnt, int32_t* __restrict__ xs_col,
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_xw_scan(const float* __restrict__ x, in
   }
 }
 
-template <bool CAPTURE>
+template <bool CAPTURE, int MINB = 1>
 static int xw_scan_launch(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
                           int32_t* xs_cnt, int32_t* xs_col, float* xs_val, int ctas_per_sm, cudaStream_t st) {
   if (N == 0) return 0;
@@ -104,11 +104,11 @@ static int xw_scan_launch(const float* x, int64_t N, int64_t K, const float* wt,
   const int cap = num_sms() * ctas_per_sm;
   if (blocks > cap) blocks = cap;
   if (n_out == 128) {
-    if (vec4) k_xw_scan<128, true, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
-    else k_xw_scan<128, false, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    if (vec4) k_xw_scan<128, true, CAPTURE, MINB><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    else k_xw_scan<128, false, CAPTURE, MINB><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
   } else {
-    if (vec4) k_xw_scan<64, true, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
-    else k_xw_scan<64, false, CAPTURE><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    if (vec4) k_xw_scan<64, true, CAPTURE, MINB><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
+    else k_xw_scan<64, false, CAPTURE, MINB><<<blocks, 256, 0, st>>>(x, N, K, wt, y, ldy, xs_cnt, xs_col, xs_val);
   }
   BIGCN_CHECK_LAUNCH("k_xw_scan");
   return 0;
@@ -122,7 +122,15 @@ int xw_fp32(const float* x, int64_t N, int64_t K, const float* wt, int n_out, fl
 // for the short kernels of the side stream to run beside it
 int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n_out, float* y, int64_t ldy,
                     const XSparse& xs, cudaStream_t st) {
-  return xw_scan_launch<true>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
+  switch (debug_knob(3)) {
+    case 1: return xw_scan_launch<true, 6>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
+    case 2: return xw_scan_launch<true, 8>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 8, st);
+    case 3: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 8, st);
+    case 4: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 4, st);
+    case 5: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 3, st);
+    case 6: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 2, st);
+    default: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
+  }
 }
 
 // y = x * wt from the CSR of x (sparse input: the dense matrix never reaches the device).
