@@ -233,10 +233,13 @@ def run_ours(args):
     for i in range(args.warmup):
         tr.step(resident[i % N_ROTATE], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
     tr.check_inputs()
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)          # NVML init before the barrier: its duration differs per rank
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align = torch.zeros(1, device=dev)
     with sampler:
+        barrier()
+        if world > 1:                      # a collective on the stream right before e0: the timed
+            torch.distributed.all_reduce(align)   # regions of all ranks start together on the devices
         t_cpu0 = time.perf_counter()
         e0.record()
         for i in range(args.steps):
