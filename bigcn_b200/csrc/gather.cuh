@@ -119,6 +119,8 @@ struct WtVal {
   __device__ __forceinline__ float edge(int e, int, float) const { return val[e]; }
 };
 
+// Post functors: operator()(row, sum, sub, half mask, scratch) finishes one row; kPairs = true
+// adds pair(row, v0, ok0, v1, ok1, ...) for rows (row, row + 1) with two scratch rows.
 // plain feature rows: val(j) = h[j, :]
 struct ValRow {
   const float* h;
@@ -266,9 +268,7 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
     cp_async_commit_wait_all();   // blocks without edges: the self rows are still in flight
     __syncwarp();
     if (cur >= 0) flush(cur);
-#pragma unroll 1
-    for (int u = 0; u < nrows; ++u) {
-      if ((longmask >> u) & 1u) continue;
+    auto finished = [&](int u) {   // the row's sum (self-loop included)
       float4 v;
       if ((flushed >> u) & 1u) {
         v = ld4(st + u * H + 4 * sub);   // a lane re-reads only what it wrote itself
@@ -279,7 +279,23 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
           acc_add<EXACT>(v, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
         }
       }
-      post(i0 + u, v, sub, hm, st + (R + (u & (Q - 1))) * H);
+      return v;
+    };
+    if constexpr (Post::kPairs) {   // epilogues that share work between two rows (one pass over W for both)
+#pragma unroll 1
+      for (int u = 0; u < nrows; u += 2) {
+        const bool ok0 = !((longmask >> u) & 1u), ok1 = u + 1 < nrows && !((longmask >> (u + 1)) & 1u);
+        if (!ok0 && !ok1) continue;
+        const float4 v0 = ok0 ? finished(u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v1 = ok1 ? finished(u + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        post.pair(i0 + u, v0, ok0, v1, ok1, sub, hm, st + R * H);
+      }
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < nrows; ++u) {
+        if ((longmask >> u) & 1u) continue;
+        post(i0 + u, finished(u), sub, hm, st + (R + (u & (Q - 1))) * H);
+      }
     }
   }
   // ---- hub rows: items (row, chunk) spread over all half-warps of the grid --------------------

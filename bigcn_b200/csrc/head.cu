@@ -211,10 +211,12 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     float4 mv = reinterpret_cast<float4*>(m)[q];
     float4 vv = reinterpret_cast<float4*>(v)[q];
     // lr groups may change inside a quad only if a segment end is not a multiple of 4
-    pv.x = upd(pv.x, gv.x, mv.x, vv.x, lr_of(4 * q + 0));
-    pv.y = upd(pv.y, gv.y, mv.y, vv.y, lr_of(4 * q + 1));
-    pv.z = upd(pv.z, gv.z, mv.z, vv.z, lr_of(4 * q + 2));
-    pv.w = upd(pv.w, gv.w, mv.w, vv.w, lr_of(4 * q + 3));
+    const float lr0 = lr_of(4 * q + 0), lr3 = lr_of(4 * q + 3);
+    const bool same = lr0 == lr3;
+    pv.x = upd(pv.x, gv.x, mv.x, vv.x, lr0);
+    pv.y = upd(pv.y, gv.y, mv.y, vv.y, same ? lr0 : lr_of(4 * q + 1));
+    pv.z = upd(pv.z, gv.z, mv.z, vv.z, same ? lr0 : lr_of(4 * q + 2));
+    pv.w = upd(pv.w, gv.w, mv.w, vv.w, lr3);
     reinterpret_cast<float4*>(p)[q] = pv;
     reinterpret_cast<float4*>(m)[q] = mv;
     reinterpret_cast<float4*>(v)[q] = vv;
@@ -309,10 +311,12 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     float4 pv = *reinterpret_cast<const float4*>(a.params[a.rank] + i);
     float4 mv = *reinterpret_cast<float4*>(a.m + i);
     float4 vv = *reinterpret_cast<float4*>(a.v + i);
-    pv.x = upd(pv.x, g.x, mv.x, vv.x, lr_of(i + 0));
-    pv.y = upd(pv.y, g.y, mv.y, vv.y, lr_of(i + 1));
-    pv.z = upd(pv.z, g.z, mv.z, vv.z, lr_of(i + 2));
-    pv.w = upd(pv.w, g.w, mv.w, vv.w, lr_of(i + 3));
+    const float lr0 = lr_of(i + 0), lr3 = lr_of(i + 3);
+    const bool same = lr0 == lr3;
+    pv.x = upd(pv.x, g.x, mv.x, vv.x, lr0);
+    pv.y = upd(pv.y, g.y, mv.y, vv.y, same ? lr0 : lr_of(i + 1));
+    pv.z = upd(pv.z, g.z, mv.z, vv.z, same ? lr0 : lr_of(i + 2));
+    pv.w = upd(pv.w, g.w, mv.w, vv.w, lr3);
     *reinterpret_cast<float4*>(a.m + i) = mv;
     *reinterpret_cast<float4*>(a.v + i) = vv;
 #pragma unroll

@@ -19,6 +19,7 @@ constexpr int MIX_R = 2, MIX_Q = 4;       // 24 KB stage + 16 KB W2a per CTA, 4 
                                           // heavy per-row epilogue wants warps in flight more than a deep stage
 
 struct PostBiasRelu {
+  static constexpr bool kPairs = false;
   const float* bias;
   float* out;
   int64_t ldo;
@@ -215,21 +216,6 @@ __device__ __forceinline__ void drop_quad(const DropSpec& ds, int64_t node, int 
   a.z = r.z >= ds.thresh ? __fmul_rn(a.z, ds.scale) : 0.f;
   a.w = r.w >= ds.thresh ? __fmul_rn(a.w, ds.scale) : 0.f;
 }
-// out[4*sub..] = sum_k v[k] * sW[k][4*sub..]  with v spread over the 16 lanes of the half
-__device__ __forceinline__ float4 matvec16(const float4& v, const float* __restrict__ sW, int sub) {
-  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 16
-  for (int k = 0; k < H; ++k) {
-    const float s = __shfl_sync(FULL_MASK, comp4(v, k & 3), k >> 2, 16);
-    const float4 w = ld4(sW + k * H + 4 * sub);
-    z.x = fmaf(s, w.x, z.x);
-    z.y = fmaf(s, w.y, z.y);
-    z.z = fmaf(s, w.z, z.z);
-    z.w = fmaf(s, w.w, z.w);
-  }
-  return z;
-}
-
 // z[4*sub..] = sum_k av[k] * sW[k][4*sub..]: the half-warp parks av in shared memory and every
 // lane reads it back as broadcast float4s (no shuffles), k ascending, one fma chain per output
 __device__ __forceinline__ float4 matvec_smem(const float4& av, const float* __restrict__ sW, float* scratch,
@@ -254,7 +240,37 @@ __device__ __forceinline__ float4 matvec_smem(const float4& av, const float* __r
   return z;
 }
 
+// two rows at once: every W row fetched from shared memory feeds both (half the LDS traffic, eight
+// independent fma chains); per row the same k-ascending chain as matvec_smem
+__device__ __forceinline__ void matvec2_smem(const float4& a0, const float4& a1, const float* __restrict__ sW,
+                                             float* scratch, int sub, unsigned hm, float4& z0, float4& z1) {
+  st4(scratch + 4 * sub, a0);
+  st4(scratch + H + 4 * sub, a1);
+  __syncwarp(hm);
+  z0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  z1 = z0;
+#pragma unroll 4
+  for (int k4 = 0; k4 < H / 4; ++k4) {
+    const float4 p4 = ld4(scratch + 4 * k4), q4 = ld4(scratch + H + 4 * k4);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float s0 = comp4(p4, c), s1 = comp4(q4, c);
+      const float4 w = ld4(sW + (4 * k4 + c) * H + 4 * sub);
+      z0.x = fmaf(s0, w.x, z0.x);
+      z0.y = fmaf(s0, w.y, z0.y);
+      z0.z = fmaf(s0, w.z, z0.z);
+      z0.w = fmaf(s0, w.w, z0.w);
+      z1.x = fmaf(s1, w.x, z1.x);
+      z1.y = fmaf(s1, w.y, z1.y);
+      z1.z = fmaf(s1, w.z, z1.z);
+      z1.w = fmaf(s1, w.w, z1.w);
+    }
+  }
+  __syncwarp(hm);
+}
+
 struct PostMix {
+  static constexpr bool kPairs = true;
   MixDir p;
   const float* sW;
   const int64_t* batch;
@@ -263,17 +279,21 @@ struct PostMix {
   const float* rnz_val;
   int64_t K, node_id_base;
   float4 b1;
-  __device__ __forceinline__ void operator()(int i, float4 h1, int sub, unsigned hm, float* scratch) const {
+  // bias, H1, relu, dropout, A1 of one row -> the conv2.lin input of its 64 hidden columns
+  __device__ __forceinline__ float4 activate(int i, float4 h1, int sub) const {
     h1.x = __fadd_rn(h1.x, b1.x);
     h1.y = __fadd_rn(h1.y, b1.y);
     h1.z = __fadd_rn(h1.z, b1.z);
     h1.w = __fadd_rn(h1.w, b1.w);
     st4(p.h1 + (int64_t)i * H + 4 * sub, h1);
     float4 av = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
-    const int64_t node = node_id_base + i;
-    if (p.drop.on) drop_quad(p.drop, node, sub, av);
+    if (p.drop.on) drop_quad(p.drop, node_id_base + i, sub, av);
     st4(p.a1 + (int64_t)i * H + 4 * sub, av);
-    float4 z = matvec_smem(av, sW, scratch, sub, hm);
+    return av;
+  }
+  // root part of conv2.lin and the store of z
+  __device__ __forceinline__ void finish(int i, float4 z, int sub, unsigned hm, float* scratch) const {
+    const int64_t node = node_id_base + i;
     const int64_t b = batch[i];
     if (p.drop.on) {
       const int n = rnz_cnt[b];
@@ -299,14 +319,28 @@ struct PostMix {
         }
         __syncwarp(hm);
         const int cnt = __popc(mine);
-        for (int q = 0; q < cnt; ++q) {
-          const int kk = reinterpret_cast<const int*>(scratch)[q];
-          const float vv = scratch[16 + q];
-          const float4 w = ld4(p.w2bT + (int64_t)kk * H + 4 * sub);
-          racc.x = fmaf(vv, w.x, racc.x);
-          racc.y = fmaf(vv, w.y, racc.y);
-          racc.z = fmaf(vv, w.z, racc.z);
-          racc.w = fmaf(vv, w.w, racc.w);
+        for (int q0 = 0; q0 < cnt; q0 += 4) {   // four W2b rows (L2) in flight, added in kept order
+          float4 w[4];
+          float vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            vv[u] = 0.f;
+            w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + u < cnt) {
+              const int kk = reinterpret_cast<const int*>(scratch)[q0 + u];
+              vv[u] = scratch[16 + q0 + u];
+              w[u] = ld4(p.w2bT + (int64_t)kk * H + 4 * sub);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (q0 + u < cnt) {
+              racc.x = fmaf(vv[u], w[u].x, racc.x);
+              racc.y = fmaf(vv[u], w[u].y, racc.y);
+              racc.z = fmaf(vv[u], w[u].z, racc.z);
+              racc.w = fmaf(vv[u], w[u].w, racc.w);
+            }
+          }
         }
         __syncwarp(hm);
       }
@@ -322,6 +356,21 @@ struct PostMix {
       z.w += pv.w;
     }
     st4(p.z + (int64_t)i * H + 4 * sub, z);
+  }
+  __device__ __forceinline__ void operator()(int i, float4 h1, int sub, unsigned hm, float* scratch) const {
+    const float4 av = activate(i, h1, sub);
+    finish(i, matvec_smem(av, sW, scratch, sub, hm), sub, hm, scratch);
+  }
+  // rows i (ok0) and i + 1 (ok1); scratch holds two rows
+  __device__ __forceinline__ void pair(int i, float4 v0, bool ok0, float4 v1, bool ok1, int sub, unsigned hm,
+                                       float* scratch) const {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = ok0 ? activate(i, v0, sub) : zero;
+    const float4 a1 = ok1 ? activate(i + 1, v1, sub) : zero;
+    float4 z0, z1;
+    matvec2_smem(a0, a1, sW, scratch, sub, hm, z0, z1);
+    if (ok0) finish(i, z0, sub, hm, scratch);
+    if (ok1) finish(i + 1, z1, sub, hm, scratch);
   }
 };
 
@@ -471,6 +520,7 @@ struct ValG2 {   // val(x) = [H2[x] > 0] * gs[batch[x]]
   }
 };
 struct PostStore {
+  static constexpr bool kPairs = false;
   float* out;
   __device__ __forceinline__ void operator()(int i, const float4& v, int sub, unsigned, float*) const {
     st4(out + (int64_t)i * H + 4 * sub, v);
@@ -499,29 +549,42 @@ __global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {
 // CTA = BM_ROWS rows: 8 warps x 8 row pairs, half-warp per row.
 __global__ void __launch_bounds__(256) k_bwd_mix(BwdMixArgs a) {
   __shared__ __align__(16) float sW[H * H];   // [o][k] = W2[o][k], k < 64
+  __shared__ __align__(16) float sT[16][2 * H];   // two T2 rows per half-warp (matvec2_smem)
   __shared__ float red[16][H];
   const BwdMixDir& p = a.d[blockIdx.y];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2[(int64_t)(i >> 6) * a.ldw2 + (i & 63)];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane & 15, half = lane >> 4;
+  const unsigned hm = half_mask(half);
+  float* scratch = sT[threadIdx.x >> 4];
   const int64_t base = (int64_t)blockIdx.x * BM_ROWS + w * 16;
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = 0; r < 8; ++r) {
-    const int64_t i = base + 2 * r + half;
-    const bool valid = i < a.N;
-    const float4 t = valid ? ld4(p.t2 + i * H + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 g = matvec16(t, sW, sub);
-    if (p.drop.on) drop_quad(p.drop, a.node_id_base + i, sub, g);
-    const float4 h = valid ? ld4(p.h1 + i * H + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-    g.x = h.x > 0.f ? g.x : 0.f;
-    g.y = h.y > 0.f ? g.y : 0.f;
-    g.z = h.z > 0.f ? g.z : 0.f;
-    g.w = h.w > 0.f ? g.w : 0.f;
-    if (valid) st4(p.g1 + i * H + 4 * sub, g);
-    cs.x += g.x;
-    cs.y += g.y;
-    cs.z += g.z;
-    cs.w += g.w;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < 8; r += 2) {   // rows in ascending order per half-warp, two per pass over W2a
+    const int64_t i0 = base + 2 * r + half, i1 = i0 + 2;
+    const bool ok0 = i0 < a.N, ok1 = i1 < a.N;
+    const float4 t0 = ok0 ? ld4(p.t2 + i0 * H + 4 * sub) : zero;
+    const float4 t1 = ok1 ? ld4(p.t2 + i1 * H + 4 * sub) : zero;
+    const float4 h0 = ok0 ? ld4(p.h1 + i0 * H + 4 * sub) : zero;
+    const float4 h1 = ok1 ? ld4(p.h1 + i1 * H + 4 * sub) : zero;
+    float4 g0, g1;
+    matvec2_smem(t0, t1, sW, scratch, sub, hm, g0, g1);
+    if (p.drop.on) {
+      drop_quad(p.drop, a.node_id_base + i0, sub, g0);
+      drop_quad(p.drop, a.node_id_base + i1, sub, g1);
+    }
+    g0.x = h0.x > 0.f ? g0.x : 0.f;
+    g0.y = h0.y > 0.f ? g0.y : 0.f;
+    g0.z = h0.z > 0.f ? g0.z : 0.f;
+    g0.w = h0.w > 0.f ? g0.w : 0.f;
+    g1.x = h1.x > 0.f ? g1.x : 0.f;
+    g1.y = h1.y > 0.f ? g1.y : 0.f;
+    g1.z = h1.z > 0.f ? g1.z : 0.f;
+    g1.w = h1.w > 0.f ? g1.w : 0.f;
+    if (ok0) st4(p.g1 + i0 * H + 4 * sub, g0);
+    if (ok1) st4(p.g1 + i1 * H + 4 * sub, g1);
+    cs.x += g0.x; cs.y += g0.y; cs.z += g0.z; cs.w += g0.w;
+    cs.x += g1.x; cs.y += g1.y; cs.z += g1.z; cs.w += g1.w;
   }
   st4(&red[w * 2 + half][4 * sub], cs);
   __syncthreads();

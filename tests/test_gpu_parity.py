@@ -462,11 +462,14 @@ def test_weibo_full_size_tree_and_powerlaw_batch(dev):
         assert_logp_parity(got, ref, b, what=shape)
         again = m(clone_batch(b, dev))
         assert torch.equal(again, got)
-        want = ref(b)
+        # gradients against the fp64 oracle: the fp32 oracle's own sequential sums over a
+        # 59k-node tree are off by ~1e-3
+        ref64 = copy.deepcopy(ref).double()
+        want = ref64(b)
         g = torch.randn_like(want)
         want.backward(g)
-        got.backward(g.to(dev))
-        compare_grads(m, ref)
+        got.backward(g.float().to(dev))
+        compare_grads(m, ref64)
 
 
 def test_single_direction_modules(dev):
