@@ -344,12 +344,21 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
       }
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* p0 = L.partial + (size_t)item0 * H + 4 * sub;
-      for (int c = 0; c < nch; ++c) {
-        const float4 pv = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)c * H));
-        tot.x = __fadd_rn(tot.x, pv.x);
-        tot.y = __fadd_rn(tot.y, pv.y);
-        tot.z = __fadd_rn(tot.z, pv.z);
-        tot.w = __fadd_rn(tot.w, pv.w);
+      for (int c0 = 0; c0 < nch; c0 += 8) {   // eight partials in flight, added in chunk order
+        float4 pv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          pv[u] = c0 + u < nch ? __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(c0 + u) * H))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (c0 + u < nch) {
+            tot.x = __fadd_rn(tot.x, pv[u].x);
+            tot.y = __fadd_rn(tot.y, pv[u].y);
+            tot.z = __fadd_rn(tot.z, pv[u].z);
+            tot.w = __fadd_rn(tot.w, pv[u].w);
+          }
+        }
       }
       cp_async_commit_wait_all();
       __syncwarp(hm);
