@@ -13,6 +13,7 @@ from .nn import GCNConv, TDrumorGCN, BUrumorGCN, BiGCN, Net  # noqa: E402,F401
 from .trainer import FusedTrainer  # noqa: E402,F401
 from . import data, ops  # noqa: E402,F401
 from .ops import SparseX, host_dense_to_csr  # noqa: E402,F401
+from .loader import DeviceForest  # noqa: E402,F401
 
 __all__ = ["GCNConv", "TDrumorGCN", "BUrumorGCN", "BiGCN", "Net", "FusedTrainer", "BigcnError",
-           "SparseX", "host_dense_to_csr", "data", "ops"]
+           "SparseX", "host_dense_to_csr", "DeviceForest", "data", "ops"]

@@ -210,18 +210,27 @@ def make_batch_shard(shape: str, n_trees_global: int, seed: int, rank: int = 0, 
     by NODE count (dist.shard_trees) and each tree is generated from its own (seed, tree index)
     stream, so any rank can build any tree and the global batch does not depend on the world
     size.  Returns (Batch, node_id_base, (lo, hi))."""
+    trees, base, rng_of, (lo, hi) = make_trees_shard(shape, n_trees_global, seed, rank, world, in_feats, num_classes)
+    rate = SHAPES[shape]["droprate"] if train else 0.0
+    if rate > 0:
+        trees = [drop_edge(t, rate, rate, rng_of(lo + j)) for j, t in enumerate(trees)]
+    return collate(trees), base, (lo, hi)
+
+
+def make_trees_shard(shape: str, n_trees_global: int, seed: int, rank: int = 0, world: int = 1,
+                     in_feats: int | None = None, num_classes: int | None = None):
+    """The trees (no DropEdge) of rank `rank`'s node-balanced range of a global batch; returns
+    (trees, node_id_base, rng_of(tree index) -> the tree's generator after make_tree, (lo, hi))."""
     from .dist import shard_trees, node_id_base
     sizes = tree_sizes(shape, n_trees_global, np.random.default_rng(seed))
     lo, hi = shard_trees(sizes, world)[rank]
-    rate = SHAPES[shape]["droprate"] if train else 0.0
+    rngs = {}
     trees = []
     for t in range(lo, hi):
         rng = np.random.default_rng([seed, t])
-        tr = make_tree(shape, int(sizes[t]), rng, in_feats, num_classes)
-        if rate > 0:
-            tr = drop_edge(tr, rate, rate, rng)
-        trees.append(tr)
-    return collate(trees), node_id_base(sizes, lo), (lo, hi)
+        trees.append(make_tree(shape, int(sizes[t]), rng, in_feats, num_classes))
+        rngs[t] = rng
+    return trees, node_id_base(sizes, lo), (lambda t: rngs[t]), (lo, hi)
 
 
 @dataclass

@@ -297,6 +297,24 @@ int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     double beta1, double beta2, double eps, double weight_decay,
                     double grad_scale, int64_t* step_count, bigcn_stream_t stream);
 
+/* ---- on-device batch assembly + DropEdge --------------------------------------
+ * For a dataset packed in HBM (all trees: node_ptr/edge_ptr [T+1], local edge lists, x as CSR over
+ * all nodes, local root index, label) builds the batch of trees tree_id[0..B): what
+ * BiGraphDataset.__getitem__ (Process/dataset.py:64-99: DropEdge keeps int(e*(1-rate)) positions of
+ * the TD and, independently, of the BU list, order preserved) and PyG's collate
+ * (BiGCN_Twitter.py:168: concatenate, offset the *index keys by the node count, batch vector) do on
+ * the host.  The caller computes the four offset arrays on the host from the tree sizes
+ * (td_off/bu_off: kept edges per tree) -- no synchronisation.  Outputs: the five attributes
+ * forward(data) reads, with data.x as CSR (ox_ptr/ox_col/ox_val), and y. */
+int bigcn_assemble_batch(const int64_t* node_ptr, const int64_t* edge_ptr, const int32_t* edge_src,
+                         const int32_t* edge_dst, const int64_t* x_ptr, const int32_t* x_col,
+                         const float* x_val, const int32_t* root_local, const int64_t* y_all,
+                         const int64_t* tree_id, const int64_t* node_off, const int64_t* td_off,
+                         const int64_t* bu_off, const int64_t* nnz_off, int64_t B, int64_t E_td,
+                         int64_t E_bu, uint64_t seed, int64_t* edge_index, int64_t* bu_edge_index,
+                         int64_t* batch, int64_t* rootindex, int64_t* y, int32_t* ox_ptr, int32_t* ox_col,
+                         float* ox_val, bigcn_stream_t stream);
+
 /* ---- data-parallel optimiser step over peer memory -----------------------------
  * One kernel instead of "NCCL all-reduce of the flat gradient + Adam on every rank": grads[q] /
  * params[q] are rank q's flat buffers mapped into this process (symmetric memory over NVLink /

@@ -1,0 +1,112 @@
+"""On-device batch assembly + DropEdge against the host collate of
+bigcn_b200.data (PyG's offset rules) and the DropEdge contract of Process/dataset.py:68-90."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigcn_oracle, gcn_oracle
+from bigcn_b200.data import Batch, collate, make_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def trees_for(k=300, sizes=(1, 60, 2, 350, 17, 90, 1, 5), shape="twitter15", seed=0):
+    rng = np.random.default_rng(seed)
+    return [make_tree(shape, int(n), rng, in_feats=k) for n in sizes]
+
+
+def test_assembly_without_dropedge_equals_collate(dev):
+    import bigcn_b200
+    trees = trees_for()
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    ids = [3, 0, 7, 1, 1, 5, 2]                       # arbitrary order, a repeated tree, single-node trees
+    got = forest.batch(ids)
+    want = collate([trees[i] for i in ids])
+    assert torch.equal(got.edge_index.cpu(), want.edge_index)
+    assert torch.equal(got.BU_edge_index.cpu(), want.BU_edge_index)
+    assert torch.equal(got.batch.cpu(), want.batch)
+    assert torch.equal(got.rootindex.cpu(), want.rootindex)
+    assert torch.equal(got.y.cpu(), want.y)
+    assert torch.equal(got.x.to_dense().cpu(), want.x)
+    empty = forest.batch([])
+    assert empty.batch.numel() == 0 and empty.x.shape == (0, 300)
+
+
+def test_dropedge_contract(dev):
+    """keep int(e*(1-rate)) positions, a subsequence of the original list (order preserved), TD and
+    BU drawn independently, reproducible per seed, every position equally likely to be dropped."""
+    import bigcn_b200
+    trees = trees_for(k=16, sizes=(6, 40, 301, 2, 1))
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    ids = [0, 1, 2, 3, 4]
+    full = collate([trees[i] for i in ids])
+    node_off = np.concatenate([[0], np.cumsum([trees[i].num_nodes for i in ids])])
+
+    def per_tree(ei, b):
+        m = (ei[1] >= node_off[b]) & (ei[1] < node_off[b + 1])
+        return ei[:, m]
+
+    def is_subsequence(sub, seq):
+        it = iter(map(tuple, seq.T.tolist()))
+        return all(any(s == t for t in it) for s in map(tuple, sub.T.tolist()))
+
+    a = forest.batch(ids, 0.2, 0.35, seed=7)
+    a2 = forest.batch(ids, 0.2, 0.35, seed=7)
+    c = forest.batch(ids, 0.2, 0.35, seed=8)
+    assert torch.equal(a.edge_index, a2.edge_index) and torch.equal(a.BU_edge_index, a2.BU_edge_index)
+    assert not torch.equal(a.edge_index, c.edge_index)
+    td, bu = a.edge_index.cpu().numpy(), a.BU_edge_index.cpu().numpy()
+    for b, i in enumerate(ids):
+        e = trees[i].edge_index.shape[1]
+        ftd = per_tree(full.edge_index.numpy(), b)
+        fbu = per_tree(full.BU_edge_index.numpy()[::-1], b)[::-1]      # BU list = [child; parent]
+        ttd = per_tree(td, b)
+        tbu = per_tree(bu[::-1], b)[::-1]
+        assert ttd.shape[1] == int(e * (1 - 0.2)) and tbu.shape[1] == int(e * (1 - 0.35))
+        assert is_subsequence(ttd, ftd) and is_subsequence(tbu, fbu)
+    # TD and BU masks of the 301-node tree differ (independent draws)
+    kept_td = set(map(tuple, per_tree(td, 2).T.tolist()))
+    kept_bu = set(map(tuple, per_tree(bu[::-1], 2).T.tolist()))
+    assert kept_td != kept_bu
+    # uniformity: 5 edges, keep 4 -> each position dropped ~1/5 of the time
+    drops = np.zeros(5)
+    full0 = list(map(tuple, trees[0].edge_index.numpy().T.tolist()))
+    n_draws = 600
+    for s in range(n_draws):
+        ei = forest.batch([0], 0.2, 0.0, seed=1000 + s).edge_index.cpu().numpy()
+        kept = set(map(tuple, ei.T.tolist()))
+        for p, ed in enumerate(full0):
+            drops[p] += ed not in kept
+    assert drops.sum() == n_draws
+    assert np.all(np.abs(drops / n_draws - 0.2) < 0.06), drops
+
+
+def test_model_on_assembled_batch_matches_oracle(dev):
+    """Train-mode step on a device-assembled, DropEdge'd batch: the oracle run on the very same
+    kept edges (read back) and the same dropout mask agrees to 1e-5 / 1e-4."""
+    import bigcn_b200
+    K = 400
+    trees = trees_for(k=K, sizes=(70, 33, 120, 9, 250, 64))
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    ids = [4, 2, 0, 5, 1, 3]
+    bd = forest.batch(ids, 0.2, 0.2, seed=3)
+    torch.manual_seed(1)
+    ref = bigcn_oracle.BiGCN(K, 64, 64).train()
+    m = bigcn_b200.BiGCN(K, 64, 64, dev, gemm_mode="sparse").to(dev).train()
+    m.load_state_dict(ref.state_dict())
+    got = m(bd)
+    m.check_inputs()
+    host = Batch(x=bd.x.to_dense().cpu(), edge_index=bd.edge_index.cpu(), BU_edge_index=bd.BU_edge_index.cpu(),
+                 batch=bd.batch.cpu(), rootindex=bd.rootindex.cpu(), y=bd.y.cpu())
+    n = host.x.shape[0]
+    s = m.TDrumorGCN.last_seed
+    ktd = torch.from_numpy(gcn_oracle.dropout_keep_mask(s, 0, np.arange(n), 64 + K, 0.5))
+    kbu = torch.from_numpy(gcn_oracle.dropout_keep_mask(s, 1, np.arange(n), 64 + K, 0.5))
+    want = ref(host, keep_td=ktd, keep_bu=kbu)
+    err = float((got.detach().cpu().double() - want.detach().double()).abs().max() / want.detach().abs().max())
+    assert err < 1e-5
+    torch.nn.functional.nll_loss(want, host.y).backward()
+    torch.nn.functional.nll_loss(got, bd.y).backward()
+    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        e = float((p.grad.cpu().double() - q.grad.double()).abs().max() / max(float(q.grad.abs().max()), 1e-30))
+        assert e < 1e-4, name
