@@ -3,7 +3,7 @@
 // Batch.from_data_list collate (model/Twitter/BiGCN_Twitter.py:168) do on the host per batch:
 //   * DropEdge: keep int(e * (1 - rate)) positions of a tree's edge list, uniformly without
 //     replacement, order preserved, drawn independently for the TD list and for the BU list
-//     (dataset.py:68-90; random.sample -> Knuth's selection sampling over a Philox stream);
+//     (dataset.py:68-90; random.sample -> the k smallest of per-position Philox keys);
 //   * collate: concatenate x, offset edge_index / BU_edge_index / rootindex by the cumulative
 //     node count, batch[i] = tree of node i, y.
 // The packed dataset keeps x as CSR (the `index:count` pairs getTwittergraph.py:16-24 reads,
@@ -67,38 +67,105 @@ __global__ void __launch_bounds__(256) k_asm_nodes(AsmArgs a) {
   }
 }
 
-// edges: one thread per (tree, direction) walks the tree's edge list once.  Selection sampling
-// (Knuth, TAOCP 3.4.2 algorithm S): position i is kept with probability (k - kept) / (e - i),
-// which yields every k-subset with equal probability -- random.sample followed by sorted().
+// edges.  DropEdge = a uniformly random k-subset of the e positions, order preserved
+// (random.sample(range(e), k) followed by sorted(), dataset.py:72-75,84-87).
+// CTA per (tree, direction): every position draws a 32-bit Philox key; a 32-step bisection finds
+// the k-th smallest key v; positions with key < v are kept, plus the first ones with key == v
+// until k are kept (ties, ~e^2 / 2^33 likely, resolved by position); an ordered block scan
+// compacts the kept edges.  Every k-subset is equally likely (up to those ties).
+constexpr int DE_MAX = 8192;   // edges per tree handled in shared memory (32 KB of keys)
+
+__device__ __forceinline__ uint32_t edge_key(const AsmArgs& a, int64_t t, int dir, int64_t i) {
+  const Philox4 r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)(t & 0xffffffffll), (uint32_t)((uint64_t)t >> 32),
+                                  0x44450000u + (uint32_t)dir, a.k0, a.k1);
+  return philox_elem(r, (int)(i & 3));
+}
+
+__device__ __forceinline__ int block_sum128(int v, int* red) {   // 128 threads, all get the total
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
 __global__ void __launch_bounds__(128) k_asm_edges(AsmArgs a) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * a.B) return;
-  const int64_t b = idx >> 1;
-  const int dir = (int)(idx & 1);          // 0: TD list [row; col], 1: BU list [col; row]
+  __shared__ uint32_t key[DE_MAX];
+  __shared__ int red[4];
+  __shared__ int wbase[4];
+  const int64_t b = blockIdx.x >> 1;
+  const int dir = (int)(blockIdx.x & 1);          // 0: TD list [row; col], 1: BU list [col; row]
   const int64_t t = a.tree_id[b];
-  const int64_t e0 = a.edge_ptr[t], e = a.edge_ptr[t + 1] - e0;
+  const int64_t e0 = a.edge_ptr[t];
+  const int e = (int)(a.edge_ptr[t + 1] - e0);
   const int64_t* offs = dir ? a.bu_off : a.td_off;
-  const int64_t o0 = offs[b], k = offs[b + 1] - o0;
+  const int64_t o0 = offs[b];
+  const int k = (int)(offs[b + 1] - o0);
   const int64_t noff = a.node_off[b];
   int64_t* out = dir ? a.bu_edge_index : a.edge_index;
   const int64_t E = dir ? a.E_bu : a.E_td;
-  int64_t kept = 0;
-  Philox4 r{0, 0, 0, 0};
-  for (int64_t i = 0; i < e && kept < k; ++i) {
-    bool take = true;
-    if (k < e) {
-      if ((i & 3) == 0) r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)(t & 0xffffffffll), (uint32_t)((uint64_t)t >> 32),
-                                          0x44450000u + (uint32_t)dir, a.k0, a.k1);
-      const uint32_t u = philox_elem(r, (int)(i & 3));
-      // u / 2^32 < (k - kept) / (e - i)   <=>   u * (e - i) < (k - kept) * 2^32   (exact in 64+ bits)
-      take = (unsigned __int128)u * (unsigned __int128)(e - i) < ((unsigned __int128)(k - kept) << 32);
+  auto emit = [&](int i, int64_t pos) {
+    const int64_t s = a.edge_src[e0 + i] + noff, d = a.edge_dst[e0 + i] + noff;
+    out[o0 + pos] = dir ? d : s;
+    out[E + o0 + pos] = dir ? s : d;
+  };
+  if (k >= e) {   // rate 0 (or nothing to drop): plain offset copy
+    for (int i = threadIdx.x; i < e; i += 128) emit(i, i);
+    return;
+  }
+  if (e > DE_MAX) {   // very large tree: Knuth's selection sampling (TAOCP 3.4.2 S) by one thread
+    if (threadIdx.x == 0) {
+      int kept = 0;
+      for (int i = 0; i < e && kept < k; ++i) {
+        const uint32_t u = edge_key(a, t, dir, i);
+        // u / 2^32 < (k - kept) / (e - i)
+        if ((unsigned long long)u * (unsigned long long)(e - i) < ((unsigned long long)(k - kept) << 32)) emit(i, kept++);
+      }
     }
-    if (take) {
-      const int64_t s = a.edge_src[e0 + i] + noff, d = a.edge_dst[e0 + i] + noff;
-      out[o0 + kept] = dir ? d : s;
-      out[E + o0 + kept] = dir ? s : d;
-      ++kept;
-    }
+    return;
+  }
+  for (int i = threadIdx.x; i < e; i += 128) key[i] = edge_key(a, t, dir, i);
+  __syncthreads();
+  // smallest v with #{key <= v} >= k
+  uint32_t lo = 0u, hi = 0xffffffffu;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+    for (int i = threadIdx.x; i < e; i += 128) c += key[i] <= mid;
+    if (block_sum128(c, red) >= k) hi = mid;
+    else lo = mid + 1;
+  }
+  const uint32_t v = lo;
+  int below = 0;
+  for (int i = threadIdx.x; i < e; i += 128) below += key[i] < v;
+  const int ties_kept = k - block_sum128(below, red);     // how many of the key == v positions are kept
+  // ordered compaction, 128 positions per round
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int base = 0, ties_seen = 0;
+  for (int i0 = 0; i0 < e; i0 += 128) {
+    const int i = i0 + threadIdx.x;
+    const bool in = i < e;
+    const bool lt = in && key[i] < v, eq = in && key[i] == v;
+    // position among the ties (block-ordered)
+    const unsigned mq = __ballot_sync(FULL_MASK, eq);
+    __syncthreads();
+    if (lane == 0) wbase[w] = __popc(mq);
+    __syncthreads();
+    int tie_rank = ties_seen + __popc(mq & ((1u << lane) - 1u));
+    for (int q = 0; q < w; ++q) tie_rank += wbase[q];
+    const int ties_round = wbase[0] + wbase[1] + wbase[2] + wbase[3];
+    const bool keep = lt || (eq && tie_rank < ties_kept);
+    const unsigned mk = __ballot_sync(FULL_MASK, keep);
+    __syncthreads();
+    if (lane == 0) wbase[w] = __popc(mk);
+    __syncthreads();
+    int pos = base + __popc(mk & ((1u << lane) - 1u));
+    for (int q = 0; q < w; ++q) pos += wbase[q];
+    if (keep) emit(i, pos);
+    base += wbase[0] + wbase[1] + wbase[2] + wbase[3];
+    ties_seen += ties_round;
   }
 }
 
@@ -130,7 +197,7 @@ extern "C" int bigcn_assemble_batch(const int64_t* node_ptr, const int64_t* edge
   cudaStream_t st = (cudaStream_t)stream;
   k_asm_nodes<<<(unsigned)B, 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_asm_nodes");
-  k_asm_edges<<<(unsigned)ceil_div(2 * B, 128), 128, 0, st>>>(a);
+  k_asm_edges<<<(unsigned)(2 * B), 128, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_asm_edges");
   return 0;
 }

@@ -33,6 +33,7 @@ class DeviceForest:
         self.x_ptr, self.x_col, self.x_val = t(x_ptr, torch.int64), t(x_col, torch.int32), t(x_val, torch.float32)
         self.root_local, self.y = t(root_local, torch.int32), t(y, torch.int64)
         self.num_trees = len(self.h_node_ptr) - 1
+        self._stage, self._turn = None, 0
 
     @staticmethod
     def from_data_list(trees, device):
@@ -80,12 +81,28 @@ class DeviceForest:
             offs[row, 1:] = np.cumsum(v)
         n, e_td, e_bu, nnz = (int(offs[r, -1]) for r in range(1, 5))
         dev = self.device
-        d_offs = torch.from_numpy(offs).to(dev, non_blocking=True)
-        i64 = dict(dtype=torch.int64, device=dev)
-        ei, bu = torch.empty(2, e_td, **i64), torch.empty(2, e_bu, **i64)
-        batch, root, y = torch.empty(n, **i64), torch.empty(b, **i64), torch.empty(b, **i64)
-        ox_ptr = torch.zeros(n + 1, dtype=torch.int32, device=dev) if b == 0 else torch.empty(n + 1, dtype=torch.int32, device=dev)
-        ox_col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        # offsets through a pinned staging buffer (two slots: the copy of the previous batch may still be in flight)
+        need = 5 * (b + 1)
+        if self._stage is None or self._stage[0].numel() < need:
+            self._stage = [torch.empty(max(need, 4096), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._turn ^= 1
+        hbuf = self._stage[self._turn]
+        hbuf[:need].copy_(torch.from_numpy(offs.reshape(-1)))
+        d_offs = torch.empty(need, dtype=torch.int64, device=dev)
+        d_offs.copy_(hbuf[:need], non_blocking=True)
+        d_offs = d_offs.view(5, b + 1)
+        # one int64 block [edge_index | BU_edge_index | batch | rootindex | y], one int32 block [x ptr | x col]
+        blk = torch.empty(2 * e_td + 2 * e_bu + n + 2 * b, dtype=torch.int64, device=dev)
+        o = 0
+        ei = blk[o:o + 2 * e_td].view(2, e_td); o += 2 * e_td
+        bu = blk[o:o + 2 * e_bu].view(2, e_bu); o += 2 * e_bu
+        batch = blk[o:o + n]; o += n
+        root = blk[o:o + b]; o += b
+        y = blk[o:o + b]
+        iblk = torch.empty(n + 1 + nnz, dtype=torch.int32, device=dev)
+        if b == 0:
+            iblk.zero_()
+        ox_ptr, ox_col = iblk[:n + 1], iblk[n + 1:]
         ox_val = torch.empty(nnz, dtype=torch.float32, device=dev)
         row = lambda r: d_offs[r].data_ptr()  # noqa: E731
         check(lib().bigcn_assemble_batch(_p(self.node_ptr), _p(self.edge_ptr), _p(self.edge_src), _p(self.edge_dst),
