@@ -124,6 +124,35 @@ __global__ void __launch_bounds__(256) k_loss_sum(const float* __restrict__ loss
   if (threadIdx.x == 0) *loss = red[0] * inv_bg;
 }
 
+// Per-class confusion counts of a batch, accumulated on the device: replaces
+// `_, pred = out.max(dim=-1)` + the Python loops of tools/evaluate.py:3-31 (evaluation4class) /
+// :93-108 (evaluationclass), without the per-batch `.item()` syncs of BiGCN_Twitter.py:188-191.
+//   counts[c] = {TP, FN, FP, TN} for class c;  totals = {trees, correct, sum of -logp[y]*1e6 (fixed point)}
+// Integer atomics only: the sums do not depend on the order of arrival.
+__global__ void __launch_bounds__(256) k_eval_counts(const float* __restrict__ logp, const int64_t* __restrict__ y,
+                                                     int64_t B, int C, unsigned long long* counts,
+                                                     unsigned long long* totals) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int pred = 0;
+  float best = logp[b * C];
+  for (int c = 1; c < C; ++c) {   // first maximum, as torch.max
+    const float v = logp[b * C + c];
+    if (v > best) {
+      best = v;
+      pred = c;
+    }
+  }
+  const int64_t act = y[b];
+  for (int c = 0; c < C; ++c) {
+    const int slot = (act == c ? (pred == c ? 0 : 1) : (pred == c ? 2 : 3));
+    atomicAdd(&counts[c * 4 + slot], 1ull);
+  }
+  atomicAdd(&totals[0], 1ull);
+  if (act == pred) atomicAdd(&totals[1], 1ull);
+  if (act >= 0 && act < C) atomicAdd(&totals[2], (unsigned long long)llrintf(-logp[b * C + act] * 1e6f));
+}
+
 // dW[c][f] = sum_b dl[b][c] feat[b][f] (+ bias column f == 256): thread per (c, f), a chunk
 // of HB_TREES trees per blockIdx.y, trees in order; chunks are summed in order by k_head_bwd_red.
 constexpr int HB_TREES = 32;
@@ -421,6 +450,16 @@ extern "C" int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, 
   BIGCN_CHECK_LAUNCH("k_head_bwd_red");
   k_loss_sum<<<1, 256, 0, ss>>>(lossvec, B, inv_bg, loss);
   BIGCN_CHECK_LAUNCH("k_loss_sum");
+  return 0;
+}
+
+extern "C" int bigcn_eval_counts(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t* counts,
+                                 int64_t* totals, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(C >= 1 && C <= 32 && counts && totals, "eval_counts: bad arguments");
+  if (B == 0) return 0;
+  k_eval_counts<<<(int)ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(
+      logp, y, B, (int)C, reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<unsigned long long*>(totals));
+  BIGCN_CHECK_LAUNCH("k_eval_counts");
   return 0;
 }
 

@@ -195,6 +195,84 @@ class FusedTrainer:
     def check_inputs(self):
         raise_on_flags(self.flags)
 
+    # ---- checkpoint interchange with the reference's torch.optim.Adam (BiGCN_Twitter.py:146-153,253-261)
+    def _ref_groups(self):
+        """Parameter names in the reference optimizer's order: group 0 = model.parameters() minus the
+        BU convs, group 1 = BUrumorGCN.conv1, group 2 = BUrumorGCN.conv2."""
+        names = [n for n, _ in self.model.named_parameters()]
+        g1 = [n for n in names if n.startswith("BUrumorGCN.conv1.")]
+        g2 = [n for n in names if n.startswith("BUrumorGCN.conv2.")]
+        g0 = [n for n in names if n not in g1 and n not in g2]
+        return [g0, g1, g2]
+
+    def _own_slice(self):
+        lo, hi = C.c_int64(), C.c_int64()
+        check(lib().bigcn_dp_slice(self.n, self.world, self._rank, C.byref(lo), C.byref(hi)), "dp_slice")
+        return lo.value, hi.value
+
+    def _full_moments(self):
+        """comm="symm" shards the Adam moments (rank r owns bigcn_dp_slice(r)); a checkpoint needs all
+        of them: every rank contributes its slice to a sum (a collective -- call on every rank)."""
+        if self.comm != "symm":
+            return self.exp_avg, self.exp_avg_sq
+        lo, hi = self._own_slice()
+        both = torch.zeros(2, self.n, dtype=torch.float32, device=self.flat.device)
+        both[0, lo:hi] = self.exp_avg[lo:hi]
+        both[1, lo:hi] = self.exp_avg_sq[lo:hi]
+        torch.distributed.all_reduce(both, group=self.pg)
+        return both[0], both[1]
+
+    def optimizer_state_dict(self):
+        """The state a ``torch.optim.Adam`` built as the reference builds it (:149-153) would hold
+        after the same steps; its ``load_state_dict`` accepts the result.  Reads the device."""
+        step = float(self.step_count[0].item())
+        m_all, v_all = self._full_moments()
+        groups, state, i = [], {}, 0
+        for gi, names in enumerate(self._ref_groups()):
+            ids = []
+            for n in names:
+                v = self.views[n]
+                off = (v.data_ptr() - self.flat.data_ptr()) // 4
+                sl = slice(off, off + v.numel())
+                if step > 0:
+                    state[i] = {"step": torch.tensor(step), "exp_avg": m_all[sl].view(v.shape).clone(),
+                                "exp_avg_sq": v_all[sl].view(v.shape).clone()}
+                ids.append(i)
+                i += 1
+            groups.append({"lr": self.lr if gi == 0 else self.lr / 5, "betas": tuple(self.betas), "eps": self.eps,
+                           "weight_decay": self.wd, "amsgrad": False, "maximize": False, "foreach": None,
+                           "capturable": False, "differentiable": False, "fused": None,
+                           "decoupled_weight_decay": False, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of ``optimizer_state_dict`` (also takes the reference optimizer's own state_dict).
+        All parameters must be at the same step, as they are under the reference's loop."""
+        names = [n for g in self._ref_groups() for n in g]
+        ids = [i for g in sd["param_groups"] for i in g["params"]]
+        if len(ids) != len(names):
+            raise L.BigcnError(f"optimizer state has {len(ids)} parameters, this model has {len(names)}")
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for n, i in zip(names, ids):
+            st = sd["state"].get(i)
+            if st is None:
+                steps.add(0)
+                continue
+            v = self.views[n]
+            if tuple(st["exp_avg"].shape) != tuple(v.shape):
+                raise L.BigcnError(f"optimizer state of {n}: shape {tuple(st['exp_avg'].shape)} != {tuple(v.shape)}")
+            off = (v.data_ptr() - self.flat.data_ptr()) // 4
+            self.exp_avg[off:off + v.numel()].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + v.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise L.BigcnError(f"optimizer state mixes step counts {sorted(steps)}")
+        self.step_count[0] = steps.pop()
+        self.lr = float(sd["param_groups"][0]["lr"])
+        self.seg_lr.copy_(torch.tensor([self.lr / d for d in _LR_DIV], dtype=torch.float32))
+
 
 def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm_mode: str = "fp32",
                       in_feats: int = 5000, comm: str = "single", sparse_input: bool = False) -> int:

@@ -285,6 +285,14 @@ int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, int64_t C, 
                      float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
                      bigcn_stream_t stream);
 
+/* Evaluation bookkeeping on the device: adds this batch to
+ * counts[C][4] = {TP, FN, FP, TN} per class and totals[3] = {trees, correct, sum(-logp[y]) * 1e6}
+ * (int64, zero-initialised by the caller, accumulated over an epoch, read back once).  Replaces
+ * out.max(dim=-1) + tools/evaluate.py:3-31 / :93-108 and the per-batch .item() syncs of
+ * BiGCN_Twitter.py:188-191,217-225. */
+int bigcn_eval_counts(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t* counts,
+                      int64_t* totals, bigcn_stream_t stream);
+
 /* ---- loss and optimiser (the step around the path, :184-189, :146-153) --
  * loss = -(1/B_global) sum_b logp[b,y[b]] (F.nll_loss, mean); grad_logp = dloss/dlogp. */
 int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t B_global,

@@ -110,3 +110,62 @@ def test_model_on_assembled_batch_matches_oracle(dev):
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         e = float((p.grad.cpu().double() - q.grad.double()).abs().max() / max(float(q.grad.abs().max()), 1e-30))
         assert e < 1e-4, name
+
+
+def test_eval_counts_match_reference_metric_functions(dev):
+    """Device-side confusion counts accumulated over several batches give the tuple the reference's
+    evaluation4class / evaluationclass return for the concatenated predictions."""
+    from bigcn_b200.metrics import EvalCounts
+    from oracle import evaluate_oracle
+    torch.manual_seed(0)
+    for C, fn in ((4, evaluate_oracle.evaluation4class), (2, evaluate_oracle.evaluationclass)):
+        ev = EvalCounts(C, dev)
+        preds, ys, nll = [], [], 0.0
+        for bsz in (128, 1, 77):
+            logp = torch.log_softmax(torch.randn(bsz, C), 1)
+            if bsz == 77:
+                logp[:5] = logp[:5, :1].expand(5, C)                  # ties: first maximum wins
+            y = torch.randint(0, C, (bsz,))
+            if C == 4:
+                y[y == 3] = 0                                          # a class that never occurs
+            ev.update(logp.to(dev), y.to(dev))
+            preds += logp.max(dim=-1)[1].tolist()
+            ys += y.tolist()
+            nll += float(-logp[torch.arange(bsz), y].sum())
+        assert ev.result() == fn(preds, ys)
+        # what the reference's validation loop logs: the mean over batches of the per-batch tuples
+        per, o = [], 0
+        for bsz in (128, 1, 77):
+            per.append(fn(preds[o:o + bsz], ys[o:o + bsz]))
+            o += bsz
+        _, vacc, means = ev.epoch_means()
+        assert means == tuple(sum(t[i] for t in per) / 3 for i in range(len(per[0])))
+        assert abs(vacc - sum(t[0] for t in per) / 3) < 1e-3
+        acc, loss = ev.accuracy_and_loss()
+        assert abs(acc - sum(p == t for p, t in zip(preds, ys)) / len(ys)) < 1e-12
+        assert abs(loss - nll / len(ys)) < 1e-4
+        ev.reset()
+        assert int(ev.totals.sum().item()) == 0
+
+
+def test_eval_counts_match_reference_golden(dev):
+    """Device counts against tuples produced by the reference's own tools/evaluate.py
+    (tests/golden/evaluate_golden.json); predictions enter as log-probs whose argmax is the
+    golden prediction, split over two updates."""
+    import json
+    import os
+    from bigcn_b200.metrics import EvalCounts
+    with open(os.path.join(os.path.dirname(__file__), "golden", "evaluate_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    g = torch.Generator().manual_seed(1)
+    for c in cases:
+        C, n = c["classes"], len(c["y"])
+        logit = torch.rand(n, C, generator=g)
+        logit[torch.arange(n), torch.tensor(c["pred"])] += 2.0
+        logp = torch.log_softmax(logit, 1).to(dev)
+        y = torch.tensor(c["y"]).to(dev)
+        ev = EvalCounts(C, dev)
+        h = n // 2
+        ev.update(logp[:h], y[:h])                       # an empty first half (n = 1) is a no-op
+        ev.update(logp[h:], y[h:])
+        assert list(ev.result()) == c["want"], c["fn"]

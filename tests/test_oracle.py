@@ -161,3 +161,33 @@ def test_tree_size_distributions():
     assert p.min() == 1 and p.max() <= 108 and 0.15 < (p == 1).mean() < 0.27
     w = tree_sizes("weibo", 4000, rng)
     assert w.min() >= 10 and 500 < w.mean() < 1200
+
+
+def test_evaluate_oracle_hand_checked():
+    """tools/evaluate.py restatement on a case small enough to check by hand."""
+    from oracle import evaluate_oracle
+    y = [0, 0, 1, 1, 1, 2]
+    pred = [0, 1, 1, 1, 0, 3]
+    r = evaluate_oracle.evaluation4class(pred, y)
+    assert r[0] == round(3 / 6, 4)
+    # class 1 (label 0): TP 1, FN 1, FP 1, TN 3
+    assert r[1:5] == (round(4 / 6, 4), 0.5, 0.5, 0.5)
+    # class 2 (label 1): TP 2, FN 1, FP 1, TN 2
+    assert r[5:9] == (round(4 / 6, 4), round(2 / 3, 4), round(2 / 3, 4), round(2 * 0.6667 * 0.6667 / (0.6667 + 0.6667), 4))
+    # class 4 (label 3): never true, predicted once: precision 0, recall 0 (no positives), F 0
+    assert r[13:17] == (round(5 / 6, 4), 0.0, 0, 0)
+    assert evaluate_oracle.evaluationclass([0, 1, 1], [0, 1, 0])[0] == round(2 / 3, 4)
+
+
+def test_evaluate_oracle_matches_reference_golden():
+    """The golden tuples were produced by the reference's own tools/evaluate.py
+    (tests/golden/make_evaluate_golden.py): this pins the restatement."""
+    import json
+    import os
+    from oracle import evaluate_oracle
+    with open(os.path.join(os.path.dirname(__file__), "golden", "evaluate_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 12
+    for c in cases:
+        got = getattr(evaluate_oracle, c["fn"])(c["pred"], c["y"])
+        assert list(got) == c["want"], c["fn"]
