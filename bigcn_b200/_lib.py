@@ -106,6 +106,15 @@ _SIGS = {
     "bigcn_head_train_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int64]),
     "bigcn_head_train": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_gcn_norm_weighted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "bigcn_gcn_norm_weighted": (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                          c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_gcnconv_weighted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "bigcn_gcnconv_weighted_forward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr,
+                                                 C.c_int32, C.c_int32, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_gcnconv_weighted_backward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr,
+                                                  c_ptr, c_ptr, c_ptr, c_ptr, C.c_int32, C.c_int32, c_ptr, C.c_size_t,
+                                                  c_ptr]),
     "bigcn_eval_counts": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_nll_loss": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_assemble_batch": (C.c_int, [c_ptr] * 14 + [C.c_int64, C.c_int64, C.c_int64, C.c_uint64] + [c_ptr] * 9),

@@ -517,6 +517,19 @@ __global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ g
   if (gq == 0) part[(int64_t)blockIdx.x * H + f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
 }
 
+
+// column sums of a [N][64] matrix (db of a conv on its own)
+int colsum64_launch(const float* g, int64_t N, float* part, float* out, cudaStream_t st) {
+  const int nchunk = N > 0 ? cs_chunks(N) : 0;
+  if (N > 0) {
+    k_colsum_part<<<nchunk, 256, 0, st>>>(g, N, part);
+    BIGCN_CHECK_LAUNCH("k_colsum_part");
+  }
+  ColsumArgs c{};
+  c.nchunk = nchunk; c.part[0] = part; c.out[0] = out;
+  return colsum_reduce_launch(c, 1, st);
+}
+
 }  // namespace bigcn
 
 using namespace bigcn;

@@ -28,6 +28,8 @@ struct PrepDir {
   const int64_t* ei;
   int64_t E;
   bigcn_graph_t g;
+  int32_t* in_eid;   // optional (edge-weighted conv): edge id of every CSR entry; the sort then carries the
+  int32_t* out_eid;  // edge id as its payload and the last pass looks the endpoint up
 };
 
 struct PrepArgs {
@@ -70,10 +72,11 @@ __global__ void k_prep_count(PrepArgs a) {
       atomicAdd(cnt_in + c, 1);
       atomicAdd(cnt_out + r, 1);
     }
+    const bool carry = pd.in_eid != nullptr;
     k_in[e] = valid ? (int32_t)c : sentinel;
-    v_in[e] = (int32_t)r;
+    v_in[e] = carry ? (int32_t)e : (int32_t)r;
     k_out[e] = valid ? (int32_t)r : sentinel;
-    v_out[e] = (int32_t)c;
+    v_out[e] = carry ? (int32_t)e : (int32_t)c;
   }
   // hub-row lists of this direction: counters and arrival flags start at zero
   for (int o = 0; o < 2; ++o) {
@@ -216,9 +219,15 @@ __global__ void k_rs_scatter(PrepArgs a, int src, int shift, int last) {
   const int32_t* vals = a.vals[src] + (int64_t)s * a.Emax;
   int32_t* keys_o = a.keys[src ^ 1] + (int64_t)s * a.Emax;
   int32_t* vals_o = a.vals[src ^ 1] + (int64_t)s * a.Emax;
+  int32_t* eid_o = nullptr;
+  const int64_t* endpoint = nullptr;
   if (last) {
-    const bigcn_graph_t& g = a.d[s >> 1].g;
-    vals_o = (s & 1) ? g.out_idx : g.in_idx;
+    const PrepDir& pd = a.d[s >> 1];
+    vals_o = (s & 1) ? pd.g.out_idx : pd.g.in_idx;
+    if (pd.in_eid != nullptr) {
+      eid_o = (s & 1) ? pd.out_eid : pd.in_eid;
+      endpoint = pd.ei + ((s & 1) ? pd.E : 0);   // by-source CSR lists targets, by-target CSR lists sources
+    }
   }
   __shared__ int dbase[256];
   __shared__ int wcnt[RS_THREADS / 32][257];
@@ -241,7 +250,12 @@ __global__ void k_rs_scatter(PrepArgs a, int src, int shift, int last) {
       for (int i = 0; i < w; ++i) pre += wcnt[i][digit];
       const int pos = dbase[digit] + pre + rank;
       if (!last) keys_o[pos] = key;
-      vals_o[pos] = val;
+      if (eid_o != nullptr) {
+        eid_o[pos] = val;
+        vals_o[pos] = (int32_t)endpoint[val];
+      } else {
+        vals_o[pos] = val;
+      }
     }
     __syncthreads();
     int tot = 0;
@@ -342,7 +356,7 @@ static PrepLayout prep_layout(int64_t N, int64_t Emax, int ndir) {
 int graph_prep_impl(int32_t n_dirs, const int64_t* const* edge_index, const int64_t* E, int64_t N,
                     const int64_t* batch, int64_t B, int32_t deg_by, const bigcn_graph_t* graphs,
                     int32_t* node_ptr, int32_t* flags, void* workspace, size_t workspace_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, int32_t* const* eids) {
   BIGCN_CHECK_ARG(n_dirs == 1 || n_dirs == 2, "graph_prep: n_dirs must be 1 or 2");
   BIGCN_CHECK_ARG(N >= 0 && N < (1ll << 31) - 1, "graph_prep: N out of int32 range");
   int64_t Emax = 0;
@@ -368,6 +382,8 @@ int graph_prep_impl(int32_t n_dirs, const int64_t* const* edge_index, const int6
     a.d[d].ei = edge_index[d];
     a.d[d].E = E[d];
     a.d[d].g = graphs[d];
+    a.d[d].in_eid = eids ? eids[2 * d] : nullptr;
+    a.d[d].out_eid = eids ? eids[2 * d + 1] : nullptr;
   }
   a.cnt = reinterpret_cast<int32_t*>(ws + L.cnt);
   a.keys[0] = reinterpret_cast<int32_t*>(ws + L.keys0);

@@ -14,8 +14,10 @@ constexpr int LONG_ROW = 32;         // CSR rows with more in-edges are split (g
 constexpr int LONG_MAX_CHUNKS = 64;  // at most this many chunks per hub row
 size_t long_ws_ints(int64_t E);
 
+// eids (optional): {in_eid, out_eid} per direction -- the edge id behind every CSR entry (weighted.cu)
 int graph_prep_impl(int32_t, const int64_t* const*, const int64_t*, int64_t, const int64_t*, int64_t,
-                    int32_t, const bigcn_graph_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+                    int32_t, const bigcn_graph_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t,
+                    int32_t* const* eids = nullptr);
 size_t graph_prep_ws_bytes(int64_t N, int64_t Emax, int ndir);
 int xw_fp32(const float*, int64_t, int64_t, const float*, int, float*, int64_t, cudaStream_t);
 int transpose_weight(const float*, int64_t, int64_t, int64_t, float*, int64_t, int64_t, cudaStream_t);

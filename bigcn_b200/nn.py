@@ -16,7 +16,7 @@ import math
 import torch
 
 from . import _lib as L
-from .ops import FeaturesFunction, GCNConvFunction, HeadFunction, raise_on_flags
+from .ops import FeaturesFunction, GCNConvFunction, GCNConvWeightedFunction, HeadFunction, raise_on_flags
 
 H = L.H
 
@@ -47,8 +47,12 @@ class GCNConv(torch.nn.Module):
         self.deg_by, self.gemm_mode = deg_by, gemm_mode
 
     def forward(self, x, edge_index, edge_weight=None):
-        if edge_weight is not None:
-            raise NotImplementedError("edge_weight (EBGCN variant) is outside the accelerated path")
+        if edge_weight is None and torch.is_tensor(x) and x.requires_grad:
+            # x is an activation (EBGCN's conv2 input is batch-normalised): the generic form returns dx
+            edge_weight = torch.ones(edge_index.shape[1], dtype=torch.float32, device=x.device)
+        if edge_weight is not None:      # EBGCN.py:84,181
+            return GCNConvWeightedFunction.apply(x, edge_index, edge_weight, self.lin.weight, self.bias, self.deg_by,
+                                                 self.gemm_mode)
         return GCNConvFunction.apply(x, edge_index, self.lin.weight, self.bias, self.deg_by, self.gemm_mode)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kw):

@@ -331,6 +331,79 @@ class GCNConvFunction(torch.autograd.Function):
         return None, None, dw, db, None, None
 
 
+class GCNConvWeightedFunction(torch.autograd.Function):
+    """conv(x, edge_index, edge_weight) -> [N,64] (EBGCN.py:84,181); gradients for the conv's weight and
+    bias, the edge weights (directly and through the degree normalisation) and x."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, edge_weight, weight, bias, deg_by, gemm_mode):
+        L.require_device()
+        x, weight, bias, ew = _f32(x), _f32(weight), _f32(bias), _f32(edge_weight)
+        ei = _i64(edge_index)
+        _need_cuda(x, ei, ew, weight, bias)
+        n, k = x.shape
+        e = int(ei.shape[1])
+        if weight.shape != (H, k):
+            raise L.BigcnError(f"GCNConv: out_channels must be {H} and weight [64,{k}], got {tuple(weight.shape)}")
+        if ew.shape != (e,):
+            raise L.BigcnError(f"GCNConv: edge_weight must be [{e}], got {tuple(ew.shape)}")
+        ws_bytes = lib().bigcn_gcnconv_weighted_workspace_bytes(n, e, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        out = torch.empty(n, H, dtype=torch.float32, device=x.device)
+        check(lib().bigcn_gcnconv_weighted_forward(_p(x), n, k, _p(ei), e, _p(ew), _p(weight), _p(bias),
+                                                   L.DEG_BY[deg_by], L.GEMM_MODE[gemm_mode], _p(out), _p(flags),
+                                                   _p(ws), ws_bytes, _stream()), "gcnconv_weighted_forward")
+        ctx.save_for_backward(x, ei, ew, weight, ws)
+        ctx.flags = flags
+        ctx.deg_by, ctx.gemm_mode = deg_by, gemm_mode
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, ei, ew, weight, ws = ctx.saved_tensors
+        n, k = x.shape
+        e = int(ei.shape[1])
+        g = _f32(grad_out)
+        dw = torch.empty(H, k, dtype=torch.float32, device=x.device)
+        db = torch.empty(H, dtype=torch.float32, device=x.device)
+        dew = torch.empty(e, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None
+        dx = torch.empty(n, k, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        check(lib().bigcn_gcnconv_weighted_backward(_p(x), n, k, _p(ei), e, _p(ew), _p(weight), _p(g), _p(dw), _p(db),
+                                                    _p(dew), _p(dx), L.DEG_BY[ctx.deg_by], L.GEMM_MODE[ctx.gemm_mode],
+                                                    _p(ws), ws.numel(), _stream()), "gcnconv_weighted_backward")
+        return dx, None, dew, dw, db, None, None
+
+
+def gcn_norm(edge_index, edge_weight=None, num_nodes=None, improved=False, add_self_loops=True, deg_by="target"):
+    """``torch_geometric.nn.conv.gcn_conv.gcn_norm`` as explain_PHEME.py:62-63 calls it
+    (``gcn_norm(edge_index, edge_weight, N, False, True)``): returns (edge_index', norm) with
+    edge_index' = [non-loop edges in order | (i, i) for every node].  No gradient (the explain
+    script uses it on constants); the differentiable form lives inside GCNConv."""
+    L.require_device()
+    if improved or not add_self_loops:
+        raise NotImplementedError("gcn_norm: only improved=False, add_self_loops=True (the reference's call)")
+    ei = _i64(edge_index)
+    _need_cuda(ei)
+    dev = ei.device
+    e = int(ei.shape[1])
+    n = int(num_nodes) if num_nodes is not None else (int(ei.max().item()) + 1 if e else 0)
+    ew = torch.ones(e, dtype=torch.float32, device=dev) if edge_weight is None else _f32(edge_weight.detach())
+    norm_e = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+    norm_self = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    dis = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib().bigcn_gcn_norm_weighted_workspace_bytes(n, e)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().bigcn_gcn_norm_weighted(_p(ei), e, _p(ew), n, L.DEG_BY[deg_by], _p(norm_e), _p(norm_self), _p(dis),
+                                        _p(flags), _p(ws), ws_bytes, _stream()), "gcn_norm_weighted")
+    raise_on_flags(flags)
+    keep = ei[0] != ei[1]
+    loops = torch.arange(n, dtype=ei.dtype, device=dev)
+    return (torch.cat([ei[:, keep], torch.stack([loops, loops])], dim=1),
+            torch.cat([norm_e[:e][keep], norm_self[:n]]))
+
+
 # ----------------------------------------------------------------------------- feature path
 _PNAMES = ("td_w1", "td_b1", "td_w2", "td_b2", "bu_w1", "bu_b1", "bu_w2", "bu_b2")
 

@@ -248,6 +248,35 @@ int bigcn_gcnconv_backward(const float* x, int64_t N, int64_t K, int64_t E,
                            int32_t gemm_mode, void* workspace /* the forward's */, size_t workspace_bytes,
                            bigcn_stream_t stream);
 
+/* ---- edge-weighted GCNConv -----------------------------
+ * conv(x, edge_index, edge_weight) as EBGCN calls it (model/Twitter/EBGCN.py:84,181:
+ * `self.conv2(x, edge_index, edge_weight=edge_pred)`), and gcn_norm with weights as
+ * explain_PHEME.py:62-63 calls it.  Semantics of torch_geometric's gcn_norm /
+ * add_remaining_self_loops(fill_value = 1): a self-loop edge in the list hands its weight to the
+ * node's loop (the last one wins), other nodes get a unit loop; deg = sum of weights at the target
+ * (source for BIGCN_DEG_BY_SOURCE) in edge-list order, then the loop; dis = deg^-1/2, inf -> 0;
+ * norm_e = (dis[row] * w_e) * dis[col].
+ *   gcn_norm_weighted: norm_e [E] per edge of the list (0 for self-loop edges: their weight sits
+ *   in norm_self), norm_self [N], dis [N].
+ *   forward: out = A-hat_w (x W^T) + bias, summed per row in edge-list order (deterministic).
+ *   backward: dw [64,K], db [64], and optionally d_edge_weight [E] (directly and through the
+ *   degrees) and dx [N,K] = (A-hat_w^T grad_out) W; NULL skips either.  Takes the forward's
+ *   workspace (it keeps x W^T and the normalised structure). */
+size_t bigcn_gcn_norm_weighted_workspace_bytes(int64_t N, int64_t E);
+int bigcn_gcn_norm_weighted(const int64_t* edge_index /*[2,E]*/, int64_t E, const float* edge_weight /*[E]*/,
+                            int64_t N, int32_t deg_by, float* norm_e, float* norm_self, float* dis,
+                            int32_t* flags, void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+size_t bigcn_gcnconv_weighted_workspace_bytes(int64_t N, int64_t E, int64_t K);
+int bigcn_gcnconv_weighted_forward(const float* x, int64_t N, int64_t K, const int64_t* edge_index, int64_t E,
+                                   const float* edge_weight, const float* w, const float* bias,
+                                   int32_t deg_by, int32_t gemm_mode, float* out, int32_t* flags,
+                                   void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+int bigcn_gcnconv_weighted_backward(const float* x, int64_t N, int64_t K, const int64_t* edge_index, int64_t E,
+                                    const float* edge_weight, const float* w, const float* grad_out,
+                                    float* dw, float* db, float* d_edge_weight /*[E] or NULL*/,
+                                    float* dx /*[N,K] or NULL*/, int32_t deg_by, int32_t gemm_mode,
+                                    void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+
 /* ---- the two-direction feature path ------------------------------------
  * Replaces TDrumorGCN.forward / BUrumorGCN.forward (BiGCN_Twitter.py:26-67,
  * 77-114): conv1, root-extend, relu, dropout, conv2, relu, root-extend,

@@ -96,7 +96,8 @@ def test_fused_trainer_optimizer_state_interchanges_with_torch_adam():
     base = [p for p in ref.parameters() if id(p) not in bu]
     opt = torch.optim.Adam([{"params": base}, {"params": ref.BUrumorGCN.conv1.parameters(), "lr": 5e-4 / 5},
                             {"params": ref.BUrumorGCN.conv2.parameters(), "lr": 5e-4 / 5}], lr=5e-4, weight_decay=1e-4)
-    opt.load_state_dict(sd)
+    import copy
+    opt.load_state_dict(copy.deepcopy(sd))        # torch keeps the tensors it is handed and updates them in place
     assert [g["lr"] for g in opt.param_groups] == [5e-4, 1e-4, 1e-4]
     ref.TDrumorGCN.seed, ref.TDrumorGCN._calls = 11, 0        # the module path then draws the mask of seed 11
     b = batches[2]

@@ -1,0 +1,204 @@
+"""Edge-weighted GCNConv (EBGCN.py:84,181, explain_PHEME.py:62-63) against the
+oracle's restatement of torch_geometric's gcn_norm / GCNConv with edge_weight."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gcn_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def bits(t):
+    return t.detach().cpu().contiguous().view(torch.int32)
+
+
+def random_graph(n, e, seed, loops=0, dups=0, hub=False):
+    g = torch.Generator().manual_seed(seed)
+    row = torch.randint(0, n, (e,), generator=g)
+    col = torch.randint(0, n, (e,), generator=g)
+    if hub:                                            # one node with hundreds of in-edges
+        col[: e // 2] = 3
+    keep = row != col
+    row, col = row[keep], col[keep]
+    if dups:
+        row = torch.cat([row, row[:dups]])
+        col = torch.cat([col, col[:dups]])
+    if loops:
+        l = torch.randint(0, n, (loops,), generator=g)
+        l[-1] = l[0]                                   # two self-loop edges on one node: the last one wins
+        row, col = torch.cat([row, l]), torch.cat([col, l])
+        p = torch.randperm(row.numel(), generator=g)
+        # keep the duplicate loop pair in a known relative order
+        row, col = row[p], col[p]
+    ei = torch.stack([row, col])
+    w = torch.rand(ei.shape[1], generator=g) * 1.5 + 0.05
+    return ei, w
+
+
+CASES = [dict(n=1, e=0, seed=0), dict(n=7, e=12, seed=1, loops=3), dict(n=300, e=900, seed=2, dups=40),
+         dict(n=2000, e=3000, seed=3, loops=20, hub=True)]
+
+
+@pytest.mark.parametrize("deg_by", ["target", "source"])
+def test_gcn_norm_weighted_bit_exact(dev, deg_by):
+    from bigcn_b200 import ops
+    for c in CASES:
+        c = dict(c)
+        n = c.pop("n")
+        ei, w = random_graph(n, **c)
+        ref_ei, ref_w = gcn_oracle.gcn_norm(ei, n, w, deg_by=deg_by)
+        got_ei, got_w = ops.gcn_norm(ei.to(dev), w.to(dev), n, False, True, deg_by=deg_by)
+        assert torch.equal(got_ei.cpu(), ref_ei)
+        assert torch.equal(bits(got_w), bits(ref_w)), (n, deg_by)
+    # unit weights reproduce the unweighted call (explain_PHEME.py:62 passes edge_weight=None)
+    ei, _ = random_graph(50, 120, 9)
+    a = ops.gcn_norm(ei.to(dev), None, 50)[1]
+    b = gcn_oracle.gcn_norm(ei, 50)[1]
+    assert torch.equal(bits(a), bits(b))
+
+
+def test_tree_edge_weights_td_and_bu(dev):
+    """Reply trees with DropEdge, both directions, weights in (0,1) as EBGCN's sigmoid produces."""
+    from bigcn_b200 import ops
+    from bigcn_b200.data import make_batch
+    b = make_batch("twitter15", 6, seed=4, train=True, in_feats=32)
+    n = b.x.shape[0]
+    g = torch.Generator().manual_seed(0)
+    for ei in (b.edge_index, b.BU_edge_index):
+        w = torch.rand(ei.shape[1], generator=g)
+        ref = gcn_oracle.gcn_norm(ei, n, w)[1]
+        got = ops.gcn_norm(ei.to(dev), w.to(dev), n)[1]
+        assert torch.equal(bits(got), bits(ref))
+
+
+@pytest.mark.parametrize("deg_by", ["target", "source"])
+def test_weighted_conv_forward_bit_exact_and_all_gradients(dev, deg_by):
+    import bigcn_b200
+    for c in CASES:
+        c = dict(c)
+        n = c.pop("n")
+        ei, w = random_graph(n, **c)
+        K = 40
+        torch.manual_seed(5)
+        ref = gcn_oracle.GCNConv(K, 64, deg_by=deg_by)
+        with torch.no_grad():
+            ref.bias.uniform_(-0.5, 0.5)
+        conv = bigcn_b200.GCNConv(K, 64, deg_by=deg_by).to(dev)
+        conv.load_state_dict(ref.state_dict())
+        x = torch.randn(n, K)
+        x[torch.rand(n, K) < 0.5] = 0
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        xg, wg = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+        out_ref = ref(xr, ei, wr)
+        out = conv(xg, ei.to(dev), wg)
+        # same x W^T (exact fp32 scan vs torch's fp32 matmul differ in summation order), so the
+        # propagate is compared bit for bit on the kernel's own product below; here: tolerance
+        scale = float(out_ref.abs().max().clamp_min(1e-30))
+        assert float((out.cpu() - out_ref).abs().max()) <= 1e-5 * scale
+        gout = torch.randn(n, 64, generator=torch.Generator().manual_seed(6))
+        out_ref.backward(gout)
+        out.backward(gout.to(dev))
+        for name, a, r in (("lin.weight", conv.lin.weight.grad, ref.lin.weight.grad), ("bias", conv.bias.grad, ref.bias.grad),
+                           ("edge_weight", wg.grad, wr.grad), ("x", xg.grad, xr.grad)):
+            if r.numel() == 0:
+                assert a.numel() == 0
+                continue
+            err = float((a.cpu().double() - r.double()).abs().max() / r.double().abs().max().clamp_min(1e-30))
+            assert err < 1e-4, (name, n, deg_by, err)
+        # against the fp64 oracle as well: edge-weight gradient is the delicate one (cancellation through deg)
+        ref64 = gcn_oracle.GCNConv(K, 64, deg_by=deg_by).double()
+        ref64.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+        w64 = w.double().requires_grad_(True)
+        ref64(x.double(), ei, w64).backward(gout.double())
+        if w.numel():
+            err = float((wg.grad.cpu().double() - w64.grad).abs().max() / w64.grad.abs().max().clamp_min(1e-30))
+            assert err < 1e-4, ("edge_weight vs fp64", err)
+
+
+def test_weighted_propagate_is_bit_exact_given_the_same_product(dev):
+    """With an identity-like weight (K = 64, W = I) the product x W^T is exact, so the whole conv must
+    equal the oracle's index_add_ order bit for bit -- including a hub row of hundreds of in-edges."""
+    import bigcn_b200
+    n = 2000
+    ei, w = random_graph(n, 3000, 3, loops=20, hub=True)
+    ref = gcn_oracle.GCNConv(64, 64)
+    conv = bigcn_b200.GCNConv(64, 64).to(dev)
+    with torch.no_grad():
+        ref.lin.weight.copy_(torch.eye(64))
+        ref.bias.uniform_(-1, 1)
+    conv.load_state_dict(ref.state_dict())
+    x = torch.randn(n, 64)
+    out = conv(x.to(dev), ei.to(dev), w.to(dev))
+    assert torch.equal(bits(out), bits(ref(x, ei, w)))
+    out2 = conv(x.to(dev), ei.to(dev), w.to(dev))
+    assert torch.equal(bits(out), bits(out2))
+
+
+def test_unweighted_conv_returns_dx_when_x_is_an_activation(dev):
+    """EBGCN's conv2 input depends on conv1 (EBGCN.py:75-84): x.requires_grad routes through the generic
+    form with unit weights; values equal the plain conv."""
+    import bigcn_b200
+    from bigcn_b200.data import make_batch
+    b = make_batch("twitter15", 4, seed=2, train=False, in_feats=24)
+    ref = gcn_oracle.GCNConv(24, 64)
+    conv = bigcn_b200.GCNConv(24, 64).to(dev)
+    conv.load_state_dict(ref.state_dict())
+    xr = b.x.clone().requires_grad_(True)
+    xg = b.x.to(dev).requires_grad_(True)
+    o_ref = ref(xr, b.edge_index)
+    o = conv(xg, b.edge_index.to(dev))
+    o_plain = conv(b.x.to(dev), b.edge_index.to(dev))
+    assert torch.equal(bits(o), bits(o_plain))
+    g = torch.randn_like(o_ref)
+    o_ref.backward(g)
+    o.backward(g.to(dev))
+    assert float((xg.grad.cpu() - xr.grad).abs().max() / xr.grad.abs().max()) < 1e-5
+
+
+def test_ebgcn_style_block_trains_through_our_convs(dev):
+    """The shape of EBGCN's TDrumorGCN.forward (EBGCN.py:61-93) with this library's GCNConv in place of
+    PyG's: conv1 -> edge weights from a small trained net on |h_i - h_j| -> BatchNorm over
+    [h1 | root_extend] -> conv2(edge_weight) ; gradients of every parameter against the oracle convs."""
+    import bigcn_b200
+    from bigcn_b200.data import make_batch
+    K = 30
+    b = make_batch("twitter15", 5, seed=8, train=False, in_feats=K)
+    torch.manual_seed(3)
+
+    class Block(torch.nn.Module):
+        def __init__(self, conv_cls):
+            super().__init__()
+            self.conv1 = conv_cls(K, 64)
+            self.conv2 = conv_cls(K + 64, 64)
+            self.sim = torch.nn.Linear(64, 1)
+            self.bn1 = torch.nn.BatchNorm1d(64 + K)
+
+        def forward(self, x, ei, batch, rootindex):
+            h = self.conv1(x, ei)
+            edge_pred = torch.sigmoid(self.sim((h[ei[0]] - h[ei[1]]).abs())).squeeze(1)
+            root_extend = x[rootindex[batch]]
+            z = torch.relu(self.bn1(torch.cat((h, root_extend), 1)))
+            return torch.relu(self.conv2(z, ei, edge_weight=edge_pred))
+
+    ref = Block(gcn_oracle.GCNConv)
+    m = Block(bigcn_b200.GCNConv).to(dev)
+    m.load_state_dict(ref.state_dict())
+    out_ref = ref(b.x, b.edge_index, b.batch, b.rootindex)
+    out = m(b.x.to(dev), b.edge_index.to(dev), b.batch.to(dev), b.rootindex.to(dev))
+    assert float((out.cpu() - out_ref).abs().max()) <= 2e-5 * float(out_ref.abs().max())
+    gout = torch.randn_like(out_ref)
+    out_ref.backward(gout)
+    out.backward(gout.to(dev))
+    # conv1.bias gets a gradient of exactly zero in exact arithmetic (BatchNorm and |h_i - h_j| both ignore
+    # a constant shift of h): errors are measured against the layer's scale, not that rounding noise
+    gmax = max(float(q.grad.abs().max()) for q in ref.parameters())
+    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        scale = max(float(q.grad.double().abs().max()), 1e-3 * gmax)
+        err = float((p.grad.cpu().double() - q.grad.double()).abs().max()) / scale
+        assert err < 2e-4, (name, err)
