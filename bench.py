@@ -267,6 +267,9 @@ def run_ours(args):
     #   "dense_h2d"    : copy the dense [N,5000] matrix to the device (644 MB over PCIe)
     #   "host_compact" : bigcn_b200.host_dense_to_csr -- one threaded pass over the host
     #                    matrix keeps the non-zero entries -- then copy the CSR (a few MB)
+    #   "hybrid_feed"  : bigcn_b200.HostFeeder -- the copy engine DMAs the last rows dense (compacted on the
+    #                    device) while the host threads compact the first rows; batch i+1 is fed on a side
+    #                    stream while step i runs (a prefetching loader loop)
     # and, separately, the loader-native sparse route ("e2e_sparse_loader": the batch is already
     # CSR on the host, as a loader that keeps the reference's index:count pairs would hand it).
     small_keys = [k for k in Batch._tensor_keys if k != "x"]
@@ -319,8 +322,38 @@ def run_ours(args):
         dst.x = ship_csr(loader_csr[i % N_ROTATE], i % 2)
         return float(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]).item())
 
-    def time_e2e(fn):
-        for i in range(max(1, min(args.warmup, 3))):
+    feeder = bigcn_b200.HostFeeder(dev, K_FEATS, max(nodes), n_threads=host_threads) if sparse_ok else None
+
+    feed_stream = torch.cuda.Stream(device=dev)
+    fed = {"i": None, "ready": None}
+
+    def feed_begin(i):
+        with torch.cuda.stream(feed_stream):
+            return (i, feeder.begin(host[i % N_ROTATE].x))      # the DMA of the last rows starts now
+
+    def feed_finish(tk):
+        i, ticket = tk
+        src, dst = host[i % N_ROTATE], stage[i % 2]
+        with torch.cuda.stream(feed_stream):
+            dst.x = feeder.finish(ticket)                        # host threads compact the first rows
+            copy_small(src, dst)
+            ev = torch.cuda.Event()
+            ev.record()
+        fed["i"], fed["ready"] = i, ev
+
+    def e2e_hybrid(i):
+        """Prefetching loader loop: batch i+1 is fed (HostFeeder, on its own stream) while the device runs
+        step i; every step still ends with the device -> host read of its loss."""
+        if fed["i"] != i:
+            feed_finish(feed_begin(i))
+        tk = feed_begin(i + 1)
+        torch.cuda.current_stream().wait_event(fed["ready"])
+        loss = tr.step(stage[i % 2], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
+        feed_finish(tk)
+        return float(loss.item())
+
+    def time_e2e(fn, warm=None):
+        for i in range(warm or max(1, min(args.warmup, 3))):
             fn(i)
         barrier()
         n_steps = max(3, min(args.steps, 12))
@@ -359,13 +392,19 @@ def run_ours(args):
         routes["host_compact"] = {"value": v, "ms_per_step": ms_,
                                   "h2d_bytes_per_step": small_bytes + host_csr[0].nbytes(),
                                   "host_threads": host_threads}
+        v, ms_, n_ = time_e2e(e2e_hybrid, warm=10)      # the split settles over the first calls
+        feeder.check()
+        routes["hybrid_feed"] = {"value": v, "ms_per_step": ms_, "host_threads": host_threads,
+                                 "dma_fraction": round(feeder.frac, 3), "last": {k: round(float(x), 3) for k, x in feeder.last.items()},
+                                 "h2d_bytes_per_step": int(small_bytes + feeder.last.get("n_dma", 0) * K_FEATS * 4
+                                                           + (1 - feeder.frac) * host_csr[0].nbytes())}
         v, ms_, n_ = time_e2e(e2e_loader)
         routes["sparse_loader"] = {"value": v, "ms_per_step": ms_,
                                    "h2d_bytes_per_step": small_bytes + loader_csr[0].nbytes()}
         v, ms_, n_ = time_e2e(e2e_forest)
         routes["device_dataset"] = {"value": v, "ms_per_step": ms_,
                                     "h2d_bytes_per_step": 5 * 8 * (len(ids_of[0]) + 1)}
-    best = max((k for k in routes if k in ("dense_h2d", "host_compact")), key=lambda k: routes[k]["value"])
+    best = max((k for k in routes if k in ("dense_h2d", "host_compact", "hybrid_feed")), key=lambda k: routes[k]["value"])
     e2e_value, e2e_ms, e2e_steps = routes[best]["value"], routes[best]["ms_per_step"], n_
     e2e_h2d = routes[best]["h2d_bytes_per_step"]
 
@@ -488,8 +527,10 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_per_step": e2e_ms, "route": best,
                     "note": "dense fp32 data.x in pinned host memory -> loss on the host, wall clock; routes timed: "
                             "dense_h2d = the matrix crosses PCIe as is, host_compact = host_dense_to_csr keeps the "
-                            "non-zeros on the host and the CSR crosses PCIe; the faster one is reported",
-                    "routes": {k: v for k, v in routes.items() if k in ("dense_h2d", "host_compact")}},
+                            "non-zeros on the host and the CSR crosses PCIe, hybrid_feed = HostFeeder.ship: the copy "
+                            "engine DMAs the last rows dense (compacted on the device) while the host threads compact "
+                            "the first rows, split adapted so both finish together; the fastest one is reported",
+                    "routes": {k: v for k, v in routes.items() if k in ("dense_h2d", "host_compact", "hybrid_feed")}},
             "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode, K_FEATS),
             "roofline": roof, "final_loss": final_loss,
             "per_rank": {"gpu_ms_per_step": [round(v, 4) for v in per_rank],

@@ -334,6 +334,21 @@ int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     double beta1, double beta2, double eps, double weight_decay,
                     double grad_scale, int64_t* step_count, bigcn_stream_t stream);
 
+/* ---- dense rows -> CSR on the device (the device half of bigcn_b200.HostFeeder) ------------------
+ * The reference's loader hands over DENSE bag-of-words rows (Process/dataset.py:64-99).  A feeder
+ * sends part of a batch's rows over PCIe as they are while the host compacts the rest
+ * (bigcn_host_dense_to_csr); these two calls turn the dense part into CSR entries that continue the
+ * host part's arrays.  dense_row_counts: non-zeros per row.  The caller forms the inclusive prefix
+ * of the counts; dense_rows_to_csr then writes row r's entries (ascending columns) at
+ * base + incl[r-1] and ptr_out[r] = base + incl[r] (ptr_out points at the combined row pointer's
+ * entry of row 0 + 1).  Entries that would pass cap (the capacity of col / val) are dropped, the
+ * row pointer stops growing and BIGCN_FLAG_X_NOT_SPARSE is set in *flags: never an out-of-bounds
+ * write, never a silent wrong answer. */
+int bigcn_dense_row_counts(const float* x, int64_t N, int64_t K, int32_t* cnt, bigcn_stream_t stream);
+int bigcn_dense_rows_to_csr(const float* x, int64_t N, int64_t K, const int32_t* incl_counts, int64_t base,
+                            int32_t* ptr_out, int32_t* col, float* val, int64_t cap, int32_t* flags,
+                            bigcn_stream_t stream);
+
 /* ---- on-device batch assembly + DropEdge --------------------------------------
  * For a dataset packed in HBM (all trees: node_ptr/edge_ptr [T+1], local edge lists, x as CSR over
  * all nodes, local root index, label) builds the batch of trees tree_id[0..B): what

@@ -14,7 +14,9 @@ anchors it on the reference's own call sites:
   model/Weibo/BiGCN_Weibo.py:16-89        (same maths, class Net, 2 classes)
   Process/dataset.py:64-99                (input contract, DropEdge)
 
-The only pin available is the hand-checkable 5-node known-answer vector of
+Pinned exception: ``evaluate_oracle`` (tools/evaluate.py) is checked against
+outputs of the reference's own file (tests/golden/make_evaluate_golden.py).
+For the GCN path the only pin available is the hand-checkable 5-node known-answer vector of
 SURVEY.md section 8c (tests/golden/kat_tree5.json) plus torch's own CPU ops
 (Linear, relu, log_softmax, nll_loss, pow(-0.5)) which are used directly.
 
