@@ -87,8 +87,11 @@ class _RumorGCN(torch.nn.Module):
         if self.training:
             self._calls += 1
         self.last_seed = seed
+        # want_grad: autograd.Function.forward cannot see torch.no_grad() (needs_input_grad is True for
+        # parameters either way); inference then skips the capture / column sort of x that only dW1 needs
         return dict(training=self.training, p=self.p, seed=seed, deg_by=self.deg_by,
-                    gemm_mode=self.gemm_mode, dir_mask=dir_mask, node_id_base=self.node_id_base)
+                    gemm_mode=self.gemm_mode, dir_mask=dir_mask, node_id_base=self.node_id_base,
+                    want_grad=torch.is_grad_enabled())
 
     def forward(self, data):
         none4 = (None,) * 4

@@ -449,7 +449,8 @@ class FeaturesFunction(torch.autograd.Function):
         o = Opts(training=int(opts["training"]), p_drop=float(opts["p"]), seed=int(opts["seed"]),
                  deg_by=L.DEG_BY[opts["deg_by"]], gemm_mode=L.GEMM_MODE[opts["gemm_mode"]],
                  dir_mask=int(opts["dir_mask"]),
-                 skip_wgrad_prep=int(not any(ctx.needs_input_grad)))   # inference: no column sort of x
+                 # inference (torch.no_grad() or no parameter wants a gradient): no column sort of x
+                 skip_wgrad_prep=int(not (opts.get("want_grad", True) and any(ctx.needs_input_grad))))
         ws_bytes = lib().bigcn_features_workspace_bytes(C.byref(dims))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         flags = opts.get("flags")
