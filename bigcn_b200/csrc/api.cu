@@ -33,6 +33,7 @@ int num_sms() {
 // work is ordered on the caller's stream (and a CUDA-graph capture sees a fork/join diamond).
 struct SideCtx {
   SideStream s;        // high priority: work the main stream will wait for soon (graph prep)
+  cudaStream_t side2;  // high priority, a second short chain beside the first (root columns; dW2b)
   cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
   cudaEvent_t ev[8];
   bool ok;
@@ -48,6 +49,7 @@ static SideCtx* side_ctx() {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess;
     for (int i = 0; i < 8 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
@@ -226,7 +228,20 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     w.xs.col = const_cast<int32_t*>(bt->x_col);
     w.xs.val = const_cast<float*>(bt->x_val);
   }
-  // 1. weights in the layouts the kernels stream
+  // 1. side stream (beside the X stream): structure of both directions and node_ptr -- depends on the
+  //    inputs only, so it forks before anything else is queued
+  SideCtx* sc = side_ctx();
+  cudaStream_t ss = sc ? sc->s.side : st;
+  cudaStream_t s2 = sc ? sc->side2 : st;
+  if (sc) stream_after(sc, 0, st, ss);
+  {
+    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
+    const int64_t E[2] = {dm->E_td, dm->E_bu};
+    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
+                                 w.prep_bytes, ss))
+      return rc;
+  }
+  // 2. weights in the layouts the kernels stream
   const int n_out = dirs.n == 2 ? 128 : 64;
   {
     TransposeJobs js{};
@@ -238,23 +253,16 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     }
     if (int rc = transpose_jobs_launch(js, st)) return rc;
   }
-  // 2. side stream (beside the X stream): structure of both directions, node_ptr, root columns
-  //    and, without dropout, the per-tree root projection
-  SideCtx* sc = side_ctx();
-  cudaStream_t ss = sc ? sc->s.side : st;
-  if (sc) stream_after(sc, 0, st, ss);
+  //    second side stream: the root rows' positive columns and, without dropout, the per-tree root
+  //    projection (needs the transposed W2b) -- a short chain of its own, not behind the graph prep
+  if (sc) stream_after(sc, 6, st, s2);
   {
-    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
-    const int64_t E[2] = {dm->E_td, dm->E_bu};
-    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
-                                 w.prep_bytes, ss))
-      return rc;
     RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
                  w.slot, w.overflow, DW2B_CAP};
     if (csr_in) {
-      if (int rc = root_nz_csr_launch(a, bt->x_ptr, bt->x_col, bt->x_val, ss)) return rc;
+      if (int rc = root_nz_csr_launch(a, bt->x_ptr, bt->x_col, bt->x_val, s2)) return rc;
     } else {
-      if (int rc = root_nz_launch(a, ss)) return rc;
+      if (int rc = root_nz_launch(a, s2)) return rc;
     }
     if (!dropping) {
       RootProjArgs pa{};
@@ -263,7 +271,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
         pa.w2bT[q] = w.w2bT[dirs.id[q]];
         pa.P[q] = w.P[dirs.id[q]];
       }
-      if (int rc = root_proj_launch(pa, dirs.n, ss)) return rc;
+      if (int rc = root_proj_launch(pa, dirs.n, s2)) return rc;
     }
   }
   // 3. X W1^T for all active directions in one pass over X (main stream)
@@ -279,7 +287,10 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   }
   // 4. the structure is needed from here on; the side stream goes on to sort the captured
   //    non-zeros of X by column for the weight gradient while the rest of the forward runs
-  if (sc) stream_after(sc, 1, ss, st);
+  if (sc) {
+    stream_after(sc, 1, ss, st);
+    stream_after(sc, 7, s2, st);
+  }
   bool side_busy = false;
   if (sparse) {
     if (o->skip_wgrad_prep || N == 0) {
@@ -358,6 +369,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   const bool join_late = o->gemm_mode == BIGCN_GEMM_SPARSE && phase == 0;
   SideCtx* sc = side_ctx();
   cudaStream_t ss = sc ? sc->s.side : st;
+  cudaStream_t s2 = sc ? sc->side2 : st;
   if (phase == 2) goto dw1_only;
   // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
@@ -384,8 +396,12 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_g2_launch(a, dirs.n, st)) return rc;
   }
-  // 3./4. on the side stream, beside the G1 -> T1 -> dW1 chain: db2, dW2a = T2^T A1 and dW2b
-  if (sc) stream_after(sc, 0, st, ss);
+  // 3./4. on the two side streams, beside the G1 -> T1 -> dW1 chain: db2 and dW2a = T2^T A1 on one,
+  //       dW2b on the other (both read T2 only)
+  if (sc) {
+    stream_after(sc, 0, st, ss);
+    cudaStreamWaitEvent(s2, sc->ev[0], 0);
+  }
   if (int rc = colsum_reduce_launch(db2_reduce, dirs.n, ss)) return rc;
   {
     OuterArgs a{};
@@ -406,7 +422,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
         sg.t[q] = t2[dirs.id[q]];
         sg.out[q] = w.dP[dirs.id[q]];
       }
-      if (int rc = segsum_launch(sg, B, dirs.n, ss)) return rc;
+      if (int rc = segsum_launch(sg, B, dirs.n, s2)) return rc;
     }
     Dw2bArgs a{};
     a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr; a.batch = bt->batch;
@@ -417,7 +433,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       const int d = dirs.id[q];
       a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d)};
     }
-    if (int rc = dw2b_launch(a, dirs.n, dropping, ss)) return rc;
+    if (int rc = dw2b_launch(a, dirs.n, dropping, s2)) return rc;
   }
   // 5. G1 = (T2 W2a) * mask * [H1 > 0]; db1
   {
@@ -447,7 +463,10 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   }
   // the dense dW1 paths reuse T2's buffer, which the side stream reads: join first.  The sparse
   // sweep touches none of the side stream's buffers and joins after it.
-  if (sc && !join_late) stream_after(sc, 1, ss, st);
+  if (sc && !join_late) {
+    stream_after(sc, 1, ss, st);
+    stream_after(sc, 7, s2, st);
+  }
   if (phase == 1) return 0;
 dw1_only:
   // 7. dW1 = T1^T X: a sweep over the column-sorted non-zeros (SPARSE) or one more pass over X
@@ -457,7 +476,10 @@ dw1_only:
     if (o->gemm_mode == BIGCN_GEMM_SPARSE) {
       if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);   // column-sorted X of the forward (no-op if none pending)
       if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
-      if (sc && join_late) stream_after(sc, 1, ss, st);
+      if (sc && join_late) {
+        stream_after(sc, 1, ss, st);
+        stream_after(sc, 7, s2, st);
+      }
     } else if (o->gemm_mode == BIGCN_GEMM_FP32) {
       if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
     } else {   // G1 (w.z) and T2 (w.xw) are dead here: they hold the TF32 hi / lo split of T1
@@ -518,7 +540,6 @@ __global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ g
 }
 
 
-// column sums of a [N][64] matrix (db of a conv on its own)
 int colsum64_launch(const float* g, int64_t N, float* part, float* out, cudaStream_t st) {
   const int nchunk = N > 0 ? cs_chunks(N) : 0;
   if (N > 0) {
@@ -551,6 +572,8 @@ extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[1], 0);
   cudaEventRecord(sc->ev[2], sc->low);
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[2], 0);
+  cudaEventRecord(sc->ev[6], sc->side2);
+  cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[6], 0);
   return 0;
 }
 // the internal low-priority stream (cudaStream_t) or NULL: lets a caching allocator be told that
@@ -587,6 +610,13 @@ extern "C" int bigcn_propagate(const int32_t* ptr, const int32_t* idx, const flo
   a.N = N; a.relu = relu;
   a.d[0] = PropDir{ptr, idx, dis, h, bias, out, ldh, ldo, long_ws, E};
   return propagate_launch(a, 1, (cudaStream_t)stream);
+}
+
+extern "C" size_t bigcn_colsum64_scratch_floats(int64_t N) { return (size_t)cs_chunks(N > 0 ? N : 1) * H; }
+
+extern "C" int bigcn_colsum64(const float* g, int64_t N, float* out, float* scratch, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(N >= 0 && out && (N == 0 || (g && scratch)), "colsum64: bad arguments");
+  return colsum64_launch(g, N, scratch, out, (cudaStream_t)stream);
 }
 
 extern "C" size_t bigcn_readout_scratch_floats(int64_t N, int64_t B) { return readout_scratch_floats(N, B, 1); }

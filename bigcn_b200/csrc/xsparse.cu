@@ -44,7 +44,7 @@ XSparse xs_carve(Carver& c, int64_t N, int64_t K) {
   x.keys[1] = c.take<int32_t>(x.cap);
   x.perm[0] = c.take<int32_t>(x.cap);
   x.perm[1] = c.take<int32_t>(x.cap);
-  x.hist = c.take<int32_t>((size_t)256 * xs_nblk(x.cap));
+  x.hist = c.take<int32_t>((size_t)256 * xs_nblk(x.cap) + 4 * 256);   // + digit totals of up to four passes
   x.bsum = c.take<int32_t>(xs_nscan(N));
   x.cptr = c.take<int32_t>(K + 1);
   x.crow = c.take<int32_t>(x.cap);
@@ -210,6 +210,11 @@ __global__ void __launch_bounds__(256) k_xs_from_csr(XSparse x) {
 }
 
 // ---- stable LSD radix sort of (column key, position), 8-bit digits ---------------------------
+// digit totals of pass p live behind the per-block histograms (zeroed by xs_build_csc)
+__device__ __forceinline__ int32_t* xs_dtot(const XSparse& x, int nblk, int pass) {
+  return x.hist + (int64_t)256 * nblk + 256 * pass;
+}
+
 __global__ void __launch_bounds__(RSX_THREADS) k_xs_hist(XSparse x, int src, int shift, int nblk) {
   __shared__ int h[256];
   h[threadIdx.x] = 0;
@@ -226,22 +231,35 @@ __global__ void __launch_bounds__(RSX_THREADS) k_xs_hist(XSparse x, int src, int
   }
   __syncthreads();
   x.hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+  // integer atomics: the totals do not depend on the order of arrival
+  if (base < n && h[threadIdx.x] != 0) atomicAdd(xs_dtot(x, nblk, shift >> 3) + threadIdx.x, h[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(256) k_xs_hscan(XSparse x, int nblk) {
-  // thread d owns digit d: offsets of (digit, block) in digit-major order; only the blocks that
-  // hold keys are walked
+// offsets of (digit, block) in digit-major order: 32 CTAs x 8 warps, warp = digit.  Every CTA scans the
+// 256 digit totals (k_xs_hist summed them); each warp then scans its digit's per-block counts with
+// coalesced loads.  Only the blocks that hold keys are walked.
+__global__ void __launch_bounds__(256) k_xs_hscan(XSparse x, int nblk, int pass) {
   const int n = x.state[0];
   const int used = (int)min((int64_t)nblk, ((int64_t)n + RSX_TILE - 1) / RSX_TILE);
-  int32_t* row = x.hist + (int64_t)threadIdx.x * nblk;
-  int tot = 0;
-  for (int b = 0; b < used; ++b) tot += row[b];
+  __shared__ int s_base[256];
   int dummy;
-  int run = block_excl_scan256(tot, &dummy);
-  for (int b = 0; b < used; ++b) {
-    const int t = row[b];
-    row[b] = run;
-    run += t;
+  s_base[threadIdx.x] = block_excl_scan256(xs_dtot(x, nblk, pass)[threadIdx.x], &dummy);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int32_t* row = x.hist + (int64_t)d * nblk;
+  int run = s_base[d];
+  for (int b0 = 0; b0 < used; b0 += 32) {
+    const int b = b0 + lane;
+    const int t = b < used ? row[b] : 0;
+    int inc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(FULL_MASK, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (b < used) row[b] = run + inc - t;
+    run += __shfl_sync(FULL_MASK, inc, 31);
   }
 }
 
@@ -352,11 +370,12 @@ int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cuda
     BIGCN_CHECK_LAUNCH("k_xs_from_csr");
   }
   const int passes = radix_passes_for(x.K);
+  cudaMemsetAsync(x.hist + (int64_t)256 * nblk, 0, 4 * 256 * sizeof(int32_t), st);   // digit totals
   int grid_keys = nblk;   // blocks past the live keys return at once
   for (int p = 0; p < passes; ++p) {
     k_xs_hist<<<grid_keys, RSX_THREADS, 0, st>>>(x, p & 1, 8 * p, nblk);
     BIGCN_CHECK_LAUNCH("k_xs_hist");
-    k_xs_hscan<<<1, 256, 0, st>>>(x, nblk);
+    k_xs_hscan<<<32, 256, 0, st>>>(x, nblk, p);
     BIGCN_CHECK_LAUNCH("k_xs_hscan");
     k_xs_scatter<<<grid_keys, RSX_THREADS, 0, st>>>(x, p & 1, 8 * p, nblk);
     BIGCN_CHECK_LAUNCH("k_xs_scatter");

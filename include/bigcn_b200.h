@@ -228,6 +228,11 @@ int bigcn_readout(const float* h2 /*[N,64]*/, const float* h1 /*[N,64]*/, const 
                   const int64_t* rootindex, int64_t N, int64_t B, float* feat, int64_t ldfeat,
                   float* pos /*[B,64] or NULL*/, float* scratch, int32_t* flags, bigcn_stream_t stream);
 
+/* out[f] = sum_i g[i, f] for a dense [N,64] matrix: the bias gradient of a propagate on its own
+ * (fixed chunks, fixed combine order: deterministic). */
+size_t bigcn_colsum64_scratch_floats(int64_t N);
+int bigcn_colsum64(const float* g, int64_t N, float* out /*[64]*/, float* scratch, bigcn_stream_t stream);
+
 /* ---- dropout mask spec (tests) -----------------------------------------
  * keep[i,c] (uint8) for c < n_cols of the concatenated [h1|root_extend] tensor
  * (BiGCN_Twitter.py:51-54); stream = 0 (TD) / 1 (BU). */
