@@ -110,11 +110,12 @@ struct FeatWs {
   float* op_part[2];        // [chunks][4096]
   float* dw_part;           // dW1 slab partials
   float* dP[2];             // [B][64]
-  int32_t* slot;            // [B][K] slot of column k in tree b's root list, or -1
+  int32_t* slot;            // [K][B] slot of column k in tree b's root list, or -1
   int32_t* overflow;        // [0] some root row has more than DW2B_CAP positive columns; [1 + k] column k is
                             // positive in some root row
   float* pos[2];            // [B][64] #{i in tree : H2[i][f] > 0}
   float* gs[2];             // [B][64] grad_feat / n_b
+  unsigned long long* keep[2];  // [N] bit t: root slot t of the node's tree survived dropout (train mode)
   float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
   float* ro_part;           // readout slice partials
   XSparse xs;               // row-sparse view of X (gemm_mode SPARSE)
@@ -167,6 +168,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
+  for (int d = 0; d < 2; ++d) w.keep[d] = c.take<unsigned long long>((size_t)(N > 0 ? N : 1));
   w.ro_part = c.take<float>(readout_scratch_floats(N, B, 2));
   w.xs = xs_carve(c, N, K);
   const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
@@ -316,6 +318,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       m.w2aT = w.w2aT[d]; m.w2bT = w.w2bT[d]; m.P = w.P[d];
       m.h1 = w.h1[d]; m.a1 = w.a1[d]; m.z = w.z[d];
       m.drop = make_drop(o, d);
+      m.keep = w.keep[d];
     }
     if (int rc = prop1_mix_launch(a, dirs.n, st)) return rc;
   }
@@ -431,7 +434,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     a.N = N; a.B = B; a.K = K; a.ld = H + K; a.node_id_base = bt->node_id_base;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d)};
+      a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d), w.keep[d]};
     }
     if (int rc = dw2b_launch(a, dirs.n, dropping, s2)) return rc;
   }
@@ -443,7 +446,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     c.nchunk = N > 0 ? bm_chunks(N) : 0;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = BwdMixDir{t2[d], w.h1[d], dir_w2(pr, d), g1[d], w.cs_part[d], make_drop(o, d)};
+      a.d[q] = BwdMixDir{t2[d], w.a1[d], dir_w2(pr, d), g1[d], w.cs_part[d], make_drop(o, d)};   // A1 stands in for (H1, mask)
       c.part[q] = w.cs_part[d]; c.out[q] = gdir_b1(gr, d);
     }
     if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;

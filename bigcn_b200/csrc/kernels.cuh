@@ -41,7 +41,7 @@ int root_nz_launch(const RootNzArgs&, cudaStream_t);
 int root_nz_csr_launch(const RootNzArgs&, const int32_t*, const int32_t*, const float*, cudaStream_t);
 struct RootProjArgs { const int32_t* cnt; const int32_t* col; const float* val; const float* w2bT[2]; float* P[2]; int64_t B, K; };
 int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
-struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; };
+struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; unsigned long long* keep; };
 struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
 constexpr int RO_SLICE = 512;  // rows per readout slice
@@ -55,7 +55,7 @@ struct PropG2Args { PropG2Dir d[2]; int64_t N; const int64_t* batch; int32_t cb;
 int propagate_g2_launch(const PropG2Args&, int, cudaStream_t);
 struct ColsumArgs { const float* part[4]; float* out[4]; int nchunk; };
 int colsum_reduce_launch(const ColsumArgs&, int, cudaStream_t);
-struct BwdMixDir { const float* t2; const float* h1; const float* w2; float* g1; float* part; DropSpec drop; };
+struct BwdMixDir { const float* t2; const float* h1 /* A1 = dropout(relu(H1)): > 0 where kept and positive */; const float* w2; float* g1; float* part; DropSpec drop; };
 struct BwdMixArgs { BwdMixDir d[2]; int64_t N, ldw2, node_id_base; };
 int bwd_mix_launch(const BwdMixArgs&, int, cudaStream_t);
 struct OuterArgs { const float* u[2]; const float* v[2]; float* part[2]; int64_t N; };
@@ -63,7 +63,7 @@ struct OuterReduceArgs { const float* part[2]; float* dst[2]; int64_t ld; int nc
 int outer64_launch(const OuterArgs&, const OuterReduceArgs&, int, cudaStream_t);
 struct SegSumArgs { const float* t[2]; float* out[2]; const int32_t* node_ptr; };
 int segsum_launch(const SegSumArgs&, int64_t, int, cudaStream_t);
-struct Dw2bDir { const float* t2; const float* dP; float* dw2; float* S; DropSpec drop; };
+struct Dw2bDir { const float* t2; const float* dP; float* dw2; float* S; DropSpec drop; const unsigned long long* keep; };
 struct Dw2bArgs { Dw2bDir d[2]; const float* x; const int64_t* rootindex; const int32_t* node_ptr; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; const int32_t* slot; const int32_t* overflow; int64_t N, B, K, ld, node_id_base; };
 int dw2b_launch(const Dw2bArgs&, int, bool, cudaStream_t);
 int dw2b_blocks(int64_t N);

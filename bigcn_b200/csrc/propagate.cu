@@ -78,8 +78,8 @@ int propagate_launch(const PropArgs& a0, int ndir, cudaStream_t st) {
 // (root_extend of BiGCN_Twitter.py:45-50 is x1[rootindex[batch]]: only these columns
 // can contribute to conv2 after the relu of :53.)
 // CTA per tree: 8 warps ballot 32-column strips, a strip-count scan orders them, a second
-// pass writes (col, val) at its rank and slot[b][k] = rank or -1 for every column (the map
-// the dW2b reduce uses to find a column's slot in a tree).
+// pass writes (col, val) at its rank and slot[k][b] = rank for the positive columns (column-major map,
+// preset to -1, that the dW2b reduce uses to find a column's slot in each tree with coalesced loads).
 __global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
   extern __shared__ int strip[];  // [nstrips] counts -> exclusive offsets
   __shared__ int s_total;
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(256) k_root_nz(RootNzArgs a) {
       a.col[b * a.K + pos] = (int32_t)k;
       a.val[b * a.K + pos] = v;
       a.overflow[1 + k] = 1;   // column k is positive in some root row (same value from every writer)
+      a.slot[k * a.B + b] = pos;  // column-major slot map, -1 (memset) everywhere else
     }
-    if (k < a.K) a.slot[b * a.K + k] = v > 0.f ? pos : -1;
   }
   if (threadIdx.x == 0) {
     a.cnt[b] = s_total;
@@ -140,8 +140,6 @@ __global__ void __launch_bounds__(256) k_root_nz_csr(RootNzArgs a, const int32_t
                                                      const int32_t* __restrict__ xcol, const float* __restrict__ xval) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
-  for (int64_t k = threadIdx.x; k < a.K; k += blockDim.x) a.slot[b * a.K + k] = -1;
-  __syncthreads();
   if (w != 0) return;
   const int64_t r = a.rootindex[b];
   const bool ok = r >= 0 && r < a.N;
@@ -162,7 +160,7 @@ __global__ void __launch_bounds__(256) k_root_nz_csr(RootNzArgs a, const int32_t
       const int pos = n + __popc(m & ((1u << lane) - 1u));
       a.col[b * a.K + pos] = k;
       a.val[b * a.K + pos] = v;
-      a.slot[b * a.K + k] = pos;
+      a.slot[(int64_t)k * a.B + b] = pos;
       a.overflow[1 + k] = 1;
     }
     n += __popc(m);
@@ -298,6 +296,7 @@ struct PostMix {
     if (p.drop.on) {
       const int n = rnz_cnt[b];
       float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned long long kept = 0ull;   // bit t = root slot t survived for this node (slots 0..63)
       for (int t0 = 0; t0 < n; t0 += 16) {
         const int t = t0 + sub;
         int k = 0;
@@ -312,6 +311,7 @@ struct PostMix {
         }
         // kept entries in ascending order: (k, v) pairs go through the scratch row
         unsigned mine = (__ballot_sync(hm, keep) >> (hm == 0xffffu ? 0 : 16)) & 0xffffu;
+        if (t0 < 64) kept |= (unsigned long long)mine << t0;
         if (keep) {
           const int pos = __popc(mine & ((1u << sub) - 1u));
           reinterpret_cast<int*>(scratch)[pos] = k;
@@ -344,6 +344,8 @@ struct PostMix {
         }
         __syncwarp(hm);
       }
+      // the backward's dW2b sums T2 rows over exactly these (node, slot) pairs: hand it the decisions
+      if (sub == 0 && p.keep != nullptr) p.keep[i] = kept;
       z.x = fmaf(p.drop.scale, racc.x, z.x);
       z.y = fmaf(p.drop.scale, racc.y, z.y);
       z.z = fmaf(p.drop.scale, racc.z, z.z);
@@ -545,7 +547,8 @@ __global__ void __launch_bounds__(256) k_colsum_reduce(ColsumArgs a) {
   if (g == 0) a.out[j][f] = ((red[0][f] + red[1][f]) + red[2][f]) + red[3][f];
 }
 
-// G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1.
+// G1 = (T2 W2a) * dropout-mask * [H1 > 0]; partial column sums for db1.  The forward kept
+// A1 = dropout(relu(H1)): A1 > 0 exactly where the mask kept a positive H1, so no Philox here.
 // CTA = BM_ROWS rows: 8 warps x 8 row pairs, half-warp per row.
 __global__ void __launch_bounds__(256) k_bwd_mix(BwdMixArgs a) {
   __shared__ __align__(16) float sW[H * H];   // [o][k] = W2[o][k], k < 64
@@ -569,18 +572,15 @@ __global__ void __launch_bounds__(256) k_bwd_mix(BwdMixArgs a) {
     const float4 h1 = ok1 ? ld4(p.h1 + i1 * H + 4 * sub) : zero;
     float4 g0, g1;
     matvec2_smem(t0, t1, sW, scratch, sub, hm, g0, g1);
-    if (p.drop.on) {
-      drop_quad(p.drop, a.node_id_base + i0, sub, g0);
-      drop_quad(p.drop, a.node_id_base + i1, sub, g1);
-    }
-    g0.x = h0.x > 0.f ? g0.x : 0.f;
-    g0.y = h0.y > 0.f ? g0.y : 0.f;
-    g0.z = h0.z > 0.f ? g0.z : 0.f;
-    g0.w = h0.w > 0.f ? g0.w : 0.f;
-    g1.x = h1.x > 0.f ? g1.x : 0.f;
-    g1.y = h1.y > 0.f ? g1.y : 0.f;
-    g1.z = h1.z > 0.f ? g1.z : 0.f;
-    g1.w = h1.w > 0.f ? g1.w : 0.f;
+    const float sc = p.drop.on ? p.drop.scale : 1.f;   // x 1.0f is exact
+    g0.x = h0.x > 0.f ? __fmul_rn(g0.x, sc) : 0.f;
+    g0.y = h0.y > 0.f ? __fmul_rn(g0.y, sc) : 0.f;
+    g0.z = h0.z > 0.f ? __fmul_rn(g0.z, sc) : 0.f;
+    g0.w = h0.w > 0.f ? __fmul_rn(g0.w, sc) : 0.f;
+    g1.x = h1.x > 0.f ? __fmul_rn(g1.x, sc) : 0.f;
+    g1.y = h1.y > 0.f ? __fmul_rn(g1.y, sc) : 0.f;
+    g1.z = h1.z > 0.f ? __fmul_rn(g1.z, sc) : 0.f;
+    g1.w = h1.w > 0.f ? __fmul_rn(g1.w, sc) : 0.f;
     if (ok0) st4(p.g1 + i0 * H + 4 * sub, g0);
     if (ok1) st4(p.g1 + i1 * H + 4 * sub, g1);
     cs.x += g0.x; cs.y += g0.y; cs.z += g0.z; cs.w += g0.w;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
         const int64_t b = b0 + q * 32 + lane;
         float v = 0.f;
         if (b < a.B) {   // relu(x_root[b][k]) through the slot map (no dense x needed)
-          const int t = a.slot[b * a.K + k];
+          const int t = a.slot[k * a.B + b];
           if (t >= 0) v = a.rnz_val[b * a.K + t];
         }
         const unsigned m = __ballot_sync(FULL_MASK, v > 0.f);
@@ -767,13 +767,16 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
 // reduce: warp per column k: trees ascending (slot map), blocks ascending:
 //   dW2[o][64 + k] = scale * sum_b relu(x_root_b[k]) * sum_blk S[(blk + b)][slot][o]
 //   eval / p = 0:   dW2[o][64 + k] = sum_b relu(x_root_b[k]) * dP[b][o]
+static_assert(DW2B_CAP <= 64, "the forward hands the keep decisions over as one 64-bit word per node");
 __global__ void __launch_bounds__(256) k_dw2b_part(Dw2bArgs a) {
   if (*a.overflow != 0) return;
   __shared__ __align__(16) float sT[DW2B_ROWS * H];
+  __shared__ unsigned long long sK[DW2B_ROWS];   // the forward's keep decisions per (row, root slot)
   const Dw2bDir& p = a.d[blockIdx.y];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * DW2B_ROWS;
   const int64_t r1 = min(a.N, r0 + DW2B_ROWS);
+  if (threadIdx.x < DW2B_ROWS) sK[threadIdx.x] = r0 + threadIdx.x < r1 ? p.keep[r0 + threadIdx.x] : 0ull;
   for (int i = threadIdx.x; i < DW2B_ROWS * H / 4; i += 256) {
     const int64_t r = r0 + (i >> 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -788,15 +791,10 @@ __global__ void __launch_bounds__(256) k_dw2b_part(Dw2bArgs a) {
     const int cnt = a.rnz_cnt[b];
     float* Sb = p.S + ((size_t)(blockIdx.x + b) * DW2B_CAP) * H;
     for (int t = w; t < cnt; t += 8) {
-      const uint32_t c = (uint32_t)(H + a.rnz_col[b * a.K + t]);
       float2 acc = make_float2(0.f, 0.f);
       for (int i0 = s; i0 < e; i0 += 32) {
         const int i = i0 + lane;
-        bool keep = false;
-        if (i < e) {
-          const Philox4 r = drop_block(p.drop, a.node_id_base + i, c >> 2);
-          keep = philox_elem(r, c & 3) >= p.drop.thresh;
-        }
+        const bool keep = i < e && ((sK[i - r0] >> t) & 1ull);   // t < DW2B_CAP = 64 on this path
         unsigned m = __ballot_sync(FULL_MASK, keep);
         while (m) {
           const int sl = __ffs(m) - 1;
@@ -826,7 +824,7 @@ __global__ void __launch_bounds__(256) k_dw2b_reduce(Dw2bArgs a) {
   if (k < a.K && a.overflow[1 + k] != 0) {
     for (int64_t b0 = (int64_t)g * 32; b0 < a.B; b0 += 128) {
       const int64_t b = b0 + lane;
-      const int t = b < a.B ? a.slot[b * a.K + k] : -1;
+      const int t = b < a.B ? a.slot[k * a.B + b] : -1;   // column-major: one coalesced load per 32 trees
       float v = 0.f;
       int s = 0, e = 0;
       if (t >= 0) {                       // lanes fetch their tree's operands in parallel
@@ -899,6 +897,7 @@ int root_nz_csr_launch(const RootNzArgs& a, const int32_t* xptr, const int32_t* 
                        cudaStream_t st) {
   cudaMemsetAsync(a.overflow, 0, (size_t)(1 + a.K) * sizeof(int32_t), st);
   if (a.B == 0) return 0;
+  cudaMemsetAsync(a.slot, 0xFF, (size_t)a.B * a.K * sizeof(int32_t), st);   // -1: column not positive in that root
   k_root_nz_csr<<<(int)a.B, 256, 0, st>>>(a, xptr, xcol, xval);
   BIGCN_CHECK_LAUNCH("k_root_nz_csr");
   return 0;
@@ -906,6 +905,7 @@ int root_nz_csr_launch(const RootNzArgs& a, const int32_t* xptr, const int32_t* 
 int root_nz_launch(const RootNzArgs& a, cudaStream_t st) {
   cudaMemsetAsync(a.overflow, 0, (size_t)(1 + a.K) * sizeof(int32_t), st);
   if (a.B == 0) return 0;
+  cudaMemsetAsync(a.slot, 0xFF, (size_t)a.B * a.K * sizeof(int32_t), st);   // -1: column not positive in that root
   const size_t smem = (size_t)((a.K + 31) / 32) * sizeof(int);
   BIGCN_CHECK_ARG(smem <= 48 * 1024, "root_nz: in_feats too large (%lld)", (long long)a.K);
   k_root_nz<<<(int)a.B, 256, smem, st>>>(a);
