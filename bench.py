@@ -325,6 +325,7 @@ def run_ours(args):
     feeder = bigcn_b200.HostFeeder(dev, K_FEATS, max(nodes), n_threads=host_threads) if sparse_ok else None
 
     feed_stream = torch.cuda.Stream(device=dev)
+    hyb_cpu = {}
     fed = {"i": None, "ready": None}
 
     def feed_begin(i):
@@ -335,8 +336,13 @@ def run_ours(args):
         i, ticket = tk
         src, dst = host[i % N_ROTATE], stage[i % 2]
         with torch.cuda.stream(feed_stream):
+            ta = time.perf_counter()
             dst.x = feeder.finish(ticket)                        # host threads compact the first rows
+            tb = time.perf_counter()
             copy_small(src, dst)
+            hyb_cpu["finish.ship"] = (tb - ta) * 1e3
+            hyb_cpu["finish.small"] = (time.perf_counter() - tb) * 1e3
+            hyb_cpu.update({"ship." + k: v for k, v in feeder.last_cpu.items()})
             ev = torch.cuda.Event()
             ev.record()
         fed["i"], fed["ready"] = i, ev
@@ -346,19 +352,28 @@ def run_ours(args):
         step i; every step still ends with the device -> host read of its loss."""
         if fed["i"] != i:
             feed_finish(feed_begin(i))
+        t0 = time.perf_counter()
         tk = feed_begin(i + 1)
+        t1 = time.perf_counter()
         torch.cuda.current_stream().wait_event(fed["ready"])
         loss = tr.step(stage[i % 2], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
+        t2 = time.perf_counter()
         feed_finish(tk)
-        return float(loss.item())
+        t3 = time.perf_counter()
+        out = float(loss.item())
+        t4 = time.perf_counter()
+        for k, v in (("begin", t1 - t0), ("step_enqueue", t2 - t1), ("finish", t3 - t2), ("loss_read", t4 - t3)):
+            hyb_cpu[k] = hyb_cpu.get(k, 0.0) * 0.7 + 0.3 * v * 1e3      # running mean, ms
+        return out
 
     def time_e2e(fn, warm=None):
-        for i in range(warm or max(1, min(args.warmup, 3))):
+        warm = warm or max(1, min(args.warmup, 3))
+        for i in range(warm):
             fn(i)
         barrier()
         n_steps = max(3, min(args.steps, 12))
         t0 = time.perf_counter()
-        for i in range(n_steps):
+        for i in range(warm, warm + n_steps):      # the step index keeps counting: a prefetching route stays primed
             fn(i)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -392,10 +407,10 @@ def run_ours(args):
         routes["host_compact"] = {"value": v, "ms_per_step": ms_,
                                   "h2d_bytes_per_step": small_bytes + host_csr[0].nbytes(),
                                   "host_threads": host_threads}
-        v, ms_, n_ = time_e2e(e2e_hybrid, warm=10)      # the split settles over the first calls
+        v, ms_, n_ = time_e2e(e2e_hybrid, warm=30)      # the split settles over the first calls
         feeder.check()
         routes["hybrid_feed"] = {"value": v, "ms_per_step": ms_, "host_threads": host_threads,
-                                 "dma_fraction": round(feeder.frac, 3), "last": {k: round(float(x), 3) for k, x in feeder.last.items()},
+                                 "dma_fraction": round(feeder.frac, 3), "host_loop_ms": {k: round(v, 3) for k, v in hyb_cpu.items()}, "last": {k: round(float(x), 3) for k, x in feeder.last.items()},
                                  "h2d_bytes_per_step": int(small_bytes + feeder.last.get("n_dma", 0) * K_FEATS * 4
                                                            + (1 - feeder.frac) * host_csr[0].nbytes())}
         v, ms_, n_ = time_e2e(e2e_loader)

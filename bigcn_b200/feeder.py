@@ -46,6 +46,7 @@ class HostFeeder:
                              torch.empty(self.cap, dtype=torch.float32, pin_memory=True), (self.max_nodes, self.k)),
                 ev=None))
         self._turn = 0
+        self._t_begin, self._loop_ms, self._c = None, 0.0, 0.0
         self.last = {}
         self.flags = torch.zeros(1, dtype=torch.int32, device=dev)   # BIGCN_FLAG_X_NOT_SPARSE: see check()
 
@@ -62,14 +63,25 @@ class HostFeeder:
         if ev is None:
             return
         s["ev"] = None
-        e0, e1, n_dma, n_host, host_ms = ev
+        e0, e1, n_dma, n_host, host_ms, dma_first = ev
         if not e1.query():
             e1.synchronize()
         dma_ms = e0.elapsed_time(e1)
         self.last = dict(dma_ms=dma_ms, host_ms=host_ms, n_dma=n_dma, n_host=n_host, frac=self.frac)
         if self.adapt and n_dma > 0 and n_host > 0 and dma_ms > 0 and host_ms > 0:
             r_dma, r_host = n_dma / dma_ms, n_host / host_ms          # rows per ms of either engine
-            target = r_dma / (r_dma + r_host)
+            # the host side of a loader loop also enqueues the step and this feeder's own work: when the
+            # DMA finished before the host pass did (the loop is host-bound), that overhead c -- the loop
+            # period minus the host pass -- goes on the host's side of the balance
+            #     n_dma / r_dma = c + (n - n_dma) / r_host
+            if dma_first and self._loop_ms > 0:
+                self._c = 0.5 * self._c + 0.5 * max(0.0, min(self._loop_ms - host_ms, 0.5 * host_ms))
+            else:
+                self._c *= 0.8                      # DMA-bound: the estimate would include waiting; let it decay
+            c = self._c
+            n = n_dma + n_host
+            target = (c + n / r_host) / (1.0 / r_dma + 1.0 / r_host) / n
+            self.last["overhead_ms"] = c
             self.frac = min(0.95, max(0.05, 0.5 * self.frac + 0.5 * target))
 
     def ship(self, x_host: torch.Tensor) -> SparseX:
@@ -84,6 +96,11 @@ class HostFeeder:
         n, k = x_host.shape
         if k != self.k or n > self.max_nodes:
             raise L.BigcnError(f"HostFeeder.ship: built for at most {self.max_nodes} rows of {self.k} features, got {n} x {k}")
+        now = time.perf_counter()
+        if self._t_begin is not None:
+            loop = (now - self._t_begin) * 1e3
+            self._loop_ms = loop if self._loop_ms == 0 else 0.5 * self._loop_ms + 0.5 * loop
+        self._t_begin = now
         s = self.slots[self._turn]
         self._turn = (self._turn + 1) % len(self.slots)
         self._settle(s)
@@ -111,18 +128,21 @@ class HostFeeder:
         t0 = time.perf_counter()
         hs = host_dense_to_csr(x_host[:n_host], n_threads=self.n_threads, out=s["host"], cap=self.cap)
         host_ms = (time.perf_counter() - t0) * 1e3
+        dma_first = e1.query() if e1 is not None else False      # did the copy engine finish before the host pass?
         nnz_h = int(hs.col.numel())
         s["ptr"][:n_host + 1].copy_(hs.ptr, non_blocking=True)
         s["col"][:nnz_h].copy_(hs.col, non_blocking=True)
         s["val"][:nnz_h].copy_(hs.val, non_blocking=True)
         s["h2d_done"] = torch.cuda.Event()
         s["h2d_done"].record()
+        t_cp = time.perf_counter()
         if n_dma > 0:
             check(lib().bigcn_dense_rows_to_csr(_p(s["dense"]), n_dma, k, _p(incl), nnz_h, _p(s["ptr"][n_host + 1:]),
                                                 _p(s["col"]), _p(s["val"]), self.cap, _p(self.flags), _stream()),
                   "dense_rows_to_csr")
-            s["ev"] = (e0, e1, n_dma, n_host, host_ms)
+            s["ev"] = (e0, e1, n_dma, n_host, host_ms, dma_first)
             s["incl"] = incl
+        self.last_cpu = dict(host_ms=host_ms, copies_ms=(t_cp - t0) * 1e3 - host_ms, fill_ms=(time.perf_counter() - t_cp) * 1e3)
         # the number of non-zeros of the DMA part is only known on the device: col / val are handed
         # over at capacity and ptr[N] bounds what is read
         return SparseX(s["ptr"][:n + 1], s["col"], s["val"], (n, k))
