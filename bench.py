@@ -407,7 +407,7 @@ def run_ours(args):
         routes["host_compact"] = {"value": v, "ms_per_step": ms_,
                                   "h2d_bytes_per_step": small_bytes + host_csr[0].nbytes(),
                                   "host_threads": host_threads}
-        v, ms_, n_ = time_e2e(e2e_hybrid, warm=30)      # the split settles over the first calls
+        v, ms_, n_ = time_e2e(e2e_hybrid, warm=30 if args.steps >= 10 else 3)      # the split settles over the first calls
         feeder.check()
         routes["hybrid_feed"] = {"value": v, "ms_per_step": ms_, "host_threads": host_threads,
                                  "dma_fraction": round(feeder.frac, 3), "host_loop_ms": {k: round(v, 3) for k, v in hyb_cpu.items()}, "last": {k: round(float(x), 3) for k, x in feeder.last.items()},
