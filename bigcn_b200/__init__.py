@@ -16,7 +16,8 @@ from .ops import SparseX, host_dense_to_csr  # noqa: E402,F401
 from .loader import DeviceForest  # noqa: E402,F401
 from .metrics import EvalCounts  # noqa: E402,F401
 from .feeder import HostFeeder  # noqa: E402,F401
+from .training import train_GCN  # noqa: E402,F401
 from .checkpoint import EarlyStopping, EarlyStopping2class, make_checkpoint  # noqa: E402,F401
 
 __all__ = ["GCNConv", "TDrumorGCN", "BUrumorGCN", "BiGCN", "Net", "FusedTrainer", "BigcnError",
-           "SparseX", "host_dense_to_csr", "DeviceForest", "EvalCounts", "HostFeeder", "EarlyStopping", "EarlyStopping2class", "make_checkpoint", "data", "ops", "torch_ops"]
+           "SparseX", "host_dense_to_csr", "DeviceForest", "EvalCounts", "HostFeeder", "train_GCN", "EarlyStopping", "EarlyStopping2class", "make_checkpoint", "data", "ops", "torch_ops"]
