@@ -90,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)     # the timed region lasts ~13 ms: a few samples inside it
 
     def __enter__(self):
         if self.nv is not None:

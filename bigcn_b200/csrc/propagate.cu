@@ -690,8 +690,8 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
   __shared__ float s_hit_v[128];
   __shared__ int s_nhit;
   const Dw2bDir& p = a.d[blockIdx.y];
-  const int64_t k = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t k = blockIdx.x; k < a.K; k += gridDim.x) {   // columns round-robin over a capped grid
   float2 acc = make_float2(0.f, 0.f);
   const uint32_t c = (uint32_t)(H + k);
   for (int64_t b0 = 0; b0 < a.B; b0 += 128) {
@@ -755,6 +755,8 @@ __global__ void __launch_bounds__(128) k_dw2b(Dw2bArgs a) {
   if (threadIdx.x < H) {
     const float s = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
     p.dw2[(int64_t)threadIdx.x * a.ld + H + k] = p.drop.on ? s * p.drop.scale : s;
+  }
+  __syncthreads();   // red[] is reused by the next column
   }
 }
 
@@ -1024,7 +1026,12 @@ int dw2b_launch(const Dw2bArgs& a, int ndir, bool dropping, cudaStream_t st) {
     k_dw2b_reduce<<<dim3((int)g, ndir), 256, 0, st>>>(a);
   }
   BIGCN_CHECK_LAUNCH("k_dw2b_reduce");
-  k_dw2b<<<dim3((int)a.K, ndir), 128, 0, st>>>(a);   // dense-root fallback, returns at once otherwise
+  {   // dense-root fallback, returns at once otherwise (a capped grid: the usual case is 1 k CTAs that exit)
+    int64_t g = a.K;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (g > cap) g = cap;
+    k_dw2b<<<dim3((int)g, ndir), 128, 0, st>>>(a);
+  }
   BIGCN_CHECK_LAUNCH("k_dw2b");
   return 0;
 }
