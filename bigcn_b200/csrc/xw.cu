@@ -129,6 +129,10 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
     case 4: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 4, st);
     case 5: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 3, st);
     case 6: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 2, st);
+    case 7: return xw_scan_launch<true, 3>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 3, st);
+    case 8: return xw_scan_launch<true, 4>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 4, st);
+    case 9: return xw_scan_launch<true, 4>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 8, st);
+    case 10: return xw_scan_launch<true, 5>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 5, st);
     default: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
   }
 }
