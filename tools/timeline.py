@@ -15,6 +15,14 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 def main():
     dev = torch.device("cuda", 0)
+    import ctypes as C
+    from bigcn_b200 import _lib as L
+    lib = L.lib()
+    lib.bigcn_debug_set.argtypes = [C.c_int, C.c_int]
+    lib.bigcn_debug_set.restype = None
+    for spec in sys.argv[1:]:               # "knob:value" pairs (bigcn_debug_set), e.g. 4:1
+        k, v = spec.split(":")
+        lib.bigcn_debug_set(int(k), int(v))
     batches = []
     for i in range(3):
         b = make_batch_shard("twitter16", 128, 1000 + i)[0]
