@@ -118,6 +118,7 @@ _SIGS = {
     "bigcn_dense_row_counts": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr]),
     "bigcn_dense_rows_to_csr": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64,
                                           c_ptr, c_ptr]),
+    "bigcn_readout_backward": (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr]),
     "bigcn_colsum64_scratch_floats": (C.c_size_t, [C.c_int64]),
     "bigcn_colsum64": (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_eval_counts": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),

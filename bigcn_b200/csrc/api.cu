@@ -637,6 +637,14 @@ extern "C" int bigcn_readout(const float* h2, const float* h1, const int32_t* no
   return readout_launch(a, (cudaStream_t)stream);
 }
 
+extern "C" int bigcn_readout_backward(const float* grad_feat, int64_t ldg, const int32_t* node_ptr, const int64_t* batch,
+                                      int64_t N, int64_t B, float* grad_h2, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(N >= 0 && B >= 0 && ldg >= H && (ldg % 4 == 0) && (N == 0 || (grad_feat && node_ptr && batch && grad_h2)),
+                  "readout_backward: bad arguments");
+  BIGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(grad_feat) & 15) == 0, "readout_backward: grad_feat must be 16 B aligned");
+  return readout_bwd_launch(grad_feat, ldg, node_ptr, batch, N, B, grad_h2, (cudaStream_t)stream);
+}
+
 extern "C" int bigcn_dropout_mask(uint64_t seed, int32_t stream_id, int64_t node_id_base, int64_t N,
                                   int64_t n_cols, float p, uint8_t* keep, bigcn_stream_t stream) {
   BIGCN_CHECK_ARG(p >= 0.f && p < 1.f, "dropout_mask: p must be in [0,1)");

@@ -48,6 +48,7 @@ constexpr int RO_SLICE = 512;  // rows per readout slice
 struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t ldfeat; int64_t N, B; int32_t* flags; float* scratch; int64_t nitems; };
 int readout_launch(const ReadoutArgs&, cudaStream_t);
 size_t readout_scratch_floats(int64_t N, int64_t B, int ndir);
+int readout_bwd_launch(const float*, int64_t, const int32_t*, const int64_t*, int64_t, int64_t, float*, cudaStream_t);
 struct GScaleArgs { const float* grad_feat; const float* pos[2]; float* gs[2]; float* part[2]; int feat_base[2]; const int32_t* node_ptr; int64_t B; };
 int gscale_launch(const GScaleArgs&, int, cudaStream_t);
 struct PropG2Dir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h2; const float* gs; float* out; int32_t* lng; int64_t E; };

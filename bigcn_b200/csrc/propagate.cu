@@ -481,6 +481,35 @@ __global__ void __launch_bounds__(256) k_readout_final(ReadoutArgs a) {
   }
 }
 
+// scatter_mean backward on its own (the fused training path forms this inside k_propagate_g2):
+// dh2[i][f] = grad_feat[batch[i]][f] / n_b.  Half-warp per row.
+__global__ void __launch_bounds__(256) k_readout_bwd(const float* __restrict__ gfeat, int64_t ldg,
+                                                     const int32_t* __restrict__ node_ptr, const int64_t* __restrict__ batch,
+                                                     int64_t N, int64_t B, float* __restrict__ dh2) {
+  const int sub = threadIdx.x & 15;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < N; i += ((int64_t)gridDim.x * blockDim.x) >> 4) {
+    const int64_t b = batch[i];
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b >= 0 && b < B) {
+      const int n = node_ptr[b + 1] - node_ptr[b];
+      const float inv_n = (float)(n > 0 ? n : 1);
+      const float4 v = ld4(gfeat + b * ldg + 4 * sub);
+      g = make_float4(__fdiv_rn(v.x, inv_n), __fdiv_rn(v.y, inv_n), __fdiv_rn(v.z, inv_n), __fdiv_rn(v.w, inv_n));
+    }
+    st4(dh2 + i * H + 4 * sub, g);
+  }
+}
+int readout_bwd_launch(const float* gfeat, int64_t ldg, const int32_t* node_ptr, const int64_t* batch, int64_t N, int64_t B,
+                       float* dh2, cudaStream_t st) {
+  if (N == 0) return 0;
+  int64_t g = ceil_div(N, 16);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  k_readout_bwd<<<(int)g, 256, 0, st>>>(gfeat, ldg, node_ptr, batch, N, B, dh2);
+  BIGCN_CHECK_LAUNCH("k_readout_bwd");
+  return 0;
+}
+
 // ---------------------------------------------------------------- backward pieces
 // Per tree: gs[d][b][f] = grad_feat[b][base_d + f] / n_b (scatter_mean backward), and the
 // partial column sums of db2 = sum_i G2[i] = sum_b gs[b] * #{i in b : H2[i] > 0} using the

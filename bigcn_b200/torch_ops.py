@@ -9,8 +9,8 @@ is a thin call into libbigcn_b200.so on the current stream; outputs come from to
   xw(x, w, mode) -> [N,64]            GCNConv.lin;  backward: xw_wgrad(x, t, mode) -> [64,K]
   propagate(h, in_ptr, in_idx, out_ptr, out_idx, dis, num_edges, in_long?, out_long?, bias?, relu) -> [N,64]
         MessagePassing.propagate + bias (+ relu); backward: the transposed CSR for dh, column sums for dbias
-  readout(h2, h1, node_ptr, rootindex) -> [B,128]   second root-extend + scatter_mean (:58-65), forward only
-        (the training path differentiates it inside bigcn_features_backward)
+  readout(h2, h1, node_ptr, rootindex, batch) -> [B,128]   second root-extend + scatter_mean (:58-65);
+        backward: readout_backward (the mean's gradient to h2; h1[root] is detached as in the reference)
 
 ``torch.ops.bigcn_b200.xw(x, w, "fp32")`` etc.; ``conv(x, edge_index)`` of torch_geometric is
 ``propagate(xw(x, W), *graph_prep(...))``, which is how tests/test_gpu_torch_ops.py checks them
@@ -158,10 +158,40 @@ propagate.register_autograd(_prop_backward, setup_context=_prop_setup)
 
 # ---------------------------------------------------------------------------------- readout
 @custom_op("bigcn_b200::readout", mutates_args=(), device_types="cuda")
-def readout(h2: Tensor, h1: Tensor, node_ptr: Tensor, rootindex: Tensor) -> Tensor:
+def readout(h2: Tensor, h1: Tensor, node_ptr: Tensor, rootindex: Tensor, batch: Tensor) -> Tensor:
     return ops.readout(h2, h1, node_ptr, rootindex)
 
 
 @readout.register_fake
-def _(h2, h1, node_ptr, rootindex):
+def _(h2, h1, node_ptr, rootindex, batch):
     return h2.new_empty(rootindex.shape[0], 2 * H)
+
+
+@custom_op("bigcn_b200::readout_backward", mutates_args=(), device_types="cuda")
+def readout_backward(grad_feat: Tensor, node_ptr: Tensor, batch: Tensor) -> Tensor:
+    L.require_device()
+    g, batch = _f32(grad_feat), _i64(batch)
+    n, b = batch.shape[0], g.shape[0]
+    out = torch.empty(n, H, dtype=torch.float32, device=g.device)
+    check(lib().bigcn_readout_backward(_p(g), g.stride(0), _p(node_ptr), _p(batch), n, b, _p(out), _stream()),
+          "readout_backward")
+    return out
+
+
+@readout_backward.register_fake
+def _(grad_feat, node_ptr, batch):
+    return grad_feat.new_empty(batch.shape[0], H)
+
+
+def _readout_setup(ctx, inputs, output):
+    h2, h1, node_ptr, rootindex, batch = inputs
+    ctx.save_for_backward(node_ptr, batch)
+
+
+def _readout_backward(ctx, g):
+    node_ptr, batch = ctx.saved_tensors
+    # only the scatter_mean half carries a gradient: the reference's copy.copy detaches h1[root] (:44,58-63)
+    return torch.ops.bigcn_b200.readout_backward(g.contiguous(), node_ptr, batch), None, None, None, None
+
+
+readout.register_autograd(_readout_backward, setup_context=_readout_setup)

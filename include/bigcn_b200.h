@@ -228,6 +228,13 @@ int bigcn_readout(const float* h2 /*[N,64]*/, const float* h1 /*[N,64]*/, const 
                   const int64_t* rootindex, int64_t N, int64_t B, float* feat, int64_t ldfeat,
                   float* pos /*[B,64] or NULL*/, float* scratch, int32_t* flags, bigcn_stream_t stream);
 
+/* scatter_mean backward on its own: grad_h2[i, :] = grad_feat[batch[i], 0:64] / n_b (the h1[root] half of
+ * feat carries no gradient: copy.copy at BiGCN_Twitter.py:44 detaches it).  The fused training path
+ * (bigcn_features_backward) forms this inside its gather instead. */
+int bigcn_readout_backward(const float* grad_feat /*[B,ldg]*/, int64_t ldg, const int32_t* node_ptr,
+                           const int64_t* batch, int64_t N, int64_t B, float* grad_h2 /*[N,64]*/,
+                           bigcn_stream_t stream);
+
 /* out[f] = sum_i g[i, f] for a dense [N,64] matrix: the bias gradient of a propagate on its own
  * (fixed chunks, fixed combine order: deterministic). */
 size_t bigcn_colsum64_scratch_floats(int64_t N);

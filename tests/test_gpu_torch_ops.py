@@ -8,7 +8,7 @@ from oracle import gcn_oracle
 
 def test_ops_are_registered_and_have_no_cpu_kernel():
     import bigcn_b200  # noqa: F401
-    names = {"graph_prep", "xw", "xw_wgrad", "propagate", "propagate_transposed", "colsum64", "readout"}
+    names = {"graph_prep", "xw", "xw_wgrad", "propagate", "propagate_transposed", "colsum64", "readout", "readout_backward"}
     assert names <= set(dir(torch.ops.bigcn_b200))
     s = str(torch.ops.bigcn_b200.graph_prep.default._schema)
     assert s.startswith("bigcn_b200::graph_prep(Tensor edge_index, SymInt num_nodes, Tensor? batch, SymInt num_graphs, str deg_by)")
@@ -55,9 +55,14 @@ def test_conv_composed_from_ops_matches_oracle_with_autograd():
                 assert float((a.cpu() - r).abs().max()) <= 1e-4 * float(r.abs().max())
     # readout = second root-extend + scatter_mean
     h2, h1 = torch.randn(n, 64), torch.randn(n, 64)
-    feat = B.readout(h2.to(dev), h1.to(dev), node_ptr, b.rootindex.to(dev))
-    want = torch.cat([gcn_oracle.scatter_mean(h2, b.batch), h1[b.rootindex]], 1)
-    assert float((feat.cpu() - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    h2r, h2g = h2.clone().requires_grad_(True), h2.to(dev).requires_grad_(True)
+    feat = B.readout(h2g, h1.to(dev), node_ptr, b.rootindex.to(dev), b.batch.to(dev))
+    want = torch.cat([gcn_oracle.scatter_mean(h2r, b.batch), h1[b.rootindex]], 1)
+    assert float((feat.detach().cpu() - want.detach()).abs().max()) <= 1e-6 * float(want.abs().max())
+    gf = torch.randn_like(want)
+    want.backward(gf)
+    feat.backward(gf.to(dev))
+    assert float((h2g.grad.cpu() - h2r.grad).abs().max()) <= 1e-6 * float(h2r.grad.abs().max())
 
 
 @pytest.mark.gpu
