@@ -47,7 +47,7 @@ class HostFeeder:
                 ev=None))
         self._turn = 0
         self._t_begin, self._loop_ms, self._c = None, 0.0, 0.0
-        self.last = {}
+        self.last, self.last_cpu = {}, {}
         self.flags = torch.zeros(1, dtype=torch.int32, device=dev)   # BIGCN_FLAG_X_NOT_SPARSE: see check()
 
     def check(self):
