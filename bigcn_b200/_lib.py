@@ -48,7 +48,7 @@ class Graph(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("training", C.c_int32), ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32),
-                ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32)]
+                ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32), ("fused_tail", C.c_int32)]
 
 
 class BigcnError(RuntimeError):
@@ -121,6 +121,8 @@ _SIGS = {
     "bigcn_readout_backward": (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr]),
     "bigcn_colsum64_scratch_floats": (C.c_size_t, [C.c_int64]),
     "bigcn_colsum64": (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr]),
+    "bigcn_train_tail": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                   c_ptr, c_ptr, C.c_size_t, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_eval_counts": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_nll_loss": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "bigcn_assemble_batch": (C.c_int, [c_ptr] * 14 + [C.c_int64, C.c_int64, C.c_int64, C.c_uint64] + [c_ptr] * 9),

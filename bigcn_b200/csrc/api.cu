@@ -343,7 +343,8 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       const int d = dirs.id[q];
       a.h2[q] = w.h2[d]; a.h1[q] = w.h1[d]; a.pos[q] = w.pos[d]; a.feat_base[q] = feat_base(d);
     }
-    if (int rc = readout_launch(a, st)) return rc;
+    // fused_tail: the second readout pass runs inside bigcn_train_tail, in one launch with the head and gscale
+    if (int rc = readout_launch(a, st, !o->fused_tail)) return rc;
   }
   // the column sort keeps running on the low-priority stream: features_backward waits for it
   // right before the sweep that needs it (event 3)
@@ -385,7 +386,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       a.pos[q] = w.pos[d]; a.gs[q] = w.gs[d]; a.part[q] = w.cs_part[d]; a.feat_base[q] = feat_base(d);
       c.part[q] = w.cs_part[d]; c.out[q] = gdir_b2(gr, d);
     }
-    if (int rc = gscale_launch(a, dirs.n, st)) return rc;
+    if (!o->fused_tail)   // bigcn_train_tail already wrote gs and the db2 partials (same chunking, GS_TREES)
+      if (int rc = gscale_launch(a, dirs.n, st)) return rc;
     db2_reduce = c;   // summed on the side stream (below)
   }
   // 2. T2 = A-hat^T G2 with G2 = [H2 > 0] * gs[batch] formed inside the gather
@@ -666,6 +668,31 @@ extern "C" int bigcn_features_forward(const bigcn_dims_t* dims, const bigcn_batc
   BIGCN_CHECK_ARG(batch && params && feat && flags, "features_forward: NULL argument");
   return features_forward(dims, batch, params, opts, feat, flags, workspace, workspace_bytes,
                           (cudaStream_t)stream);
+}
+
+extern "C" int bigcn_train_tail(const bigcn_dims_t* dims, const bigcn_batch_t* batch, const bigcn_opts_t* opts, float* feat,
+                                const int64_t* y, int64_t B_global, const float* fc_w, const float* fc_b, float* logp,
+                                float* loss, float* grad_feat, float* d_fc_w, float* d_fc_b, float* scratch,
+                                size_t scratch_floats, int32_t* flags, void* workspace, size_t workspace_bytes,
+                                bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(dims && batch && opts && feat && flags, "train_tail: NULL argument");
+  if (int rc = check_common(dims, opts, "train_tail")) return rc;
+  BIGCN_CHECK_ARG(opts->fused_tail && opts->dir_mask == (BIGCN_DIR_TD | BIGCN_DIR_BU),
+                  "train_tail: needs opts.fused_tail = 1 (as passed to features_forward) and both directions");
+  FeatWs w = carve_features(dims, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace != nullptr && workspace_bytes >= w.total, "train_tail: workspace too small");
+  const int64_t N = dims->N, B = dims->B;
+  TailArgs ta{};
+  ta.ro.ndir = 2; ta.ro.node_ptr = w.node_ptr; ta.ro.rootindex = batch->rootindex; ta.ro.feat = feat; ta.ro.ldfeat = 4 * H;
+  ta.ro.N = N; ta.ro.B = B; ta.ro.flags = flags; ta.ro.scratch = w.ro_part;
+  ta.ro.nitems = ceil_div(N > 0 ? N : 1, RO_SLICE) + B;
+  ta.gs.grad_feat = grad_feat; ta.gs.node_ptr = w.node_ptr; ta.gs.B = B;
+  for (int d = 0; d < 2; ++d) {
+    ta.ro.h2[d] = w.h2[d]; ta.ro.h1[d] = w.h1[d]; ta.ro.pos[d] = w.pos[d]; ta.ro.feat_base[d] = feat_base(d);
+    ta.gs.pos[d] = w.pos[d]; ta.gs.gs[d] = w.gs[d]; ta.gs.part[d] = w.cs_part[d]; ta.gs.feat_base[d] = feat_base(d);
+  }
+  return train_tail_run(ta, feat, y, B, dims->C, B_global, fc_w, fc_b, logp, loss, grad_feat, d_fc_w, d_fc_b, scratch,
+                        scratch_floats, (cudaStream_t)stream);
 }
 
 extern "C" int bigcn_features_backward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,

@@ -60,26 +60,20 @@ __global__ void __launch_bounds__(256) k_head_bwd_feat(const float* __restrict__
   for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
 }
 
-// Training head in one launch: fc + log_softmax (:129-130), F.nll_loss's gradient (:184) and the
-// log_softmax / fc backward towards the features.  Warp per tree, lane c holds class c.
+// One tree's training head, by one warp (lane c holds class c): fv = the lane's eight feature columns
+// (j * 32 + lane); returns the lane's eight columns of grad_feat in out.
 //   logp = log_softmax(feat W^T + b);  g = -[c == y] / B_global;  dl = g - exp(logp) * sum(g)
 //   grad_feat = dl W;  lossvec[b] = -logp[b][y_b]   (summed in tree order by k_loss_sum)
-__global__ void __launch_bounds__(256) k_head_train(const float* __restrict__ feat, const int64_t* __restrict__ y,
-                                                    int64_t B, int C, float inv_bg, const float* __restrict__ W,
-                                                    const float* __restrict__ bias, float* __restrict__ logp,
-                                                    float* __restrict__ dl_out, float* __restrict__ gfeat,
-                                                    float* __restrict__ lossvec) {
-  const int lane = threadIdx.x & 31;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
-  float fv[FEAT / 32];
-#pragma unroll
-  for (int j = 0; j < FEAT / 32; ++j) fv[j] = feat[b * FEAT + j * 32 + lane];
+__device__ __forceinline__ void head_train_tree(const float (&fv)[4 * H / 32], int lane, int64_t b, const int64_t* __restrict__ y,
+                                                int C, float inv_bg, const float* __restrict__ W, const float* __restrict__ bias,
+                                                float* __restrict__ logp, float* __restrict__ dl_out, float* __restrict__ lossvec,
+                                                float (&out)[4 * H / 32]) {
+  constexpr int NJ = 4 * H / 32;
   float mine = -INFINITY;
   for (int c = 0; c < C; ++c) {
     float p = 0.f;
 #pragma unroll
-    for (int j = 0; j < FEAT / 32; ++j) p = fmaf(fv[j], W[c * FEAT + j * 32 + lane], p);
+    for (int j = 0; j < NJ; ++j) p = fmaf(fv[j], W[c * (4 * H) + j * 32 + lane], p);
     p = warp_sum(p) + bias[c];
     if (lane == c) mine = p;
   }
@@ -98,17 +92,86 @@ __global__ void __launch_bounds__(256) k_head_train(const float* __restrict__ fe
   if (lane < C) dl_out[b * C + lane] = dl;
   const float mylp = __shfl_sync(FULL_MASK, lp, hit ? (int)t : 0);
   if (lane == 0) lossvec[b] = hit ? -mylp : 0.f;
-  float out[FEAT / 32];
 #pragma unroll
-  for (int j = 0; j < FEAT / 32; ++j) out[j] = 0.f;
+  for (int j = 0; j < NJ; ++j) out[j] = 0.f;
   for (int c = 0; c < C; ++c) {
     const float d = __shfl_sync(FULL_MASK, dl, c);
 #pragma unroll
-    for (int j = 0; j < FEAT / 32; ++j) out[j] = fmaf(d, W[c * FEAT + j * 32 + lane], out[j]);
+    for (int j = 0; j < NJ; ++j) out[j] = fmaf(d, W[c * (4 * H) + j * 32 + lane], out[j]);
   }
+}
+
+// Training head in one launch: fc + log_softmax (:129-130), F.nll_loss's gradient (:184) and the
+// log_softmax / fc backward towards the features.  Warp per tree (head_train_tree).
+__global__ void __launch_bounds__(256) k_head_train(const float* __restrict__ feat, const int64_t* __restrict__ y,
+                                                    int64_t B, int C, float inv_bg, const float* __restrict__ W,
+                                                    const float* __restrict__ bias, float* __restrict__ logp,
+                                                    float* __restrict__ dl_out, float* __restrict__ gfeat,
+                                                    float* __restrict__ lossvec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float fv[FEAT / 32], out[FEAT / 32];
+#pragma unroll
+  for (int j = 0; j < FEAT / 32; ++j) fv[j] = feat[b * FEAT + j * 32 + lane];
+  head_train_tree(fv, lane, b, y, C, inv_bg, W, bias, logp, dl_out, lossvec, out);
 #pragma unroll
   for (int j = 0; j < FEAT / 32; ++j) gfeat[b * FEAT + j * 32 + lane] = out[j];
 }
+// The step's tail in ONE launch (was three: k_readout_final -> k_head_train -> k_gscale, each a few
+// microseconds of work behind a launch gap on the critical path).  CTA = 4 trees:
+//   256 threads: (tree, column) pairs finish the readout of both directions (readout_final_tree), feat -> shared;
+//   4 warps    : one per tree, the head exactly as k_head_train (fc, log_softmax, nll gradient, grad_feat -> shared);
+//   256 threads: gs = grad_feat / n_b per direction and the db2 partial of the CTA's four trees (k_gscale's order).
+__global__ void __launch_bounds__(256) k_train_tail(TailArgs a) {
+  __shared__ float s_feat[4][FEAT];
+  __shared__ float s_g[4][FEAT];
+  __shared__ float red[2][4][H];
+  const int tl = threadIdx.x >> 6, f = threadIdx.x & 63;
+  const int64_t b = (int64_t)blockIdx.x * 4 + tl;
+  const bool valid = b < a.ro.B;
+  float cnt[2] = {0.f, 0.f};
+  if (valid) {
+    float mean[2], root[2];
+    readout_final_tree(a.ro, b, f, mean, root, cnt);
+    for (int d = 0; d < a.ro.ndir; ++d) {
+      s_feat[tl][a.ro.feat_base[d] + f] = mean[d];
+      s_feat[tl][a.ro.feat_base[d] + H + f] = root[d];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < 4) {                      // warp w: the head of tree 4 * blockIdx.x + w
+    const int64_t bw = (int64_t)blockIdx.x * 4 + w;
+    if (bw < a.ro.B) {
+      float fv[FEAT / 32], out[FEAT / 32];
+#pragma unroll
+      for (int j = 0; j < FEAT / 32; ++j) fv[j] = s_feat[w][j * 32 + lane];
+      head_train_tree(fv, lane, bw, a.y, a.C, a.inv_bg, a.W, a.bias, a.logp, a.dl, a.lossvec, out);
+#pragma unroll
+      for (int j = 0; j < FEAT / 32; ++j) {
+        s_g[w][j * 32 + lane] = out[j];
+        a.gfeat[bw * FEAT + j * 32 + lane] = out[j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = 0; d < a.ro.ndir; ++d) {
+    float acc = 0.f;
+    if (valid) {
+      const int n = a.gs.node_ptr[b + 1] - a.gs.node_ptr[b];
+      const float gv = __fdiv_rn(s_g[tl][a.gs.feat_base[d] + f], (float)(n > 0 ? n : 1));
+      a.gs.gs[d][b * H + f] = gv;
+      acc = fmaf(gv, cnt[d], acc);
+    }
+    red[d][tl][f] = acc;
+  }
+  __syncthreads();
+  if (tl == 0)
+    for (int d = 0; d < a.ro.ndir; ++d)
+      a.gs.part[d][(int64_t)blockIdx.x * H + f] = ((red[d][0][f] + red[d][1][f]) + red[d][2][f]) + red[d][3][f];
+}
+
 // loss = (1/Bg) * sum_b lossvec[b], same strided order as k_nll
 __global__ void __launch_bounds__(256) k_loss_sum(const float* __restrict__ lossvec, int64_t B, float inv_bg,
                                                   float* __restrict__ loss) {
@@ -415,6 +478,14 @@ extern "C" int bigcn_head_backward(const float* grad_logp, const float* logp, co
   return 0;
 }
 
+static_assert(GS_TREES == 4, "k_train_tail writes one db2 partial per four trees, as k_gscale does");
+int bigcn::train_tail_launch(const TailArgs& a, cudaStream_t st) {
+  if (a.ro.B == 0) return 0;
+  k_train_tail<<<(int)ceil_div(a.ro.B, 4), 256, 0, st>>>(a);
+  BIGCN_CHECK_LAUNCH("k_train_tail");
+  return 0;
+}
+
 extern "C" size_t bigcn_head_train_scratch_floats(int64_t B, int64_t C) {
   return bigcn_head_backward_scratch_floats(B, C) + (size_t)(B > 0 ? B : 1);
 }
@@ -442,6 +513,33 @@ extern "C" int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, 
                                                       lossvec);
     BIGCN_CHECK_LAUNCH("k_head_train");
   }
+  cudaStream_t ss = side_fork(st);
+  const int tot = (int)C * (FEAT + 1);
+  k_head_bwd_w<<<dim3((tot + 127) / 128, nchunk), 128, 0, ss>>>(dl, feat, B, (int)C, part);
+  BIGCN_CHECK_LAUNCH("k_head_bwd_w");
+  k_head_bwd_red<<<(tot + 127) / 128, 128, 0, ss>>>(part, nchunk, (int)C, d_fc_w, d_fc_b);
+  BIGCN_CHECK_LAUNCH("k_head_bwd_red");
+  k_loss_sum<<<1, 256, 0, ss>>>(lossvec, B, inv_bg, loss);
+  BIGCN_CHECK_LAUNCH("k_loss_sum");
+  return 0;
+}
+
+// the fused tail: `ta` arrives with the readout / gscale halves filled in by api.cu (they live in the features workspace)
+int bigcn::train_tail_run(TailArgs ta, const float* feat, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
+                          const float* fc_w, const float* fc_b, float* logp, float* loss, float* grad_feat,
+                          float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats, cudaStream_t st) {
+  BIGCN_CHECK_ARG(C >= 1 && C <= 32, "train_tail: C must be in [1,32]");
+  BIGCN_CHECK_ARG(B_global > 0, "train_tail: B_global must be positive");
+  BIGCN_CHECK_ARG(feat && y && fc_w && fc_b && logp && loss && grad_feat && d_fc_w && d_fc_b, "train_tail: NULL argument");
+  BIGCN_CHECK_ARG(scratch && scratch_floats >= bigcn_head_train_scratch_floats(B, C), "train_tail: scratch too small");
+  float* dl = scratch;
+  float* part = scratch + B * C;
+  const int nchunk = B > 0 ? (int)ceil_div(B, HB_TREES) : 1;
+  float* lossvec = part + (size_t)nchunk * C * (FEAT + 1);
+  const float inv_bg = 1.0f / (float)B_global;
+  ta.y = y; ta.C = (int)C; ta.inv_bg = inv_bg; ta.W = fc_w; ta.bias = fc_b; ta.logp = logp; ta.dl = dl;
+  ta.gfeat = grad_feat; ta.lossvec = lossvec;
+  if (int rc = train_tail_launch(ta, st)) return rc;
   cudaStream_t ss = side_fork(st);
   const int tot = (int)C * (FEAT + 1);
   k_head_bwd_w<<<dim3((tot + 127) / 128, nchunk), 128, 0, ss>>>(dl, feat, B, (int)C, part);

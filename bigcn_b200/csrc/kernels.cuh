@@ -5,7 +5,7 @@
 namespace bigcn {
 
 constexpr int CS_ROWS = 256;  // rows per CTA for column-sum partials
-constexpr int GS_TREES = 16;  // trees per CTA in k_gscale
+constexpr int GS_TREES = 4;   // trees per CTA in k_gscale (= trees per CTA of the fused tail, k_train_tail)
 constexpr int BM_ROWS = 128;  // rows per CTA in k_bwd_mix (8 warps x 16 rows)
 constexpr int OP_ROWS = 128;  // rows per CTA in k_outer64
 constexpr int DW2B_ROWS = 128; // rows per CTA in k_dw2b_part
@@ -46,11 +46,53 @@ struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_ba
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
 constexpr int RO_SLICE = 512;  // rows per readout slice
 struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t ldfeat; int64_t N, B; int32_t* flags; float* scratch; int64_t nitems; };
-int readout_launch(const ReadoutArgs&, cudaStream_t);
+int readout_launch(const ReadoutArgs&, cudaStream_t, bool with_final = true);
+#ifdef __CUDACC__
+// One tree's readout, second pass (thread = column f of tree b): the slice partials in slice order, the divide,
+// the positive counts the backward uses for db2, and the root row of H1; writes feat / pos and hands the values back
+// (k_readout_final, and the fused tail k_train_tail which goes on with the head in the same launch).
+__device__ __forceinline__ void readout_final_tree(const ReadoutArgs& a, int64_t b, int f, float (&mean)[2], float (&root)[2],
+                                                   float (&cnt_out)[2]) {
+  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
+  const int n = e - s;
+  int64_t r = -1;
+  if (n > 0) {
+    r = a.rootindex[b];
+    if (r < 0 || r >= a.N) {
+      if (f == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
+      r = -1;
+    }
+  }
+  for (int d = 0; d < a.ndir; ++d) {
+    float sum = 0.f, cnt = 0.f;
+    if (n > 0) {
+      const int64_t x0 = s / RO_SLICE + b, x1 = (e - 1) / RO_SLICE + b;
+      for (int64_t x = x0; x <= x1; ++x) {
+        const float* p = a.scratch + (((int64_t)d * a.nitems + x) * 2) * H + f;
+        sum += p[0];
+        cnt += p[H];
+      }
+    }
+    if (a.pos[d]) a.pos[d][b * H + f] = cnt;
+    float* fr = a.feat + b * a.ldfeat + a.feat_base[d];
+    mean[d] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
+    root[d] = r >= 0 ? a.h1[d][r * H + f] : 0.f;
+    cnt_out[d] = cnt;
+    fr[f] = mean[d];
+    fr[H + f] = root[d];
+  }
+}
+#endif
 size_t readout_scratch_floats(int64_t N, int64_t B, int ndir);
 int readout_bwd_launch(const float*, int64_t, const int32_t*, const int64_t*, int64_t, int64_t, float*, cudaStream_t);
 struct GScaleArgs { const float* grad_feat; const float* pos[2]; float* gs[2]; float* part[2]; int feat_base[2]; const int32_t* node_ptr; int64_t B; };
 int gscale_launch(const GScaleArgs&, int, cudaStream_t);
+// readout-final + head (fc, log_softmax, nll gradient, grad_feat) + gscale in one launch (head.cu)
+struct TailArgs { ReadoutArgs ro; GScaleArgs gs; const int64_t* y; int C; float inv_bg; const float* W; const float* bias; float* logp; float* dl; float* gfeat; float* lossvec; };
+int train_tail_launch(const TailArgs&, cudaStream_t);
+int train_tail_run(TailArgs ta, const float* feat, const int64_t* y, int64_t B, int64_t C, int64_t B_global, const float* fc_w,
+                   const float* fc_b, float* logp, float* loss, float* grad_feat, float* d_fc_w, float* d_fc_b, float* scratch,
+                   size_t scratch_floats, cudaStream_t st);
 struct PropG2Dir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* h2; const float* gs; float* out; int32_t* lng; int64_t E; };
 struct PropG2Args { PropG2Dir d[2]; int64_t N; const int64_t* batch; int32_t cb; };
 int propagate_g2_launch(const PropG2Args&, int, cudaStream_t);

@@ -454,31 +454,8 @@ __global__ void __launch_bounds__(256) k_readout_final(ReadoutArgs a) {
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 6);
   const int f = threadIdx.x & 63;
   if (b >= a.B) return;
-  const int s = a.node_ptr[b], e = a.node_ptr[b + 1];
-  const int n = e - s;
-  int64_t r = -1;
-  if (n > 0) {
-    r = a.rootindex[b];
-    if (r < 0 || r >= a.N) {
-      if (f == 0) atomicOr(a.flags, BIGCN_FLAG_ROOT_RANGE);
-      r = -1;
-    }
-  }
-  for (int d = 0; d < a.ndir; ++d) {
-    float sum = 0.f, cnt = 0.f;
-    if (n > 0) {
-      const int64_t x0 = s / RO_SLICE + b, x1 = (e - 1) / RO_SLICE + b;
-      for (int64_t x = x0; x <= x1; ++x) {
-        const float* p = a.scratch + (((int64_t)d * a.nitems + x) * 2) * H + f;
-        sum += p[0];
-        cnt += p[H];
-      }
-    }
-    if (a.pos[d]) a.pos[d][b * H + f] = cnt;
-    float* fr = a.feat + b * a.ldfeat + a.feat_base[d];
-    fr[f] = __fdiv_rn(sum, (float)(n > 0 ? n : 1));
-    fr[H + f] = r >= 0 ? a.h1[d][r * H + f] : 0.f;
-  }
+  float mean[2], root[2], cnt[2];
+  readout_final_tree(a, b, f, mean, root, cnt);
 }
 
 // scatter_mean backward on its own (the fused training path forms this inside k_propagate_g2):
@@ -978,7 +955,7 @@ int prop1_mix_launch(const MixArgs& a, int ndir, cudaStream_t st) {
 size_t readout_scratch_floats(int64_t N, int64_t B, int ndir) {
   return (size_t)ndir * (size_t)(ceil_div(N > 0 ? N : 1, RO_SLICE) + B) * 2 * H;
 }
-int readout_launch(const ReadoutArgs& a0, cudaStream_t st) {
+int readout_launch(const ReadoutArgs& a0, cudaStream_t st, bool with_final) {
   if (a0.B == 0) return 0;
   ReadoutArgs a = a0;
   a.nitems = ceil_div(a.N > 0 ? a.N : 1, RO_SLICE) + a.B;
@@ -986,6 +963,7 @@ int readout_launch(const ReadoutArgs& a0, cudaStream_t st) {
     k_readout_part<<<dim3((unsigned)a.nitems, a.ndir), 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_readout_part");
   }
+  if (!with_final) return 0;       // the fused tail (k_train_tail) finishes the trees
   k_readout_final<<<(int)ceil_div(a.B, 4), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_readout_final");
   return 0;

@@ -140,7 +140,7 @@ class FusedTrainer:
             seed = (td.seed + self._calls) & ((1 << 64) - 1)
         self._calls += 1
         o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(seed), deg_by=L.DEG_BY[td.deg_by],
-                 gemm_mode=L.GEMM_MODE[td.gemm_mode], dir_mask=L.DIR_TD | L.DIR_BU)
+                 gemm_mode=L.GEMM_MODE[td.gemm_mode], dir_mask=L.DIR_TD | L.DIR_BU, fused_tail=1)
         dev = xs.device if xs is not None else x.device
         ws = self._workspace(dims, dev)
         b = dims.B
@@ -154,8 +154,10 @@ class FusedTrainer:
                                        _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
         nscr = l.bigcn_head_train_scratch_floats(b, c)
         scr = torch.empty(nscr, dtype=torch.float32, device=dev)
-        check(l.bigcn_head_train(_p(feat), _p(y), b, c, int(b_global or b), self._pr.fc_w, self._pr.fc_b, _p(logp),
-                                 _p(loss), _p(gfeat), self._gr.fc_w, self._gr.fc_b, _p(scr), nscr, st), "head_train")
+        # readout's second pass + fc / log_softmax / nll and their backward + the per-tree gradient scaling: one launch
+        check(l.bigcn_train_tail(C.byref(dims), C.byref(bt), C.byref(o), _p(feat), _p(y), int(b_global or b),
+                                 self._pr.fc_w, self._pr.fc_b, _p(logp), _p(loss), _p(gfeat), self._gr.fc_w,
+                                 self._gr.fc_b, _p(scr), nscr, _p(self.flags), _p(ws), ws.numel(), st), "train_tail")
         if self.comm == "symm":
             check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                             C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
@@ -301,6 +303,6 @@ def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm
     # gscale+colsum, propT(g2), outer x2, [segsum | dw2b part], dw2b reduce + dense fallback,
     # bwdmix+colsum, propT, dW
     bwd = 2 + 1 + 2 + 1 + 2 + 2 + 1 + dw
-    head = 1 + 3                               # fused head (fwd + nll + grad_feat), then dW / db / loss sum
+    head = 1 + 3 - 2                           # fused tail (readout final + head + gscale in one launch), then dW / db / loss sum
     adam = 1                                   # Adam (or the fused peer-memory reduce + Adam) incl. the step counter
     return fwd + head + bwd + adam

@@ -131,6 +131,8 @@ typedef struct bigcn_opts {
   int32_t skip_wgrad_prep; /* BIGCN_GEMM_SPARSE forward: 1 = inference, do not sort the
                               non-zeros of x by column (features_backward would then
                               return NaN for the conv1 weight gradient)              */
+  int32_t fused_tail; /* training step through bigcn_train_tail: features_forward leaves the second
+                         readout pass, features_backward the gscale pass, to that one launch   */
 } bigcn_opts_t;
 
 const char* bigcn_last_error(void);
@@ -324,6 +326,17 @@ size_t bigcn_head_train_scratch_floats(int64_t B, int64_t C);
 int bigcn_head_train(const float* feat, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
                      const float* fc_w, const float* fc_b, float* logp, float* loss, float* grad_feat,
                      float* d_fc_w, float* d_fc_b, float* scratch, size_t scratch_floats,
+                     bigcn_stream_t stream);
+
+/* The training step's tail in ONE launch on `stream`: the readout's second pass (feat), bigcn_head_train's
+ * arithmetic (logp, loss, grad_feat, fc gradients on the side stream) and the scatter_mean backward's
+ * per-tree scaling that bigcn_features_backward starts with.  Call order, all with opts.fused_tail = 1 and
+ * the same dims / workspace: bigcn_features_forward -> bigcn_train_tail -> bigcn_features_backward.
+ * scratch: bigcn_head_train_scratch_floats(B, C) floats. */
+int bigcn_train_tail(const bigcn_dims_t* dims, const bigcn_batch_t* batch, const bigcn_opts_t* opts, float* feat,
+                     const int64_t* y, int64_t B_global, const float* fc_w, const float* fc_b, float* logp,
+                     float* loss, float* grad_feat, float* d_fc_w, float* d_fc_b, float* scratch,
+                     size_t scratch_floats, int32_t* flags, void* workspace, size_t workspace_bytes,
                      bigcn_stream_t stream);
 
 /* Evaluation bookkeeping on the device: adds this batch to
