@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""One step of an ncu launch list (--metrics gpu__time_duration.sum --csv): per-launch times, per-kernel totals and shares.
+Usage: python tools/parse_launches.py launches.csv [launches_per_step [first_launch_of_the_step]]"""
 import csv, collections, sys
 path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches.csv'
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 43
