@@ -12,8 +12,12 @@ buffers (H2D of every input inside the timed region, loss read back).  `roofline
 dominant kernel (the X stream) timed alone with CUDA events; `cpu_baseline` is the oracle's
 restatement of the reference module -- including its Python max()/mask loops, which is what
 the reference executes -- on this host's cores, on a bounded sample of the same workload.
-Multi-GPU: trees are sharded per rank (weak scaling, 128 trees per GPU), one NCCL all-reduce of
-the flat 5.16 MB gradient per step.
+Multi-GPU: trees are sharded per rank (weak scaling, 128 trees per GPU); the gradient exchange is the fused
+peer-memory reduce-scatter + Adam + all-gather kernel (or two NCCL all-reduces with --comm nccl).  Under torchrun
+the line also carries `dp_parity`: three fixed-seed steps whose parameters must be bit-identical on every rank and
+within 2e-6 of a single-process replay of the same global batches on rank 0.
+`configs` holds the other BASELINE.json configurations (bench_configs.py): the Twitter16 epoch, Weibo training in
+the fp32-class and tensor-core modes, PHEME 9-fold inference, the 1 M-tree power-law stream.
 """
 from __future__ import annotations
 
@@ -23,6 +27,14 @@ import os
 import sys
 import threading
 import time
+
+T0 = time.time()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries the one JSON line)."""
+    sys.stderr.write(f"[bench {time.time() - T0:7.1f}s] {msg}\n")
+    sys.stderr.flush()
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -41,9 +53,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="bigcn_b200", choices=["bigcn_b200", "reference"])
     ap.add_argument("--gemm-mode", default="sparse", choices=["fp32", "tf32", "tf32x3", "mixed", "sparse"])
+    ap.add_argument("--no-graphs", action="store_true", help="enqueue every launch instead of replaying CUDA graphs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (c2..c5)")
+    ap.add_argument("--configs", default="c2,c3,c4,c5", help="which of c2,c3,c4,c5 to run")
     ap.add_argument("--comm", default="auto", choices=["auto", "symm", "nccl"],
                     help="N > 1: fused peer-memory optimiser step (symm) or NCCL all-reduce + Adam")
-    ap.add_argument("--cpu-sample-trees", type=int, default=32)
+    ap.add_argument("--cpu-sample-trees", type=int, default=TREES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the large-N propagate micro-benchmark")
     return ap.parse_args()
@@ -112,19 +127,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_reference_run(steps, warmup, sample_trees, seed=0):
-    """The reference's own CPU implementation of the path (oracle restatement with the
-    reference's Python loops), train mode, fwd + nll_loss + bwd + Adam, all host threads."""
+def _load_data_module():
+    """bigcn_b200/data.py loaded BY PATH: the synthetic generators without importing the package (whose __init__
+    dlopens libbigcn_b200.so) -- the reference arm must not map the product's library."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bigcn_b200_data_standalone", os.path.join(ROOT, "bigcn_b200", "data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_run(steps, warmup, sample_trees, seed=1000, shape=SHAPE, optimizer=True):
+    """The reference's own CPU implementation of the path (oracle restatement of BiGCN_Twitter.py:26-131 with the
+    reference's Python max()/mask loops), train mode, fwd + nll_loss + bwd (+ Adam), all host threads."""
     import torch
     from oracle import bigcn_oracle
-    from bigcn_b200.data import make_batch
+    data = _load_data_module()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    b = make_batch(SHAPE, sample_trees, seed=seed, train=True)
+    b = data.make_batch(shape, sample_trees, seed=seed, train=True)
     model = bigcn_oracle.BiGCN(K_FEATS, 64, 64, num_classes=N_CLASSES, reference_loops=True).train()
     opt = bigcn_oracle.make_optimizer(model)
-    times = []
+    times, opt_times = [], []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         out = model(b)
@@ -132,15 +158,28 @@ def cpu_reference_run(steps, warmup, sample_trees, seed=0):
         opt.zero_grad()
         loss.backward()
         float(loss.item())
+        t1 = time.perf_counter()
         opt.step()
+        t2 = time.perf_counter()
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append((t2 - t0) if optimizer else (t1 - t0))
+            opt_times.append(t2 - t1)
     times.sort()
+    opt_times.sort()
     med = times[len(times) // 2]
     return {"value": sample_trees / med, "unit": "trees/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_trees} {SHAPE}-shaped trees ({int(b.x.shape[0])} nodes), {steps} timed steps "
-                      f"after {warmup} warm-up, median; oracle restatement incl. the reference's Python loops",
-            "ms_per_step": med * 1e3, "nodes": int(b.x.shape[0])}
+            "sample": f"{sample_trees} {shape}-shaped trees ({int(b.x.shape[0])} nodes) per step, {steps} timed steps "
+                      f"after {warmup} warm-up, median; oracle restatement incl. the reference's Python loops; "
+                      + ("fwd+nll+bwd+Adam" if optimizer else "fwd+nll+bwd (optimizer step reported separately)"),
+            "ms_per_step": med * 1e3, "optimizer_ms": opt_times[len(opt_times) // 2] * 1e3, "nodes": int(b.x.shape[0]),
+            "torch_threads": cores}
+
+
+def cpu_config1():
+    """BASELINE.md section 4, to the letter: config 1 = Twitter15-shaped, 128 trees, seed 0, fwd + nll_loss + bwd,
+    1 warm-up + 3 timed steps, median."""
+    r = cpu_reference_run(3, 1, 128, seed=0, shape="twitter15", optimizer=False)
+    return {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "optimizer_ms", "nodes")}
 
 
 def run_reference(args):
@@ -154,12 +193,15 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
             "data": "synthetic",
-            "config": {"workload": f"{SHAPE}-shaped BiGCN training step (fwd+nll+bwd+Adam), K={K_FEATS}, C={N_CLASSES}, "
-                                   f"DropEdge 0.2/0.2; CPU arm runs a bounded sample of {args.cpu_sample_trees} trees per step",
-                       "trees_per_step": args.cpu_sample_trees},
+            "config": {"workload": f"{SHAPE}-shaped BiGCN training step (graph prep+fwd+nll+bwd+Adam), "
+                                   f"{TREES_PER_GPU} trees/GPU, K={K_FEATS}, C={N_CLASSES}, DropEdge 0.2/0.2, dropout 0.5",
+                       "trees_per_step": args.cpu_sample_trees, "trees_per_gpu": TREES_PER_GPU,
+                       "note": "CPU arm: the same batch shape as the GPU arm (seed 1000), one process, all host threads"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_configs:
+        line["configs"] = {"c1_cpu_twitter15": cpu_config1()}
     print(json.dumps(line), flush=True)
 
 
@@ -211,7 +253,8 @@ def run_ours(args):
     model = bigcn_b200.BiGCN(K_FEATS, 64, 64, dev, num_classes=N_CLASSES, gemm_mode=args.gemm_mode,
                              validate="off").to(dev).train()
     tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world,
-                                 comm=args.comm)
+                                 comm=args.comm, graphs=False if args.no_graphs else "auto")
+    log(f"data + model ready ({nodes} nodes), comm={tr.comm}, graphs={tr.graphs}")
     b_global = TREES_PER_GPU * world
     sparse_ok = args.gemm_mode == "sparse"
     tr_comm, tr_comm_note = tr.comm, tr.comm_note
@@ -230,6 +273,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------
+    # CUDA graphs: a batch's first step is enqueued, its second is captured; prime both before the W warm-up
+    # steps so that the timed region only replays
+    for i in range(2 * N_ROTATE if tr.graphs else 0):
+        tr.step(resident[i % N_ROTATE], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
     for i in range(args.warmup):
         tr.step(resident[i % N_ROTATE], b_global=b_global, node_id_base=id_base[i % N_ROTATE])
     tr.check_inputs()
@@ -259,6 +306,9 @@ def run_ours(args):
         per_rank_cpu = [float(x[1]) for x in g]
     value = TREES_PER_GPU * world * args.steps / (ms * 1e-3)
     final_loss = float(loss.item())
+    graph_info = {"enabled": bool(tr.graphs), "captures": tr.graph_captures, "replays": tr.graph_replays}
+    log(f"resident: {ms / args.steps:.4f} ms/step, cpu enqueue {cpu_enqueue_ms:.4f} ms/step, graphs {graph_info}")
+    dp_parity = dp_parity_check(torch, bigcn_b200, tr, dev, rank, world, args) if world > 1 else None
 
     # ---- end to end: host buffers in, loss out ---------------------------------------
     # Every step starts from the PINNED HOST tensors of a batch (the dense fp32 data.x the
@@ -423,6 +473,32 @@ def run_ours(args):
     e2e_value, e2e_ms, e2e_steps = routes[best]["value"], routes[best]["ms_per_step"], n_
     e2e_h2d = routes[best]["h2d_bytes_per_step"]
 
+    log(f"e2e routes done: {({k: round(v['ms_per_step'], 3) for k, v in routes.items()})}")
+    del feeder, forest, stage, dev_csr, loader_csr
+    configs = {}
+    if not args.no_configs:
+        import bench_configs as bc
+        want = set(args.configs.split(","))
+        try:
+            if world == 1 and "c2" in want:
+                configs["c2_epoch"] = bc.c2_epoch(torch, bigcn_b200, dev)
+                log("c2 done")
+            if world == 1 and "c3" in want:
+                configs["c3_weibo"] = bc.c3_weibo(torch, bigcn_b200, dev)
+                log("c3 done")
+            if "c4" in want:
+                configs["c4_pheme_infer"] = bc.c4_pheme_infer(torch, bigcn_b200, dev, rank, world, max_over_ranks)
+                log("c4 done")
+            if "c5" in want:
+                configs["c5_powerlaw"] = bc.c5_powerlaw(torch, bigcn_b200, dev, rank, world, pg, max_over_ranks)
+                log("c5 done")
+        except Exception as e:  # noqa: BLE001  (a failing side configuration must not lose the headline line)
+            if world > 1:
+                raise
+            configs["error"] = f"{type(e).__name__}: {e}"
+            log(f"configs failed: {configs['error']}")
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -503,26 +579,56 @@ def run_ours(args):
                          "achieved": sw_bytes / (dw_ms * 1e-3) / 1e9, "frac": None, "peak": None,
                          "algorithmic_bytes": sw_bytes, "nnz": nnz, "frac_of_8TBs_nominal": None,
                          "note": "the dense-mode second pass over X (%.0f MB) is gone" % (nodes[0] * K_FEATS * 4 / 1e6)})
+    # the tcgen05 / TMA / TMEM GEMMs on the same matrices (gemm_mode tf32 / tf32x3; what 'auto' picks for dense features)
+    tc = {}
+    wscr_tc = torch.empty(max(lib.bigcn_xw_wgrad_scratch_floats(n, K_FEATS, 2) for n in nodes), device=dev)
+    for mode, kname in (("tf32", "k_xw_tc<1> (tcgen05.mma kind::tf32, TMA, TMEM)"),
+                        ("tf32x3", "k_xw_tc<2,true> (tcgen05.mma kind::tf32 x3: X split hi/lo in shared memory, W hi/lo; fp32-class)")):
+        def fn(i, mode=mode):
+            j = i % N_ROTATE
+            L.check(lib.bigcn_xw(resident[j].x.data_ptr(), nodes[j], K_FEATS, w0.data_ptr(), w1.data_ptr(), K_FEATS,
+                                 ys[j].data_ptr(), 128, L.GEMM_MODE[mode], scr.data_ptr(), st))
+        t_ms = time_kernel(fn, 12, torch)
+        g = xw_bytes / (t_ms * 1e-3) / 1e9
+        tc["xw_" + mode] = {"kernel": kname, "bound": "hbm", "achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak,
+                            "ms": t_ms, "algorithmic_bytes": xw_bytes, "tflops": 2 * mean_nodes * K_FEATS * 128 / (t_ms * 1e-3) / 1e12,
+                            "note": "ms includes the weight hi/lo split kernel of the mode"}
+
+    def dw_tc_fn(i):
+        j = i % N_ROTATE
+        L.check(lib.bigcn_xw_wgrad(resident[j].x.data_ptr(), nodes[j], K_FEATS, ts[j].data_ptr(), 2, dws[0].data_ptr(),
+                                   dws[1].data_ptr(), K_FEATS, L.GEMM_MODE["tf32x3"], wscr_tc.data_ptr(), st))
+    t_ms = time_kernel(dw_tc_fn, 12, torch)
+    g = xw_bytes / (t_ms * 1e-3) / 1e9
+    tc["dw_tf32x3"] = {"kernel": "k_split + k_dw_tc<2> (tcgen05 kind::tf32, MN-major, T hi+lo) + k_dw_reduce", "bound": "hbm",
+                       "achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak, "ms": t_ms,
+                       "algorithmic_bytes": xw_bytes}
+    del wscr_tc
+    log("kernel rooflines done")
     # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if args.gemm_mode in ("fp32", "mixed", "sparse"):
-            key = "k_xw_scan_capture" if sparse and "k_xw_scan_capture" in tr else "k_xw_scan"
-            roof_fwd["traffic"] = tr[key]["bytes"]
-            roof_fwd["traffic_note"] = f"ncu capture of {key} at N = {tr[key]['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
+            key = "k_xw_scan_capture" if sparse and "k_xw_scan_capture" in traffic else "k_xw_scan"
+            roof_fwd["traffic"] = traffic[key]["bytes"]
+            roof_fwd["traffic_note"] = f"ncu capture of {key} at N = {traffic[key]['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
         if args.gemm_mode in ("tf32x3", "mixed"):
-            roof_bwd["traffic"] = tr["k_dw_tc"]["bytes"]
-            roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {tr['k_dw_tc']['nodes']} nodes"
+            roof_bwd["traffic"] = traffic["k_dw_tc"]["bytes"]
+            roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {traffic['k_dw_tc']['nodes']} nodes"
     except Exception:  # noqa: BLE001
         pass
     roof, other_gemm = (roof_bwd, roof_fwd) if (dw_ms >= xw_ms and not sparse) else (roof_fwd, roof_bwd)
-    others = {"weight_gradient_dW1" if sparse else "other_x_stream": other_gemm}
+    others = {"weight_gradient_dW1" if sparse else "other_x_stream": other_gemm, "xw_tcgen05": tc}
     if not args.no_kernels:
         others.update(kernel_microbench(torch, L, ops, dev, hbm_peak))
 
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_reference_run(1, 1, args.cpu_sample_trees)
+        cpu = cpu_reference_run(3, 1, args.cpu_sample_trees)
+        log("cpu baseline done")
+        if not args.no_configs:
+            configs["c1_cpu_twitter15"] = cpu_config1()
+            log("cpu config 1 done")
 
     line = {"metric": "BiGCN train trees/sec", "value": value, "unit": "trees/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -547,7 +653,7 @@ def run_ours(args):
                             "the first rows, split adapted so both finish together; the fastest one is reported",
                     "routes": {k: v for k, v in routes.items() if k in ("dense_h2d", "host_compact", "hybrid_feed")}},
             "gpu_launches": args.steps * launches_per_step(nodes[0], 2, True, args.gemm_mode, K_FEATS),
-            "roofline": roof, "final_loss": final_loss,
+            "roofline": roof, "final_loss": final_loss, "cuda_graphs": graph_info,
             "per_rank": {"gpu_ms_per_step": [round(v, 4) for v in per_rank],
                          "cpu_enqueue_ms_per_step": [round(v, 4) for v in per_rank_cpu],
                          "nodes_per_step_mean": sum(nodes) / len(nodes)}}
@@ -562,11 +668,66 @@ def run_ours(args):
                                               "index:count pairs): SURVEY 8f N1, an API extension, not the dense contract")
     if others:
         line["roofline_others"] = others
+    if configs:
+        line["configs"] = configs
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity["status"]
+        line["dp_parity_detail"] = dp_parity
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def dp_parity_check(torch, bigcn_b200, tr, dev, rank, world, args, n_steps=3, trees_per_rank=16):
+    """Multi-GPU correctness under the driver's own launch: from a common fixed state, three fixed-seed steps on
+    a sharded global batch; then (a) the flat parameters must be BIT-IDENTICAL on every rank, (b) rank 0 replays
+    the same global batches in a single-process trainer and the result must agree within 2e-6 of the parameter
+    scale (only the summation order of the gradient differs)."""
+    import torch.distributed as dist
+    from bigcn_b200.data import Batch, make_batch_shard
+    torch.manual_seed(1234)
+    ref_model = bigcn_b200.BiGCN(K_FEATS, 64, 64, dev, num_classes=N_CLASSES, gemm_mode=args.gemm_mode,
+                                 validate="off").to(dev).train()
+    ref_tr = bigcn_b200.FusedTrainer(ref_model, lr=5e-4, weight_decay=1e-4, graphs=False)   # same seed on every rank
+    init = ref_tr.flat.detach().clone()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tr.flat.copy_(init)
+    tr.exp_avg.zero_()
+    tr.exp_avg_sq.zero_()
+    tr.step_count.zero_()
+    tr._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    glob = trees_per_rank * world
+    for i in range(n_steps):
+        b, base, _ = make_batch_shard(SHAPE, glob, seed=7000 + i, rank=rank, world=world, train=True)
+        bd = Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys})
+        tr.step(bd, b_global=glob, node_id_base=base, seed=4242 + i)
+    tr.check_inputs()
+    torch.cuda.synchronize()
+    mine = tr.flat.detach().clone()
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    identical = all(torch.equal(g, gathered[0]) for g in gathered)
+    res = {"status": "n/a", "ranks_bit_identical": bool(identical), "steps": n_steps, "global_trees_per_step": glob}
+    if rank == 0:
+        for i in range(n_steps):
+            b, base, _ = make_batch_shard(SHAPE, glob, seed=7000 + i, rank=0, world=1, train=True)
+            bd = Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys})
+            ref_tr.step(bd, b_global=glob, node_id_base=base, seed=4242 + i)
+        ref_tr.check_inputs()
+        torch.cuda.synchronize()
+        diff = float((ref_tr.flat.double() - mine.double()).abs().max())
+        scale = float(ref_tr.flat.abs().max())
+        moved = float((ref_tr.flat.double() - init.double()).abs().max())
+        ok = identical and diff <= 2e-6 * scale
+        res.update(status="ok" if ok else "FAIL", max_abs_diff_vs_single_process=diff, param_scale=scale,
+                   max_abs_update=moved, tolerance=2e-6 * scale)
+    dist.barrier()
+    return res
 
 
 def kernel_microbench(torch, L, ops, dev, hbm_peak):

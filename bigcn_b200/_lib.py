@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libbigcn_b200.so")
 H = 64
 FLAG_EDGE_RANGE, FLAG_BATCH_ORDER, FLAG_ROOT_RANGE = 1, 2, 4
 DEG_BY = {"target": 0, "source": 1}
-GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3, "sparse": 4}
+GEMM_MODE = {"fp32": 0, "tf32": 1, "tf32x3": 2, "mixed": 3, "sparse": 4, "tf32x2": 5}
 FLAG_X_NOT_SPARSE = 8
 FLAG_X_CSR_RANGE = 16
 DIR_TD, DIR_BU = 1, 2
@@ -48,7 +48,8 @@ class Graph(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("training", C.c_int32), ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32),
-                ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32), ("fused_tail", C.c_int32)]
+                ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32), ("fused_tail", C.c_int32),
+                ("seed_dev", c_ptr)]
 
 
 class BigcnError(RuntimeError):

@@ -88,7 +88,7 @@ int xw_dispatch(const float* x, int64_t N, int64_t K, const float* const* w, int
     if (int rc = transpose_jobs_launch(js, st)) return rc;
     return xw_fp32(x, N, K, scratch, n_out, y, ldy, st);
   }
-  BIGCN_CHECK_ARG(mode == BIGCN_GEMM_TF32 || mode == BIGCN_GEMM_TF32X3, "xw: unknown gemm_mode %d", mode);
+  BIGCN_CHECK_ARG(mode == BIGCN_GEMM_TF32 || mode == BIGCN_GEMM_TF32X3 || mode == BIGCN_GEMM_TF32X2, "xw: unknown gemm_mode %d", mode);
   return xw_tc_weights(x, N, K, w, ldw, n_out, scratch, y, ldy, mode, st);
 }
 
@@ -106,7 +106,9 @@ struct FeatWs {
   float* a1[2];             // [N][64]
   float* z[2];              // [N][64]       (backward: G2 then G1)
   float* h2[2];             // [N][64]       (backward: T1cat [N][128] once G2 is formed)
-  float* cs_part[2];        // [chunks][64]  column-sum partials
+  float* cs_part[2];        // [chunks][64]  column-sum partials of db2 (written by the tail, summed on the side stream)
+  float* cs_part1[2];       // [chunks][64]  ... of db1 (k_bwd_mix): a buffer of its own -- the side stream may still be
+                            //               reading the db2 partials when k_bwd_mix writes these
   float* op_part[2];        // [chunks][4096]
   float* dw_part;           // dW1 slab partials
   float* dP[2];             // [B][64]
@@ -160,6 +162,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   int csn = cs_chunks(N) > bm_chunks(N) ? cs_chunks(N) : bm_chunks(N);
   if (gs_chunks(B) > csn) csn = gs_chunks(B);
   for (int d = 0; d < 2; ++d) w.cs_part[d] = c.take<float>((size_t)csn * H);
+  for (int d = 0; d < 2; ++d) w.cs_part1[d] = c.take<float>((size_t)csn * H);
   for (int d = 0; d < 2; ++d) w.op_part[d] = c.take<float>((size_t)op_chunks(N) * H * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
   for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
@@ -448,8 +451,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     c.nchunk = N > 0 ? bm_chunks(N) : 0;
     for (int q = 0; q < dirs.n; ++q) {
       const int d = dirs.id[q];
-      a.d[q] = BwdMixDir{t2[d], w.a1[d], dir_w2(pr, d), g1[d], w.cs_part[d], make_drop(o, d)};   // A1 stands in for (H1, mask)
-      c.part[q] = w.cs_part[d]; c.out[q] = gdir_b1(gr, d);
+      a.d[q] = BwdMixDir{t2[d], w.a1[d], dir_w2(pr, d), g1[d], w.cs_part1[d], make_drop(o, d)};   // A1 stands in for (H1, mask)
+      c.part[q] = w.cs_part1[d]; c.out[q] = gdir_b1(gr, d);
     }
     if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;
     if (sc) stream_after(sc, 2, st, ss);           // db1: ordered sum of the partials, beside T1

@@ -124,10 +124,17 @@ struct DropSpec {
   uint32_t stream;     // 0 TD, 1 BU
   float scale;         // 1/(1-p)
   int32_t on;          // training
+  const unsigned long long* ctr;   // device counter added to the seed (CUDA-graph replays draw fresh masks), or NULL
 };
 __device__ __forceinline__ Philox4 drop_block(const DropSpec& d, int64_t node, uint32_t col_block) {
+  uint32_t k0 = d.k0, k1 = d.k1;
+  if (d.ctr != nullptr) {   // seed + *ctr as one 64-bit sum; the counter only moves between launches
+    const unsigned long long s = (((unsigned long long)k1 << 32) | k0) + __ldg(d.ctr);
+    k0 = (uint32_t)s;
+    k1 = (uint32_t)(s >> 32);
+  }
   return philox4x32_10(col_block, (uint32_t)(node & 0xffffffffll), (uint32_t)((uint64_t)node >> 32),
-                       d.stream, d.k0, d.k1);
+                       d.stream, k0, k1);
 }
 __device__ __forceinline__ uint32_t philox_elem(const Philox4& r, int e) {
   return e == 0 ? r.x : (e == 1 ? r.y : (e == 2 ? r.z : r.w));
@@ -151,6 +158,7 @@ static inline DropSpec make_drop(const bigcn_opts_t* o, int stream_id) {
   d.stream = (uint32_t)stream_id;
   d.scale = 1.0f / (1.0f - o->p_drop);
   d.on = o->training && o->p_drop > 0.f;
+  d.ctr = reinterpret_cast<const unsigned long long*>(o->seed_dev);
   return d;
 }
 

@@ -2,9 +2,13 @@
 //
 // Replaces GCNConv.lin (cuBLAS SGEMM) at BiGCN_Twitter.py:42,92 in the tensor-core modes:
 //   BIGCN_GEMM_TF32   : one kind::tf32 MMA per K step (operands truncated to TF32 by the MMA)
-//   BIGCN_GEMM_TF32X3 : W = W_hi + W_lo with W_lo = W - tf32(W) as a second B operand (two
+//   BIGCN_GEMM_TF32X2 : W = W_hi + W_lo with W_lo = W - tf32(W) as a second B operand (two
 //                       MMAs per K step); exact to ~2^-22 whenever X is representable in TF32
-//                       (bag-of-words counts are).  [third term X_lo * W_hi: see DESIGN.md]
+//                       (bag-of-words counts are)
+//   BIGCN_GEMM_TF32X3 : X is split as well: four converter warps rewrite every X tile in shared memory
+//                       as X_hi (in place) and X_lo (a sibling buffer with the same swizzle) between the TMA
+//                       load and the MMA, three MMAs per K step (X_hi W_hi + X_hi W_lo + X_lo W_hi):
+//                       fp32-class accuracy on dense signed features, X still read from HBM once
 // Both operands are K-major exactly as they sit in HBM: X is [N, K] row-major and the PyG
 // weights are [64, K] row-major, so TMA loads them straight into 128B-swizzled shared memory
 // (no transposed copy).  The TD and BU weights are two 64-row boxes of one B tile, so X is
@@ -24,6 +28,27 @@ constexpr int TC_BLOCK_K = 32;                      // 32 fp32 = 128 B = one swi
 constexpr int TC_UMMA_K = 8;                        // kind::tf32
 constexpr int TC_A_BYTES = TC_BLOCK_M * 128;        // 32 KB
 constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS_XS = 384;                  // + warps 8..11: X hi/lo converters (TF32X3)
+
+// generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Converter warps (cw = 0..3 of 4): split `bytes` of fp32 at `x_smem` into hi (in place, low 13 mantissa bits
+// cleared: exactly what a TF32 MMA can represent) and lo = tf32(x - hi) at `lo_smem`.  Position-preserving, so
+// the TMA swizzle of the tile carries over (both buffers are 1024 B aligned).
+__device__ __forceinline__ void split_tile_hi_lo(uint32_t x_smem, uint32_t lo_smem, int bytes, int cw, int lane) {
+  for (int off = (cw * 32 + lane) * 16; off < bytes; off += 128 * 16) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(x_smem + off));
+    const uint32_t ha = a & 0xFFFFE000u, hb = b & 0xFFFFE000u, hc = c & 0xFFFFE000u, hd = d & 0xFFFFE000u;
+    const uint32_t la = __float_as_uint(__uint_as_float(a) - __uint_as_float(ha)) & 0xFFFFE000u;
+    const uint32_t lb = __float_as_uint(__uint_as_float(b) - __uint_as_float(hb)) & 0xFFFFE000u;
+    const uint32_t lc = __float_as_uint(__uint_as_float(c) - __uint_as_float(hc)) & 0xFFFFE000u;
+    const uint32_t ld = __float_as_uint(__uint_as_float(d) - __uint_as_float(hd)) & 0xFFFFE000u;
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(x_smem + off), "r"(ha), "r"(hb), "r"(hc), "r"(hd) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lo_smem + off), "r"(la), "r"(lb), "r"(lc), "r"(ld) : "memory");
+  }
+}
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -90,17 +115,21 @@ struct TcParams {
   int num_kb;      // ceil(K / 32)
 };
 
-// NB = number of B operands per stage (1: W, 2: W and W_lo)
-template <int NB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NB = number of B operands per stage (1: W, 2: W and W_lo); XS: X split hi / lo in shared memory (TF32X3)
+template <int NB, bool XS>
+__global__ void __launch_bounds__(XS ? TC_THREADS_XS : TC_THREADS, 1)
 k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w0,
         const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_l0,
         const __grid_constant__ CUtensorMap map_l1, const TcParams p) {
-  constexpr int STAGES = NB == 1 ? 4 : 3;
+  static_assert(!XS || NB == 2, "the X split goes with the W split");
+  constexpr int STAGES = XS ? 2 : (NB == 1 ? 4 : 3);
+  constexpr int A_SLOTS = XS ? 2 : 1;                          // [X | X_lo]
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   const int b_bytes = p.n_out * 128;                           // one B operand tile
-  const int stage_bytes = TC_A_BYTES + NB * 16384;             // B slots are 16 KB apart (1024 B aligned)
+  constexpr int B_OFF = A_SLOTS * TC_A_BYTES;
+  constexpr int stage_bytes = B_OFF + NB * 16384;              // B slots are 16 KB apart (1024 B aligned)
   __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_conv[STAGES];           // XS: the stage's X tile is split (4 converter warps)
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full, bar_tmem_empty;
   __shared__ uint32_t tmem_base_s;
@@ -116,6 +145,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_conv[s]), 4);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
     mbar_init(smem_u32(&bar_tmem_empty), 4);
@@ -143,11 +173,11 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
           const uint32_t sa = smem0 + s * stage_bytes;
           mbar_expect_tx(full, tx);
           tma_load_2d(sa, &map_x, full, kb * TC_BLOCK_K, m0);
-          tma_load_2d(sa + TC_A_BYTES, &map_w0, full, kb * TC_BLOCK_K, 0);
-          if (p.n_out == 128) tma_load_2d(sa + TC_A_BYTES + 64 * 128, &map_w1, full, kb * TC_BLOCK_K, 0);
+          tma_load_2d(sa + B_OFF, &map_w0, full, kb * TC_BLOCK_K, 0);
+          if (p.n_out == 128) tma_load_2d(sa + B_OFF + 64 * 128, &map_w1, full, kb * TC_BLOCK_K, 0);
           if (NB == 2) {
-            tma_load_2d(sa + TC_A_BYTES + 16384, &map_l0, full, kb * TC_BLOCK_K, 0);
-            if (p.n_out == 128) tma_load_2d(sa + TC_A_BYTES + 16384 + 64 * 128, &map_l1, full, kb * TC_BLOCK_K, 0);
+            tma_load_2d(sa + B_OFF + 16384, &map_l0, full, kb * TC_BLOCK_K, 0);
+            if (p.n_out == 128) tma_load_2d(sa + B_OFF + 16384 + 64 * 128, &map_l1, full, kb * TC_BLOCK_K, 0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -162,7 +192,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
         mbar_wait(smem_u32(&bar_tmem_empty), tile_ph ^ 1);   // epilogue has drained the accumulators
         tc_fence_after();
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(smem_u32(&bar_full[s]), ph);
+          mbar_wait(smem_u32(XS ? &bar_conv[s] : &bar_full[s]), ph);
           tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes;
 #pragma unroll
@@ -170,14 +200,20 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
             const uint32_t koff = k * TC_UMMA_K * 4;           // 32 B per K step inside the 128 B atom
             const uint64_t da0 = make_desc_k_sw128(sa + koff);
             const uint64_t da1 = make_desc_k_sw128(sa + 128 * 128 + koff);
-            const uint64_t db = make_desc_k_sw128(sa + TC_A_BYTES + koff);
+            const uint64_t db = make_desc_k_sw128(sa + B_OFF + koff);
             const uint32_t acc = (kb | k) ? 1u : 0u;
             tc_mma_tf32(tmem_base, da0, db, idesc, acc);
             tc_mma_tf32(tmem_base + 128, da1, db, idesc, acc);
             if (NB == 2) {
-              const uint64_t dl = make_desc_k_sw128(sa + TC_A_BYTES + 16384 + koff);
+              const uint64_t dl = make_desc_k_sw128(sa + B_OFF + 16384 + koff);
               tc_mma_tf32(tmem_base, da0, dl, idesc, 1u);
               tc_mma_tf32(tmem_base + 128, da1, dl, idesc, 1u);
+            }
+            if (XS) {                                          // X_lo * W_hi
+              const uint64_t dx0 = make_desc_k_sw128(sa + TC_A_BYTES + koff);
+              const uint64_t dx1 = make_desc_k_sw128(sa + TC_A_BYTES + 128 * 128 + koff);
+              tc_mma_tf32(tmem_base, dx0, db, idesc, 1u);
+              tc_mma_tf32(tmem_base + 128, dx1, db, idesc, 1u);
             }
           }
           tc_commit(smem_u32(&bar_empty[s]));                 // frees the stage when the MMAs retire
@@ -186,7 +222,22 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp >= 4) {   // ===== epilogue: TMEM -> registers -> global =====
+  } else if (XS && warp >= 8) {   // ===== converters: X tile -> X_hi (in place) | X_lo =====
+    const int cw = warp - 8;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        const uint32_t sa = smem0 + s * stage_bytes;
+        split_tile_hi_lo(sa, sa + TC_A_BYTES, TC_A_BYTES, cw, lane);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_conv[s]));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {   // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     uint32_t tile_ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_ph ^= 1) {
@@ -279,8 +330,9 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
   BIGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "xw_tc: x must be 16-byte aligned");
   BIGCN_CHECK_ARG(n_out == 64 || n_out == 128, "xw_tc: n_out must be 64 or 128");
   if (N == 0) return 0;
-  const int nb = mode == BIGCN_GEMM_TF32X3 ? 2 : 1;
-  BIGCN_CHECK_ARG(nb == 1 || scratch != nullptr, "xw_tc: TF32X3 needs the split scratch");
+  const int nb = mode == BIGCN_GEMM_TF32 ? 1 : 2;
+  const bool xsplit = mode == BIGCN_GEMM_TF32X3;
+  BIGCN_CHECK_ARG(nb == 1 || scratch != nullptr, "xw_tc: TF32X2 / TF32X3 need the split scratch");
   CUtensorMap mx, mw0, mw1, ml0, ml1;
   if (int rc = make_map(&mx, x, N, K, K, 256)) return rc;
   if (nb == 1) {
@@ -305,18 +357,20 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
   p.y = y; p.ldy = ldy; p.N = N; p.K = K; p.n_out = n_out;
   p.num_tiles = (int)ceil_div(N, TC_BLOCK_M);
   p.num_kb = (int)ceil_div(K, TC_BLOCK_K);
-  const int stage_bytes = TC_A_BYTES + nb * 16384;
-  const int stages = nb == 1 ? 4 : 3;
+  const int stage_bytes = (xsplit ? 2 : 1) * TC_A_BYTES + nb * 16384;
+  const int stages = xsplit ? 2 : (nb == 1 ? 4 : 3);
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_xw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (TC_A_BYTES + 16384) + 1024);
-    cudaFuncSetAttribute(k_xw_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (TC_A_BYTES + 32768) + 1024);
+    cudaFuncSetAttribute(k_xw_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (TC_A_BYTES + 16384) + 1024);
+    cudaFuncSetAttribute(k_xw_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (TC_A_BYTES + 32768) + 1024);
+    cudaFuncSetAttribute(k_xw_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * TC_A_BYTES + 32768) + 1024);
     attr = true;
   }
-  if (nb == 1) k_xw_tc<1><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
-  else k_xw_tc<2><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
+  if (nb == 1) k_xw_tc<1, false><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
+  else if (!xsplit) k_xw_tc<2, false><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
+  else k_xw_tc<2, true><<<grid, TC_THREADS_XS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
   BIGCN_CHECK_LAUNCH("k_xw_tc");
   return 0;
 }
@@ -360,15 +414,17 @@ struct DwtParams {
   int rows_per_split; // multiple of DWT_BK
 };
 
-template <int NA>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NA, bool XS>
+__global__ void __launch_bounds__(XS ? TC_THREADS_XS : TC_THREADS, 1)
 k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_t,
         const __grid_constant__ CUtensorMap map_tlo, const DwtParams p) {
-  constexpr int STAGES = NA == 1 ? 4 : 3;
-  constexpr int STAGE_BYTES = NA * DWT_A_BYTES + DWT_B_BYTES;
+  static_assert(!XS || NA == 2, "the X split goes with the T split");
+  constexpr int STAGES = XS ? 2 : (NA == 1 ? 4 : 3);
+  constexpr int STAGE_BYTES = NA * DWT_A_BYTES + (XS ? 2 : 1) * DWT_B_BYTES;   // [T | T_lo | X | X_lo]
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_conv[STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,6 +440,7 @@ k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_conv[s]), 4);
     }
     mbar_init(smem_u32(&bar_tmem_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -403,7 +460,7 @@ k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
       int s = 0;
       uint32_t ph = 0;
       // all 4 output blocks are always loaded: blocks beyond n_out are out of bounds -> zero filled
-      const uint32_t tx = (uint32_t)STAGE_BYTES;
+      const uint32_t tx = (uint32_t)(NA * DWT_A_BYTES + DWT_B_BYTES);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
         const uint32_t full = smem_u32(&bar_full[s]);
@@ -427,7 +484,7 @@ k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&bar_full[s]), ph);
+        mbar_wait(smem_u32(XS ? &bar_conv[s] : &bar_full[s]), ph);
         tc_fence_after();
         const uint32_t sa = smem0 + s * STAGE_BYTES;
 #pragma unroll
@@ -440,13 +497,30 @@ k_dw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
             const uint64_t dl = make_desc_mn_sw128_32b(sa + DWT_A_BYTES + koff, DWT_BK * 128);
             tc_mma_tf32(tmem_base, dl, db, idesc, 1u);
           }
+          if (XS) {                                            // T_hi^T X_lo
+            const uint64_t dxl = make_desc_mn_sw128_32b(sa + NA * DWT_A_BYTES + DWT_B_BYTES + koff, DWT_BK * 128);
+            tc_mma_tf32(tmem_base, da, dxl, idesc, 1u);
+          }
         }
         tc_commit(smem_u32(&bar_empty[s]));
         if (kb == num_kb - 1) tc_commit(smem_u32(&bar_tmem_full));
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 4) {   // ===== epilogue =====
+  } else if (XS && warp >= 8) {   // ===== converters: X tile -> X_hi (in place) | X_lo =====
+    const int cw = warp - 8;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(smem_u32(&bar_full[s]), ph);
+      const uint32_t sx = smem0 + s * STAGE_BYTES + NA * DWT_A_BYTES;
+      split_tile_hi_lo(sx, sx + DWT_B_BYTES, DWT_B_BYTES, cw, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_conv[s]));
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {   // ===== epilogue =====
     const int q = warp & 3;
     float* out = p.partial + (size_t)blockIdx.y * p.K * p.n_out;
     const int m = q * 32 + lane;
@@ -514,7 +588,8 @@ int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int
   BIGCN_CHECK_ARG(K % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "dw_tc: x must be TMA-addressable");
   BIGCN_CHECK_ARG(ldt == n_out && (n_out == 64 || n_out == 128), "dw_tc: t must be dense [N, 64|128]");
   if (K == 0) return 0;
-  const int na = mode == BIGCN_GEMM_TF32 ? 1 : 2;   // TF32X3 and MIXED split T
+  const int na = mode == BIGCN_GEMM_TF32 ? 1 : 2;   // TF32X2, TF32X3 and MIXED split T
+  const bool xsplit = mode == BIGCN_GEMM_TF32X3;    // ... and TF32X3 splits X in shared memory as well
   const int tiles = (int)ceil_div(K, DWT_N);
   int nsplit = 1;
   if (N == 0) {
@@ -543,16 +618,18 @@ int dw_tc(const float* x, int64_t N, int64_t K, const float* t, int64_t ldt, int
     if (int rc = make_map_mn(&ml, t_lo, N, n_out, n_out)) return rc;
     DwtParams p;
     p.partial = partial; p.N = N; p.K = K; p.n_out = n_out; p.rows_per_split = (int)rps;
-    const int stages = na == 1 ? 4 : 3;
-    const size_t smem = (size_t)stages * (na * DWT_A_BYTES + DWT_B_BYTES) + 1024;
+    const int stages = xsplit ? 2 : (na == 1 ? 4 : 3);
+    const size_t smem = (size_t)stages * (na * DWT_A_BYTES + (xsplit ? 2 : 1) * DWT_B_BYTES) + 1024;
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(k_dw_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (DWT_A_BYTES + DWT_B_BYTES) + 1024);
-      cudaFuncSetAttribute(k_dw_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * DWT_A_BYTES + DWT_B_BYTES) + 1024);
+      cudaFuncSetAttribute(k_dw_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (DWT_A_BYTES + DWT_B_BYTES) + 1024);
+      cudaFuncSetAttribute(k_dw_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * DWT_A_BYTES + DWT_B_BYTES) + 1024);
+      cudaFuncSetAttribute(k_dw_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * DWT_A_BYTES + 2 * DWT_B_BYTES) + 1024);
       attr = true;
     }
-    if (na == 1) k_dw_tc<1><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
-    else k_dw_tc<2><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
+    if (na == 1) k_dw_tc<1, false><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
+    else if (!xsplit) k_dw_tc<2, false><<<dim3(tiles, nsplit), TC_THREADS, smem, st>>>(mx, mt, ml, p);
+    else k_dw_tc<2, true><<<dim3(tiles, nsplit), TC_THREADS_XS, smem, st>>>(mx, mt, ml, p);
     BIGCN_CHECK_LAUNCH("k_dw_tc");
   }
   return dw_reduce_launch(partial, nsplit, K, n_out, dw_a, ldw_a, k0_a, dw_b, ldw_b, k0_b, st);

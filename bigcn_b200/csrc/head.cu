@@ -213,7 +213,12 @@ __global__ void __launch_bounds__(256) k_eval_counts(const float* __restrict__ l
   }
   atomicAdd(&totals[0], 1ull);
   if (act == pred) atomicAdd(&totals[1], 1ull);
-  if (act >= 0 && act < C) atomicAdd(&totals[2], (unsigned long long)llrintf(-logp[b * C + act] * 1e6f));
+  if (act >= 0 && act < C) {
+    // fixed-point loss term; a non-finite or absurd log-prob (NaN parameters) saturates instead of llrintf's UB
+    const float t = -logp[b * C + act] * 1e6f;
+    const float tc = t == t ? fminf(fmaxf(t, 0.f), 1e15f) : 1e15f;
+    atomicAdd(&totals[2], (unsigned long long)llrintf(tc));
+  }
 }
 
 // dW[c][f] = sum_b dl[b][c] feat[b][f] (+ bias column f == 256): thread per (c, f), a chunk
@@ -328,10 +333,14 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     if (atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1) {
       *arrive = 0ull;
       *step_count += 1;
+      step_count[2] += 1;   // calls counter: the dropout seed offset of the next step (opts.seed_dev)
     }
   }
 }
-__global__ void k_step_inc(int64_t* step_count) { *step_count += 1; }
+__global__ void k_step_inc(int64_t* step_count) {
+  *step_count += 1;
+  step_count[2] += 1;
+}
 
 // ---- data-parallel optimiser step over peer memory (NVLink 5 / NVSwitch) ---------------------
 // Replaces "all-reduce the flat gradient, then Adam on every rank" (the reference trains on one
@@ -431,6 +440,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     if (atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1) {
       *arrive = 0ull;
       *a.step_count += 1;
+      a.step_count[2] += 1;
     }
   }
 }

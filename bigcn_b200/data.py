@@ -264,3 +264,76 @@ def make_device_forest(n_trees: int, nodes_per_tree: int, device, seed: int = 0,
     batch = torch.arange(n, device=device, dtype=torch.int64) // nodes_per_tree
     root = torch.arange(n_trees, device=device, dtype=torch.int64) * nodes_per_tree
     return DeviceTrees(ei, ei.flip(0).contiguous(), batch, root)
+
+
+def synth_forest_device(shape: str, n_trees: int, device, seed: int = 0, in_feats: int | None = None,
+                        num_classes: int | None = None):
+    """A whole synthetic DATASET generated on the device in a few vectorised passes (the per-tree Python
+    generators above take minutes for Weibo's 3.7 M nodes or the 1 M-tree scale-out config): tree sizes of
+    SURVEY.md 8(d), hub-heavy random recursive topology (parent of local node i = floor(u^2 * i)), the root at a
+    random local index (a per-tree rotation of the local ids; PHEME keeps it at 0), TD edges sorted by
+    (parent, child), BoW rows of 1+Poisson(12) distinct Zipf-ish columns with counts 1..3 (kept as CSR) or,
+    for PHEME, dense tanh(N(0,1)) rows.  Returns a dict of device tensors + host size arrays:
+    node_ptr / edge_ptr (host int64 [T+1]), edge_src / edge_dst (int32, local ids), root_local, y, and either
+    x_ptr / x_col / x_val (CSR over all nodes) or x (dense [N, K])."""
+    spec = SHAPES[shape]
+    k = spec["in_feats"] if in_feats is None else in_feats
+    c = spec["num_classes"] if num_classes is None else num_classes
+    sizes = tree_sizes(shape, n_trees, np.random.default_rng(seed))
+    node_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    edge_ptr = node_ptr - np.arange(n_trees + 1, dtype=np.int64)
+    n = int(node_ptr[-1])
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) * 7919 + 17)
+    d_sizes = torch.from_numpy(sizes).to(device)
+    d_ptr = torch.from_numpy(node_ptr).to(device)
+    tree = torch.repeat_interleave(torch.arange(n_trees, device=device), d_sizes)
+    local = torch.arange(n, device=device) - d_ptr[tree]
+    nt = d_sizes[tree]
+    u = torch.rand(n, device=device, generator=g, dtype=torch.float64)
+    par = (u * u * local.to(torch.float64)).to(torch.int64)
+    if shape == "pheme":
+        shift = torch.zeros(n_trees, dtype=torch.int64, device=device)
+    else:
+        shift = (torch.rand(n_trees, device=device, generator=g, dtype=torch.float64) * d_sizes.to(torch.float64)).to(torch.int64)
+        shift = torch.minimum(shift, d_sizes - 1)
+    sh = shift[tree]
+    is_child = local > 0
+    ch = ((local + sh) % nt)[is_child]
+    pa = ((par + sh) % nt)[is_child]
+    tr = tree[is_child]
+    order = torch.argsort((tr << 40) | (pa << 20) | ch)       # (tree, parent, child); local ids < 2^20
+    out = dict(node_ptr=node_ptr, edge_ptr=edge_ptr, edge_src=pa[order].to(torch.int32), edge_dst=ch[order].to(torch.int32),
+               root_local=shift.to(torch.int32), y=torch.randint(0, c, (n_trees,), device=device, generator=g),
+               in_feats=k, num_classes=c, sizes=sizes)
+    if shape == "pheme":
+        out["x"] = torch.tanh(torch.randn(n, k, device=device, generator=g))
+        return out
+    nnz = 1 + torch.poisson(torch.full((n,), 12.0, device=device), generator=g).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n, device=device), nnz)
+    uz = torch.rand(rows.numel(), device=device, generator=g, dtype=torch.float64).clamp_(min=1e-12)
+    z = torch.clamp(torch.floor(uz ** (-1.0 / 0.3)), max=float(1 << 40)).to(torch.int64)     # Zipf(1.3)-like head
+    cols = ((z - 1).clamp_(max=k - 1) * 2654435761) % k
+    key = torch.unique(rows * k + cols)                        # distinct columns per row, ascending
+    rows, cols = key // k, key % k
+    x_ptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    x_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    out.update(x_ptr=x_ptr, x_col=cols.to(torch.int32),
+               x_val=torch.randint(1, 4, (cols.numel(),), device=device, generator=g).to(torch.float32))
+    return out
+
+
+def forest_slice_batch(f: dict, t0: int, t1: int) -> Batch:
+    """Trees [t0, t1) of a ``synth_forest_device`` dataset with DENSE features as one collated batch on the device
+    (no DropEdge: the test split of Process/process.py:63); x is a view of the dataset's rows."""
+    node_ptr, edge_ptr = f["node_ptr"], f["edge_ptr"]
+    n0, n1, e0, e1 = int(node_ptr[t0]), int(node_ptr[t1]), int(edge_ptr[t0]), int(edge_ptr[t1])
+    dev = f["edge_src"].device
+    sizes = torch.from_numpy(f["sizes"][t0:t1]).to(dev)
+    starts = torch.from_numpy(node_ptr[t0:t1] - n0).to(dev)
+    etree = torch.repeat_interleave(torch.arange(t1 - t0, device=dev), torch.clamp(sizes - 1, min=0))
+    off = starts[etree]
+    ei = torch.stack([f["edge_src"][e0:e1].to(torch.int64) + off, f["edge_dst"][e0:e1].to(torch.int64) + off])
+    return Batch(x=f["x"][n0:n1], edge_index=ei, BU_edge_index=ei.flip(0).contiguous(),
+                 batch=torch.repeat_interleave(torch.arange(t1 - t0, device=dev), sizes),
+                 rootindex=starts + f["root_local"][t0:t1].to(torch.int64), y=f["y"][t0:t1])

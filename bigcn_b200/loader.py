@@ -36,6 +36,25 @@ class DeviceForest:
         self._stage, self._turn = None, 0
 
     @staticmethod
+    def from_device_arrays(f):
+        """From ``data.synth_forest_device`` (sparse features): everything already sits on the device; only the
+        size arrays live on the host."""
+        self = DeviceForest.__new__(DeviceForest)
+        dev = f["edge_src"].device
+        self.h_node_ptr = np.asarray(f["node_ptr"], np.int64)
+        self.h_edge_ptr = np.asarray(f["edge_ptr"], np.int64)
+        self.node_ptr = torch.from_numpy(self.h_node_ptr).to(dev)
+        self.edge_ptr = torch.from_numpy(self.h_edge_ptr).to(dev)
+        self.h_x_ptr_at_tree = f["x_ptr"][self.node_ptr].cpu().numpy()
+        self.in_feats, self.device = int(f["in_feats"]), dev
+        self.edge_src, self.edge_dst = f["edge_src"], f["edge_dst"]
+        self.x_ptr, self.x_col, self.x_val = f["x_ptr"], f["x_col"], f["x_val"]
+        self.root_local, self.y = f["root_local"], f["y"].to(torch.int64)
+        self.num_trees = len(self.h_node_ptr) - 1
+        self._stage, self._turn = None, 0
+        return self
+
+    @staticmethod
     def from_data_list(trees, device):
         """Pack ``Data`` objects with the attribute layout of dataset.py:91-98 (x dense or SparseX,
         edge_index [2,e] = [parent; child] WITHOUT DropEdge, rootindex, y)."""
@@ -81,15 +100,26 @@ class DeviceForest:
             offs[row, 1:] = np.cumsum(v)
         n, e_td, e_bu, nnz = (int(offs[r, -1]) for r in range(1, 5))
         dev = self.device
-        # offsets through a pinned staging buffer (two slots: the copy of the previous batch may still be in flight)
+        # offsets through a ring of pinned staging buffers; a slot is rewritten only after the H2D copy that last
+        # read it has completed (the epoch loop never synchronises the host, so the device may lag many batches)
         need = 5 * (b + 1)
-        if self._stage is None or self._stage[0].numel() < need:
-            self._stage = [torch.empty(max(need, 4096), dtype=torch.int64).pin_memory() for _ in range(2)]
-        self._turn ^= 1
-        hbuf = self._stage[self._turn]
+        if self._stage is None or self._stage[0][0].numel() < need:
+            if self._stage is not None:
+                for _, ev in self._stage:
+                    if ev is not None:
+                        ev.synchronize()
+            self._stage = [[torch.empty(max(need, 4096), dtype=torch.int64).pin_memory(), None] for _ in range(4)]
+        self._turn = (self._turn + 1) % len(self._stage)
+        slot = self._stage[self._turn]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        hbuf = slot[0]
         hbuf[:need].copy_(torch.from_numpy(offs.reshape(-1)))
         d_offs = torch.empty(need, dtype=torch.int64, device=dev)
         d_offs.copy_(hbuf[:need], non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record()
         d_offs = d_offs.view(5, b + 1)
         # one int64 block [edge_index | BU_edge_index | batch | rootindex | y], one int32 block [x ptr | x col]
         blk = torch.empty(2 * e_td + 2 * e_bu + n + 2 * b, dtype=torch.int64, device=dev)

@@ -18,6 +18,31 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_capture_streams = {}
+
+
+def capture_graph(enqueue):
+    """Stream-capture ``enqueue()`` (C-ABI launches only: nothing allocates, nothing synchronises) into a
+    torch.cuda.CUDAGraph on a side stream.  The bare capture_begin / capture_end pair instead of the
+    ``torch.cuda.graph`` context manager: no device synchronise, gc.collect or empty_cache per capture, so a
+    capture costs about one enqueue plus the instantiation."""
+    dev = torch.cuda.current_device()
+    s = _capture_streams.get(dev)
+    if s is None:
+        s = _capture_streams[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream()
+    s.wait_stream(cur)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        g.capture_begin(capture_error_mode="thread_local")
+        try:
+            enqueue()
+        finally:
+            g.capture_end()
+    cur.wait_stream(s)
+    return g
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -113,6 +138,29 @@ def _as_x(x):
     if isinstance(x, torch.Tensor) and x.layout != torch.strided:
         return None, SparseX.from_torch_csr(x)
     return _f32(x), None
+
+
+def pick_gemm_mode(x, sample_rows=4096):
+    """``gemm_mode='auto'``: which conv1 product suits this feature matrix.  Counts the non-zeros of (up to)
+    the first ``sample_rows`` rows on the device (bigcn_dense_row_counts) and reads the counts back ONCE per
+    model: row-sparse bag-of-words features (Twitter / Weibo: ~14 of 5000 columns) take 'sparse' (exact fp32
+    scan that also captures the non-zeros, X read once per step); dense features (PHEME's 768-d BERT
+    embeddings) take 'tf32x3' (tcgen05 kind::tf32 with the hi/lo weight split, fp32-class accuracy)."""
+    L.require_device()
+    x = _f32(x)
+    _need_cuda(x)
+    n, k = x.shape
+    m = min(int(n), int(sample_rows))
+    if m == 0:
+        return "sparse"
+    tma_ok = k % 4 == 0 and x.data_ptr() % 16 == 0       # TMA needs 16 B aligned rows; otherwise the exact FFMA scan
+    cnt = torch.empty(m, dtype=torch.int32, device=x.device)
+    check(lib().bigcn_dense_row_counts(_p(x), m, k, _p(cnt), _stream()), "dense_row_counts")
+    c = cnt.cpu().numpy()
+    cap = min(int(k), 48)
+    if float(c.mean()) <= cap / 2 and int(c.max()) <= 4 * cap:
+        return "sparse"
+    return "tf32x3" if tma_ok else "fp32"
 
 
 # ----------------------------------------------------------------------------- graph prep

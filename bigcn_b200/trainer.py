@@ -9,12 +9,13 @@ groups (BU convs at lr/5).  Nothing in a step synchronises the host.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
 from . import _lib as L
 from ._lib import H, Opts, Params, check, lib
-from .ops import _make_structs, _p, _stream, _i64, _f32, _as_x, raise_on_flags
+from .ops import _make_structs, _p, _stream, _i64, _f32, _as_x, capture_graph, raise_on_flags
 
 # flat layout: the two conv1 weights (the gradients the second X stream produces LAST) first, so
 # the gradient splits into two contiguous all-reduce buckets: [W1_td | W1_bu] and [everything else]
@@ -33,12 +34,15 @@ class FusedTrainer:
     """Adam(lr, weight_decay) with BU conv1/conv2 at lr/5 over a flat parameter buffer."""
 
     def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=1, validate=False, comm="auto"):
+                 process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=8):
         """``comm`` (world_size > 1): "symm" = one fused kernel over NVLink peer memory
         (reduce-scatter of the gradients in rank order + Adam on the owned shard + all-gather of
         the parameters, bigcn_dp_reduce_adam) between two symmetric-memory barriers; "nccl" = two
         bucketed NCCL all-reduces overlapping the last backward kernels + Adam on every rank;
-        "auto" = symm when the symmetric-memory rendezvous succeeds, else nccl."""
+        "auto" = symm when the symmetric-memory rendezvous succeeds, else nccl.
+        ``graphs``: replay a CUDA graph of the whole step for batches seen before (True / False;
+        "auto" = on for a single GPU and for comm="symm", off for the NCCL path whose collectives
+        run on NCCL's own stream); at most ``max_graphs`` batches are kept captured."""
         L.require_device()
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -83,10 +87,11 @@ class FusedTrainer:
             torch.distributed.broadcast(self.flat, src=0, group=self.pg)
         # lr groups: TD convs + fc at lr, BU convs at lr/5  (BiGCN_Twitter.py:146-153)
         self.seg_end = torch.tensor(offs[1:], dtype=torch.int64, device=dev)
-        self.seg_lr = torch.tensor([lr / d for d in _LR_DIV], dtype=torch.float32, device=dev)
+        self.seg_lr_host = [lr / d for d in _LR_DIV]
+        self.seg_lr = torch.tensor(self.seg_lr_host, dtype=torch.float32, device=dev)
         self.n_seg = len(_LR_DIV)
         self.w1_end = offs[2]                    # [0, w1_end) = the two conv1 weight gradients
-        self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)   # [step, arrival counter]
+        self.step_count = torch.zeros(4, dtype=torch.int64, device=dev)   # [step, arrival counter, calls, spare]
         self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pr, self._gr = Params(), Params()
         for name in _ORDER:
@@ -95,6 +100,10 @@ class FusedTrainer:
         self._ws = None
         self._calls = 0
         self.launches_per_step = None
+        self.graphs = (self.comm in ("single", "symm")) if graphs == "auto" else bool(graphs)
+        self.max_graphs = int(max_graphs)
+        self._graphs, self._seen = {}, {}   # captured steps by batch identity; batch identities seen once
+        self.graph_captures = self.graph_replays = 0
 
     # -------------------------------------------------------------------------------
     def _setup_symm(self, dev):
@@ -123,11 +132,12 @@ class FusedTrainer:
     def _workspace(self, dims, dev):
         need = lib().bigcn_features_workspace_bytes(C.byref(dims))
         if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            # head room: captured graphs hold pointers into the workspace, a slightly larger batch should not move it
+            self._ws = torch.empty(need + need // 4 if self.graphs else need, dtype=torch.uint8, device=dev)
         return self._ws
 
-    def step(self, data, b_global=None, node_id_base=0, seed=None):
-        """One optimisation step on a device-resident batch; returns the loss (device scalar)."""
+    def _plan(self, data, b_global, node_id_base, seed):
+        """Everything one step needs besides the launches: argument structs, output buffers, workspace."""
         m = self.model
         x, xs = _as_x(data.x)
         ei, bu, batch, root = _i64(data.edge_index), _i64(data.BU_edge_index), _i64(data.batch), \
@@ -136,28 +146,36 @@ class FusedTrainer:
         td = m.TDrumorGCN
         c = m.fc.weight.shape[0]
         dims, bt, _ = _make_structs(x, ei, bu, batch, root, (None,) * 8, c, node_id_base, xs)
-        if seed is None:
-            seed = (td.seed + self._calls) & ((1 << 64) - 1)
-        self._calls += 1
-        o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(seed), deg_by=L.DEG_BY[td.deg_by],
-                 gemm_mode=L.GEMM_MODE[td.gemm_mode], dir_mask=L.DIR_TD | L.DIR_BU, fused_tail=1)
+        # seed=None: the module's seed plus the device-side calls counter (step_count[2], advanced by the
+        # optimiser kernel) -- the same value whether the step is enqueued or replayed from a CUDA graph
+        o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(td.seed if seed is None else seed) & ((1 << 64) - 1),
+                 deg_by=L.DEG_BY[td.deg_by], gemm_mode=L.GEMM_MODE[td.resolved_gemm_mode(data.x)], dir_mask=L.DIR_TD | L.DIR_BU,
+                 fused_tail=1, seed_dev=self.step_count[2:].data_ptr() if seed is None else None)
         dev = xs.device if xs is not None else x.device
-        ws = self._workspace(dims, dev)
         b = dims.B
-        feat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
-        logp = torch.empty(b, c, dtype=torch.float32, device=dev)
-        gfeat = torch.empty(b, 4 * H, dtype=torch.float32, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        p = {"dims": dims, "bt": bt, "o": o, "b": b, "c": c, "dev": dev, "y": y, "b_global": int(b_global or b),
+             "keep": (x, xs, ei, bu, batch, root, y),
+             "feat": torch.empty(b, 4 * H, dtype=torch.float32, device=dev),
+             "logp": torch.empty(b, c, dtype=torch.float32, device=dev),
+             "gfeat": torch.empty(b, 4 * H, dtype=torch.float32, device=dev),
+             "loss": torch.empty(1, dtype=torch.float32, device=dev)}
+        p["nscr"] = lib().bigcn_head_train_scratch_floats(b, c)
+        p["scr"] = torch.empty(p["nscr"], dtype=torch.float32, device=dev)
+        return p
+
+    def _enqueue(self, p):
+        """The launches of one step on the current stream (nothing allocates, nothing synchronises)."""
+        dims, bt, o = p["dims"], p["bt"], p["o"]
+        feat, logp, gfeat, loss, scr = p["feat"], p["logp"], p["gfeat"], p["loss"], p["scr"]
+        ws = self._ws
         st = _stream()
         l = lib()
         check(l.bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(feat),
                                        _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
-        nscr = l.bigcn_head_train_scratch_floats(b, c)
-        scr = torch.empty(nscr, dtype=torch.float32, device=dev)
         # readout's second pass + fc / log_softmax / nll and their backward + the per-tree gradient scaling: one launch
-        check(l.bigcn_train_tail(C.byref(dims), C.byref(bt), C.byref(o), _p(feat), _p(y), int(b_global or b),
+        check(l.bigcn_train_tail(C.byref(dims), C.byref(bt), C.byref(o), _p(feat), _p(p["y"]), p["b_global"],
                                  self._pr.fc_w, self._pr.fc_b, _p(logp), _p(loss), _p(gfeat), self._gr.fc_w,
-                                 self._gr.fc_b, _p(scr), nscr, _p(self.flags), _p(ws), ws.numel(), st), "train_tail")
+                                 self._gr.fc_b, _p(scr), p["nscr"], _p(self.flags), _p(ws), ws.numel(), st), "train_tail")
         if self.comm == "symm":
             check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                             C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
@@ -167,10 +185,7 @@ class FusedTrainer:
                                          self.betas[0], self.betas[1], self.eps, self.wd, 1.0, _p(self.step_count),
                                          st), "dp_reduce_adam")
             self._hf.barrier(channel=1)        # every rank's parameters are written; gradients are free again
-            self.last_logp = logp
-            if self.validate:
-                raise_on_flags(self.flags)
-            return loss
+            return
         if self.world > 1:
             # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
             o.bwd_phase = 1
@@ -180,6 +195,7 @@ class FusedTrainer:
             o.bwd_phase = 2
             check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                             C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+            o.bwd_phase = 0
             h_w1 = torch.distributed.all_reduce(self.grad[:self.w1_end], group=self.pg, async_op=True)
             h_rest.wait()
             h_w1.wait()
@@ -189,10 +205,62 @@ class FusedTrainer:
         check(l.bigcn_adam_step(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
                                 _p(self.seg_end), _p(self.seg_lr), self.n_seg, self.betas[0], self.betas[1],
                                 self.eps, self.wd, 1.0, _p(self.step_count), st), "adam_step")
-        self.last_logp = logp
-        if self.validate:
-            raise_on_flags(self.flags)
-        return loss
+
+    def _graph_key(self, data, b_global, node_id_base):
+        m, td = self.model, self.model.TDrumorGCN
+        x = data.x
+        xk = (x.ptr.data_ptr(), x.col.data_ptr(), x.val.data_ptr(), x.shape) if hasattr(x, "ptr") else \
+            (x.data_ptr(), tuple(x.shape), x.dtype, x.layout)
+        small = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in
+                      (data.edge_index, data.BU_edge_index, data.batch, data.rootindex, data.y))
+        return (id(data), xk, small, b_global, node_id_base, m.training, td.p, td.deg_by, td.gemm_mode, td.seed)
+
+    def step(self, data, b_global=None, node_id_base=0, seed=None):
+        """One optimisation step on a device-resident batch; returns the loss (device scalar).
+
+        With ``graphs`` on, a batch OBJECT stepped on for the second time (the same ``data``, same device
+        buffers, same shapes -- a resident batch, not a freshly assembled one that happens to reuse freed
+        memory) has its whole step captured into a CUDA graph: ~45 launches over four streams become one
+        ``cudaGraphLaunch``, and every later step on it is a replay.  The dropout seed of a replay comes
+        from the device-side calls counter, so replays draw fresh masks exactly as enqueued steps do."""
+        self._calls += 1
+        if not (self.graphs and seed is None and not self.validate):
+            p = self._plan(data, b_global, node_id_base, seed)
+            self._workspace(p["dims"], p["dev"])
+            self._enqueue(p)
+            self.last_logp = p["logp"]
+            if self.validate:
+                raise_on_flags(self.flags)
+            return p["loss"]
+        key = self._graph_key(data, b_global, node_id_base)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["ws"] is self._ws:
+            ent["graph"].replay()
+            self.graph_replays += 1
+            self.last_logp = ent["plan"]["logp"]
+            return ent["plan"]["loss"]
+        p = self._plan(data, b_global, node_id_base, None)
+        ws_before = self._ws
+        self._workspace(p["dims"], p["dev"])
+        if self._ws is not ws_before:
+            self._graphs.clear()               # the workspace moved: every captured pointer into it is stale
+        ref = self._seen.get(key)
+        if ref is None or ref() is not data:   # first sighting: enqueue (also warms the library's lazy state)
+            if len(self._seen) >= 256:
+                self._seen.clear()
+            self._seen[key] = weakref.ref(data)
+            self._enqueue(p)
+            self.last_logp = p["logp"]
+            return p["loss"]
+        g = capture_graph(lambda: self._enqueue(p))     # seen before: capture, then replay
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = {"ws": self._ws, "graph": g, "plan": p, "data": data}   # the strong reference pins id(data)
+        self.graph_captures += 1
+        g.replay()
+        self.graph_replays += 1
+        self.last_logp = p["logp"]
+        return p["loss"]
 
     def check_inputs(self):
         raise_on_flags(self.flags)
@@ -229,6 +297,7 @@ class FusedTrainer:
         after the same steps; its ``load_state_dict`` accepts the result.  Reads the device."""
         step = float(self.step_count[0].item())
         m_all, v_all = self._full_moments()
+        seg_lr_host = self.seg_lr_host
         groups, state, i = [], {}, 0
         for gi, names in enumerate(self._ref_groups()):
             ids = []
@@ -241,7 +310,9 @@ class FusedTrainer:
                                 "exp_avg_sq": v_all[sl].view(v.shape).clone()}
                 ids.append(i)
                 i += 1
-            groups.append({"lr": self.lr if gi == 0 else self.lr / 5, "betas": tuple(self.betas), "eps": self.eps,
+            lrs = {float(seg_lr_host[_ORDER.index(n)]) for n in names}
+            groups.append({"lr": lrs.pop() if len(lrs) == 1 else (self.lr if gi == 0 else self.lr / 5),
+                           "betas": tuple(self.betas), "eps": self.eps,
                            "weight_decay": self.wd, "amsgrad": False, "maximize": False, "foreach": None,
                            "capturable": False, "differentiable": False, "fused": None,
                            "decoupled_weight_decay": False, "params": ids})
@@ -272,8 +343,28 @@ class FusedTrainer:
         if len(steps) != 1:
             raise L.BigcnError(f"optimizer state mixes step counts {sorted(steps)}")
         self.step_count[0] = steps.pop()
-        self.lr = float(sd["param_groups"][0]["lr"])
-        self.seg_lr.copy_(torch.tensor([self.lr / d for d in _LR_DIV], dtype=torch.float32))
+        # hyper-parameters travel with the state (torch.optim.Adam.load_state_dict restores them too)
+        groups = sd["param_groups"]
+        g0 = groups[0]
+        for g in groups[1:]:
+            for k in ("betas", "eps", "weight_decay"):
+                if k in g and k in g0 and (tuple(g[k]) != tuple(g0[k]) if k == "betas" else g[k] != g0[k]):
+                    raise L.BigcnError(f"optimizer state: param groups disagree on {k}; the fused Adam kernel takes one value")
+        self.lr = float(g0["lr"])
+        if "betas" in g0:
+            self.betas = (float(g0["betas"][0]), float(g0["betas"][1]))
+        self.eps = float(g0.get("eps", self.eps))
+        self.wd = float(g0.get("weight_decay", self.wd))
+        if g0.get("amsgrad") or g0.get("maximize") or g0.get("decoupled_weight_decay"):
+            raise L.BigcnError("optimizer state: amsgrad / maximize / decoupled weight decay are not what the reference uses")
+        # per-tensor lr from the group each tensor sits in (reference: group 0 at lr, BU conv1 / conv2 at lr/5)
+        lr_of = {}
+        for g, gnames in zip(groups, self._ref_groups()):
+            for n in gnames:
+                lr_of[n] = float(g["lr"])
+        self.seg_lr_host = [lr_of[n] for n in _ORDER]
+        self.seg_lr.copy_(torch.tensor(self.seg_lr_host, dtype=torch.float32))
+        self._graphs.clear()      # betas / eps / weight decay are baked into captured launches
 
 
 def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm_mode: str = "fp32",

@@ -55,10 +55,15 @@ extern "C" {
 #define BIGCN_DEG_BY_TARGET 0
 #define BIGCN_DEG_BY_SOURCE 1
 
-/* X*W arithmetic: exact fp32 FFMA scan, or tcgen05 kind::tf32 with 1 / 3 passes */
+/* X*W arithmetic: exact fp32 FFMA scan, or tcgen05 kind::tf32 with 1 / 2 / 3 MMAs per K step.
+ * TF32X3: both operands split hi + lo (x_hi w_hi + x_hi w_lo + x_lo w_hi): fp32-class on ANY input; the x split
+ *         happens in shared memory between the TMA load and the MMA, x is still read from HBM once.
+ * TF32X2: only the small operand (W forward, T backward) is split: exact to ~2^-22 when x is representable in
+ *         TF32 (bag-of-words counts are), one MMA less per K step. */
 #define BIGCN_GEMM_FP32 0
 #define BIGCN_GEMM_TF32 1
 #define BIGCN_GEMM_TF32X3 2
+#define BIGCN_GEMM_TF32X2 5
 /* exact fp32 scan for X*W (forward), tcgen05 hi/lo-split GEMM for the weight gradient */
 #define BIGCN_GEMM_MIXED 3
 /* exact fp32 scan forward that also captures the non-zeros of x; the weight gradient is a sweep
@@ -133,6 +138,9 @@ typedef struct bigcn_opts {
                               return NaN for the conv1 weight gradient)              */
   int32_t fused_tail; /* training step through bigcn_train_tail: features_forward leaves the second
                          readout pass, features_backward the gscale pass, to that one launch   */
+  const uint64_t* seed_dev; /* NULL, or a device counter: the Philox key is seed + *seed_dev, read when the
+                               kernels run.  bigcn_adam_step / bigcn_dp_reduce_adam advance step_count[2] once
+                               per step, so a captured CUDA graph of the step draws fresh masks at every replay */
 } bigcn_opts_t;
 
 const char* bigcn_last_error(void);
@@ -352,8 +360,10 @@ int bigcn_eval_counts(const float* logp, const int64_t* y, int64_t B, int64_t C,
 int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C, int64_t B_global,
                    float* loss /*[1]*/, float* grad_logp /*[B,C] or NULL*/, bigcn_stream_t stream);
 /* torch.optim.Adam (coupled L2) over one flat buffer; lr_of_segment: n_seg pairs
- * (end_offset, lr) on the DEVICE; step_count: device int64[2], zero-initialised by the caller:
- * [0] the step, advanced here by the last block of the update kernel, [1] its arrival counter. */
+ * (end_offset, lr) on the DEVICE; step_count: device int64[4], zero-initialised by the caller:
+ * [0] the step, advanced here by the last block of the update kernel, [1] its arrival counter,
+ * [2] calls counter (advanced with [0]; never rewound by a checkpoint load): what opts.seed_dev points
+ * at so that every step -- eager or a CUDA-graph replay -- draws a fresh dropout mask, [3] spare. */
 int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                     int64_t n, const int64_t* seg_end, const float* seg_lr, int32_t n_seg,
                     double beta1, double beta2, double eps, double weight_decay,

@@ -505,7 +505,7 @@ def test_dp_reduce_adam_two_ranks_emulated_on_one_device(dev):
     params = [p0.clone().to(dev) for _ in range(world)]
     ms = [torch.zeros(n, device=dev) for _ in range(world)]
     vs = [torch.zeros(n, device=dev) for _ in range(world)]
-    steps = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    steps = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
     seg_end = torch.tensor([n], dtype=torch.int64, device=dev)
     seg_lr = torch.tensor([1e-3], dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream().cuda_stream

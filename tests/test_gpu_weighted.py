@@ -128,7 +128,7 @@ def test_weighted_propagate_is_bit_exact_given_the_same_product(dev):
     n = 2000
     ei, w = random_graph(n, 3000, 3, loops=20, hub=True)
     ref = gcn_oracle.GCNConv(64, 64)
-    conv = bigcn_b200.GCNConv(64, 64).to(dev)
+    conv = bigcn_b200.GCNConv(64, 64, gemm_mode="fp32").to(dev)      # the exact FFMA product ('auto' takes tf32x3 for dense x)
     with torch.no_grad():
         ref.lin.weight.copy_(torch.eye(64))
         ref.bias.uniform_(-1, 1)
