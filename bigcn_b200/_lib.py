@@ -32,7 +32,7 @@ class Dims(C.Structure):
 class BatchPtrs(C.Structure):
     _fields_ = [("x", c_ptr), ("edge_index", c_ptr), ("bu_edge_index", c_ptr), ("batch", c_ptr),
                 ("rootindex", c_ptr), ("node_id_base", C.c_int64),
-                ("x_ptr", c_ptr), ("x_col", c_ptr), ("x_val", c_ptr)]
+                ("x_ptr", c_ptr), ("x_col", c_ptr), ("x_val", c_ptr), ("prepared", c_ptr)]
 
 
 class Params(C.Structure):
@@ -95,6 +95,9 @@ _SIGS = {
     "bigcn_gcnconv_backward": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr,
                                          C.c_int32, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_features_workspace_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "bigcn_batch_prepare_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "bigcn_batch_prepare": (C.c_int, [C.POINTER(Dims), C.POINTER(BatchPtrs), C.POINTER(Opts), c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_batch_prepare_join": (C.c_int, [c_ptr]),
     "bigcn_features_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(BatchPtrs), C.POINTER(Params),
                                          C.POINTER(Opts), c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_features_backward": (C.c_int, [C.POINTER(Dims), C.POINTER(BatchPtrs), C.POINTER(Params),

@@ -35,7 +35,8 @@ struct SideCtx {
   SideStream s;        // high priority: work the main stream will wait for soon (graph prep)
   cudaStream_t side2;  // high priority, a second short chain beside the first (root columns; dW2b)
   cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
-  cudaEvent_t ev[8];
+  cudaStream_t prep[2];  // lowest priority: bigcn_batch_prepare of the NEXT batch, beside the whole current step
+  cudaEvent_t ev[12];
   bool ok;
 };
 static SideCtx* side_ctx() {
@@ -50,8 +51,10 @@ static SideCtx* side_ctx() {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi) == cudaSuccess &&
-           cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess;
-    for (int i = 0; i < 8 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.prep[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.prep[1], cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < 12 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
     if (e && e[0] == '1') c.ok = false;
   }
@@ -125,8 +128,20 @@ struct FeatWs {
   size_t total;
 };
 
-static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
-  FeatWs w{};
+// The weight-independent part of a step's workspace: what bigcn_batch_prepare fills for a batch (one step ahead of
+// the step that consumes it) -- or, without a prepared buffer, the tail of the features workspace that
+// features_forward fills itself.
+struct PrepWs {
+  bigcn_graph_t g[2];
+  int32_t* node_ptr;
+  int32_t* rnz_cnt; int32_t* rnz_col; float* rnz_val;
+  int32_t* slot; int32_t* overflow;
+  XSparse xs;
+  void* prep_ws; size_t prep_bytes;
+  size_t total;
+};
+static PrepWs carve_prepared(const bigcn_dims_t* dm, void* ws, size_t bytes) {
+  PrepWs w{};
   Carver c(ws, bytes);
   const int64_t N = dm->N, B = dm->B, K = dm->K;
   const int64_t E[2] = {dm->E_td, dm->E_bu};
@@ -142,14 +157,28 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
     w.g[d].out_long = c.take<int32_t>(long_ws_ints(E[d]));
   }
   w.node_ptr = c.take<int32_t>(B + 1);
+  w.rnz_cnt = c.take<int32_t>(B > 0 ? B : 1);
+  w.rnz_col = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
+  w.rnz_val = c.take<float>((size_t)(B > 0 ? B : 1) * K);
+  w.slot = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
+  w.overflow = c.take<int32_t>(1 + K);
+  w.xs = xs_carve(c, N, K);
+  const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
+  w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
+  w.prep_ws = c.take<char>(w.prep_bytes);
+  w.total = align_up(c.off, 256);
+  return w;
+}
+
+static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes, void* prepared = nullptr) {
+  FeatWs w{};
+  Carver c(ws, bytes);
+  const int64_t N = dm->N, B = dm->B, K = dm->K;
   w.w1T = c.take<float>((size_t)K * 256);   // fp32: [K][128] transposed; tensor-core modes: hi/lo split
   for (int d = 0; d < 2; ++d) {
     w.w2aT[d] = c.take<float>(H * H);
     w.w2bT[d] = c.take<float>((size_t)K * H);
   }
-  w.rnz_cnt = c.take<int32_t>(B > 0 ? B : 1);
-  w.rnz_col = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
-  w.rnz_val = c.take<float>((size_t)(B > 0 ? B : 1) * K);
   const size_t nh = (size_t)(N > 0 ? N : 1) * H;
   for (int d = 0; d < 2; ++d) w.P[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   w.xw = c.take<float>(2 * nh);
@@ -166,20 +195,26 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes) {
   for (int d = 0; d < 2; ++d) w.op_part[d] = c.take<float>((size_t)op_chunks(N) * H * H);
   w.dw_part = c.take<float>(dw_partial_floats(N, K, 128));
   for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
-  w.slot = c.take<int32_t>((size_t)(B > 0 ? B : 1) * K);
-  w.overflow = c.take<int32_t>(1 + K);
   for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
   for (int d = 0; d < 2; ++d) w.keep[d] = c.take<unsigned long long>((size_t)(N > 0 ? N : 1));
   w.ro_part = c.take<float>(readout_scratch_floats(N, B, 2));
-  w.xs = xs_carve(c, N, K);
-  const int64_t Emax = E[0] > E[1] ? E[0] : E[1];
-  w.prep_bytes = graph_prep_ws_bytes(N, Emax, 2);
-  w.prep_ws = c.take<char>(w.prep_bytes);
-  w.total = align_up(c.off, 256);
+  // the weight-independent part: the caller's prepared buffer, or the tail of this workspace
+  const size_t step_bytes = align_up(c.off, 256);
+  char* tail = ws ? reinterpret_cast<char*>(ws) + step_bytes : nullptr;
+  const PrepWs pw = carve_prepared(dm, prepared ? prepared : tail, 0);
+  w.g[0] = pw.g[0]; w.g[1] = pw.g[1];
+  w.node_ptr = pw.node_ptr;
+  w.rnz_cnt = pw.rnz_cnt; w.rnz_col = pw.rnz_col; w.rnz_val = pw.rnz_val;
+  w.slot = pw.slot; w.overflow = pw.overflow;
+  w.xs = pw.xs;
+  w.prep_ws = pw.prep_ws; w.prep_bytes = pw.prep_bytes;
+  w.total = step_bytes + pw.total;   // sized for the self-contained case whether or not `prepared` is given
   return w;
 }
+
+int batch_prepare_join(cudaStream_t st);
 
 // active directions: order TD (0), BU (1); feat base: BU -> 0, TD -> 128 (cat order of :128)
 struct Dirs {
@@ -216,9 +251,10 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
                      const bigcn_opts_t* o, float* feat, int32_t* flags, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
   if (int rc = check_common(dm, o, "features_forward")) return rc;
-  FeatWs w = carve_features(dm, ws, ws_bytes);
+  FeatWs w = carve_features(dm, ws, ws_bytes, bt->prepared);
   BIGCN_CHECK_ARG(ws != nullptr && ws_bytes >= w.total, "features_forward: workspace too small (%zu < %zu)",
                   ws_bytes, w.total);
+  const bool prepared = bt->prepared != nullptr;   // graph structure, root columns, CSR / CSC of x: already there
   const int64_t N = dm->N, B = dm->B, K = dm->K;
   const Dirs dirs = active_dirs(o->dir_mask);
   const bool scan_mode = o->gemm_mode == BIGCN_GEMM_FP32 || o->gemm_mode == BIGCN_GEMM_MIXED ||
@@ -228,6 +264,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   const bool csr_in = bt->x == nullptr && N > 0;
   BIGCN_CHECK_ARG(!csr_in || (sparse && bt->x_ptr && bt->x_col && bt->x_val),
                   "features_forward: x == NULL needs gemm_mode SPARSE and x_ptr / x_col / x_val");
+  BIGCN_CHECK_ARG(!(prepared && sparse && o->skip_wgrad_prep), "features_forward: a prepared batch carries the column-sorted x");
   if (csr_in) {
     w.xs.ptr = const_cast<int32_t*>(bt->x_ptr);
     w.xs.col = const_cast<int32_t*>(bt->x_col);
@@ -238,8 +275,8 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   SideCtx* sc = side_ctx();
   cudaStream_t ss = sc ? sc->s.side : st;
   cudaStream_t s2 = sc ? sc->side2 : st;
-  if (sc) stream_after(sc, 0, st, ss);
-  {
+  if (sc && !prepared) stream_after(sc, 0, st, ss);
+  if (!prepared) {
     const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
     const int64_t E[2] = {dm->E_td, dm->E_bu};
     if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws,
@@ -264,7 +301,9 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   {
     RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
                  w.slot, w.overflow, DW2B_CAP};
-    if (csr_in) {
+    if (prepared) {
+      // done by bigcn_batch_prepare
+    } else if (csr_in) {
       if (int rc = root_nz_csr_launch(a, bt->x_ptr, bt->x_col, bt->x_val, s2)) return rc;
     } else {
       if (int rc = root_nz_launch(a, s2)) return rc;
@@ -280,7 +319,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     }
   }
   // 3. X W1^T for all active directions in one pass over X (main stream)
-  if (csr_in) {
+  if (csr_in || (prepared && sparse)) {   // prepared: the capture scan ran a step ahead; same entries, same order
     if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st)) return rc;
   } else if (sparse && !o->skip_wgrad_prep) {
     if (int rc = xw_fp32_capture(bt->x, N, K, w.w1T, n_out, w.xw, n_out, w.xs, st)) return rc;
@@ -293,11 +332,11 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   // 4. the structure is needed from here on; the side stream goes on to sort the captured
   //    non-zeros of X by column for the weight gradient while the rest of the forward runs
   if (sc) {
-    stream_after(sc, 1, ss, st);
+    if (!prepared) stream_after(sc, 1, ss, st);
     stream_after(sc, 7, s2, st);
   }
   bool side_busy = false;
-  if (sparse) {
+  if (sparse && !prepared) {
     if (o->skip_wgrad_prep || N == 0) {
       cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), st);
     } else {
@@ -355,11 +394,76 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   return 0;
 }
 
+// ---- the weight-independent half of a step, for a batch the caller will step on NEXT ------------------------
+// graph structure of both directions + node_ptr, the root rows' positive columns, and (SPARSE) the non-zeros of
+// x as CSR and column-sorted CSC: none of it depends on the parameters, so it runs on two lowest-priority streams
+// beside the whole current step -- the HBM-bound pass over the next batch's x hides under the latency-bound
+// kernels of this one (what the reference's DataLoader workers do for collate, BiGCN_Twitter.py:168).
+int batch_prepare(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_opts_t* o, int32_t* flags, void* prepared,
+                  size_t prepared_bytes, cudaStream_t st) {
+  if (int rc = check_common(dm, o, "batch_prepare")) return rc;
+  PrepWs w = carve_prepared(dm, prepared, prepared_bytes);
+  BIGCN_CHECK_ARG(prepared != nullptr && prepared_bytes >= w.total, "batch_prepare: buffer too small (%zu < %zu)",
+                  prepared_bytes, w.total);
+  const int64_t N = dm->N, B = dm->B, K = dm->K;
+  const bool sparse = o->gemm_mode == BIGCN_GEMM_SPARSE;
+  const bool csr_in = bt->x == nullptr && N > 0;
+  BIGCN_CHECK_ARG(!csr_in || (sparse && bt->x_ptr && bt->x_col && bt->x_val),
+                  "batch_prepare: x == NULL needs gemm_mode SPARSE and x_ptr / x_col / x_val");
+  SideCtx* sc = side_ctx();
+  cudaStream_t pa = sc ? sc->prep[0] : st, pb = sc ? sc->prep[1] : st;
+  if (sc) {
+    cudaEventRecord(sc->ev[8], st);
+    cudaStreamWaitEvent(pa, sc->ev[8], 0);
+    cudaStreamWaitEvent(pb, sc->ev[8], 0);
+  }
+  // stream A: x -> CSR -> CSC (the long one: one pass over x, then the column sort)
+  if (sparse) {
+    if (csr_in) {
+      w.xs.ptr = const_cast<int32_t*>(bt->x_ptr);
+      w.xs.col = const_cast<int32_t*>(bt->x_col);
+      w.xs.val = const_cast<float*>(bt->x_val);
+    }
+    if (N == 0) {
+      cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), pa);
+    } else {
+      if (!csr_in)
+        if (int rc = x_capture(bt->x, N, K, w.xs, pa)) return rc;
+      w.xs.flags = flags;
+      if (int rc = xs_build_csc(w.xs, bt->x, !csr_in, pa)) return rc;
+    }
+  }
+  // stream B: structure of both directions, then the root columns
+  {
+    const int64_t* ei[2] = {bt->edge_index, bt->bu_edge_index};
+    const int64_t E[2] = {dm->E_td, dm->E_bu};
+    if (int rc = graph_prep_impl(2, ei, E, N, bt->batch, B, o->deg_by, w.g, w.node_ptr, flags, w.prep_ws, w.prep_bytes, pb))
+      return rc;
+    RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags, w.slot, w.overflow, DW2B_CAP};
+    if (csr_in) {
+      if (int rc = root_nz_csr_launch(a, bt->x_ptr, bt->x_col, bt->x_val, pb)) return rc;
+    } else {
+      if (int rc = root_nz_launch(a, pb)) return rc;
+    }
+  }
+  return 0;
+}
+// `st` waits for everything bigcn_batch_prepare has queued so far
+int batch_prepare_join(cudaStream_t st) {
+  SideCtx* sc = side_ctx();
+  if (!sc) return 0;
+  cudaEventRecord(sc->ev[9], sc->prep[0]);
+  cudaStreamWaitEvent(st, sc->ev[9], 0);
+  cudaEventRecord(sc->ev[10], sc->prep[1]);
+  cudaStreamWaitEvent(st, sc->ev[10], 0);
+  return 0;
+}
+
 int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_params_t* pr,
                       const bigcn_opts_t* o, const float* grad_feat, const bigcn_params_t* gr,
                       void* ws, size_t ws_bytes, cudaStream_t st) {
   if (int rc = check_common(dm, o, "features_backward")) return rc;
-  FeatWs w = carve_features(dm, ws, ws_bytes);
+  FeatWs w = carve_features(dm, ws, ws_bytes, bt->prepared);
   BIGCN_CHECK_ARG(ws != nullptr && ws_bytes >= w.total, "features_backward: workspace too small");
   const int64_t N = dm->N, B = dm->B, K = dm->K;
   const Dirs dirs = active_dirs(o->dir_mask);
@@ -482,7 +586,8 @@ dw1_only:
     float* da = gdir_w1(gr, dirs.id[0]);
     float* db = dirs.n == 2 ? gdir_w1(gr, dirs.id[1]) : nullptr;
     if (o->gemm_mode == BIGCN_GEMM_SPARSE) {
-      if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);   // column-sorted X of the forward (no-op if none pending)
+      // column-sorted X: built by this step's forward on the low-priority stream (a prepared batch brought it along)
+      if (sc && bt->prepared == nullptr) cudaStreamWaitEvent(st, sc->ev[3], 0);
       if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
       if (sc && join_late) {
         stream_after(sc, 1, ss, st);
@@ -582,7 +687,7 @@ extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[2], 0);
   cudaEventRecord(sc->ev[6], sc->side2);
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[6], 0);
-  return 0;
+  return batch_prepare_join((cudaStream_t)stream);
 }
 // the internal low-priority stream (cudaStream_t) or NULL: lets a caching allocator be told that
 // a workspace is in use there (torch: Tensor.record_stream(ExternalStream(handle)))
@@ -664,6 +769,17 @@ extern "C" size_t bigcn_features_workspace_bytes(const bigcn_dims_t* dims) {
   return carve_features(dims, nullptr, 0).total;
 }
 
+extern "C" size_t bigcn_batch_prepare_bytes(const bigcn_dims_t* dims) {
+  if (!dims) return 0;
+  return carve_prepared(dims, nullptr, 0).total;
+}
+extern "C" int bigcn_batch_prepare(const bigcn_dims_t* dims, const bigcn_batch_t* batch, const bigcn_opts_t* opts,
+                                   int32_t* flags, void* prepared, size_t prepared_bytes, bigcn_stream_t stream) {
+  BIGCN_CHECK_ARG(batch && flags, "batch_prepare: NULL argument");
+  return batch_prepare(dims, batch, opts, flags, prepared, prepared_bytes, (cudaStream_t)stream);
+}
+extern "C" int bigcn_batch_prepare_join(bigcn_stream_t stream) { return batch_prepare_join((cudaStream_t)stream); }
+
 extern "C" int bigcn_features_forward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
                                       const bigcn_params_t* params, const bigcn_opts_t* opts,
                                       float* feat, int32_t* flags, void* workspace,
@@ -682,7 +798,7 @@ extern "C" int bigcn_train_tail(const bigcn_dims_t* dims, const bigcn_batch_t* b
   if (int rc = check_common(dims, opts, "train_tail")) return rc;
   BIGCN_CHECK_ARG(opts->fused_tail && opts->dir_mask == (BIGCN_DIR_TD | BIGCN_DIR_BU),
                   "train_tail: needs opts.fused_tail = 1 (as passed to features_forward) and both directions");
-  FeatWs w = carve_features(dims, workspace, workspace_bytes);
+  FeatWs w = carve_features(dims, workspace, workspace_bytes, batch->prepared);
   BIGCN_CHECK_ARG(workspace != nullptr && workspace_bytes >= w.total, "train_tail: workspace too small");
   const int64_t N = dims->N, B = dims->B;
   TailArgs ta{};

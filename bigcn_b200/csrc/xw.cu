@@ -20,7 +20,8 @@ constexpr int XW_U = 8;
 
 // CAPTURE: lane 0 also records every non-zero (column, value) in the row's ELL slots and the
 // exact count (xsparse.cu turns that into the CSR / CSC the sparse weight gradient sweeps).
-template <int NOUT, bool VEC4, bool CAPTURE, int MINB = 1>
+// PRODUCT = false: capture only (bigcn_batch_prepare: the weights of the step that will use the batch do not exist yet).
+template <int NOUT, bool VEC4, bool CAPTURE, int MINB = 1, bool PRODUCT = true>
 __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__ x, int64_t N, int64_t K,
                                                  const float* __restrict__ wt,
                                                  float* __restrict__ y, int64_t ldy,
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
               }
               ++nz;
             }
+            if (!PRODUCT) continue;
             const float* wr = wt + k * NOUT + lane * V;
             if (V == 4) {
               const float4 w = *reinterpret_cast<const float4*>(wr);
@@ -86,11 +88,13 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
         }
       }
     }
-    float* yr = y + row * ldy + lane * V;
-    if (V == 4)
-      *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    else
-      *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+    if (PRODUCT) {
+      float* yr = y + row * ldy + lane * V;
+      if (V == 4)
+        *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else
+        *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+    }
     if (CAPTURE && lane == 0) xs_cnt[row] = nz;
   }
 }
@@ -135,6 +139,20 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
     case 10: return xw_scan_launch<true, 5>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 5, st);
     default: return xw_scan_launch<true, 1>(x, N, K, wt, n_out, y, ldy, xs.cnt, xs.ell_col, xs.ell_val, 6, st);
   }
+}
+
+// the same pass over x without the product: only the capture of the non-zeros (bigcn_batch_prepare).  4 CTAs per SM:
+// it runs beside the kernels of the current step and should leave them room.
+int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStream_t st) {
+  if (N == 0) return 0;
+  const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int blocks = (int)ceil_div(N, 8);
+  const int cap = num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (vec4) k_xw_scan<64, true, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
+  else k_xw_scan<64, false, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
+  BIGCN_CHECK_LAUNCH("k_xw_scan (capture only)");
+  return 0;
 }
 
 // y = x * wt from the CSR of x (sparse input: the dense matrix never reaches the device).

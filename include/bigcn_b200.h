@@ -100,6 +100,10 @@ typedef struct bigcn_batch {
   const int32_t* x_ptr;         /* [N+1]                                   */
   const int32_t* x_col;         /* [x_ptr[N]]                              */
   const float* x_val;           /* [x_ptr[N]]                              */
+  /* NULL, or the buffer bigcn_batch_prepare filled for THIS batch (same dims, same pointers above): features_forward /
+   * bigcn_train_tail / features_backward then skip graph prep, the root columns and -- BIGCN_GEMM_SPARSE -- the pass
+   * over x (the product becomes a sweep over the prepared CSR, bit-identical to the fused scan). */
+  void* prepared;
 } bigcn_batch_t;
 
 /* Parameters in PyG-2.x state_dict layout:
@@ -309,6 +313,17 @@ int bigcn_features_forward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
                            const bigcn_params_t* params, const bigcn_opts_t* opts,
                            float* feat /*[B,256]*/, int32_t* flags, void* workspace,
                            size_t workspace_bytes, bigcn_stream_t stream);
+/* The weight-independent half of a step, one step AHEAD: graph structure of both directions, node pointers, the root
+ * rows' positive columns and (BIGCN_GEMM_SPARSE) the non-zeros of x as CSR + column-sorted CSC, written into
+ * `prepared` (bigcn_batch_prepare_bytes(dims) bytes) on two lowest-priority internal streams that fork from
+ * `stream` at the call.  Call it for batch i+1 right before enqueuing step i and bigcn_batch_prepare_join(stream)
+ * right after step i: the HBM-bound pass over the next x then overlaps the latency-bound kernels of the current
+ * step (the role of the reference's DataLoader worker processes, BiGCN_Twitter.py:168).  Capturable: fork and join
+ * sit on `stream`.  Then pass the buffer as batch->prepared to the three calls of step i+1. */
+size_t bigcn_batch_prepare_bytes(const bigcn_dims_t* dims);
+int bigcn_batch_prepare(const bigcn_dims_t* dims, const bigcn_batch_t* batch, const bigcn_opts_t* opts, int32_t* flags,
+                        void* prepared, size_t prepared_bytes, bigcn_stream_t stream);
+int bigcn_batch_prepare_join(bigcn_stream_t stream);
 /* grad_feat[B,256] -> gradients of the eight conv tensors (fc_* untouched).
  * The gradient through the second root-extend is dropped, as copy.copy does at :44. */
 int bigcn_features_backward(const bigcn_dims_t* dims, const bigcn_batch_t* batch,
