@@ -320,7 +320,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   }
   // 3. X W1^T for all active directions in one pass over X (main stream)
   if (csr_in || (prepared && sparse)) {   // prepared: the capture scan ran a step ahead; same entries, same order
-    if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st)) return rc;
+    if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st, prepared && !csr_in)) return rc;
   } else if (sparse && !o->skip_wgrad_prep) {
     if (int rc = xw_fp32_capture(bt->x, N, K, w.w1T, n_out, w.xw, n_out, w.xs, st)) return rc;
   } else if (scan_mode) {

@@ -141,14 +141,14 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
   }
 }
 
-// the same pass over x without the product: only the capture of the non-zeros (bigcn_batch_prepare).  4 CTAs per SM:
-// it runs beside the kernels of the current step and should leave them room.
+// the same pass over x without the product: only the capture of the non-zeros (bigcn_batch_prepare).  It runs on a
+// lowest-priority stream beside the kernels of the current step, so it is launched as MANY SHORT CTAs (8 rows each,
+// one per warp, ~160 KB of x): slots free up every few microseconds and the block scheduler hands them to the
+// step's own (higher-priority) kernels first -- a persistent grid would sit on the register file for 100 us.
 int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStream_t st) {
   if (N == 0) return 0;
   const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  int blocks = (int)ceil_div(N, 8);
-  const int cap = num_sms() * 4;
-  if (blocks > cap) blocks = cap;
+  const int blocks = (int)ceil_div(N, 8);
   if (vec4) k_xw_scan<64, true, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
   else k_xw_scan<64, false, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
   BIGCN_CHECK_LAUNCH("k_xw_scan (capture only)");
@@ -160,13 +160,16 @@ int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStrea
 // output in CSR order (ascending columns).
 template <int NOUT>
 __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restrict__ wt, float* __restrict__ y,
-                                                int64_t ldy) {
+                                                int64_t ldy, const int32_t* __restrict__ state) {
   constexpr int V = NOUT / 32;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // a CSR compacted from a capture that overflowed the sparse layout (BIGCN_FLAG_X_NOT_SPARSE is set) is not
+  // walkable: the product is NaN, never a silent wrong answer and never an out-of-bounds read
+  const bool bad = state != nullptr && state[1] != 0;
   for (int64_t row = warp0; row < xs.N; row += nwarp) {
-    const int s = xs.ptr[row], e = xs.ptr[row + 1];
+    const int s = bad ? 0 : xs.ptr[row], e = bad ? 0 : xs.ptr[row + 1];
     float acc[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = 0.f;
@@ -200,6 +203,10 @@ __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restr
         }
       }
     }
+    if (bad) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = __int_as_float(0x7fc00000);
+    }
     float* yr = y + row * ldy + lane * V;
     if (V == 4)
       *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -208,13 +215,14 @@ __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restr
   }
 }
 
-int xw_csr(const XSparse& xs, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st) {
+int xw_csr(const XSparse& xs, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st, bool check_state) {
   if (xs.N == 0) return 0;
   int blocks = (int)ceil_div(xs.N, 8);
   const int cap = num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (n_out == 128) k_xw_csr<128><<<blocks, 256, 0, st>>>(xs, wt, y, ldy);
-  else k_xw_csr<64><<<blocks, 256, 0, st>>>(xs, wt, y, ldy);
+  const int32_t* state = check_state ? xs.state : nullptr;
+  if (n_out == 128) k_xw_csr<128><<<blocks, 256, 0, st>>>(xs, wt, y, ldy, state);
+  else k_xw_csr<64><<<blocks, 256, 0, st>>>(xs, wt, y, ldy, state);
   BIGCN_CHECK_LAUNCH("k_xw_csr");
   return 0;
 }

@@ -19,6 +19,22 @@ def _p(t):
 
 
 _capture_streams = {}
+_step_streams = {}
+
+
+def step_stream(device=None):
+    """A stream one priority level above the default one, per device: FusedTrainer runs (and captures) its steps
+    on it so that bigcn_batch_prepare's lowest-priority streams -- the next batch's preparation -- really yield
+    to the step's own kernels (the caller's default stream already has the lowest priority there is)."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    s = _step_streams.get(dev)
+    if s is None:
+        try:
+            lo, hi = torch.cuda.Stream.priority_range()
+        except Exception:  # noqa: BLE001
+            lo, hi = 0, -1
+        s = _step_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 1) if hi < lo else lo)
+    return s
 
 
 def capture_graph(enqueue):
@@ -28,8 +44,12 @@ def capture_graph(enqueue):
     capture costs about one enqueue plus the instantiation."""
     dev = torch.cuda.current_device()
     s = _capture_streams.get(dev)
-    if s is None:
-        s = _capture_streams[dev] = torch.cuda.Stream(device=dev)
+    if s is None:       # kernel nodes inherit the capturing stream's priority: one level above the default stream
+        try:
+            lo, hi = torch.cuda.Stream.priority_range()
+        except Exception:  # noqa: BLE001
+            lo, hi = 0, -1
+        s = _capture_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 1) if hi < lo else lo)
     cur = torch.cuda.current_stream()
     s.wait_stream(cur)
     g = torch.cuda.CUDAGraph()

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib as L
 from ._lib import H, Opts, Params, check, lib
-from .ops import _make_structs, _p, _stream, _i64, _f32, _as_x, capture_graph, raise_on_flags
+from .ops import _make_structs, _p, _stream, _i64, _f32, _as_x, capture_graph, raise_on_flags, step_stream
 
 # flat layout: the two conv1 weights (the gradients the second X stream produces LAST) first, so
 # the gradient splits into two contiguous all-reduce buckets: [W1_td | W1_bu] and [everything else]
@@ -34,7 +34,7 @@ class FusedTrainer:
     """Adam(lr, weight_decay) with BU conv1/conv2 at lr/5 over a flat parameter buffer."""
 
     def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=8):
+                 process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=16):
         """``comm`` (world_size > 1): "symm" = one fused kernel over NVLink peer memory
         (reduce-scatter of the gradients in rank order + Adam on the owned shard + all-gather of
         the parameters, bigcn_dp_reduce_adam) between two symmetric-memory barriers; "nccl" = two
@@ -103,6 +103,7 @@ class FusedTrainer:
         self.graphs = (self.comm in ("single", "symm")) if graphs == "auto" else bool(graphs)
         self.max_graphs = int(max_graphs)
         self._graphs, self._seen = {}, {}   # captured steps by batch identity; batch identities seen once
+        self._prep_buf, self._prep_owner = None, [None, None]   # two prepared-batch buffers and what they hold
         self.graph_captures = self.graph_replays = 0
 
     # -------------------------------------------------------------------------------
@@ -170,6 +171,16 @@ class FusedTrainer:
         ws = self._ws
         st = _stream()
         l = lib()
+        if p.get("prep_inline"):     # this batch was not prepared a step ahead: do it now, on the critical path
+            buf = self._prep_buf[p["slot"]]
+            check(l.bigcn_batch_prepare(C.byref(dims), C.byref(bt), C.byref(o), _p(self.flags), _p(buf), buf.numel(), st),
+                  "batch_prepare")
+            check(l.bigcn_batch_prepare_join(st), "batch_prepare_join")
+        nxt = p.get("next")
+        if nxt is not None:          # the NEXT batch's weight-independent half, beside everything below
+            buf = self._prep_buf[nxt["slot"]]
+            check(l.bigcn_batch_prepare(C.byref(nxt["dims"]), C.byref(nxt["bt"]), C.byref(o), _p(self.flags), _p(buf),
+                                        buf.numel(), st), "batch_prepare")
         check(l.bigcn_features_forward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(feat),
                                        _p(self.flags), _p(ws), ws.numel(), st), "features_forward")
         # readout's second pass + fc / log_softmax / nll and their backward + the per-tree gradient scaling: one launch
@@ -185,26 +196,96 @@ class FusedTrainer:
                                          self.betas[0], self.betas[1], self.eps, self.wd, 1.0, _p(self.step_count),
                                          st), "dp_reduce_adam")
             self._hf.barrier(channel=1)        # every rank's parameters are written; gradients are free again
-            return
-        if self.world > 1:
-            # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
-            o.bwd_phase = 1
-            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
-                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
-            h_rest = torch.distributed.all_reduce(self.grad[self.w1_end:], group=self.pg, async_op=True)
-            o.bwd_phase = 2
-            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
-                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
-            o.bwd_phase = 0
-            h_w1 = torch.distributed.all_reduce(self.grad[:self.w1_end], group=self.pg, async_op=True)
-            h_rest.wait()
-            h_w1.wait()
         else:
-            check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
-                                            C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
-        check(l.bigcn_adam_step(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
-                                _p(self.seg_end), _p(self.seg_lr), self.n_seg, self.betas[0], self.betas[1],
-                                self.eps, self.wd, 1.0, _p(self.step_count), st), "adam_step")
+            if self.world > 1:
+                # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
+                o.bwd_phase = 1
+                check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                                C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+                h_rest = torch.distributed.all_reduce(self.grad[self.w1_end:], group=self.pg, async_op=True)
+                o.bwd_phase = 2
+                check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                                C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+                o.bwd_phase = 0
+                h_w1 = torch.distributed.all_reduce(self.grad[:self.w1_end], group=self.pg, async_op=True)
+                h_rest.wait()
+                h_w1.wait()
+            else:
+                check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
+                                                C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
+            check(l.bigcn_adam_step(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n,
+                                    _p(self.seg_end), _p(self.seg_lr), self.n_seg, self.betas[0], self.betas[1],
+                                    self.eps, self.wd, 1.0, _p(self.step_count), st), "adam_step")
+        if nxt is not None:          # the next step may start: its batch is prepared
+            check(l.bigcn_batch_prepare_join(st), "batch_prepare_join")
+
+    def _enqueue_prio(self, p, raised):
+        """_enqueue; with a prepared / preparing batch, on a stream one priority level above the caller's so the
+        next batch's preparation (lowest priority) yields to this step's kernels."""
+        if not raised:
+            return self._enqueue(p)
+        cur = torch.cuda.current_stream()
+        s = step_stream(p["dev"])
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            self._enqueue(p)
+        cur.wait_stream(s)
+        for t in (p["feat"], p["logp"], p["gfeat"], p["loss"], p["scr"]):
+            t.record_stream(s)
+
+    # ---- batches prepared one step ahead (bigcn_batch_prepare) ---------------------------------------------
+    def _prep_key(self, data):
+        td = self.model.TDrumorGCN
+        x = data.x
+        xk = (x.ptr.data_ptr(), x.col.data_ptr(), x.val.data_ptr(), x.shape) if hasattr(x, "ptr") else \
+            (x.data_ptr(), tuple(x.shape), x.dtype, x.layout)
+        small = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in
+                      (data.edge_index, data.BU_edge_index, data.batch, data.rootindex))
+        return (id(data), xk, small, td.deg_by, td.resolved_gemm_mode(data.x))
+
+    def _prep_setup(self, p, data, next_data, node_id_base):
+        """Decide which prepared buffer this step reads (or prepares inline) and which one the next batch's
+        preparation writes; returns the part of the CUDA-graph key that pins those decisions."""
+        l = lib()
+        pk = self._prep_key(data)
+        need = l.bigcn_batch_prepare_bytes(C.byref(p["dims"]))
+        nxt = None
+        if next_data is not None:
+            nx, nxs = _as_x(next_data.x)
+            nd, nbt, _ = _make_structs(nx, _i64(next_data.edge_index), _i64(next_data.BU_edge_index), _i64(next_data.batch),
+                                       _i64(next_data.rootindex), (None,) * 8, p["c"], 0, nxs)
+            need = max(need, l.bigcn_batch_prepare_bytes(C.byref(nd)))
+            nxt = {"dims": nd, "bt": nbt, "keep": (nx, nxs, next_data), "key": self._prep_key(next_data)}
+        if self._prep_buf is None or self._prep_buf[0].numel() < need:
+            self._prep_buf = [torch.empty(need + need // 4, dtype=torch.uint8, device=p["dev"]) for _ in range(2)]
+            self._prep_owner = [None, None]
+            self._graphs.clear()               # captured pointers into the old buffers are stale
+        slot = next((i for i in (0, 1) if self._prep_owner[i] is not None and self._prep_owner[i][0] == pk
+                     and self._prep_owner[i][1]() is data), None)
+        p["prep_inline"] = slot is None
+        if slot is None:
+            slot = 0
+        p["slot"] = slot
+        p["bt"].prepared = self._prep_buf[slot].data_ptr()
+        if nxt is not None:
+            nxt["slot"] = 1 - slot
+            p["next"] = nxt
+        return (slot, p["prep_inline"], None if nxt is None else nxt["key"])
+
+    def _prep_peek(self, data, next_data):
+        """(slot, inline, key of the next batch) as _prep_setup would decide them, without building anything."""
+        slot = None
+        if self._prep_buf is not None:
+            pk = self._prep_key(data)
+            slot = next((i for i in (0, 1) if self._prep_owner[i] is not None and self._prep_owner[i][0] == pk
+                         and self._prep_owner[i][1]() is data), None)
+        return (0 if slot is None else slot, slot is None, None if next_data is None else self._prep_key(next_data))
+
+    def _prep_commit(self, p, data, next_data):
+        """Host-side record of what the prepared buffers hold after this step (enqueued or replayed)."""
+        self._prep_owner[p["slot"]] = (self._prep_key(data), weakref.ref(data))
+        if p.get("next") is not None:
+            self._prep_owner[p["next"]["slot"]] = (p["next"]["key"], weakref.ref(next_data))
 
     def _graph_key(self, data, b_global, node_id_base):
         m, td = self.model, self.model.TDrumorGCN
@@ -215,8 +296,14 @@ class FusedTrainer:
                       (data.edge_index, data.BU_edge_index, data.batch, data.rootindex, data.y))
         return (id(data), xk, small, b_global, node_id_base, m.training, td.p, td.deg_by, td.gemm_mode, td.seed)
 
-    def step(self, data, b_global=None, node_id_base=0, seed=None):
+    def step(self, data, b_global=None, node_id_base=0, seed=None, next_data=None):
         """One optimisation step on a device-resident batch; returns the loss (device scalar).
+
+        ``next_data``: the batch of the NEXT step, if the caller knows it (a loader loop does).  Its
+        weight-independent half -- graph prep, root columns, the HBM-bound pass over its ``x`` and the
+        column sort -- is then enqueued on low-priority streams beside this step (bigcn_batch_prepare), and
+        the next ``step(next_data, ...)`` finds it done: the step's chain shrinks to the latency-bound
+        kernels, with the memory-bound work of the following batch hidden underneath.
 
         With ``graphs`` on, a batch OBJECT stepped on for the second time (the same ``data``, same device
         buffers, same shapes -- a resident batch, not a freshly assembled one that happens to reuse freed
@@ -224,42 +311,54 @@ class FusedTrainer:
         ``cudaGraphLaunch``, and every later step on it is a replay.  The dropout seed of a replay comes
         from the device-side calls counter, so replays draw fresh masks exactly as enqueued steps do."""
         self._calls += 1
-        if not (self.graphs and seed is None and not self.validate):
-            p = self._plan(data, b_global, node_id_base, seed)
-            self._workspace(p["dims"], p["dev"])
-            self._enqueue(p)
-            self.last_logp = p["logp"]
-            if self.validate:
-                raise_on_flags(self.flags)
-            return p["loss"]
-        key = self._graph_key(data, b_global, node_id_base)
-        ent = self._graphs.get(key)
-        if ent is not None and ent["ws"] is self._ws:
-            ent["graph"].replay()
-            self.graph_replays += 1
-            self.last_logp = ent["plan"]["logp"]
-            return ent["plan"]["loss"]
-        p = self._plan(data, b_global, node_id_base, None)
+        use_graph = self.graphs and seed is None and not self.validate
+        pk_any = next_data is not None or (self._prep_buf is not None and any(
+            o is not None and o[1]() is data for o in self._prep_owner))
+        key = None
+        if use_graph:
+            key = self._graph_key(data, b_global, node_id_base)
+            if pk_any:                          # which prepared buffer holds this batch, what the next batch is
+                key = key + self._prep_peek(data, next_data)
+            ent = self._graphs.get(key)
+            if ent is not None and ent["ws"] is self._ws and (not pk_any or ent["prep"] is self._prep_buf):
+                ent["graph"].replay()
+                self.graph_replays += 1
+                if pk_any:
+                    self._prep_commit(ent["plan"], data, next_data)
+                self.last_logp = ent["plan"]["logp"]
+                return ent["plan"]["loss"]
+        p = self._plan(data, b_global, node_id_base, seed)
         ws_before = self._ws
         self._workspace(p["dims"], p["dev"])
         if self._ws is not ws_before:
             self._graphs.clear()               # the workspace moved: every captured pointer into it is stale
-        ref = self._seen.get(key)
-        if ref is None or ref() is not data:   # first sighting: enqueue (also warms the library's lazy state)
-            if len(self._seen) >= 256:
-                self._seen.clear()
-            self._seen[key] = weakref.ref(data)
-            self._enqueue(p)
-            self.last_logp = p["logp"]
-            return p["loss"]
-        g = capture_graph(lambda: self._enqueue(p))     # seen before: capture, then replay
-        while len(self._graphs) >= self.max_graphs:
-            self._graphs.pop(next(iter(self._graphs)))
-        self._graphs[key] = {"ws": self._ws, "graph": g, "plan": p, "data": data}   # the strong reference pins id(data)
-        self.graph_captures += 1
-        g.replay()
-        self.graph_replays += 1
+        if pk_any:
+            pkey = self._prep_setup(p, data, next_data, node_id_base)
+            if use_graph:
+                key = self._graph_key(data, b_global, node_id_base) + pkey   # (the buffers may just have moved)
+        if not use_graph:
+            self._enqueue_prio(p, pk_any)
+        else:
+            ref = self._seen.get(key)
+            if ref is None or ref() is not data:   # first sighting: enqueue (also warms the library's lazy state)
+                if len(self._seen) >= 256:
+                    self._seen.clear()
+                self._seen[key] = weakref.ref(data)
+                self._enqueue_prio(p, pk_any)
+            else:                                   # seen before: capture, then replay
+                g = capture_graph(lambda: self._enqueue(p))
+                while len(self._graphs) >= self.max_graphs:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = {"ws": self._ws, "prep": self._prep_buf, "graph": g, "plan": p,
+                                     "data": (data, next_data)}   # the strong references pin id(data)
+                self.graph_captures += 1
+                g.replay()
+                self.graph_replays += 1
+        if pk_any:
+            self._prep_commit(p, data, next_data)
         self.last_logp = p["logp"]
+        if self.validate:
+            raise_on_flags(self.flags)
         return p["loss"]
 
     def check_inputs(self):

@@ -14,6 +14,14 @@ anchors it on the reference's own call sites:
   model/Weibo/BiGCN_Weibo.py:16-89        (same maths, class Net, 2 classes)
   Process/dataset.py:64-99                (input contract, DropEdge)
 
+Probed again on the GPU box this round (profiles/r02_pyg_probe.log, one ``gpurun`` call: ``import
+torch_geometric`` / ``torch_scatter`` / ``torch_sparse`` -> ModuleNotFoundError, no ``baseline/_ref``, nothing
+on disk): the box runs this same image, so no fixture can be generated from the real GCNConv / scatter_mean
+and the parity of the GCN path stays UNPINNED at the library boundary.  What the restatement is held to
+instead: the hand-checkable 5-node vector below, torch's own CPU ops wherever the reference calls torch,
+and an independent dense-matrix derivation of the published formula D^-1/2 (A + I) D^-1/2 X W in fp64
+(tests/test_oracle.py::test_gcnconv_matches_dense_normalised_adjacency).
+
 Pinned exception: ``evaluate_oracle`` (tools/evaluate.py) is checked against
 outputs of the reference's own file (tests/golden/make_evaluate_golden.py).
 For the GCN path the only pin available is the hand-checkable 5-node known-answer vector of

@@ -1,5 +1,7 @@
-"""EBGCN (the fork's second GCN model, /root/reference/model/Twitter/EBGCN.py) on this library's
-kernels -- SURVEY.md 8f N3, the module-level drop-in: ``TDrumorGCN(args)``, ``BUrumorGCN(args)``,
+"""TEST HARNESS (not part of the product package): EBGCN (the fork's second GCN model,
+/root/reference/model/Twitter/EBGCN.py) assembled on this library's edge-weighted GCNConv -- SURVEY.md 8f N3 asks for
+the weighted propagate only; this scaffolding (edge-inference sub-networks, BatchNorm, KL loss: plain torch modules
+as in the reference) exists to exercise it end to end.  The module-level shape: ``TDrumorGCN(args)``, ``BUrumorGCN(args)``,
 ``EBGCN(args)`` with the reference's sub-module names (state_dict keys match) and the same
 ``forward(data) -> (log-probs, TD_edge_loss, BU_edge_loss)``.
 
@@ -20,8 +22,8 @@ from collections import OrderedDict
 import torch
 import torch.nn.functional as F
 
-from . import ops
-from .nn import GCNConv
+from bigcn_b200 import ops
+from bigcn_b200.nn import GCNConv
 
 
 def _create_network(hidden, name):

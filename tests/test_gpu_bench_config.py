@@ -104,3 +104,47 @@ def test_graph_replay_inference_matches_eager(dev):
             p.mul_(1.01)
             q.mul_(1.01)
         assert torch.equal(m(b), e(b))
+
+
+def test_prefetched_batches_match_unprefetched_steps(dev):
+    """step(data, next_data=...) prepares the next batch a step ahead (bigcn_batch_prepare: graph prep, root
+    columns, x -> CSR -> CSC); the result must be the step's own -- bit-identical for bag-of-words rows (the
+    product over the prepared CSR runs in the order of the fused scan), with or without CUDA graphs."""
+    batches = [to_dev(make_batch("twitter16", 20, seed=60 + i, train=True), dev) for i in range(3)]
+    out = {}
+    for name, graphs, prefetch in (("plain", False, False), ("prefetch", False, True), ("prefetch+graphs", True, True)):
+        m, tr = _trainer(dev, graphs)
+        losses = []
+        for i in range(14):
+            nxt = batches[(i + 1) % 3] if prefetch else None
+            losses.append(tr.step(batches[i % 3], next_data=nxt).clone())
+        tr.check_inputs()
+        out[name] = (tr.flat.clone(), tr.exp_avg.clone(), torch.cat(losses), tr)
+    assert out["prefetch+graphs"][3].graph_replays >= 2
+    for name in ("prefetch", "prefetch+graphs"):
+        for a, c in zip(out["plain"][:3], out[name][:3]):
+            assert torch.equal(a, c), name
+    # a batch that was NOT announced is prepared inline and still right; so is a dense-mode model
+    m, tr = _trainer(dev, False)
+    l0 = tr.step(batches[0], next_data=batches[2]).clone()
+    l1 = tr.step(batches[1]).clone()            # buffer holds batch 2: batch 1 goes the self-contained way
+    l2 = tr.step(batches[2]).clone()            # prepared two steps ago
+    m2, tr2 = _trainer(dev, False)
+    for l, b in zip((l0, l1, l2), batches):
+        assert torch.equal(l, tr2.step(b))
+    assert torch.equal(tr.flat, tr2.flat)
+
+
+def test_prefetch_pheme_dense_features(dev):
+    import bigcn_b200
+    batches = [to_dev(make_batch("pheme", 24, seed=80 + i, train=True), dev) for i in range(3)]
+    res = []
+    for prefetch in (False, True):
+        torch.manual_seed(4)
+        m = bigcn_b200.BiGCN(768, 64, 64, dev, validate="off").to(dev).train()      # auto -> tf32x3 for dense features
+        tr = bigcn_b200.FusedTrainer(m, graphs=prefetch)
+        ls = [tr.step(batches[i % 3], next_data=batches[(i + 1) % 3] if prefetch else None).clone() for i in range(9)]
+        tr.check_inputs()
+        assert m.TDrumorGCN.resolved_gemm_mode(batches[0].x) == "tf32x3"
+        res.append((tr.flat.clone(), torch.cat(ls)))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

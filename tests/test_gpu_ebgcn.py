@@ -1,4 +1,4 @@
-"""EBGCN on this library's convs (bigcn_b200/ebgcn.py) against the same module built from the oracle's
+"""EBGCN on this library's convs (tests/ebgcn_harness.py) against the same module built from the oracle's
 GCNConv / scatter_mean and the reference's Python loops (model/Twitter/EBGCN.py:61-93, 217-233)."""
 import copy
 from types import SimpleNamespace
@@ -56,7 +56,7 @@ class OracleDir(torch.nn.Module):
 @pytest.mark.parametrize("infer", [True, False])
 def test_ebgcn_matches_oracle_module(infer, monkeypatch):
     import bigcn_b200
-    from bigcn_b200 import ebgcn
+    import ebgcn_harness as ebgcn
     from bigcn_b200.data import make_batch
     dev = torch.device("cuda:0")
     # the edge-inference sub-networks are plain torch modules: keep cuDNN / cuBLAS from running them in TF32,

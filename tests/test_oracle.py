@@ -191,3 +191,41 @@ def test_evaluate_oracle_matches_reference_golden():
     for c in cases:
         got = getattr(evaluate_oracle, c["fn"])(c["pred"], c["y"])
         assert list(got) == c["want"], c["fn"]
+
+
+def test_gcnconv_matches_dense_normalised_adjacency():
+    """An independent derivation of what GCNConv computes -- the published formula
+    out = D^-1/2 (A + I) D^-1/2 X W^T + b with A[target, source] = #edges source -> target (self-loops of the
+    input dropped, one unit loop per node), D = row sums, as dense fp64 matrices (scipy) -- against the
+    oracle's edge-list restatement (add_remaining_self_loops / scatter_add degree / index_add_ aggregation,
+    the PyG formulation).  Not a pin on PyG itself (it is not installable here, oracle/__init__.py), but the two
+    forms share no code: duplicate edges, pre-existing self-loops, isolated nodes and both directions of a
+    reply tree are covered, and so is scatter_mean against a dense averaging matrix."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    cases = []
+    for n, e in ((1, 0), (6, 0), (12, 30), (80, 300)):
+        cases.append((n, rng.integers(0, n, (2, e))))
+    tree = np.array([[0, 0, 1, 1, 3, 3, 3], [1, 2, 3, 4, 5, 6, 7]])
+    cases += [(8, tree), (8, tree[::-1].copy())]                 # TD [parent; child] and BU [child; parent]
+    for n, ei in cases:
+        x = rng.standard_normal((n, 5))
+        conv = gcn_oracle.GCNConv(5, 4).double()
+        with torch.no_grad():
+            conv.bias.uniform_(-1, 1)
+        got = conv(torch.from_numpy(x), torch.from_numpy(ei)).detach().numpy()
+        keep = ei[0] != ei[1]
+        a = sp.coo_matrix((np.ones(int(keep.sum())), (ei[1][keep], ei[0][keep])), shape=(n, n)).toarray() + np.eye(n)
+        d = a.sum(1)                                                # degree by target incl. the loop (PyG 2.x)
+        a_hat = a / np.sqrt(d)[:, None] / np.sqrt(d)[None, :]
+        want = a_hat @ (x @ conv.lin.weight.detach().numpy().T) + conv.bias.detach().numpy()
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    # scatter_mean == dense averaging matrix (empty trees give zero rows)
+    batch = np.array([0, 0, 0, 2, 2, 3])
+    src = rng.standard_normal((6, 3))
+    m = np.zeros((5, 6))
+    for i, b in enumerate(batch):
+        m[b, i] = 1.0
+    cnt = np.maximum(m.sum(1, keepdims=True), 1.0)
+    got = gcn_oracle.scatter_mean(torch.from_numpy(src), torch.from_numpy(batch), 5).numpy()
+    assert np.abs(got - (m / cnt) @ src).max() <= 1e-14

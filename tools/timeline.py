@@ -30,12 +30,14 @@ def main():
     torch.manual_seed(0)
     model = bigcn_b200.BiGCN(5000, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
     tr = bigcn_b200.FusedTrainer(model)
-    for i in range(6):
-        tr.step(batches[i % 3])
+    prefetch = os.environ.get("BIGCN_PREFETCH", "1") != "0"
+    nxt = lambda i: batches[(i + 1) % 3] if prefetch else None  # noqa: E731
+    for i in range(24):
+        tr.step(batches[i % 3], next_data=nxt(i))
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(4):
-            tr.step(batches[i % 3])
+        for i in range(24, 28):
+            tr.step(batches[i % 3], next_data=nxt(i))
         torch.cuda.synchronize()
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda e: e.time_range.start)
