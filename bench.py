@@ -58,6 +58,7 @@ def parse():
                     help="do not prepare the next batch (graph prep, pass over x, column sort) beside the current step")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (c2..c5)")
     ap.add_argument("--configs", default="c2,c3,c4,c5", help="which of c2,c3,c4,c5 to run")
+    ap.add_argument("--no-fused-sync", action="store_true", help="symm: torch symmetric-memory barriers around the optimiser kernel")
     ap.add_argument("--comm", default="auto", choices=["auto", "symm", "nccl"],
                     help="N > 1: fused peer-memory optimiser step (symm) or NCCL all-reduce + Adam")
     ap.add_argument("--cpu-sample-trees", type=int, default=TREES_PER_GPU)
@@ -255,7 +256,8 @@ def run_ours(args):
     model = bigcn_b200.BiGCN(K_FEATS, 64, 64, dev, num_classes=N_CLASSES, gemm_mode=args.gemm_mode,
                              validate="off").to(dev).train()
     tr = bigcn_b200.FusedTrainer(model, lr=5e-4, weight_decay=1e-4, process_group=pg, world_size=world,
-                                 comm=args.comm, graphs=False if args.no_graphs else "auto")
+                                 comm=args.comm, graphs=False if args.no_graphs else "auto",
+                                 fused_sync=not args.no_fused_sync)
     log(f"data + model ready ({nodes} nodes), comm={tr.comm}, graphs={tr.graphs}")
     b_global = TREES_PER_GPU * world
     sparse_ok = args.gemm_mode == "sparse"
@@ -716,7 +718,7 @@ def dp_parity_check(torch, bigcn_b200, tr, dev, rank, world, args, n_steps=3, tr
     tr.flat.copy_(init)
     tr.exp_avg.zero_()
     tr.exp_avg_sq.zero_()
-    tr.step_count.zero_()
+    tr.step_count[0] = 0                 # the Adam step; [2] (calls counter = barrier epoch, dropout seed offset) never rewinds
     tr._graphs.clear()
     torch.cuda.synchronize()
     dist.barrier()

@@ -36,6 +36,8 @@ struct SideCtx {
   cudaStream_t side2;  // high priority, a second short chain beside the first (root columns; dW2b)
   cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
   cudaStream_t prep[2];  // lowest priority: bigcn_batch_prepare of the NEXT batch, beside the whole current step
+  cudaStream_t bw[2];    // lowest priority: the backward's dW2 / db chains -- nobody waits for them before the optimiser,
+                         // so they must not take SM slots from G1 -> T1 -> dW1 (the caller's stream, see ops.step_stream)
   cudaEvent_t ev[12];
   bool ok;
 };
@@ -53,7 +55,9 @@ static SideCtx* side_ctx() {
            cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.prep[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
-           cudaStreamCreateWithPriority(&c.prep[1], cudaStreamNonBlocking, lo) == cudaSuccess;
+           cudaStreamCreateWithPriority(&c.prep[1], cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.bw[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.bw[1], cudaStreamNonBlocking, lo) == cudaSuccess;
     for (int i = 0; i < 12 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
     if (e && e[0] == '1') c.ok = false;
@@ -264,7 +268,6 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   const bool csr_in = bt->x == nullptr && N > 0;
   BIGCN_CHECK_ARG(!csr_in || (sparse && bt->x_ptr && bt->x_col && bt->x_val),
                   "features_forward: x == NULL needs gemm_mode SPARSE and x_ptr / x_col / x_val");
-  BIGCN_CHECK_ARG(!(prepared && sparse && o->skip_wgrad_prep), "features_forward: a prepared batch carries the column-sorted x");
   if (csr_in) {
     w.xs.ptr = const_cast<int32_t*>(bt->x_ptr);
     w.xs.col = const_cast<int32_t*>(bt->x_col);
@@ -336,6 +339,12 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     stream_after(sc, 7, s2, st);
   }
   bool side_busy = false;
+  if (sparse && prepared && N > 0 && !o->skip_wgrad_prep) {   // the CSR came prepared; sort it by column beside the rest of this step
+    if (sc) stream_after(sc, 2, st, sc->low);
+    w.xs.flags = flags;
+    if (int rc = xs_sort_csc(w.xs, sc ? sc->low : st)) return rc;
+    side_busy = sc != nullptr;
+  }
   if (sparse && !prepared) {
     if (o->skip_wgrad_prep || N == 0) {
       cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), st);
@@ -396,7 +405,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
 
 // ---- the weight-independent half of a step, for a batch the caller will step on NEXT ------------------------
 // graph structure of both directions + node_ptr, the root rows' positive columns, and (SPARSE) the non-zeros of
-// x as CSR and column-sorted CSC: none of it depends on the parameters, so it runs on two lowest-priority streams
+// x as CSR (its column sort follows in the consuming step): none of it depends on the parameters, so it runs on two lowest-priority streams
 // beside the whole current step -- the HBM-bound pass over the next batch's x hides under the latency-bound
 // kernels of this one (what the reference's DataLoader workers do for collate, BiGCN_Twitter.py:168).
 int batch_prepare(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_opts_t* o, int32_t* flags, void* prepared,
@@ -430,7 +439,9 @@ int batch_prepare(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_o
       if (!csr_in)
         if (int rc = x_capture(bt->x, N, K, w.xs, pa)) return rc;
       w.xs.flags = flags;
-      if (int rc = xs_build_csc(w.xs, bt->x, !csr_in, pa)) return rc;
+      // CSR now (the next forward's product walks it); the column sort runs in the consuming step, on its
+      // low-priority stream under the forward / backward, and is awaited right before the dW1 sweep
+      if (int rc = xs_build_csr(w.xs, bt->x, !csr_in, pa)) return rc;
     }
   }
   // stream B: structure of both directions, then the root columns
@@ -479,8 +490,8 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   ColsumArgs db2_reduce{};
   const bool join_late = o->gemm_mode == BIGCN_GEMM_SPARSE && phase == 0;
   SideCtx* sc = side_ctx();
-  cudaStream_t ss = sc ? sc->s.side : st;
-  cudaStream_t s2 = sc ? sc->side2 : st;
+  cudaStream_t ss = sc ? (debug_knob(7) ? sc->s.side : sc->bw[0]) : st;
+  cudaStream_t s2 = sc ? (debug_knob(7) ? sc->side2 : sc->bw[1]) : st;
   if (phase == 2) goto dw1_only;
   // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
@@ -587,7 +598,7 @@ dw1_only:
     float* db = dirs.n == 2 ? gdir_w1(gr, dirs.id[1]) : nullptr;
     if (o->gemm_mode == BIGCN_GEMM_SPARSE) {
       // column-sorted X: built by this step's forward on the low-priority stream (a prepared batch brought it along)
-      if (sc && bt->prepared == nullptr) cudaStreamWaitEvent(st, sc->ev[3], 0);
+      if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);
       if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
       if (sc && join_late) {
         stream_after(sc, 1, ss, st);
@@ -687,6 +698,10 @@ extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[2], 0);
   cudaEventRecord(sc->ev[6], sc->side2);
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[6], 0);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventRecord(sc->ev[11], sc->bw[i]);
+    cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[11], 0);
+  }
   return batch_prepare_join((cudaStream_t)stream);
 }
 // the internal low-priority stream (cudaStream_t) or NULL: lets a caching allocator be told that

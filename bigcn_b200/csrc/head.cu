@@ -366,13 +366,40 @@ struct DpArgs {
   double beta1, beta2;
   float eps, wd, gscale;
   int64_t* step_count;
+  // in-kernel cross-rank barriers (or all NULL: the caller brackets the launch with its own barriers).  sig[q] is
+  // rank q's signal block in symmetric memory, 2 * DP_MAX_WORLD uint64: [r] = "rank r's gradient is complete",
+  // [DP_MAX_WORLD + r] = "rank r has read every gradient slice it needs and written its parameter slice everywhere";
+  // values are epochs (step_count[2] + 1: never rewound), so nothing is ever reset.
+  unsigned long long* sig[DP_MAX_WORLD];
 };
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
   __shared__ float s_bc[2];
+  const bool fused_sync = a.sig[0] != nullptr;
+  const unsigned long long epoch = (unsigned long long)(*(volatile int64_t*)(a.step_count + 2)) + 1ull;
   if (threadIdx.x == 0) {
     const double step = (double)(*(volatile int64_t*)a.step_count + 1);
     s_bc[0] = (float)(1.0 - pow(a.beta1, step));
     s_bc[1] = (float)sqrt(1.0 - pow(a.beta2, step));
+  }
+  if (fused_sync) {
+    // barrier 1: this rank's gradient is complete (everything before this kernel on the stream has finished):
+    // tell every rank, then wait until every rank has told us.  One CTA signals, every CTA waits on LOCAL flags.
+    if (blockIdx.x == 0 && threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(a.sig[threadIdx.x] + a.rank, epoch);
+    }
+    if (threadIdx.x < a.world) {
+      const unsigned long long* f = a.sig[a.rank] + threadIdx.x;
+      while (ld_acquire_sys(f) < epoch) __nanosleep(32);
+    }
   }
   __syncthreads();
   const float bc1 = s_bc[0], bc2s = s_bc[1];
@@ -434,14 +461,30 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     for (int r = 0; r < a.world; ++r) a.params[r][i] = pn;
   }
   __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x == 0) {   // last block: advance the step, reset the arrival counter (step_count[1])
     unsigned long long* arrive = reinterpret_cast<unsigned long long*>(a.step_count + 1);
-    __threadfence();
-    if (atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1) {
-      *arrive = 0ull;
-      *a.step_count += 1;
-      a.step_count[2] += 1;
+    __threadfence_system();
+    s_last = atomicAdd(arrive, 1ull) == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (fused_sync) {
+    // barrier 2: every block of this rank is done (peer loads of the gradients, peer stores of the parameters,
+    // fenced above): tell every rank, and leave only when every rank has said the same -- at kernel exit all
+    // parameters are in place everywhere and every gradient buffer is free again.
+    if (threadIdx.x < a.world) {
+      st_release_sys(a.sig[threadIdx.x] + DP_MAX_WORLD + a.rank, epoch);
+      const unsigned long long* f = a.sig[a.rank] + DP_MAX_WORLD + threadIdx.x;
+      while (ld_acquire_sys(f) < epoch) __nanosleep(32);
     }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long* arrive = reinterpret_cast<unsigned long long*>(a.step_count + 1);
+    *arrive = 0ull;
+    *a.step_count += 1;
+    a.step_count[2] += 1;
   }
 }
 
@@ -592,7 +635,7 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
                                     float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
                                     const float* seg_lr, int32_t n_seg, double beta1, double beta2, double eps,
                                     double weight_decay, double grad_scale, int64_t* step_count,
-                                    bigcn_stream_t stream) {
+                                    void* const* signals, bigcn_stream_t stream) {
   BIGCN_CHECK_ARG(grads && params && world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world,
                   "dp_reduce_adam: world must be 1..%d", DP_MAX_WORLD);
   BIGCN_CHECK_ARG(n_seg >= 1, "dp_reduce_adam: need at least one lr segment");
@@ -605,16 +648,19 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
                     "dp_reduce_adam: peer buffers must be 16 B aligned");
     a.grads[r] = grads[r];
     a.params[r] = params[r];
+    a.sig[r] = signals ? reinterpret_cast<unsigned long long*>(signals[r]) : nullptr;
+    BIGCN_CHECK_ARG(!signals || signals[r], "dp_reduce_adam: NULL signal block");
   }
   a.world = world; a.rank = rank; a.m = exp_avg; a.v = exp_avg_sq;
   bigcn_dp_slice(n, world, rank, &a.lo, &a.hi);
   a.seg_end = seg_end; a.seg_lr = seg_lr; a.n_seg = n_seg;
   a.beta1 = beta1; a.beta2 = beta2; a.eps = (float)eps; a.wd = (float)weight_decay; a.gscale = (float)grad_scale;
   a.step_count = step_count;
-  if (a.hi > a.lo) {
+  if (a.hi > a.lo || signals) {   // with in-kernel barriers even an empty slice takes part
     int blocks = (int)ceil_div((a.hi - a.lo + 3) / 4, 256);
-    const int cap = num_sms() * 4;
+    const int cap = num_sms() * 4;   // every CTA resident: the barrier spins must not starve the signalling CTA
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     k_dp_reduce_adam<<<blocks, 256, 0, st>>>(a);
     BIGCN_CHECK_LAUNCH("k_dp_reduce_adam");
   } else {

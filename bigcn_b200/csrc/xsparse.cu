@@ -351,9 +351,8 @@ static int radix_passes_for(int64_t K) {
   return (bits + 7) / 8;
 }
 
-// everything between the row capture / a caller's CSR and the column-sorted copy
-int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st) {
-  const int nblk = (int)xs_nblk(x.cap);
+// row capture (or a caller's CSR) -> CSR (col, val, row) + sort keys / identity permutation
+int xs_build_csr(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st) {
   int grid_rows = (int)ceil_div(x.N > 0 ? x.N : 1, 8);
   const int cap_ctas = num_sms() * 4;
   if (grid_rows > cap_ctas) grid_rows = cap_ctas;
@@ -369,6 +368,13 @@ int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cuda
     k_xs_from_csr<<<grid_rows, 256, 0, st>>>(x);
     BIGCN_CHECK_LAUNCH("k_xs_from_csr");
   }
+  return 0;
+}
+
+// CSR -> column-sorted CSC (stable LSD radix sort of the column keys) + hub-column lists
+int xs_sort_csc(const XSparse& x, cudaStream_t st) {
+  const int nblk = (int)xs_nblk(x.cap);
+  const int cap_ctas = num_sms() * 4;
   const int passes = radix_passes_for(x.K);
   cudaMemsetAsync(x.hist + (int64_t)256 * nblk, 0, 4 * 256 * sizeof(int32_t), st);   // digit totals
   int grid_keys = nblk;   // blocks past the live keys return at once
@@ -388,6 +394,12 @@ int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cuda
   k_long_build<<<dim3(gl, 2), 256, 0, st>>>(x.cptr, x.K, x.clong[0], x.clong[1], x.cap);
   BIGCN_CHECK_LAUNCH("k_long_build");
   return 0;
+}
+
+// everything between the row capture / a caller's CSR and the column-sorted copy
+int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st) {
+  if (int rc = xs_build_csr(x, x_dense, from_capture, st)) return rc;
+  return xs_sort_csc(x, st);
 }
 
 // ---- dW1[o, k] = sum_{(i,v) in column k} v * T[i, o]: CSR sweep over the columns ------------

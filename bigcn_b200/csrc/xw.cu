@@ -26,11 +26,12 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
                                                  const float* __restrict__ wt,
                                                  float* __restrict__ y, int64_t ldy,
                                                  int32_t* __restrict__ xs_cnt, int32_t* __restrict__ xs_col,
-                                                 float* __restrict__ xs_val) {
+                                                 float* __restrict__ xs_val, int pace_ns = 0) {
   constexpr int V = NOUT / 32;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t pol = l2_evict_first_policy();
   for (int64_t row = warp0; row < N; row += nwarp) {
     const float* xr = x + row * K;
     float acc[V];
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
       for (int u = 0; u < XW_U; ++u) {
         const int64_t kk = k0 + u * 128 + lane * 4;
         if (VEC4) {
-          v[u] = kk < K ? ldg_stream_f4(xr + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = kk < K ? ldg_stream_f4_ef(xr + kk, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
           v[u].x = kk + 0 < K ? __ldg(xr + kk + 0) : 0.f;
           v[u].y = kk + 1 < K ? __ldg(xr + kk + 1) : 0.f;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
         *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
     }
     if (CAPTURE && lane == 0) xs_cnt[row] = nz;
+    if (!PRODUCT && pace_ns > 0) __nanosleep(pace_ns);   // background pass: leave HBM headroom for the step's own kernels
   }
 }
 
@@ -148,9 +150,18 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
 int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStream_t st) {
   if (N == 0) return 0;
   const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const int blocks = (int)ceil_div(N, 8);
-  if (vec4) k_xw_scan<64, true, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
-  else k_xw_scan<64, false, true, 1, false><<<blocks, 256, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val);
+  int blocks = (int)ceil_div(N, 8), threads = 256;
+  switch (debug_knob(5)) {   // tools/stepbench.py: grid shape of the background pass
+    case 1: blocks = min(blocks, num_sms() * 2); break;
+    case 2: blocks = min(blocks, num_sms()); break;
+    case 3: threads = 128; blocks = min((int)ceil_div(N, 4), num_sms()); break;
+    case 4: threads = 128; blocks = (int)ceil_div(N, 4); break;
+    case 5: threads = 64; blocks = min((int)ceil_div(N, 2), num_sms() * 2); break;
+    default: break;
+  }
+  const int pace = debug_knob(6) * 100;
+  if (vec4) k_xw_scan<64, true, true, 1, false><<<blocks, threads, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val, pace);
+  else k_xw_scan<64, false, true, 1, false><<<blocks, threads, 0, st>>>(x, N, K, nullptr, nullptr, 0, xs.cnt, xs.ell_col, xs.ell_val, pace);
   BIGCN_CHECK_LAUNCH("k_xw_scan (capture only)");
   return 0;
 }

@@ -34,7 +34,8 @@ class FusedTrainer:
     """Adam(lr, weight_decay) with BU conv1/conv2 at lr/5 over a flat parameter buffer."""
 
     def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=16):
+                 process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=16,
+                 fused_sync=True):
         """``comm`` (world_size > 1): "symm" = one fused kernel over NVLink peer memory
         (reduce-scatter of the gradients in rank order + Adam on the owned shard + all-gather of
         the parameters, bigcn_dp_reduce_adam) between two symmetric-memory barriers; "nccl" = two
@@ -42,12 +43,16 @@ class FusedTrainer:
         "auto" = symm when the symmetric-memory rendezvous succeeds, else nccl.
         ``graphs``: replay a CUDA graph of the whole step for batches seen before (True / False;
         "auto" = on for a single GPU and for comm="symm", off for the NCCL path whose collectives
-        run on NCCL's own stream); at most ``max_graphs`` batches are kept captured."""
+        run on NCCL's own stream); at most ``max_graphs`` batches are kept captured.
+        ``fused_sync`` (comm="symm"): the two cross-rank barriers around the optimiser kernel happen inside it
+        (release / acquire on signal words in symmetric memory) instead of as two more launches."""
         L.require_device()
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg, self.world = process_group, world_size
         self.validate = validate
+        self.fused_sync = bool(fused_sync)     # comm="symm": cross-rank barriers inside the optimiser kernel
+        self.raise_priority = True
         self.comm, self.comm_note = "single", ""
         named = dict(model.named_parameters())
         dev = named[_ORDER[0]].device
@@ -129,6 +134,16 @@ class FusedTrainer:
         self._rank = hf.rank
         self._pptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
         self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in hg.buffer_ptrs])
+        # signal blocks of the in-kernel barriers of bigcn_dp_reduce_adam (32 uint64 per rank, epochs: never reset)
+        self._sptrs = None
+        if self.fused_sync:
+            sig = symm.empty(32, dtype=torch.int64, device=dev)
+            hs = symm.rendezvous(sig, group)
+            sig.zero_()
+            torch.cuda.synchronize()
+            dist.barrier(group=group)          # every rank's block is zero before anyone signals
+            self._sig, self._hs = sig, hs
+            self._sptrs = (C.c_void_p * self.world)(*[int(p) for p in hs.buffer_ptrs])
 
     def _workspace(self, dims, dev):
         need = lib().bigcn_features_workspace_bytes(C.byref(dims))
@@ -190,12 +205,15 @@ class FusedTrainer:
         if self.comm == "symm":
             check(l.bigcn_features_backward(C.byref(dims), C.byref(bt), C.byref(self._pr), C.byref(o), _p(gfeat),
                                             C.byref(self._gr), _p(ws), ws.numel(), st), "features_backward")
-            self._hg.barrier(channel=0)        # every rank's gradient is complete
+            if self._sptrs is None:
+                self._hg.barrier(channel=0)    # every rank's gradient is complete
+            # with signal blocks both cross-rank barriers happen inside the kernel (one launch instead of three)
             check(l.bigcn_dp_reduce_adam(self._gptrs, self._pptrs, self.world, self._rank, _p(self.exp_avg),
                                          _p(self.exp_avg_sq), self.n, _p(self.seg_end), _p(self.seg_lr), self.n_seg,
                                          self.betas[0], self.betas[1], self.eps, self.wd, 1.0, _p(self.step_count),
-                                         st), "dp_reduce_adam")
-            self._hf.barrier(channel=1)        # every rank's parameters are written; gradients are free again
+                                         self._sptrs, st), "dp_reduce_adam")
+            if self._sptrs is None:
+                self._hf.barrier(channel=1)    # every rank's parameters are written; gradients are free again
         else:
             if self.world > 1:
                 # everything but dW1, then its all-reduce runs (on NCCL's stream) under the second X stream
@@ -220,9 +238,10 @@ class FusedTrainer:
             check(l.bigcn_batch_prepare_join(st), "batch_prepare_join")
 
     def _enqueue_prio(self, p, raised):
-        """_enqueue; with a prepared / preparing batch, on a stream one priority level above the caller's so the
-        next batch's preparation (lowest priority) yields to this step's kernels."""
-        if not raised:
+        """_enqueue on a stream one priority level above the caller's (the default stream has the lowest priority
+        there is): the library's lowest-priority streams -- the next batch's preparation, the backward's dW2 / db
+        chains -- then really yield SM slots to the step's critical chain."""
+        if not (raised or self.raise_priority):
             return self._enqueue(p)
         cur = torch.cuda.current_stream()
         s = step_stream(p["dev"])

@@ -423,14 +423,17 @@ int bigcn_assemble_batch(const int64_t* node_ptr, const int64_t* edge_ptr, const
  * NVSwitch; HOST arrays of `world` device pointers).  This rank reduces the slice
  * bigcn_dp_slice(n, world, rank) of all ranks' gradients in rank order through peer loads, runs
  * Adam on its shard of exp_avg / exp_avg_sq (full-length local arrays, only the slice is used)
- * and stores the new parameters into every rank's buffer.  The caller puts a cross-rank barrier
- * before (all gradients written) and after (all parameters written, gradients free again). */
+ * and stores the new parameters into every rank's buffer.  signals == NULL: the caller puts a cross-rank
+ * barrier before (all gradients written) and after (all parameters written, gradients free again).
+ * signals != NULL: HOST array of `world` device pointers, signals[q] = rank q's signal block in symmetric memory
+ * (32 uint64, zero-initialised once): both barriers then happen INSIDE the kernel (st.release.sys of an epoch
+ * into every peer's block, ld.acquire.sys spins on the local one) -- one launch per step instead of three. */
 int bigcn_dp_slice(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);
 int bigcn_dp_reduce_adam(const float* const* grads, float* const* params, int32_t world, int32_t rank,
                          float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
                          const float* seg_lr, int32_t n_seg, double beta1, double beta2, double eps,
                          double weight_decay, double grad_scale, int64_t* step_count,
-                         bigcn_stream_t stream);
+                         void* const* signals, bigcn_stream_t stream);
 
 #ifdef __cplusplus
 }

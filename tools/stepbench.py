@@ -24,16 +24,20 @@ def main():
         batches.append(Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys}))
     torch.manual_seed(0)
     model = bigcn_b200.BiGCN(5000, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
-    tr = bigcn_b200.FusedTrainer(model)
+    tr = bigcn_b200.FusedTrainer(model)      # CUDA graphs (host enqueue would hide the differences): re-captured per knob value
+    prefetch = os.environ.get("BIGCN_PREFETCH", "1") != "0"
+    nxt = lambda i: batches[(i + 1) % 3] if prefetch else None  # noqa: E731
 
-    def run(steps=40):
-        for i in range(6):
-            tr.step(batches[i % 3])
+    def run(steps=60):
+        tr._graphs.clear()                   # knobs are read at enqueue / capture time
+        tr._seen.clear()
+        for i in range(18):
+            tr.step(batches[i % 3], next_data=nxt(i))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            tr.step(batches[i % 3])
+        for i in range(18, 18 + steps):
+            tr.step(batches[i % 3], next_data=nxt(i))
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
