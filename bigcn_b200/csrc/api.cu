@@ -105,6 +105,7 @@ struct FeatWs {
   int32_t* node_ptr;
   float* w1T;               // [K][128]  (TD cols 0..63, BU cols 64..127) | hi/lo split [4][64][K]
   float* w2aT[2];           // [64][64]
+  float* w2a_split;         // [2][4][64][64] hi / lo of W2a and W2a^T (tcgen05 mix kernels)
   float* w2bT[2];           // [K][64]
   int32_t* rnz_cnt; int32_t* rnz_col; float* rnz_val;
   float* P[2];              // [B][64]
@@ -183,6 +184,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes, voi
     w.w2aT[d] = c.take<float>(H * H);
     w.w2bT[d] = c.take<float>((size_t)K * H);
   }
+  w.w2a_split = c.take<float>(mix_tc_scratch_floats());
   const size_t nh = (size_t)(N > 0 ? N : 1) * H;
   for (int d = 0; d < 2; ++d) w.P[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   w.xw = c.take<float>(2 * nh);
@@ -311,6 +313,10 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     } else {
       if (int rc = root_nz_launch(a, s2)) return rc;
     }
+    if (mix_tc_available() && !o->skip_wgrad_prep) {   // hi / lo split of W2a, W2a^T for the tensor-core 64 x 64 products
+      const float* w2[2] = {dir_w2(pr, dirs.id[0]), dirs.n == 2 ? dir_w2(pr, dirs.id[1]) : nullptr};
+      if (int rc = mix_tc_split_weights(w2, dirs.n, H + K, w.w2a_split, s2)) return rc;
+    }
     if (!dropping) {
       RootProjArgs pa{};
       pa.cnt = w.rnz_cnt; pa.col = w.rnz_col; pa.val = w.rnz_val; pa.B = B; pa.K = K;
@@ -371,7 +377,13 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       m.drop = make_drop(o, d);
       m.keep = w.keep[d];
     }
-    if (int rc = prop1_mix_launch(a, dirs.n, st)) return rc;
+    // the tcgen05 form of the forward product (sweep + activate, then k_h64_tc) is measured slower than the fused
+    // sweep at these sizes: kept behind a knob for the A/B
+    if (mix_tc_available() && (debug_knob(8) == 2 || debug_knob(8) == 3)) {
+      if (int rc = mix_tc_forward(a, dirs.n, w.w2a_split, st)) return rc;
+    } else {
+      if (int rc = prop1_mix_launch(a, dirs.n, st)) return rc;
+    }
   }
   // 6. conv2 propagate + bias + relu
   {
@@ -569,7 +581,11 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       a.d[q] = BwdMixDir{t2[d], w.a1[d], dir_w2(pr, d), g1[d], w.cs_part1[d], make_drop(o, d)};   // A1 stands in for (H1, mask)
       c.part[q] = w.cs_part1[d]; c.out[q] = gdir_b1(gr, d);
     }
-    if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;
+    if (mix_tc_available() && (debug_knob(8) == 0 || debug_knob(8) == 2)) {   // tensor cores (tcgen05, TMEM)
+      if (int rc = mix_tc_backward(a, dirs.n, w.w2a_split, st)) return rc;
+    } else {
+      if (int rc = bwd_mix_launch(a, dirs.n, st)) return rc;
+    }
     if (sc) stream_after(sc, 2, st, ss);           // db1: ordered sum of the partials, beside T1
     if (int rc = colsum_reduce_launch(c, dirs.n, ss)) return rc;
   }
@@ -682,9 +698,27 @@ using namespace bigcn;
 // tuning knobs for tools/stepbench.py (0 = the shipped configuration); not part of the documented ABI
 namespace bigcn {
 static int g_knob[16];
-int debug_knob(int key) { return key >= 0 && key < 16 ? g_knob[key] : 0; }
+static bool g_knob_init = false;
+static void knob_defaults() {
+  if (g_knob_init) return;
+  g_knob_init = true;
+  // knob 8: which form of the 64 x 64 products runs.  1 (default) = the fused FFMA kernels (k_prop1_mix, k_bwd_mix);
+  // 0 = backward on the tensor cores (k_h64_tc<bwd>); 2 = forward and backward; 3 = forward only.  Measured at the
+  // bench configuration (tools/stepbench.py 8:0,1,2,3): 0.3706 / 0.3697 / 0.3744 / 0.3719 ms per step.
+  g_knob[8] = 1;
+  if (const char* e = getenv("BIGCN_MIX_TC")) {
+    if (e[0] == 'b' && e[1] == 'w') g_knob[8] = 0;        // "bwd"
+    else if (e[0] == 'b') g_knob[8] = 2;                  // "both"
+    else if (e[0] == 'f') g_knob[8] = 3;                  // "fwd"
+  }
+}
+int debug_knob(int key) {
+  knob_defaults();
+  return key >= 0 && key < 16 ? g_knob[key] : 0;
+}
 }  // namespace bigcn
 extern "C" void bigcn_debug_set(int key, int value) {
+  bigcn::knob_defaults();
   if (key >= 0 && key < 16) bigcn::g_knob[key] = value;
 }
 extern "C" const char* bigcn_last_error(void) { return g_err; }

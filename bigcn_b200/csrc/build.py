@@ -6,9 +6,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "graph_prep.cu", "xw.cu", "xsparse.cu", "gemm_tc.cu", "propagate.cu", "head.cu", "loader.cu", "weighted.cu", "feeder.cu"]
+SOURCES = ["api.cu", "graph_prep.cu", "xw.cu", "xsparse.cu", "gemm_tc.cu", "mix_tc.cu", "propagate.cu", "head.cu", "loader.cu", "weighted.cu", "feeder.cu"]
 HOST_SOURCES = ["host_compact.cpp"]      # host-only C++ (g++), linked into the same library
-HEADERS = ["common.cuh", "kernels.cuh", "gather.cuh", os.path.join("..", "..", "include", "bigcn_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "gather.cuh", "tc.cuh", os.path.join("..", "..", "include", "bigcn_b200.h")]
 LIB = os.path.join(HERE, "..", "libbigcn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

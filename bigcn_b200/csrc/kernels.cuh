@@ -44,6 +44,11 @@ int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
 struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; unsigned long long* keep; };
 struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
+// tcgen05 form (mix_tc.cu): sweep + activate, then the 64 x 64 product on the tensor cores with the root part in the epilogue
+bool mix_tc_available();
+size_t mix_tc_scratch_floats();
+int mix_tc_split_weights(const float* const* w2, int ndir, int64_t ldw2, float* scratch, cudaStream_t);
+int mix_tc_forward(const MixArgs&, int ndir, float* scratch, cudaStream_t);
 constexpr int RO_SLICE = 512;  // rows per readout slice
 struct ReadoutArgs { const float* h2[2]; const float* h1[2]; float* pos[2]; int feat_base[2]; int ndir; const int32_t* node_ptr; const int64_t* rootindex; float* feat; int64_t ldfeat; int64_t N, B; int32_t* flags; float* scratch; int64_t nitems; };
 int readout_launch(const ReadoutArgs&, cudaStream_t, bool with_final = true);
@@ -101,6 +106,7 @@ int colsum_reduce_launch(const ColsumArgs&, int, cudaStream_t);
 struct BwdMixDir { const float* t2; const float* h1 /* A1 = dropout(relu(H1)): > 0 where kept and positive */; const float* w2; float* g1; float* part; DropSpec drop; };
 struct BwdMixArgs { BwdMixDir d[2]; int64_t N, ldw2, node_id_base; };
 int bwd_mix_launch(const BwdMixArgs&, int, cudaStream_t);
+int mix_tc_backward(const BwdMixArgs&, int ndir, const float* scratch, cudaStream_t);
 struct OuterArgs { const float* u[2]; const float* v[2]; float* part[2]; int64_t N; };
 struct OuterReduceArgs { const float* part[2]; float* dst[2]; int64_t ld; int nchunk; };
 int outer64_launch(const OuterArgs&, const OuterReduceArgs&, int, cudaStream_t);
