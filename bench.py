@@ -491,7 +491,17 @@ def run_ours(args):
     e2e_value, e2e_ms, e2e_steps = routes[best]["value"], routes[best]["ms_per_step"], n_
     e2e_h2d = routes[best]["h2d_bytes_per_step"]
 
-    log(f"e2e routes done: {({k: round(v['ms_per_step'], 3) for k, v in routes.items()})}")
+    # what bounds the dense-host routes: host-memory read bandwidth of this rank's threads, all ranks probing at once
+    barrier()
+    hx = host[0].x
+    my_gbs = float(L.lib().bigcn_host_read_gbs(hx.data_ptr(), hx.numel() * 4, host_threads, 3))
+    host_gbs = [my_gbs]
+    if world > 1:
+        t = torch.tensor([my_gbs], dtype=torch.float64, device=dev)
+        g = [torch.empty_like(t) for _ in range(world)]
+        torch.distributed.all_gather(g, t)
+        host_gbs = [float(v[0]) for v in g]
+    log(f"e2e routes done: {({k: round(v['ms_per_step'], 3) for k, v in routes.items()})}; host read GB/s per rank {host_gbs}")
     del feeder, forest, stage, dev_csr, loader_csr
     configs = {}
     if not args.no_configs:
@@ -671,7 +681,13 @@ def run_ours(args):
                             "non-zeros on the host and the CSR crosses PCIe, hybrid_feed = HostFeeder.ship: the copy "
                             "engine DMAs the last rows dense (compacted on the device) while the host threads compact "
                             "the first rows, split adapted so both finish together; the fastest one is reported",
-                    "routes": {k: v for k, v in routes.items() if k in ("dense_h2d", "host_compact", "hybrid_feed")}},
+                    "routes": {k: v for k, v in routes.items() if k in ("dense_h2d", "host_compact", "hybrid_feed")},
+                    "host_read_gbs": {"per_rank": [round(v, 1) for v in host_gbs], "sum": round(sum(host_gbs), 1),
+                                      "threads_per_rank": host_threads,
+                                      "note": "STREAM-style read probe (bigcn_host_read_gbs) run by every rank at the same "
+                                              "time over its pinned feature matrix: the dense-host routes read "
+                                              f"{nodes[0] * K_FEATS * 4 / 1e6:.0f} MB of host memory per step and rank, so "
+                                              "trees/s <= trees_per_step x (this + PCIe share) / that size"}},
             "gpu_launches": args.steps * (launches_per_step(nodes[0], 2, True, args.gemm_mode, K_FEATS)
                                           + (1 if prefetch and sparse_ok else 0)),
             "roofline": roof, "final_loss": final_loss, "cuda_graphs": graph_info,

@@ -79,6 +79,7 @@ _SIGS = {
                                         C.c_size_t, c_ptr]),
     "bigcn_xsparse_view": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_size_t] + [C.POINTER(c_ptr)] * 7),
     "bigcn_host_dense_to_csr": (C.c_int64, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int32]),
+    "bigcn_host_read_gbs": (C.c_double, [c_ptr, C.c_int64, C.c_int32, C.c_int32]),
     "bigcn_transpose_weight": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int64, c_ptr, C.c_int64,
                                          C.c_int64, c_ptr]),
     "bigcn_long_ws_ints": (C.c_size_t, [C.c_int64]),

@@ -120,7 +120,8 @@ struct WtVal {
 };
 
 // Post functors: operator()(row, sum, sub, half mask, scratch) finishes one row; kPairs = true
-// adds pair(row, v0, ok0, v1, ok1, ...) for rows (row, row + 1) with two scratch rows.
+// adds pair(row, v0, ok0, v1, ok1, ...) for rows (row, row + 1) with two scratch rows; kInline = true: a light
+// epilogue that needs no scratch row and is called as soon as a row's sum is complete (no trip through the stage).
 // plain feature rows: val(j) = h[j, :]
 struct ValRow {
   const float* h;
@@ -200,22 +201,25 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
         if (u < nrows) val.fetch(st + u * H, i0 + u, sub);
     }
     __syncwarp();
-    // offsets of the rows in the block's edge stream; hub rows are left to the split path
-    unsigned longmask = 0;
-    int ne = 0;
-    if (sub == 0) {
-      int off = 0;
-      for (int u = 0; u < nrows; ++u) {
-        sq[u] = off;
-        const int len = sp[u + 1] - sp[u];
-        if (len > LONG_ROW && g.lng != nullptr) longmask |= 1u << u;
-        else off += len;
-      }
-      for (int u = nrows; u <= R; ++u) sq[u] = off;
-      ne = off;
+    // offsets of the rows in the block's edge stream (a 16-lane prefix sum of the row lengths); hub rows are left
+    // to the split path and take no room in the stream
+    int len = 0;
+    bool is_long = false;
+    if (sub < nrows) {
+      len = sp[sub + 1] - sp[sub];
+      is_long = len > LONG_ROW && g.lng != nullptr;
+      if (is_long) len = 0;
     }
-    longmask = __shfl_sync(FULL_MASK, longmask, 0, 16);
-    ne = __shfl_sync(FULL_MASK, ne, 0, 16);
+    int inc = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int t_up = __shfl_up_sync(FULL_MASK, inc, o, 16);
+      if (sub >= o) inc += t_up;
+    }
+    const int ne = __shfl_sync(FULL_MASK, inc, 15, 16);
+    if (sub <= R) sq[sub] = sub < nrows ? inc - len : ne;
+    const unsigned longmask = (__ballot_sync(FULL_MASK, is_long) >> (half * 16)) & 0xffffu;
+    __syncwarp();
     const int nemax = max(ne, __shfl_xor_sync(FULL_MASK, ne, 16));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = -1;              // row whose sum is being accumulated
@@ -226,7 +230,8 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
         const float d = sd[u];
         acc_add<EXACT>(acc, __fmul_rn(d, d), val.value(st + u * H, sa[Q + u], sub));
       }
-      st4(st + u * H + 4 * sub, acc);
+      if constexpr (Post::kInline) post(i0 + u, acc, sub, hm, nullptr);   // light epilogue: finish the row right here
+      else st4(st + u * H + 4 * sub, acc);
       flushed |= 1u << u;
     };
     for (int r0 = 0; r0 < nemax; r0 += Q) {
@@ -294,6 +299,7 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
 #pragma unroll 1
       for (int u = 0; u < nrows; ++u) {
         if ((longmask >> u) & 1u) continue;
+        if (Post::kInline && ((flushed >> u) & 1u)) continue;   // posted when its last edge was added
         post(i0 + u, finished(u), sub, hm, st + (R + (u & (Q - 1))) * H);
       }
     }

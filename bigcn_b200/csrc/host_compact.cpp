@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -188,4 +189,39 @@ extern "C" int64_t bigcn_host_dense_to_csr(const float* x, int64_t N, int64_t K,
   copy_out(0);
   for (auto& h : th) h.join();
   return total;
+}
+
+
+// Host-memory read bandwidth as the compaction threads see it (a STREAM-style probe: `n_threads` threads each sum their
+// slice of the buffer with 64-bit loads, `reps` passes; returns GB/s).  bench.py reports it beside the end-to-end
+// numbers fed from dense pinned host matrices: that route cannot run faster than PCIe plus this number allow.
+extern "C" double bigcn_host_read_gbs(const void* buf, int64_t bytes, int32_t n_threads, int32_t reps) {
+  if (!buf || bytes < 8 || reps < 1) return 0.0;
+  int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (T < 1) T = 1;
+  const int64_t words = bytes / 8;
+  std::vector<uint64_t> sink(T, 0);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) {
+    th.emplace_back([&, t] {
+      const uint64_t* p = reinterpret_cast<const uint64_t*>(buf);
+      const int64_t lo = words * t / T, hi = words * (t + 1) / T;
+      uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int r = 0; r < reps; ++r) {
+        int64_t i = lo;
+        for (; i + 4 <= hi; i += 4) {
+          a0 += p[i]; a1 += p[i + 1]; a2 += p[i + 2]; a3 += p[i + 3];
+        }
+        for (; i < hi; ++i) a0 += p[i];
+      }
+      sink[t] = a0 + a1 + a2 + a3;
+    });
+  }
+  for (auto& x : th) x.join();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  volatile uint64_t keep = 0;
+  for (int t = 0; t < T; ++t) keep += sink[t];
+  (void)keep;
+  return sec > 0 ? (double)bytes * reps / sec / 1e9 : 0.0;
 }

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(256) k_w2a_split(W2aSplitArgs a) {
 // ---- conv1 propagate + bias + relu + dropout: H1, A1 (the sweep half of the forward mix) -----------------------
 struct PostAct {
   static constexpr bool kPairs = false;
+  static constexpr bool kInline = true;
   float* h1;
   float* a1;
   DropSpec drop;

@@ -20,6 +20,7 @@ constexpr int MIX_R = 2, MIX_Q = 4;       // 24 KB stage + 16 KB W2a per CTA, 4 
 
 struct PostBiasRelu {
   static constexpr bool kPairs = false;
+  static constexpr bool kInline = true;
   const float* bias;
   float* out;
   int64_t ldo;
@@ -269,6 +270,7 @@ __device__ __forceinline__ void matvec2_smem(const float4& a0, const float4& a1,
 
 struct PostMix {
   static constexpr bool kPairs = true;
+  static constexpr bool kInline = false;
   MixDir p;
   const float* sW;
   const int64_t* batch;
@@ -529,6 +531,7 @@ struct ValG2 {   // val(x) = [H2[x] > 0] * gs[batch[x]]
 };
 struct PostStore {
   static constexpr bool kPairs = false;
+  static constexpr bool kInline = true;
   float* out;
   __device__ __forceinline__ void operator()(int i, const float4& v, int sub, unsigned, float*) const {
     st4(out + (int64_t)i * H + 4 * sub, v);

@@ -405,6 +405,7 @@ int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cuda
 // ---- dW1[o, k] = sum_{(i,v) in column k} v * T[i, o]: CSR sweep over the columns ------------
 struct PostDw {
   static constexpr bool kPairs = false;
+  static constexpr bool kInline = true;
   float* dw;          // [64][ldw] rows of this direction's lin.weight gradient
   int64_t ldw;
   const int32_t* state;

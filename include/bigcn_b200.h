@@ -213,6 +213,8 @@ int bigcn_xsparse_view(int64_t N, int64_t K, void* workspace, size_t workspace_b
 int64_t bigcn_host_dense_to_csr(const float* x, int64_t N, int64_t K, int32_t* ptr /*[N+1]*/,
                                 int32_t* col /*[cap]*/, float* val /*[cap]*/, int64_t cap,
                                 int32_t n_threads);
+/* STREAM-style probe of the host-memory read bandwidth the compaction threads get (GB/s); data movement only. */
+double bigcn_host_read_gbs(const void* buf, int64_t bytes, int32_t n_threads, int32_t reps);
 /* wt[k, col0+o] = w[o, k0+k] for o<64: lays PyG [out,in] weights out for bigcn_xw */
 int bigcn_transpose_weight(const float* w, int64_t ldw, int64_t k0, int64_t K,
                            float* wt, int64_t ldwt, int64_t col0, bigcn_stream_t stream);

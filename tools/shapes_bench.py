@@ -7,7 +7,8 @@ torchrun the global batch is sharded over the ranks like bench.py does):
   c4    pheme                   B = 24 (reference) and 4096   inference, K = 768 dense features
   c5    powerlaw                B = 128 and 2048              train (Pareto(2) sizes up to 10k nodes)
 
-Batches are device-resident (3 in rotation), timed with CUDA events after warm-up, max over ranks.
+Batches are device-resident (3 in rotation; training steps prepare the next batch beside the current one and replay
+CUDA graphs, inference replays CUDA graphs), timed with CUDA events after warm-up, max over ranks.
 Prints one JSON line per (shape, batch, mode, phase); `python tools/shapes_bench.py > profiles/...`."""
 import json
 import os
@@ -26,9 +27,10 @@ CASES = [
     ("weibo", 128, "sparse", ("train", "infer")),
     ("weibo", 128, "tf32x3", ("train",)),
     ("weibo", 128, "tf32", ("train",)),
-    ("pheme", 24, "fp32", ("infer", "train")),
-    ("pheme", 4096, "fp32", ("infer",)),
+    ("pheme", 24, "auto", ("infer", "train")),          # auto -> tf32x3 (fp32-class, X split in shared memory)
+    ("pheme", 4096, "auto", ("infer", "train")),
     ("pheme", 4096, "tf32", ("infer",)),
+    ("pheme", 4096, "fp32", ("infer",)),                # the exact FFMA scan on dense features, for comparison
     ("powerlaw", 128, "sparse", ("train",)),
     ("powerlaw", 2048, "sparse", ("train", "infer")),
 ]
@@ -62,25 +64,25 @@ def main():
         nodes = [int(b.x.shape[0]) for b in res]
         torch.manual_seed(0)
         model = bigcn_b200.BiGCN(cfg["in_feats"], 64, 64, dev, num_classes=cfg["num_classes"], gemm_mode=mode,
-                                 validate="off").to(dev)
+                                 validate="off", graphs=True).to(dev)
         tr = bigcn_b200.FusedTrainer(model, process_group=pg, world_size=world)
         for phase in phases:
             model.train(phase == "train")
 
             def one(i):
                 if phase == "train":
-                    return tr.step(res[i % 3], b_global=bsz * world, node_id_base=base[i % 3])
+                    return tr.step(res[i % 3], b_global=bsz * world, node_id_base=base[i % 3], next_data=res[(i + 1) % 3])
                 with torch.no_grad():
                     return model(res[i % 3])
             steps = 30
-            for i in range(5):
+            for i in range(24):          # every (batch, next batch, buffer) combination: enqueued once, then captured
                 one(i)
             torch.cuda.synchronize()
             if world > 1:
                 torch.distributed.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(steps):
+            for i in range(24, 24 + steps):
                 one(i)
             e1.record()
             torch.cuda.synchronize()
