@@ -124,6 +124,7 @@ struct WtVal {
 // epilogue that needs no scratch row and is called as soon as a row's sum is complete (no trip through the stage).
 // plain feature rows: val(j) = h[j, :]
 struct ValRow {
+  static constexpr bool kHasAux = false;
   const float* h;
   int64_t ldh;
   __device__ __forceinline__ void fetch(float* dst, int j, int sub) const {
@@ -193,7 +194,7 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
     if (sub <= nrows && nrows > 0) sp[sub] = g.ptr[i0 + sub];
     if (sub < nrows) {
       sd[sub] = wt.row(i0 + sub);
-      if (Wt::kSelf) sa[Q + sub] = val.aux(i0 + sub);
+      if constexpr (Wt::kSelf && Val::kHasAux) sa[Q + sub] = val.aux(i0 + sub);
     }
     if (Wt::kSelf) {
 #pragma unroll
@@ -240,14 +241,20 @@ __device__ __forceinline__ void csr_sweep(const Csr g, const Wt wt, const int n,
       int j = 0;
       if (sub < nb) {
         const int s = r0 + sub;
-        int u = 0;
+        int u = 0;   // largest u with sq[u] <= s (sq is non-decreasing, sq[0] = 0): binary search over the R offsets
+        if constexpr (R == 8) {
+          u = s >= sq[4] ? 4 : 0;
+          u += s >= sq[u + 2] ? 2 : 0;
+          u += s >= sq[u + 1] ? 1 : 0;
+        } else {
 #pragma unroll
-        for (int k = 1; k < R; ++k) u += (s >= sq[k]) ? 1 : 0;   // sq is non-decreasing
+          for (int k = 1; k < R; ++k) u += (s >= sq[k]) ? 1 : 0;
+        }
         const int e = sp[u] + (s - sq[u]);
         j = g.idx[e];
         sw[sub] = wt.edge(e, j, sd[u]);
         su[sub] = u;
-        sa[sub] = val.aux(j);
+        if constexpr (Val::kHasAux) sa[sub] = val.aux(j);
       }
 #pragma unroll
       for (int q = 0; q < Q; ++q) {

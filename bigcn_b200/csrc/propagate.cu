@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(256) k_gscale(GScaleArgs a) {
 // T2[j] = sum_{x in out(j)} (dis[j]*dis[x]) * G2[x] + dis[j]^2 * G2[j],
 // G2[x] = [H2[x] > 0] * gs[batch[x]]   (relu and scatter_mean backward fused into the gather)
 struct ValG2 {   // val(x) = [H2[x] > 0] * gs[batch[x]]
+  static constexpr bool kHasAux = true;
   const float* h2;
   const float* gs;
   const int64_t* batch;
