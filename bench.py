@@ -384,11 +384,15 @@ def run_ours(args):
     host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     loader_csr = [bigcn_b200.host_dense_to_csr(b.x, cap=cap) for b in host] if sparse_ok else None
 
+    lpipe = {"prev": None}
+
     def e2e_loader(i):
         src, dst = host[i % N_ROTATE], stage[i % 2]
         copy_small(src, dst)
         dst.x = ship_csr(loader_csr[i % N_ROTATE], i % 2)
-        return float(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]).item())
+        loss = tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE])
+        prev, lpipe["prev"] = lpipe["prev"], loss       # the loss read back every step is the previous step's
+        return float(prev.item()) if prev is not None else 0.0
 
     feeder = bigcn_b200.HostFeeder(dev, K_FEATS, max(nodes), n_threads=host_threads) if sparse_ok else None
 
@@ -461,10 +465,19 @@ def run_ours(args):
             all_trees += trs
         forest = bigcn_b200.DeviceForest.from_data_list(all_trees, dev)
 
+    pipe = {"prev": None, "cur": None}
+
     def e2e_forest(i):
+        """A pipelined loader loop over the device-resident dataset: batch i+1 is assembled (collate + DropEdge on the
+        device) and handed to step i as next_data, so its preparation runs beside step i; the loss read back every
+        step is the PREVIOUS step's (the host enqueues step i while the device still runs step i-1)."""
         j = i % N_ROTATE
-        bd = forest.batch(ids_of[j], 0.2, 0.2, seed=i)
-        return float(tr.step(bd, b_global=b_global, node_id_base=id_base[j]).item())
+        cur = pipe["cur"] if pipe["cur"] is not None and pipe["cur"][0] == i else (i, forest.batch(ids_of[j], 0.2, 0.2, seed=i))
+        nxt = (i + 1, forest.batch(ids_of[(i + 1) % N_ROTATE], 0.2, 0.2, seed=i + 1))
+        loss = tr.step(cur[1], b_global=b_global, node_id_base=id_base[j], next_data=nxt[1] if prefetch else None)
+        pipe["cur"] = nxt
+        prev, pipe["prev"] = pipe["prev"], loss
+        return float(prev.item()) if prev is not None else 0.0
 
     small_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in small_keys)
     routes = {}
@@ -502,6 +515,7 @@ def run_ours(args):
         torch.distributed.all_gather(g, t)
         host_gbs = [float(v[0]) for v in g]
     log(f"e2e routes done: {({k: round(v['ms_per_step'], 3) for k, v in routes.items()})}; host read GB/s per rank {host_gbs}")
+    loader_nnz = [int(c.col.numel()) for c in loader_csr] if loader_csr is not None else [0] * N_ROTATE
     del feeder, forest, stage, dev_csr, loader_csr
     configs = {}
     if not args.no_configs:
@@ -562,12 +576,31 @@ def run_ours(args):
     xw_bytes = mean_nodes * K_FEATS * 4 + K_FEATS * 128 * 4 + mean_nodes * 128 * 4
     xw_gbs = xw_bytes / (xw_ms * 1e-3) / 1e9
     fwd_kernel = {"fp32": "k_xw_scan<128>", "mixed": "k_xw_scan<128>", "tf32": "k_xw_tc<1> (tcgen05 kind::tf32)",
-                  "tf32x3": "k_xw_tc<2> (tcgen05 kind::tf32, W hi+lo)",
+                  "tf32x3": "k_xw_tc<2,true> (tcgen05 kind::tf32, X and W split hi+lo)",
                   "sparse": "k_transpose_jobs + k_xw_scan<128, capture>"}[args.gemm_mode]
     roof_fwd = {"kernel": fwd_kernel + ": X * [W1_td;W1_bu]^T, conv1.lin of both directions in one pass over X",
                 "bound": "hbm", "achieved": xw_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xw_gbs / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "ms": xw_ms, "algorithmic_bytes": xw_bytes,
                 "frac_of_8TBs_nominal": xw_gbs / 8000.0}
+    # the pipelined step (prefetch) reads x in bigcn_batch_prepare instead: the same pass without the product
+    roof_cap = None
+    if sparse:
+        nnz_mean = sum(int(loader_nnz[i % N_ROTATE]) for i in range(12)) / 12
+
+        def cap_fn(i):
+            j = i % N_ROTATE
+            L.check(lib.bigcn_x_capture(resident[j].x.data_ptr(), nodes[j], K_FEATS, 0, xs_flags.data_ptr(), xs_ws[j].data_ptr(),
+                                        xs_ws[j].numel(), st))
+        cap_ms = time_kernel(cap_fn, 12, torch)
+        cap_bytes = mean_nodes * K_FEATS * 4 + nnz_mean * 8 + mean_nodes * 4      # x once; (col, val) per non-zero + a count per row
+        cap_gbs = cap_bytes / (cap_ms * 1e-3) / 1e9
+        roof_cap = {"kernel": "k_xw_scan<64, capture, no product> (bigcn_batch_prepare: the one pass over the dense x of a step, "
+                              "run a step ahead on a lowest-priority stream)",
+                    "bound": "hbm", "achieved": cap_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": cap_gbs / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "ms": cap_ms, "algorithmic_bytes": cap_bytes,
+                    "frac_of_8TBs_nominal": cap_gbs / 8000.0,
+                    "note": "timed alone (CUDA events, 12 launches over the 3 batches in rotation, each 625 MB >> L2); inside the "
+                            "step it shares the machine with the step's own kernels and stretches to ~190 us"}
     # the weight gradient dW1 = T1^T X
     ts = [torch.randn(n, 128, device=dev) for n in nodes]
     dws = [torch.empty(64, K_FEATS, device=dev) for _ in range(2)]
@@ -640,6 +673,10 @@ def run_ours(args):
             key = "k_xw_scan_capture" if sparse and "k_xw_scan_capture" in traffic else "k_xw_scan"
             roof_fwd["traffic"] = traffic[key]["bytes"]
             roof_fwd["traffic_note"] = f"ncu capture of {key} at N = {traffic[key]['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
+            if roof_cap is not None and "k_x_capture" in traffic:
+                roof_cap["traffic"] = traffic["k_x_capture"]["bytes"]
+                roof_cap["traffic_note"] = (f"ncu --set full capture at N = {traffic['k_x_capture']['nodes']} nodes "
+                                            "(profiles/r02_prof_step_summary.txt); algorithmic bytes above are the mean over the rotation")
         if args.gemm_mode in ("tf32x3", "mixed"):
             roof_bwd["traffic"] = traffic["k_dw_tc"]["bytes"]
             roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {traffic['k_dw_tc']['nodes']} nodes"
@@ -647,6 +684,9 @@ def run_ours(args):
         pass
     roof, other_gemm = (roof_bwd, roof_fwd) if (dw_ms >= xw_ms and not sparse) else (roof_fwd, roof_bwd)
     others = {"weight_gradient_dW1" if sparse else "other_x_stream": other_gemm, "xw_tcgen05": tc}
+    if roof_cap is not None and prefetch:      # the dominant kernel of the step as it is timed: the background pass over x
+        others["xw_scan_fused_product"] = roof
+        roof = roof_cap
     if not args.no_kernels:
         others.update(kernel_microbench(torch, L, ops, dev, hbm_peak))
 

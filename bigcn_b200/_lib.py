@@ -75,6 +75,7 @@ _SIGS = {
     "bigcn_xsparse_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "bigcn_xw_sparse": (C.c_int, [c_ptr, C.c_int64, C.c_int64, c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_int32,
                                   c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "bigcn_x_capture": (C.c_int, [c_ptr, C.c_int64, C.c_int64, C.c_int32, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "bigcn_xw_wgrad_sparse": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_int32, c_ptr, c_ptr, C.c_int64, c_ptr,
                                         C.c_size_t, c_ptr]),
     "bigcn_xsparse_view": (C.c_int, [C.c_int64, C.c_int64, c_ptr, C.c_size_t] + [C.POINTER(c_ptr)] * 7),

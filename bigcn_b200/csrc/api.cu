@@ -51,13 +51,19 @@ static SideCtx* side_ctx() {
     SideCtx& c = ctx[dev];
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    // four levels when the device has them (B200: 0 .. -3, lower = more urgent):
+    //   hi      side / side2   short chains the main chain is about to wait for (graph prep inline, root columns)
+    //   lo - 2  [the caller's step stream: bigcn_b200.ops.step_stream]
+    //   lo - 1  low / bw       this step's column sort of x and dW2 / db chains: needed before the step ends
+    //   lo      prep           the NEXT batch's preparation: needed only by the next step
+    const int mid = lo - 1 < hi ? hi : lo - 1;
     c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi) == cudaSuccess &&
-           cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, mid) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.prep[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.prep[1], cudaStreamNonBlocking, lo) == cudaSuccess &&
-           cudaStreamCreateWithPriority(&c.bw[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
-           cudaStreamCreateWithPriority(&c.bw[1], cudaStreamNonBlocking, lo) == cudaSuccess;
+           cudaStreamCreateWithPriority(&c.bw[0], cudaStreamNonBlocking, mid) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.bw[1], cudaStreamNonBlocking, mid) == cudaSuccess;
     for (int i = 0; i < 12 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
     if (e && e[0] == '1') c.ok = false;
@@ -964,6 +970,21 @@ extern "C" int bigcn_xw_sparse(const float* x, int64_t N, int64_t K, const float
   }
   w.xs.flags = flags;
   return xs_build_csc(w.xs, x, true, st);
+}
+
+// the pass over x of bigcn_batch_prepare on its own: capture of the non-zeros into the ELL slots of a
+// bigcn_xw_sparse workspace (no product); with build_csr != 0 also the exclusive scan + compaction into CSR
+extern "C" int bigcn_x_capture(const float* x, int64_t N, int64_t K, int32_t build_csr, int32_t* flags, void* workspace,
+                               size_t workspace_bytes, bigcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BIGCN_CHECK_ARG(N >= 0 && K > 0 && flags && (N == 0 || x), "x_capture: bad arguments");
+  XsWs w = carve_xs(N, K, workspace, workspace_bytes);
+  BIGCN_CHECK_ARG(workspace && workspace_bytes >= w.total, "x_capture: workspace too small");
+  if (N == 0) return 0;
+  if (int rc = x_capture(x, N, K, w.xs, st)) return rc;
+  if (!build_csr) return 0;
+  w.xs.flags = flags;
+  return xs_build_csr(w.xs, x, true, st);
 }
 
 extern "C" int bigcn_xw_wgrad_sparse(int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0, float* dw1,

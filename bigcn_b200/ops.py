@@ -23,7 +23,7 @@ _step_streams = {}
 
 
 def step_stream(device=None):
-    """A stream one priority level above the default one, per device: FusedTrainer runs (and captures) its steps
+    """A stream two priority levels above the default one (the library's own levels are listed in csrc/api.cu), per device: FusedTrainer runs (and captures) its steps
     on it so that bigcn_batch_prepare's lowest-priority streams -- the next batch's preparation -- really yield
     to the step's own kernels (the caller's default stream already has the lowest priority there is)."""
     dev = torch.cuda.current_device() if device is None else torch.device(device).index
@@ -33,7 +33,7 @@ def step_stream(device=None):
             lo, hi = torch.cuda.Stream.priority_range()
         except Exception:  # noqa: BLE001
             lo, hi = 0, -1
-        s = _step_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 1) if hi < lo else lo)
+        s = _step_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 2) if hi < lo else lo)
     return s
 
 
@@ -44,12 +44,12 @@ def capture_graph(enqueue):
     capture costs about one enqueue plus the instantiation."""
     dev = torch.cuda.current_device()
     s = _capture_streams.get(dev)
-    if s is None:       # kernel nodes inherit the capturing stream's priority: one level above the default stream
+    if s is None:       # kernel nodes inherit the capturing stream's priority: the step stream's level
         try:
             lo, hi = torch.cuda.Stream.priority_range()
         except Exception:  # noqa: BLE001
             lo, hi = 0, -1
-        s = _capture_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 1) if hi < lo else lo)
+        s = _capture_streams[dev] = torch.cuda.Stream(device=dev, priority=max(hi, lo - 2) if hi < lo else lo)
     cur = torch.cuda.current_stream()
     s.wait_stream(cur)
     g = torch.cuda.CUDAGraph()

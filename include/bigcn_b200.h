@@ -201,6 +201,10 @@ size_t bigcn_xsparse_workspace_bytes(int64_t N, int64_t K);
 int bigcn_xw_sparse(const float* x, int64_t N, int64_t K, const float* w0, const float* w1, int64_t ldw,
                     float* y, int64_t ldy, int32_t build_csc /* 0: product only (inference) */,
                     int32_t* flags, void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
+/* The pass over x that bigcn_batch_prepare runs a step ahead, on its own: captures the non-zeros of every row into
+ * the ELL slots of a bigcn_xw_sparse workspace (no product); build_csr != 0 adds the scan + compaction into CSR. */
+int bigcn_x_capture(const float* x, int64_t N, int64_t K, int32_t build_csr, int32_t* flags, void* workspace,
+                    size_t workspace_bytes, bigcn_stream_t stream);
 int bigcn_xw_wgrad_sparse(int64_t N, int64_t K, const float* t, int32_t n_w, float* dw0, float* dw1,
                           int64_t ldw, void* workspace, size_t workspace_bytes, bigcn_stream_t stream);
 int bigcn_xsparse_view(int64_t N, int64_t K, void* workspace, size_t workspace_bytes, int32_t** state,
