@@ -52,7 +52,7 @@ class FusedTrainer:
         self.pg, self.world = process_group, world_size
         self.validate = validate
         self.fused_sync = bool(fused_sync)     # comm="symm": cross-rank barriers inside the optimiser kernel
-        self.raise_priority = True
+        self.raise_priority = False            # enqueued (not replayed) steps without a prepared batch: stay on the caller's stream
         self.comm, self.comm_note = "single", ""
         named = dict(model.named_parameters())
         dev = named[_ORDER[0]].device
