@@ -384,15 +384,33 @@ def run_ours(args):
     host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     loader_csr = [bigcn_b200.host_dense_to_csr(b.x, cap=cap) for b in host] if sparse_ok else None
 
-    lpipe = {"prev": None}
+    class LateRead:
+        """Every step's loss crosses to pinned host memory right behind the step (non-blocking copy + event); the host
+        reads it one step LATER, waiting on that event only -- so it enqueues step i while the device runs step i-1
+        (a plain .item() would wait for everything enqueued so far, step i included)."""
+
+        def __init__(self):
+            self.pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.ev = [torch.cuda.Event() for _ in range(2)]
+            self.n = 0
+
+        def __call__(self, loss):
+            k = self.n % 2
+            self.pin[k].copy_(loss, non_blocking=True)
+            self.ev[k].record()
+            self.n += 1
+            if self.n == 1:
+                return 0.0
+            self.ev[1 - k].synchronize()
+            return float(self.pin[1 - k][0])
+
+    late_loader, late_forest = LateRead(), LateRead()
 
     def e2e_loader(i):
         src, dst = host[i % N_ROTATE], stage[i % 2]
         copy_small(src, dst)
         dst.x = ship_csr(loader_csr[i % N_ROTATE], i % 2)
-        loss = tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE])
-        prev, lpipe["prev"] = lpipe["prev"], loss       # the loss read back every step is the previous step's
-        return float(prev.item()) if prev is not None else 0.0
+        return late_loader(tr.step(dst, b_global=b_global, node_id_base=id_base[i % N_ROTATE]))
 
     feeder = bigcn_b200.HostFeeder(dev, K_FEATS, max(nodes), n_threads=host_threads) if sparse_ok else None
 
@@ -465,8 +483,6 @@ def run_ours(args):
             all_trees += trs
         forest = bigcn_b200.DeviceForest.from_data_list(all_trees, dev)
 
-    pipe = {"prev": None, "cur": None}
-
     def e2e_forest(i):
         """A loader loop over the device-resident dataset: every step assembles its batch on the device (collate + a
         fresh DropEdge) and enqueues the step; the loss read back every step is the PREVIOUS step's, so the host
@@ -474,9 +490,7 @@ def run_ours(args):
         replay, the host's enqueue rate is what this route measures)."""
         j = i % N_ROTATE
         bd = forest.batch(ids_of[j], 0.2, 0.2, seed=i)
-        loss = tr.step(bd, b_global=b_global, node_id_base=id_base[j])
-        prev, pipe["prev"] = pipe["prev"], loss
-        return float(prev.item()) if prev is not None else 0.0
+        return late_forest(tr.step(bd, b_global=b_global, node_id_base=id_base[j]))
 
     small_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in small_keys)
     routes = {}
