@@ -135,7 +135,8 @@ _SIGS = {
     "bigcn_dp_slice": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bigcn_dp_reduce_adam": (C.c_int, [C.POINTER(c_ptr), C.POINTER(c_ptr), C.c_int32, C.c_int32, c_ptr, c_ptr,
                                        C.c_int64, c_ptr, c_ptr, C.c_int32, C.c_double, C.c_double, C.c_double,
-                                       C.c_double, C.c_double, c_ptr, C.POINTER(c_ptr), c_ptr]),
+                                       C.c_double, C.c_double, c_ptr, C.POINTER(c_ptr), C.POINTER(c_ptr), c_ptr]),
+    "bigcn_dp_stage_chunk": (C.c_int64, [C.c_int64, C.c_int32]),
     "bigcn_adam_step": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int32,
                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr,
                                   c_ptr]),

@@ -371,6 +371,11 @@ struct DpArgs {
   // [DP_MAX_WORLD + r] = "rank r has read every gradient slice it needs and written its parameter slice everywhere";
   // values are epochs (step_count[2] + 1: never rewound), so nothing is ever reset.
   unsigned long long* sig[DP_MAX_WORLD];
+  // PUSH form (with sig): stage[q] is rank q's staging buffer in symmetric memory, world x chunk floats; rank r writes
+  // its gradient slice q into stage[q][r * chunk ...] with plain peer STORES (one way, bandwidth-bound) before the
+  // first barrier, and every rank then reduces its own slice from LOCAL memory -- no peer loads (round trips) at all.
+  float* stage[DP_MAX_WORLD];
+  int64_t chunk, n;
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -384,15 +389,53 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
   __shared__ float s_bc[2];
   const bool fused_sync = a.sig[0] != nullptr;
   const unsigned long long epoch = (unsigned long long)(*(volatile int64_t*)(a.step_count + 2)) + 1ull;
+  // timestamps of the last launch (globaltimer, ns) in the local signal block [32..35]: kernel start, gradients of all
+  // ranks complete, own slice done, every rank done -- where a data-parallel step waits (tools/dp_phases.py)
+  unsigned long long* dbg = fused_sync ? a.sig[a.rank] + 2 * DP_MAX_WORLD : nullptr;
+  auto stamp = [&](int k) {
+    if (dbg != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[k] = t;
+    }
+  };
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(0);
   if (threadIdx.x == 0) {
     const double step = (double)(*(volatile int64_t*)a.step_count + 1);
     s_bc[0] = (float)(1.0 - pow(a.beta1, step));
     s_bc[1] = (float)sqrt(1.0 - pow(a.beta2, step));
   }
+  const bool push = fused_sync && a.stage[0] != nullptr;
+  __shared__ int s_signal;
   if (fused_sync) {
-    // barrier 1: this rank's gradient is complete (everything before this kernel on the stream has finished):
-    // tell every rank, then wait until every rank has told us.  One CTA signals, every CTA waits on LOCAL flags.
-    if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    if (push) {
+      // phase 0: my gradient slice q -> rank q's staging row [rank] (peer stores), all CTAs, grid-stride
+      const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth0 = (int64_t)gridDim.x * blockDim.x;
+      for (int q = 0; q < a.world; ++q) {
+        if (q == a.rank) continue;
+        const int64_t qlo = min(a.chunk * q, a.n), qhi = min(qlo + a.chunk, a.n);
+        const float4* src = reinterpret_cast<const float4*>(a.grads[a.rank] + qlo);
+        float4* dst = reinterpret_cast<float4*>(a.stage[q] + (int64_t)a.rank * a.chunk);
+        const int64_t n4q = (qhi - qlo) / 4;
+        for (int64_t t = tid0; t < n4q; t += nth0) dst[t] = src[t];
+        for (int64_t t = 4 * n4q + tid0; t < qhi - qlo; t += nth0)
+          a.stage[q][(int64_t)a.rank * a.chunk + t] = a.grads[a.rank][qlo + t];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {   // the last CTA to finish pushing tells every rank (step_count[3]: its arrival counter)
+        __threadfence_system();
+        unsigned long long* arrive0 = reinterpret_cast<unsigned long long*>(a.step_count + 3);
+        s_signal = atomicAdd(arrive0, 1ull) == (unsigned long long)gridDim.x - 1;
+        if (s_signal) *arrive0 = 0ull;
+      }
+      __syncthreads();
+    } else if (threadIdx.x == 0) {
+      s_signal = blockIdx.x == 0;   // pull form: the gradient was complete before this kernel started
+    }
+    if (!push) __syncthreads();
+    // barrier 1: this rank's gradient is complete (and, push form, delivered): tell every rank, then wait until
+    // every rank has told us.  One CTA signals, every CTA waits on LOCAL flags.
+    if (s_signal && threadIdx.x < a.world) {
       __threadfence_system();
       st_release_sys(a.sig[threadIdx.x] + a.rank, epoch);
     }
@@ -402,6 +445,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(1);
   const float bc1 = s_bc[0], bc2s = s_bc[1];
   const float beta2 = (float)a.beta2;
   const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
@@ -429,7 +473,9 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     float4 gq[DP_MAX_WORLD];
 #pragma unroll
     for (int r = 0; r < DP_MAX_WORLD; ++r)
-      if (r < a.world) gq[r] = *reinterpret_cast<const float4*>(a.grads[r] + i);   // peer loads, all in flight
+      if (r < a.world)   // push form: every slice sits in local memory (rank r's in my staging row r); pull form: peer loads
+        gq[r] = (push && r != a.rank) ? __ldcg(reinterpret_cast<const float4*>(a.stage[a.rank] + (int64_t)r * a.chunk + (i - a.lo)))
+                                      : *reinterpret_cast<const float4*>(a.grads[r] + i);
     float4 g = gq[0];
 #pragma unroll
     for (int r = 1; r < DP_MAX_WORLD; ++r)
@@ -453,7 +499,8 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
   }
   for (int64_t i = a.lo + 4 * n4 + tid; i < a.hi; i += nth) {   // tail of the last rank's slice
     float g = 0.f;
-    for (int r = 0; r < a.world; ++r) g += a.grads[r][i];
+    for (int r = 0; r < a.world; ++r)
+      g += (push && r != a.rank) ? __ldcg(a.stage[a.rank] + (int64_t)r * a.chunk + (i - a.lo)) : a.grads[r][i];
     float mi = a.m[i], vi = a.v[i];
     const float pn = upd(a.params[a.rank][i], g, mi, vi, lr_of(i));
     a.m[i] = mi;
@@ -469,6 +516,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
   }
   __syncthreads();
   if (!s_last) return;
+  if (threadIdx.x == 0) stamp(2);
   if (fused_sync) {
     // barrier 2: every block of this rank is done (peer loads of the gradients, peer stores of the parameters,
     // fenced above): tell every rank, and leave only when every rank has said the same -- at kernel exit all
@@ -481,6 +529,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_adam(DpArgs a) {
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    stamp(3);
     unsigned long long* arrive = reinterpret_cast<unsigned long long*>(a.step_count + 1);
     *arrive = 0ull;
     *a.step_count += 1;
@@ -631,11 +680,15 @@ extern "C" int bigcn_dp_slice(int64_t n, int32_t world, int32_t rank, int64_t* l
   return 0;
 }
 
+extern "C" int64_t bigcn_dp_stage_chunk(int64_t n, int32_t world) {
+  return world >= 1 ? ceil_div(ceil_div(n, 4), world) * 4 : 0;
+}
+
 extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* params, int32_t world, int32_t rank,
                                     float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
                                     const float* seg_lr, int32_t n_seg, double beta1, double beta2, double eps,
                                     double weight_decay, double grad_scale, int64_t* step_count,
-                                    void* const* signals, bigcn_stream_t stream) {
+                                    void* const* signals, float* const* stage, bigcn_stream_t stream) {
   BIGCN_CHECK_ARG(grads && params && world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world,
                   "dp_reduce_adam: world must be 1..%d", DP_MAX_WORLD);
   BIGCN_CHECK_ARG(n_seg >= 1, "dp_reduce_adam: need at least one lr segment");
@@ -650,7 +703,12 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
     a.params[r] = params[r];
     a.sig[r] = signals ? reinterpret_cast<unsigned long long*>(signals[r]) : nullptr;
     BIGCN_CHECK_ARG(!signals || signals[r], "dp_reduce_adam: NULL signal block");
+    a.stage[r] = (signals && stage) ? stage[r] : nullptr;
+    BIGCN_CHECK_ARG(!(signals && stage) || (stage[r] && (reinterpret_cast<uintptr_t>(stage[r]) & 15) == 0),
+                    "dp_reduce_adam: NULL / unaligned staging buffer");
   }
+  a.n = n;
+  a.chunk = ceil_div(ceil_div(n, 4), world) * 4;   // = the slice length of bigcn_dp_slice
   a.world = world; a.rank = rank; a.m = exp_avg; a.v = exp_avg_sq;
   bigcn_dp_slice(n, world, rank, &a.lo, &a.hi);
   a.seg_end = seg_end; a.seg_lr = seg_lr; a.n_seg = n_seg;
@@ -658,7 +716,14 @@ extern "C" int bigcn_dp_reduce_adam(const float* const* grads, float* const* par
   a.step_count = step_count;
   if (a.hi > a.lo || signals) {   // with in-kernel barriers even an empty slice takes part
     int blocks = (int)ceil_div((a.hi - a.lo + 3) / 4, 256);
-    const int cap = num_sms() * 4;   // every CTA resident: the barrier spins must not starve the signalling CTA
+    // Every CTA must be able to be resident at once: in the push form the rank signals only when ALL of its CTAs have
+    // delivered their slices, while the CTAs that are done spin on the peers' flags and keep their slots.  (Kernels of
+    // other streams may hold slots for a while; they finish on their own and the remaining CTAs then start.)
+    static int per_sm = 0;
+    if (per_sm == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_reduce_adam, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int cap = num_sms() * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     k_dp_reduce_adam<<<blocks, 256, 0, st>>>(a);

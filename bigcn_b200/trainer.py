@@ -35,7 +35,7 @@ class FusedTrainer:
 
     def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  process_group=None, world_size=1, validate=False, comm="auto", graphs="auto", max_graphs=16,
-                 fused_sync=True):
+                 fused_sync=True, dp_push=True):
         """``comm`` (world_size > 1): "symm" = one fused kernel over NVLink peer memory
         (reduce-scatter of the gradients in rank order + Adam on the owned shard + all-gather of
         the parameters, bigcn_dp_reduce_adam) between two symmetric-memory barriers; "nccl" = two
@@ -52,6 +52,7 @@ class FusedTrainer:
         self.pg, self.world = process_group, world_size
         self.validate = validate
         self.fused_sync = bool(fused_sync)     # comm="symm": cross-rank barriers inside the optimiser kernel
+        self.dp_push = bool(dp_push)           # ... and gradient slices pushed to their owners (peer stores) instead of pulled
         self.raise_priority = False            # enqueued (not replayed) steps without a prepared batch: stay on the caller's stream
         self.comm, self.comm_note = "single", ""
         named = dict(model.named_parameters())
@@ -134,16 +135,24 @@ class FusedTrainer:
         self._rank = hf.rank
         self._pptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
         self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in hg.buffer_ptrs])
-        # signal blocks of the in-kernel barriers of bigcn_dp_reduce_adam (32 uint64 per rank, epochs: never reset)
-        self._sptrs = None
+        # signal blocks of the in-kernel barriers of bigcn_dp_reduce_adam (64 uint64 per rank: 2 x 16 epoch words, never reset, + time stamps)
+        self._sptrs = self._stptrs = None
         if self.fused_sync:
-            sig = symm.empty(32, dtype=torch.int64, device=dev)
+            sig = symm.empty(64, dtype=torch.int64, device=dev)
             hs = symm.rendezvous(sig, group)
             sig.zero_()
             torch.cuda.synchronize()
             dist.barrier(group=group)          # every rank's block is zero before anyone signals
             self._sig, self._hs = sig, hs
             self._sptrs = (C.c_void_p * self.world)(*[int(p) for p in hs.buffer_ptrs])
+            # staging rows for the PUSH form: rank r writes its gradient slice q into rank q's row r before the barrier
+            self._stptrs = None
+            if self.dp_push:
+                chunk = lib().bigcn_dp_stage_chunk(self.n, self.world)
+                stage = symm.empty(self.world * chunk, dtype=torch.float32, device=dev)
+                hst = symm.rendezvous(stage, group)
+                self._stage, self._hst = stage, hst
+                self._stptrs = (C.c_void_p * self.world)(*[int(p) for p in hst.buffer_ptrs])
 
     def _workspace(self, dims, dev):
         need = lib().bigcn_features_workspace_bytes(C.byref(dims))
@@ -211,7 +220,7 @@ class FusedTrainer:
             check(l.bigcn_dp_reduce_adam(self._gptrs, self._pptrs, self.world, self._rank, _p(self.exp_avg),
                                          _p(self.exp_avg_sq), self.n, _p(self.seg_end), _p(self.seg_lr), self.n_seg,
                                          self.betas[0], self.betas[1], self.eps, self.wd, 1.0, _p(self.step_count),
-                                         self._sptrs, st), "dp_reduce_adam")
+                                         self._sptrs, self._stptrs if self._sptrs is not None else None, st), "dp_reduce_adam")
             if self._sptrs is None:
                 self._hf.barrier(channel=1)    # every rank's parameters are written; gradients are free again
         else:

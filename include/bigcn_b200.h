@@ -384,7 +384,8 @@ int bigcn_nll_loss(const float* logp, const int64_t* y, int64_t B, int64_t C, in
  * (end_offset, lr) on the DEVICE; step_count: device int64[4], zero-initialised by the caller:
  * [0] the step, advanced here by the last block of the update kernel, [1] its arrival counter,
  * [2] calls counter (advanced with [0]; never rewound by a checkpoint load): what opts.seed_dev points
- * at so that every step -- eager or a CUDA-graph replay -- draws a fresh dropout mask, [3] spare. */
+ * at so that every step -- eager or a CUDA-graph replay -- draws a fresh dropout mask, [3] arrival counter of the
+ * push phase of bigcn_dp_reduce_adam. */
 int bigcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                     int64_t n, const int64_t* seg_end, const float* seg_lr, int32_t n_seg,
                     double beta1, double beta2, double eps, double weight_decay,
@@ -432,14 +433,19 @@ int bigcn_assemble_batch(const int64_t* node_ptr, const int64_t* edge_ptr, const
  * and stores the new parameters into every rank's buffer.  signals == NULL: the caller puts a cross-rank
  * barrier before (all gradients written) and after (all parameters written, gradients free again).
  * signals != NULL: HOST array of `world` device pointers, signals[q] = rank q's signal block in symmetric memory
- * (32 uint64, zero-initialised once): both barriers then happen INSIDE the kernel (st.release.sys of an epoch
- * into every peer's block, ld.acquire.sys spins on the local one) -- one launch per step instead of three. */
+ * (64 uint64, zero-initialised once; [32..35] receive globaltimer stamps of the last launch): both barriers then happen INSIDE the kernel (st.release.sys of an epoch
+ * into every peer's block, ld.acquire.sys spins on the local one) -- one launch per step instead of three.
+ * stage != NULL (needs signals): HOST array of `world` device pointers, stage[q] = rank q's staging buffer in symmetric
+ * memory, world * bigcn_dp_stage_chunk(n, world) floats: every rank first PUSHES its gradient slices to their owners
+ * (peer stores, one way) and then reduces its own slice from local memory -- no peer loads (NVLink round trips).
+ * step_count[3] is that phase's arrival counter. */
+int64_t bigcn_dp_stage_chunk(int64_t n, int32_t world);
 int bigcn_dp_slice(int64_t n, int32_t world, int32_t rank, int64_t* lo, int64_t* hi);
 int bigcn_dp_reduce_adam(const float* const* grads, float* const* params, int32_t world, int32_t rank,
                          float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
                          const float* seg_lr, int32_t n_seg, double beta1, double beta2, double eps,
                          double weight_decay, double grad_scale, int64_t* step_count,
-                         void* const* signals, bigcn_stream_t stream);
+                         void* const* signals, float* const* stage, bigcn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -23,11 +23,14 @@ def _worker(rank, world, port, out):
     bd = Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys})
     res = {}
     # symm: in-kernel barriers (default) and torch's symmetric-memory barriers around the kernel; nccl: all-reduce + Adam
-    for name, comm, fused in (("symm", "symm", True), ("symm_ext", "symm", False), ("nccl", "nccl", True)):
+    # symm: gradient slices PUSHED to their owners + in-kernel barriers (default); symm_pull: peer loads + in-kernel
+    # barriers; symm_ext: peer loads between torch's symmetric-memory barriers; nccl: all-reduce + Adam on every rank
+    for name, comm, fused, push in (("symm", "symm", True, True), ("symm_pull", "symm", True, False),
+                                    ("symm_ext", "symm", False, False), ("nccl", "nccl", True, False)):
         torch.manual_seed(0)
         m = bigcn_b200.BiGCN(600, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
         tr = bigcn_b200.FusedTrainer(m, process_group=dist.group.WORLD, world_size=world, comm=comm, fused_sync=fused,
-                                     graphs=False)
+                                     dp_push=push, graphs=False)
         assert tr.comm == comm
         for i in range(3):
             tr.step(bd, b_global=6 * world, seed=7 + i)
@@ -61,7 +64,8 @@ def _worker(rank, world, port, out):
     if rank == 0:
         d = (res["symm"][0].double() - res["nccl"][0].double()).abs().max().item()
         torch.save({"same_symm": res["symm"][1], "same_nccl": res["nccl"][1], "same_symm_ext": res["symm_ext"][1],
-                    "fused_equals_ext": bool(torch.equal(res["symm"][0], res["symm_ext"][0])), "diff": d,
+                    "fused_equals_ext": bool(torch.equal(res["symm"][0], res["symm_ext"][0])) and
+                                        bool(torch.equal(res["symm_pull"][0], res["symm_ext"][0])) and res["symm_pull"][1], "diff": d,
                     "scale": res["nccl"][0].abs().max().item(), "graph_replays": res["graph_replays"],
                     "graph_same_ranks": res["graph_same_ranks"], "graph_equals_eager": res["graph_equals_eager"]}, out)
     dist.barrier()

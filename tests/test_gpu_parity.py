@@ -519,7 +519,7 @@ def test_dp_reduce_adam_two_ranks_emulated_on_one_device(dev):
         for r in range(world):
             L.check(lib.bigcn_dp_reduce_adam(gp, pp, world, r, ms[r].data_ptr(), vs[r].data_ptr(), n,
                                              seg_end.data_ptr(), seg_lr.data_ptr(), 1, 0.9, 0.999, 1e-8, 1e-4, 1.0,
-                                             steps[r].data_ptr(), None, st))
+                                             steps[r].data_ptr(), None, None, st))
         for r in range(1, world):
             assert torch.equal(params[r], params[0])           # every copy got the owner's value
         assert rel_err(params[0], ref.data) < 2e-6

@@ -14,7 +14,15 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 
 def main():
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:      # torchrun: the data-parallel step (rank 0 prints its own timeline)
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
     import ctypes as C
     from bigcn_b200 import _lib as L
     lib = L.lib()
@@ -25,20 +33,24 @@ def main():
         lib.bigcn_debug_set(int(k), int(v))
     batches = []
     for i in range(3):
-        b = make_batch_shard("twitter16", 128, 1000 + i)[0]
+        b = make_batch_shard("twitter16", 128 * world, 1000 + i, rank=rank, world=world)[0]
         batches.append(Batch(**{k: getattr(b, k).to(dev) for k in Batch._tensor_keys}))
     torch.manual_seed(0)
     model = bigcn_b200.BiGCN(5000, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
-    tr = bigcn_b200.FusedTrainer(model)
+    tr = bigcn_b200.FusedTrainer(model, process_group=pg, world_size=world)
     prefetch = os.environ.get("BIGCN_PREFETCH", "1") != "0"
     nxt = lambda i: batches[(i + 1) % 3] if prefetch else None  # noqa: E731
     for i in range(24):
-        tr.step(batches[i % 3], next_data=nxt(i))
+        tr.step(batches[i % 3], b_global=128 * world, next_data=nxt(i))
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(24, 28):
-            tr.step(batches[i % 3], next_data=nxt(i))
+            tr.step(batches[i % 3], b_global=128 * world, next_data=nxt(i))
         torch.cuda.synchronize()
+    if rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        return
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda e: e.time_range.start)
     # last step = from the last k_transpose_jobs on
@@ -59,6 +71,9 @@ def main():
         last_end = max(last_end, e.time_range.end)
         end_by_stream[stream] = e.time_range.end
     print("step span us", last_end - t0)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
