@@ -131,7 +131,7 @@ def c4_pheme_infer(torch, bigcn_b200, dev, rank, world, max_over_ranks):
             for t0 in range(a, b, bsz):
                 batches.append(forest_slice_batch(f, t0, min(b, t0 + bsz)))
         row = {"batches_per_rank": len(batches)}
-        for mode, label in (("tf32x3", "fp32_class_tf32x3"), ("tf32", "tf32")):
+        for mode, label in (("auto", "fp32_class_tf32x3"), ("tf32", "tf32")):     # auto resolves to tf32x3 on dense features
             torch.manual_seed(0)
             model = bigcn_b200.BiGCN(768, 64, 64, dev, num_classes=4, gemm_mode=mode, validate="off", graphs=True,
                                      max_graphs=len(batches) + 1).to(dev).eval()
