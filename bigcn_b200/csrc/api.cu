@@ -112,6 +112,7 @@ struct FeatWs {
   float* w1T;               // [K][128]  (TD cols 0..63, BU cols 64..127) | hi/lo split [4][64][K]
   float* w2aT[2];           // [64][64]
   float* w2a_split;         // [2][4][64][64] hi / lo of W2a and W2a^T (tcgen05 mix kernels)
+  float* xw_part;           // split-K partials of the tcgen05 X * W on small batches
   float* w2bT[2];           // [K][64]
   int32_t* rnz_cnt; int32_t* rnz_col; float* rnz_val;
   float* P[2];              // [B][64]
@@ -191,6 +192,7 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes, voi
     w.w2bT[d] = c.take<float>((size_t)K * H);
   }
   w.w2a_split = c.take<float>(mix_tc_scratch_floats());
+  w.xw_part = c.take<float>(xw_tc_partial_floats());
   const size_t nh = (size_t)(N > 0 ? N : 1) * H;
   for (int d = 0; d < 2; ++d) w.P[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   w.xw = c.take<float>(2 * nh);
@@ -342,7 +344,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     if (int rc = xw_fp32(bt->x, N, K, w.w1T, n_out, w.xw, n_out, st)) return rc;
   } else {
     const float* ws[2] = {dir_w1(pr, dirs.id[0]), dirs.n == 2 ? dir_w1(pr, dirs.id[1]) : nullptr};
-    if (int rc = xw_tc_weights(bt->x, N, K, ws, K, n_out, w.w1T, w.xw, n_out, o->gemm_mode, st)) return rc;
+    if (int rc = xw_tc_weights(bt->x, N, K, ws, K, n_out, w.w1T, w.xw, n_out, o->gemm_mode, st, w.xw_part)) return rc;
   }
   // 4. the structure is needed from here on; the side stream goes on to sort the captured
   //    non-zeros of X by column for the weight gradient while the rest of the forward runs

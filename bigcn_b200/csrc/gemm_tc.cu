@@ -35,6 +35,10 @@ struct TcParams {
   int n_out;       // 64 or 128
   int num_tiles;   // ceil(N / 256)
   int num_kb;      // ceil(K / 32)
+  // split-K for small N (a PHEME batch of 24 trees is ONE 256-row tile: one SM would walk all K blocks alone):
+  // grid.y CTAs take kb_per K blocks each and write partial[y][row][n_out]; k_xw_splitk_reduce adds them in order
+  int kb_per;      // K blocks per CTA (= num_kb when not split)
+  float* partial;  // [grid.y][N][n_out] or NULL
 };
 
 // NB = number of B operands per stage (1: W, 2: W and W_lo); XS: X split hi / lo in shared memory (TF32X3)
@@ -59,6 +63,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024 B alignment of the dynamic region (SWIZZLE_128B atoms)
   const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const int kb0 = blockIdx.y * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);   // this CTA's K blocks (split-K: grid.y > 1)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -89,7 +94,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
       const uint32_t tx = (uint32_t)(TC_A_BYTES + NB * b_bytes);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m0 = tile * TC_BLOCK_M;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
           const uint32_t sa = smem0 + s * stage_bytes;
@@ -113,7 +118,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_ph ^= 1) {
         mbar_wait(smem_u32(&bar_tmem_empty), tile_ph ^ 1);   // epilogue has drained the accumulators
         tc_fence_after();
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(XS ? &bar_conv[s] : &bar_full[s]), ph);
           tc_fence_after();
           const uint32_t sa = smem0 + s * stage_bytes;
@@ -123,7 +128,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
             const uint64_t da0 = make_desc_k_sw128(sa + koff);
             const uint64_t da1 = make_desc_k_sw128(sa + 128 * 128 + koff);
             const uint64_t db = make_desc_k_sw128(sa + B_OFF + koff);
-            const uint32_t acc = (kb | k) ? 1u : 0u;
+            const uint32_t acc = ((kb - kb0) | k) ? 1u : 0u;
             tc_mma_tf32(tmem_base, da0, db, idesc, acc);
             tc_mma_tf32(tmem_base + 128, da1, db, idesc, acc);
             if (NB == 2) {
@@ -139,7 +144,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
             }
           }
           tc_commit(smem_u32(&bar_empty[s]));                 // frees the stage when the MMAs retire
-          if (kb == p.num_kb - 1) tc_commit(smem_u32(&bar_tmem_full));
+          if (kb == kb1 - 1) tc_commit(smem_u32(&bar_tmem_full));
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -149,7 +154,7 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_full[s]), ph);
         const uint32_t sa = smem0 + s * stage_bytes;
         split_tile_hi_lo(sa, sa + TC_A_BYTES, TC_A_BYTES, cw, lane);
@@ -174,7 +179,8 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c0), r);
           tc_wait_ld();
           if (row < p.N) {
-            float4* dst = reinterpret_cast<float4*>(p.y + row * p.ldy + c0);
+            float4* dst = p.partial ? reinterpret_cast<float4*>(p.partial + ((int64_t)blockIdx.y * p.N + row) * p.n_out + c0)
+                                    : reinterpret_cast<float4*>(p.y + row * p.ldy + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -192,6 +198,21 @@ k_xw_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUten
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  }
+}
+
+// y[row][c] = sum over the K splits, in split order (deterministic)
+__global__ void __launch_bounds__(256) k_xw_splitk_reduce(const float* __restrict__ partial, int nsplit, int64_t N, int n_out,
+                                                          float* __restrict__ y, int64_t ldy) {
+  const int64_t n4 = N * (n_out / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (n_out / 4), c4 = i % (n_out / 4);
+    float4 acc = reinterpret_cast<const float4*>(partial)[i];
+    for (int s = 1; s < nsplit; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(partial)[(int64_t)s * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(y + row * ldy + 4 * c4) = acc;
   }
 }
 
@@ -213,8 +234,11 @@ bool xw_tc_available() { return encode_fn() != nullptr; }
 
 // w[0], w[1]: the [64, K] PyG weights of the active directions (row pitch ldw); scratch:
 // 2 * n_out * K floats for the TF32X3 split (may be NULL in TF32 mode)
+size_t xw_tc_partial_floats() { return (size_t)num_sms() * TC_BLOCK_M * 128; }
+
+// partial: xw_tc_partial_floats() floats or NULL (no split-K)
 int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, int64_t ldw, int n_out,
-                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st) {
+                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st, float* partial) {
   BIGCN_CHECK_ARG(encode_fn() != nullptr, "xw_tc: cuTensorMapEncodeTiled is unavailable in this driver");
   BIGCN_CHECK_ARG(K % 4 == 0 && ldw % 4 == 0, "xw_tc: in_feats must be a multiple of 4 for TMA (got %lld)", (long long)K);
   BIGCN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "xw_tc: x must be 16-byte aligned");
@@ -250,7 +274,23 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
   const int stage_bytes = (xsplit ? 2 : 1) * TC_A_BYTES + nb * 16384;
   const int stages = xsplit ? 2 : (nb == 1 ? 4 : 3);
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid_x = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  // few tiles (small batch): split K so that the SMs share the K blocks, at least three per CTA
+  int nsplit = 1;
+  p.kb_per = p.num_kb;
+  p.partial = nullptr;
+  if (partial != nullptr && p.num_tiles * 4 <= num_sms() && p.num_kb >= 6) {
+    int want = num_sms() / p.num_tiles;
+    const int max_by_kb = p.num_kb / 3;
+    if (want > max_by_kb) want = max_by_kb;
+    if (want > 1) {
+      p.kb_per = (int)ceil_div(p.num_kb, want);
+      nsplit = (int)ceil_div(p.num_kb, p.kb_per);
+      if (nsplit > 1) p.partial = partial;
+      else p.kb_per = p.num_kb;
+    }
+  }
+  const dim3 grid(grid_x, nsplit);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_xw_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (TC_A_BYTES + 16384) + 1024);
@@ -262,6 +302,12 @@ int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, i
   else if (!xsplit) k_xw_tc<2, false><<<grid, TC_THREADS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
   else k_xw_tc<2, true><<<grid, TC_THREADS_XS, smem, st>>>(mx, mw0, mw1, ml0, ml1, p);
   BIGCN_CHECK_LAUNCH("k_xw_tc");
+  if (nsplit > 1) {
+    int rb = (int)ceil_div(N * (n_out / 4), 256);
+    if (rb > num_sms() * 4) rb = num_sms() * 4;
+    k_xw_splitk_reduce<<<rb, 256, 0, st>>>(partial, nsplit, N, n_out, y, ldy);
+    BIGCN_CHECK_LAUNCH("k_xw_splitk_reduce");
+  }
   return 0;
 }
 

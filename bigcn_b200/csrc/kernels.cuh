@@ -122,7 +122,8 @@ int gs_chunks(int64_t B);
 int bm_chunks(int64_t N);
 int op_chunks(int64_t N);
 int xw_tc_weights(const float* x, int64_t N, int64_t K, const float* const* w, int64_t ldw, int n_out,
-                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st);
+                  float* scratch, float* y, int64_t ldy, int mode, cudaStream_t st, float* partial = nullptr);
+size_t xw_tc_partial_floats();
 bool xw_tc_available();
 
 // ---- row-sparse view of X (xsparse.cu) -------------------------------------------------------
