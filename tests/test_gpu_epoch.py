@@ -43,3 +43,25 @@ def test_train_gcn_learns_and_stops(tmp_path, monkeypatch):
         m2 = bigcn_b200.BiGCN(K, 64, 64, dev, gemm_mode="sparse").to(dev)
         m2.load_state_dict(ck["model_state_dict"])
         assert len(ck["optimizer_state_dict"]["param_groups"]) == 3
+
+
+def test_final_checkpoint_when_epochs_run_out(tmp_path, monkeypatch):
+    """BiGCN_Twitter.py:311-325: a run that exhausts n_epochs without early stopping leaves
+    checkpoints/final_bigcn_f{fold}_i{iter}_e{epoch}_l{loss}.pt (the for/else branch)."""
+    import bigcn_b200
+    from bigcn_b200.data import make_trees_shard
+    monkeypatch.chdir(tmp_path)
+    dev = torch.device("cuda:0")
+    K = 64
+    trees = make_trees_shard("twitter16", 24, seed=6, in_feats=K)[0]
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    torch.manual_seed(0)
+    model = bigcn_b200.BiGCN(K, 64, 64, dev, gemm_mode="sparse").to(dev)
+    out = bigcn_b200.train_GCN(model, forest, np.arange(16), np.arange(16, 24), 0.2, 0.2, lr=5e-4, weight_decay=1e-4,
+                               patience=100, n_epochs=2, batchsize=8, datasetname="Twitter16", iter=3, fold=2, log=lambda s: None)
+    assert len(out[0]) == 2
+    files = os.listdir(tmp_path / "checkpoints")
+    assert len(files) == 1 and files[0].startswith("final_bigcn_f2_i3_e00001_l") and files[0].endswith(".pt")
+    ck = torch.load(tmp_path / "checkpoints" / files[0], weights_only=False)
+    assert ck["epoch"] == 1 and "model_state_dict" in ck and "optimizer_state_dict" in ck
+    assert bigcn_b200.train_GCN.last_final_checkpoint.endswith(files[0])

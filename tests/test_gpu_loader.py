@@ -169,3 +169,54 @@ def test_eval_counts_match_reference_golden(dev):
         ev.update(logp[:h], y[:h])                       # an empty first half (n = 1) is a no-op
         ev.update(logp[h:], y[h:])
         assert list(ev.result()) == c["want"], c["fn"]
+
+
+def test_unsynchronised_epoch_loop_keeps_every_batch_intact(dev):
+    """The epoch loop never synchronises the host (forest.batch, FusedTrainer.step and EvalCounts.update are all
+    asynchronous): with the device many batches behind, a staging slot of the per-batch offsets must not be rewritten
+    while the copy that reads it is still pending.  Hold the device up with a long kernel queue, assemble many
+    batches back to back, and compare each one with the host collate afterwards."""
+    import bigcn_b200
+    trees = trees_for(k=32, sizes=tuple(int(s) for s in np.random.default_rng(3).integers(1, 400, 40)))
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    rng = np.random.default_rng(9)
+    busy = torch.randn(4096, 4096, device=dev)
+    for _ in range(20):                                   # ~100 ms of queued device work ahead of the batches
+        busy = busy @ busy * 1e-4
+    got, want = [], []
+    for i in range(24):                                   # six times the depth of the staging ring
+        ids = rng.integers(0, len(trees), int(rng.integers(1, 12))).tolist()
+        got.append(forest.batch(ids))
+        want.append(collate([trees[j] for j in ids]))
+    torch.cuda.synchronize()
+    for g, w in zip(got, want):
+        assert torch.equal(g.edge_index.cpu(), w.edge_index) and torch.equal(g.batch.cpu(), w.batch)
+        assert torch.equal(g.rootindex.cpu(), w.rootindex) and torch.equal(g.x.to_dense().cpu(), w.x)
+
+
+def test_synthetic_forest_generator_is_a_valid_dataset(dev):
+    """data.synth_forest_device (the vectorised generator bench.py uses for the Weibo / power-law / PHEME configurations):
+    every tree is a tree (each non-root node has exactly one parent inside its tree), the root sits at root_local, TD
+    edges are sorted by (parent, child), bag-of-words rows have distinct ascending columns and counts in 1..3."""
+    import bigcn_b200
+    from bigcn_b200.data import synth_forest_device, forest_slice_batch
+    for shape in ("twitter16", "powerlaw"):
+        f = synth_forest_device(shape, 300, dev, seed=4)
+        forest = bigcn_b200.DeviceForest.from_device_arrays(f)
+        b = forest.batch(list(range(300)))
+        n = int(b.batch.numel())
+        assert n == int(f["node_ptr"][-1]) and int(b.edge_index.shape[1]) == n - 300
+        ei = b.edge_index
+        assert bool((b.batch[ei[0]] == b.batch[ei[1]]).all())
+        indeg = torch.bincount(ei[1], minlength=n)
+        indeg[b.rootindex] += 1
+        assert bool((indeg == 1).all())
+        key = (b.batch[ei[0]] << 40) | (ei[0] << 20) | ei[1]
+        assert bool((key[1:] > key[:-1]).all())
+        x = b.x
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), (x.ptr[1:] - x.ptr[:-1]).long())
+        k2 = rows * 5000 + x.col.long()
+        assert bool((k2[1:] > k2[:-1]).all()) and float(x.val.min()) >= 1 and float(x.val.max()) <= 3
+    f = synth_forest_device("pheme", 200, dev, seed=5)
+    b = forest_slice_batch(f, 17, 60)
+    assert b.x.shape[1] == 768 and int(b.rootindex.numel()) == 43 and bool((b.batch[b.rootindex] == torch.arange(43, device=dev)).all())
