@@ -336,8 +336,10 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     }
   }
   // 3. X W1^T for all active directions in one pass over X (main stream)
-  if (csr_in || (prepared && sparse)) {   // prepared: the capture scan ran a step ahead; same entries, same order
-    if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st, prepared && !csr_in)) return rc;
+  if (csr_in) {
+    if (int rc = xw_csr(w.xs, w.w1T, n_out, w.xw, n_out, st)) return rc;
+  } else if (prepared && sparse) {   // the capture pass ran a step ahead: same entries in the same order as the fused scan
+    if (int rc = xw_ell(w.xs, bt->x, w.w1T, n_out, w.xw, n_out, st)) return rc;
   } else if (sparse && !o->skip_wgrad_prep) {
     if (int rc = xw_fp32_capture(bt->x, N, K, w.w1T, n_out, w.xw, n_out, w.xs, st)) return rc;
   } else if (scan_mode) {
@@ -356,7 +358,11 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   if (sparse && prepared && N > 0 && !o->skip_wgrad_prep) {   // the CSR came prepared; sort it by column beside the rest of this step
     if (sc) stream_after(sc, 2, st, sc->low);
     w.xs.flags = flags;
-    if (int rc = xs_sort_csc(w.xs, sc ? sc->low : st)) return rc;
+    if (csr_in) {
+      if (int rc = xs_sort_csc(w.xs, sc ? sc->low : st)) return rc;
+    } else {
+      if (int rc = xs_build_csc(w.xs, bt->x, true, sc ? sc->low : st)) return rc;
+    }
     side_busy = sc != nullptr;
   }
   if (sparse && !prepared) {
@@ -456,12 +462,15 @@ int batch_prepare(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigcn_o
     if (N == 0) {
       cudaMemsetAsync(w.xs.state, 0, 4 * sizeof(int32_t), pa);
     } else {
-      if (!csr_in)
-        if (int rc = x_capture(bt->x, N, K, w.xs, pa)) return rc;
+      // dense x: the capture only -- the next forward's product walks the ELL slots directly, and the compaction into
+      // CSR and the column sort run in the consuming step, on its low-priority stream under the forward / backward
+      // (awaited right before the dW1 sweep).  A caller's CSR: the sort keys now, the sort itself in the step.
       w.xs.flags = flags;
-      // CSR now (the next forward's product walks it); the column sort runs in the consuming step, on its
-      // low-priority stream under the forward / backward, and is awaited right before the dW1 sweep
-      if (int rc = xs_build_csr(w.xs, bt->x, !csr_in, pa)) return rc;
+      if (!csr_in) {
+        if (int rc = x_capture(bt->x, N, K, w.xs, pa)) return rc;
+      } else {
+        if (int rc = xs_build_csr(w.xs, bt->x, false, pa)) return rc;
+      }
     }
   }
   // stream B: structure of both directions, then the root columns

@@ -115,6 +115,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// the same with an L2 cache policy (evict-first for data that is read exactly once)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+
 // Philox4x32-10 (Salmon et al. SC'11); spec mirrored by oracle/gcn_oracle.py.
 struct Philox4 {
   uint32_t x, y, z, w;

@@ -160,6 +160,7 @@ int dw_sparse(const XSparse& x, const float* t, int64_t ldt, int n_out, float* d
 int xw_fp32_capture(const float*, int64_t, int64_t, const float*, int, float*, int64_t, const XSparse&, cudaStream_t);
 int xw_csr(const XSparse& x, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st, bool check_state = false);
 int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStream_t st);
+int xw_ell(const XSparse& xs, const float* x, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st);
 
 // fork / join onto the library's side stream (independent short kernels run beside the main chain)
 struct SideStream {

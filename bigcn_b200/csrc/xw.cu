@@ -143,13 +143,119 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
   }
 }
 
-// the same pass over x without the product: only the capture of the non-zeros (bigcn_batch_prepare).  It runs on a
-// lowest-priority stream beside the kernels of the current step, so it is launched as MANY SHORT CTAs (8 rows each,
-// one per warp, ~160 KB of x): slots free up every few microseconds and the block scheduler hands them to the
-// step's own (higher-priority) kernels first -- a persistent grid would sit on the register file for 100 us.
+// ---- the background pass over x (bigcn_batch_prepare): capture only, fed by the TMA engine -----------------------------
+// One small persistent CTA per SM, CAPW warps, one ROW each: lane 0 of a warp streams its row into the warp's ring in shared
+// memory with cp.async.bulk (4 KB chunks = the 1024-column blocks of the fused scan, L2 evict-first), the warp ballots the
+// chunks and record the non-zeros in exactly the order of k_xw_scan (same ELL contents).  The point is the footprint:
+// 160 threads, ~40 registers, 32 KB of shared memory per SM and at most CAPW * CAPS * 4 KB in flight per SM, so the pass
+// runs the whole length of a step at a third of the HBM bandwidth without taking slots or registers from, or queueing the
+// memory system ahead of, the step's own latency-bound kernels.
+constexpr int CAP_CHUNK = 1024;   // floats per chunk
+template <int CAPW, int CAPS>
+__global__ void __launch_bounds__(32 * CAPW) k_x_capture_tma(const float* __restrict__ x, int64_t N, int64_t K,
+                                                             int32_t* __restrict__ xs_cnt, int32_t* __restrict__ xs_col,
+                                                             float* __restrict__ xs_val) {
+  extern __shared__ __align__(128) float cap_smem[];
+  float (*buf)[CAPS][CAP_CHUNK] = reinterpret_cast<float (*)[CAPS][CAP_CHUNK]>(cap_smem);
+  __shared__ __align__(8) uint64_t full[CAPW][CAPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < CAPW; ++w)
+      for (int s = 0; s < CAPS; ++s) mbar_init(smem_u32(&full[w][s]), 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  // every warp is its own producer: lane 0 keeps CAPS chunks of the warp's row stream in flight (the chunk sequence of
+  // a warp runs over its rows: row r0, chunks 0..nchunk-1, then row r0 + stride, ...)
+  const int nchunk = (int)((K + CAP_CHUNK - 1) / CAP_CHUNK);
+  const int64_t stride = (int64_t)gridDim.x * CAPW;
+  const int64_t row0 = (int64_t)blockIdx.x * CAPW + warp;
+  const uint64_t pol = l2_evict_first_policy();
+  int64_t prow = row0;   // producer cursor
+  int pc = 0;
+  auto issue = [&](int s) {
+    if (prow >= N) return;
+    const int nfl = (int)min((int64_t)CAP_CHUNK, K - (int64_t)pc * CAP_CHUNK);
+    const uint32_t fb = smem_u32(&full[warp][s]);
+    mbar_expect_tx(fb, (uint32_t)nfl * 4);
+    bulk_g2s_hint(smem_u32(&buf[warp][s][0]), x + prow * K + (int64_t)pc * CAP_CHUNK, (uint32_t)nfl * 4, fb, pol);
+    if (++pc == nchunk) { pc = 0; prow += stride; }
+  };
+  if (lane == 0)
+    for (int s = 0; s < CAPS; ++s) issue(s);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t row = row0; row < N; row += stride) {
+    int nz = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int nfl = (int)min((int64_t)CAP_CHUNK, K - (int64_t)c * CAP_CHUNK);
+      mbar_wait(smem_u32(&full[warp][s]), ph);
+      const float* b = &buf[warp][s][0];
+#pragma unroll
+      for (int u = 0; u < CAP_CHUNK / 128; ++u) {
+        const int f0 = u * 128 + lane * 4;
+        const float4 v = f0 < nfl ? *reinterpret_cast<const float4*>(b + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool any = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+        if (__ballot_sync(FULL_MASK, any) == 0u) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float comp = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+          unsigned m = __ballot_sync(FULL_MASK, comp != 0.f);
+          while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            const float val = __shfl_sync(FULL_MASK, comp, sl);
+            if (lane == 0 && nz < XS_ELL) {
+              xs_col[row * XS_ELL + nz] = (int32_t)((int64_t)c * CAP_CHUNK + u * 128 + sl * 4 + q);
+              xs_val[row * XS_ELL + nz] = val;
+            }
+            ++nz;
+          }
+        }
+      }
+      // the stage is read: hand it back to the TMA engine (generic-proxy reads before the async-proxy write)
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(s);
+      }
+      if (++s == CAPS) { s = 0; ph ^= 1; }
+    }
+    if (lane == 0) xs_cnt[row] = nz;
+  }
+}
+
+// The LDG form of the same pass (k_xw_scan<..., capture, no product>): launched as MANY SHORT CTAs (8 rows each, one per warp,
+// ~160 KB of x) so that slots free up every few microseconds and the block scheduler hands them to the step's own
+// (higher-priority) kernels first.  Used when x is not 16-byte addressable, and for the A/B (tools/stepbench.py knob 10).
 int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStream_t st) {
   if (N == 0) return 0;
   const bool vec4 = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec4 && debug_knob(10) != 9) {   // TMA-fed persistent form (knob 10: consumer warps / stages; 9 = the LDG form below)
+    const int grid = (int)min((int64_t)num_sms(), ceil_div(N, 4));
+#define CAP_LAUNCH(W_, S_)                                                                                           \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    constexpr int smem = W_ * S_ * CAP_CHUNK * 4;                                                                    \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(k_x_capture_tma<W_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);              \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    k_x_capture_tma<W_, S_><<<grid, 32 * W_, smem, st>>>(x, N, K, xs.cnt, xs.ell_col, xs.ell_val);                     \
+  } while (0)
+    switch (debug_knob(10)) {
+      case 1: CAP_LAUNCH(4, 2); break;
+      case 2: CAP_LAUNCH(4, 3); break;
+      case 3: CAP_LAUNCH(8, 2); break;
+      case 4: CAP_LAUNCH(4, 4); break;
+      case 5: CAP_LAUNCH(6, 3); break;
+      case 6: CAP_LAUNCH(8, 3); break;
+      default: CAP_LAUNCH(6, 2); break;
+    }
+#undef CAP_LAUNCH
+    BIGCN_CHECK_LAUNCH("k_x_capture_tma");
+    return 0;
+  }
   int blocks = (int)ceil_div(N, 8), threads = 256;
   switch (debug_knob(5)) {   // tools/stepbench.py: grid shape of the background pass
     case 1: blocks = min(blocks, num_sms() * 2); break;
@@ -224,6 +330,83 @@ __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restr
     else
       *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
   }
+}
+
+// y = x * wt straight from the ELL capture of bigcn_batch_prepare (no CSR yet: the compaction runs beside this
+// kernel, in the consuming step).  Rows with at most XS_ELL non-zeros walk their captured (col, val) slots -- the
+// order of the fused scan, hence the same sums bit for bit; the few longer rows re-read their dense row in that
+// same order (128-column strips, component-major inside a strip).
+template <int NOUT>
+__global__ void __launch_bounds__(256) k_xw_ell(const int32_t* __restrict__ cnt, const int32_t* __restrict__ ell_col,
+                                                const float* __restrict__ ell_val, const float* __restrict__ x, int64_t N,
+                                                int64_t K, const float* __restrict__ wt, float* __restrict__ y, int64_t ldy) {
+  constexpr int V = NOUT / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < N; row += nwarp) {
+    const int c = cnt[row];
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    auto add = [&](int64_t k, float val) {
+      const float* wr = wt + k * NOUT + lane * V;
+      if (V == 4) {
+        const float4 w = *reinterpret_cast<const float4*>(wr);
+        acc[0] = fmaf(val, w.x, acc[0]);
+        acc[1] = fmaf(val, w.y, acc[1]);
+        acc[2] = fmaf(val, w.z, acc[2]);
+        acc[3] = fmaf(val, w.w, acc[3]);
+      } else {
+        const float2 w = *reinterpret_cast<const float2*>(wr);
+        acc[0] = fmaf(val, w.x, acc[0]);
+        acc[1] = fmaf(val, w.y, acc[1]);
+      }
+    };
+    if (c <= XS_ELL) {
+      int k = 0;
+      float v = 0.f;
+      if (lane < c) {
+        k = ell_col[row * XS_ELL + lane];
+        v = ell_val[row * XS_ELL + lane];
+      }
+      for (int l = 0; l < c; ++l) add(__shfl_sync(FULL_MASK, k, l), __shfl_sync(FULL_MASK, v, l));
+    } else {
+      const float* xr = x + row * K;
+      for (int64_t s0 = 0; s0 < K; s0 += 128) {
+        float comp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t kk = s0 + lane * 4 + q;
+          comp[q] = kk < K ? __ldg(xr + kk) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          unsigned m = __ballot_sync(FULL_MASK, comp[q] != 0.f);
+          while (m) {
+            const int sl = __ffs(m) - 1;
+            m &= m - 1;
+            add(s0 + sl * 4 + q, __shfl_sync(FULL_MASK, comp[q], sl));
+          }
+        }
+      }
+    }
+    float* yr = y + row * ldy + lane * V;
+    if (V == 4)
+      *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else
+      *reinterpret_cast<float2*>(yr) = make_float2(acc[0], acc[1]);
+  }
+}
+int xw_ell(const XSparse& xs, const float* x, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st) {
+  if (xs.N == 0) return 0;
+  int blocks = (int)ceil_div(xs.N, 8);
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (n_out == 128) k_xw_ell<128><<<blocks, 256, 0, st>>>(xs.cnt, xs.ell_col, xs.ell_val, x, xs.N, xs.K, wt, y, ldy);
+  else k_xw_ell<64><<<blocks, 256, 0, st>>>(xs.cnt, xs.ell_col, xs.ell_val, x, xs.N, xs.K, wt, y, ldy);
+  BIGCN_CHECK_LAUNCH("k_xw_ell");
+  return 0;
 }
 
 int xw_csr(const XSparse& xs, const float* wt, int n_out, float* y, int64_t ldy, cudaStream_t st, bool check_state) {
