@@ -607,15 +607,29 @@ def run_ours(args):
         cap_ms = time_kernel(cap_fn, 12, torch)
         cap_bytes = mean_nodes * K_FEATS * 4 + nnz_mean * 8 + mean_nodes * 4      # x once; (col, val) per non-zero + a count per row
         cap_gbs = cap_bytes / (cap_ms * 1e-3) / 1e9
-        roof_cap = {"kernel": "k_xw_scan<64, capture, no product> (bigcn_batch_prepare: the one pass over the dense x of a step, "
-                              "run a step ahead on a lowest-priority stream)",
+        # the same pass as an UNPACED kernel (LDG form, all the bytes in flight the SMs can hold): what the pass can do alone
+        lib.bigcn_debug_set.argtypes = [C.c_int, C.c_int]
+        lib.bigcn_debug_set.restype = None
+        lib.bigcn_debug_set(10, 9)
+        unp_ms = time_kernel(cap_fn, 12, torch)
+        lib.bigcn_debug_set(10, 0)
+        unp_gbs = cap_bytes / (unp_ms * 1e-3) / 1e9
+        roof_cap = {"kernel": "k_x_capture_tma<6,2> (bigcn_batch_prepare: the one pass over the dense x of a step, run a step ahead "
+                              "beside the current step's chain; TMA-fed, persistent, PACED: at most 48 KB in flight per SM)",
                     "bound": "hbm", "achieved": cap_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": cap_gbs / hbm_peak,
                     "traffic": None, "peak_source": peak_src, "ms": cap_ms, "algorithmic_bytes": cap_bytes,
                     "frac_of_8TBs_nominal": cap_gbs / 8000.0,
-                    "frac_note": "a read-only stream: `peak` is the measured COPY bandwidth (read + write traffic, MEASURED_PEAKS.json), "
-                                 "which a pure read stream can exceed slightly; against the ~8 TB/s nominal figure see frac_of_8TBs_nominal",
+                    "paced_by_design": "the pass has a whole step (~0.33 ms) to read 625 MB, i.e. needs ~1.9 TB/s; it keeps 6 warps x 2 x 4 KB "
+                                       "of bulk copies in flight per SM (192 threads, 48 KB of shared memory) so that the step's "
+                                       "latency-bound kernels do not queue behind a saturated memory system.  `unpaced` below is the same "
+                                       "pass as a kernel that takes the whole machine: faster alone, but the step is 7 % slower with it "
+                                       "(tools/stepbench.py 10:0,9: 0.337 vs 0.362 ms)",
+                    "unpaced": {"kernel": "k_xw_scan<64, capture, no product> (LDG form, 3.9 k short CTAs)", "ms": unp_ms,
+                                "achieved": unp_gbs, "frac": unp_gbs / hbm_peak, "frac_of_8TBs_nominal": unp_gbs / 8000.0,
+                                "note": "a read-only stream: `peak` is the measured COPY bandwidth (read + write traffic), which a "
+                                        "pure read stream can exceed slightly"},
                     "note": "timed alone (CUDA events, 12 launches over the 3 batches in rotation, each 625 MB >> L2); inside the "
-                            "step it shares the machine with the step's own kernels and stretches to ~190 us"}
+                            "step it runs the whole length of the step underneath the chain (~320 us)"}
     # the weight gradient dW1 = T1^T X
     ts = [torch.randn(n, 128, device=dev) for n in nodes]
     dws = [torch.empty(64, K_FEATS, device=dev) for _ in range(2)]
@@ -689,9 +703,10 @@ def run_ours(args):
             roof_fwd["traffic"] = traffic[key]["bytes"]
             roof_fwd["traffic_note"] = f"ncu capture of {key} at N = {traffic[key]['nodes']} nodes; algorithmic bytes above are the mean over the rotation"
             if roof_cap is not None and "k_x_capture" in traffic:
-                roof_cap["traffic"] = traffic["k_x_capture"]["bytes"]
-                roof_cap["traffic_note"] = (f"ncu --set full capture at N = {traffic['k_x_capture']['nodes']} nodes "
-                                            "(profiles/r02_prof_step_summary.txt); algorithmic bytes above are the mean over the rotation")
+                key = "k_x_capture_tma" if "k_x_capture_tma" in traffic else "k_x_capture"
+                roof_cap["traffic"] = traffic[key]["bytes"]
+                roof_cap["traffic_note"] = (f"ncu --set full capture of {key} at N = {traffic[key]['nodes']} nodes "
+                                            "(profiles/); algorithmic bytes above are the mean over the rotation")
         if args.gemm_mode in ("tf32x3", "mixed"):
             roof_bwd["traffic"] = traffic["k_dw_tc"]["bytes"]
             roof_bwd["traffic_note"] = f"GEMM kernel only, ncu capture at N = {traffic['k_dw_tc']['nodes']} nodes"
@@ -746,6 +761,9 @@ def run_ours(args):
             "gpu_launches": args.steps * (launches_per_step(nodes[0], 2, True, args.gemm_mode, K_FEATS)
                                           + (1 if prefetch and sparse_ok else 0)),
             "roofline": roof, "final_loss": final_loss, "cuda_graphs": graph_info,
+            "step_vs_hbm_floor": {"floor_ms": nodes[0] * K_FEATS * 4 / (hbm_peak * 1e9) * 1e3, "step_ms": ms / args.steps,
+                                  "frac": nodes[0] * K_FEATS * 4 / (hbm_peak * 1e9) * 1e3 / (ms / args.steps),
+                                  "note": "x read once at the measured HBM peak vs the whole step (graph prep + fwd + bwd + Adam)"},
             "per_rank": {"gpu_ms_per_step": [round(v, 4) for v in per_rank],
                          "cpu_enqueue_ms_per_step": [round(v, 4) for v in per_rank_cpu],
                          "nodes_per_step_mean": sum(nodes) / len(nodes)}}
