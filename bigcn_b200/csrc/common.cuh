@@ -77,6 +77,22 @@ __device__ __forceinline__ float4 ldg_stream_f4_ef(const float* p, uint64_t pol)
   return r;
 }
 
+// Two independent IEEE fp32 fmas in ONE instruction (sm_100 FFMA2, scalar x pair + pair): (z0, z1) = s * (w0, w1) + (z0, z1).
+// Same results bit for bit as two fmaf(); half the issue slots -- the sweeps and 64 x 64 products here are issue-bound.
+// (mul.rn.f32x2 + add.rn.f32x2 is NOT used for the separately-rounded sums of the EXACT sweeps: ptxas contracts the pair.)
+__device__ __forceinline__ void fma2(float& z0, float& z1, float s, float w0, float w1) {
+  unsigned long long a, b, c, d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(w0), "f"(w1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(z0), "f"(z1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(d));
+}
+__device__ __forceinline__ void fma4(float4& z, float s, const float4& w) {
+  fma2(z.x, z.y, s, w.x, w.y);
+  fma2(z.z, z.w, s, w.z, w.w);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

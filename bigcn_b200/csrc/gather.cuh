@@ -41,10 +41,7 @@ __device__ __forceinline__ void acc_add(float4& acc, float w, const float4& v) {
   if (EXACT) {
     wadd4(acc, w, v);
   } else {
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+    fma4(acc, w, v);
   }
 }
 __device__ __forceinline__ unsigned half_mask(int half) { return half ? 0xffff0000u : 0x0000ffffu; }

@@ -229,10 +229,7 @@ __device__ __forceinline__ float4 matvec_smem(const float4& av, const float* __r
     for (int c = 0; c < 4; ++c) {
       const float s = comp4(a4, c);
       const float4 w = ld4(sW + (4 * k4 + c) * H + 4 * sub);
-      z.x = fmaf(s, w.x, z.x);
-      z.y = fmaf(s, w.y, z.y);
-      z.z = fmaf(s, w.z, z.z);
-      z.w = fmaf(s, w.w, z.w);
+      fma4(z, s, w);
     }
   }
   __syncwarp(hm);
@@ -255,14 +252,8 @@ __device__ __forceinline__ void matvec2_smem(const float4& a0, const float4& a1,
     for (int c = 0; c < 4; ++c) {
       const float s0 = comp4(p4, c), s1 = comp4(q4, c);
       const float4 w = ld4(sW + (4 * k4 + c) * H + 4 * sub);
-      z0.x = fmaf(s0, w.x, z0.x);
-      z0.y = fmaf(s0, w.y, z0.y);
-      z0.z = fmaf(s0, w.z, z0.z);
-      z0.w = fmaf(s0, w.w, z0.w);
-      z1.x = fmaf(s1, w.x, z1.x);
-      z1.y = fmaf(s1, w.y, z1.y);
-      z1.z = fmaf(s1, w.z, z1.z);
-      z1.w = fmaf(s1, w.w, z1.w);
+      fma4(z0, s0, w);
+      fma4(z1, s1, w);
     }
   }
   __syncwarp(hm);
@@ -336,12 +327,7 @@ struct PostMix {
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (q0 + u < cnt) {
-              racc.x = fmaf(vv[u], w[u].x, racc.x);
-              racc.y = fmaf(vv[u], w[u].y, racc.y);
-              racc.z = fmaf(vv[u], w[u].z, racc.z);
-              racc.w = fmaf(vv[u], w[u].w, racc.w);
-            }
+            if (q0 + u < cnt) fma4(racc, vv[u], w[u]);
           }
         }
         __syncwarp(hm);
@@ -640,9 +626,10 @@ __global__ void __launch_bounds__(256) k_outer64(OuterArgs a) {
       const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
       const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        fma2(acc[i][0], acc[i][1], uu[i], vv[0], vv[1]);
+        fma2(acc[i][2], acc[i][3], uu[i], vv[2], vv[3]);
+      }
     }
     __syncthreads();
   }

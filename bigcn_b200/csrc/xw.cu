@@ -76,14 +76,11 @@ __global__ void __launch_bounds__(256, MINB) k_xw_scan(const float* __restrict__
             const float* wr = wt + k * NOUT + lane * V;
             if (V == 4) {
               const float4 w = *reinterpret_cast<const float4*>(wr);
-              acc[0] = fmaf(val, w.x, acc[0]);
-              acc[1] = fmaf(val, w.y, acc[1]);
-              acc[2] = fmaf(val, w.z, acc[2]);
-              acc[3] = fmaf(val, w.w, acc[3]);
+              fma2(acc[0], acc[1], val, w.x, w.y);
+              fma2(acc[2], acc[3], val, w.z, w.w);
             } else {
               const float2 w = *reinterpret_cast<const float2*>(wr);
-              acc[0] = fmaf(val, w.x, acc[0]);
-              acc[1] = fmaf(val, w.y, acc[1]);
+              fma2(acc[0], acc[1], val, w.x, w.y);
             }
           }
         }
@@ -309,14 +306,11 @@ __global__ void __launch_bounds__(256) k_xw_csr(XSparse xs, const float* __restr
         const float* wr = wt + (int64_t)kk * NOUT + lane * V;
         if (V == 4) {
           const float4 w = *reinterpret_cast<const float4*>(wr);
-          acc[0] = fmaf(vv, w.x, acc[0]);
-          acc[1] = fmaf(vv, w.y, acc[1]);
-          acc[2] = fmaf(vv, w.z, acc[2]);
-          acc[3] = fmaf(vv, w.w, acc[3]);
+          fma2(acc[0], acc[1], vv, w.x, w.y);
+          fma2(acc[2], acc[3], vv, w.z, w.w);
         } else {
           const float2 w = *reinterpret_cast<const float2*>(wr);
-          acc[0] = fmaf(vv, w.x, acc[0]);
-          acc[1] = fmaf(vv, w.y, acc[1]);
+          fma2(acc[0], acc[1], vv, w.x, w.y);
         }
       }
     }
@@ -353,14 +347,11 @@ __global__ void __launch_bounds__(256) k_xw_ell(const int32_t* __restrict__ cnt,
       const float* wr = wt + k * NOUT + lane * V;
       if (V == 4) {
         const float4 w = *reinterpret_cast<const float4*>(wr);
-        acc[0] = fmaf(val, w.x, acc[0]);
-        acc[1] = fmaf(val, w.y, acc[1]);
-        acc[2] = fmaf(val, w.z, acc[2]);
-        acc[3] = fmaf(val, w.w, acc[3]);
+        fma2(acc[0], acc[1], val, w.x, w.y);
+        fma2(acc[2], acc[3], val, w.z, w.w);
       } else {
         const float2 w = *reinterpret_cast<const float2*>(wr);
-        acc[0] = fmaf(val, w.x, acc[0]);
-        acc[1] = fmaf(val, w.y, acc[1]);
+        fma2(acc[0], acc[1], val, w.x, w.y);
       }
     };
     if (c <= XS_ELL) {
