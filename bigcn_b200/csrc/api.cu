@@ -36,9 +36,11 @@ struct SideCtx {
   cudaStream_t side2;  // high priority, a second short chain beside the first (root columns; dW2b)
   cudaStream_t low;    // lowest priority: work nobody waits for until much later (column sort of X)
   cudaStream_t prep[2];  // lowest priority: bigcn_batch_prepare of the NEXT batch, beside the whole current step
-  cudaStream_t bw[2];    // lowest priority: the backward's dW2 / db chains -- nobody waits for them before the optimiser,
+  cudaStream_t tail;     // the step stream's priority: the last two launches of the column sort (knob 12 bit 1)
+  cudaStream_t bwlo[2];  // the prep streams' priority: the dW2 / db chains (knob 12 bit 0, the default)
+  cudaStream_t bw[2];    // one level above (knob 12 = 0): the backward's dW2 / db chains -- nobody waits for them before the optimiser,
                          // so they must not take SM slots from G1 -> T1 -> dW1 (the caller's stream, see ops.step_stream)
-  cudaEvent_t ev[12];
+  cudaEvent_t ev[14];
   bool ok;
 };
 static SideCtx* side_ctx() {
@@ -54,17 +56,20 @@ static SideCtx* side_ctx() {
     // four levels when the device has them (B200: 0 .. -3, lower = more urgent):
     //   hi      side / side2   short chains the main chain is about to wait for (graph prep inline, root columns)
     //   lo - 2  [the caller's step stream: bigcn_b200.ops.step_stream]
-    //   lo - 1  low / bw       this step's column sort of x and dW2 / db chains: needed before the step ends
-    //   lo      prep           the NEXT batch's preparation: needed only by the next step
+    //   lo - 1  low            this step's column sort of x: the dW1 sweep at the end of the chain waits for it
+    //   lo      prep / bwlo    the NEXT batch's preparation; this step's dW2 / db chains (only the optimiser waits for them)
     const int mid = lo - 1 < hi ? hi : lo - 1;
     c.ok = cudaStreamCreateWithPriority(&c.s.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, mid) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.prep[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.prep[1], cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.tail, cudaStreamNonBlocking, lo - 2 < hi ? hi : lo - 2) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.bwlo[0], cudaStreamNonBlocking, lo) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&c.bwlo[1], cudaStreamNonBlocking, lo) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.bw[0], cudaStreamNonBlocking, mid) == cudaSuccess &&
            cudaStreamCreateWithPriority(&c.bw[1], cudaStreamNonBlocking, mid) == cudaSuccess;
-    for (int i = 0; i < 12 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 14 && c.ok; ++i) c.ok = cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) == cudaSuccess;
     const char* e = getenv("BIGCN_NO_SIDE_STREAM");
     if (e && e[0] == '1') c.ok = false;
   }
@@ -354,14 +359,15 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     if (!prepared) stream_after(sc, 1, ss, st);
     stream_after(sc, 7, s2, st);
   }
-  bool side_busy = false;
+  bool side_busy = false, sort_tail = false;
   if (sparse && prepared && N > 0 && !o->skip_wgrad_prep) {   // the CSR came prepared; sort it by column beside the rest of this step
     if (sc) stream_after(sc, 2, st, sc->low);
     w.xs.flags = flags;
+    sort_tail = sc && (debug_knob(12) & 2);
     if (csr_in) {
-      if (int rc = xs_sort_csc(w.xs, sc ? sc->low : st)) return rc;
+      if (int rc = xs_sort_csc(w.xs, sc ? sc->low : st, sort_tail)) return rc;
     } else {
-      if (int rc = xs_build_csc(w.xs, bt->x, true, sc ? sc->low : st)) return rc;
+      if (int rc = xs_build_csc(w.xs, bt->x, true, sc ? sc->low : st, sort_tail)) return rc;
     }
     side_busy = sc != nullptr;
   }
@@ -425,7 +431,13 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   }
   // the column sort keeps running on the low-priority stream: features_backward waits for it
   // right before the sweep that needs it (event 3)
-  if (side_busy) cudaEventRecord(sc->ev[3], sc->low);
+  if (side_busy && sort_tail) {   // the passes fill gaps at low priority; the last two launches must not queue behind the dW2 chains
+    stream_after(sc, 12, sc->low, sc->tail);
+    if (int rc = xs_sort_finish(w.xs, sc->tail)) return rc;
+    cudaEventRecord(sc->ev[3], sc->tail);
+  } else if (side_busy) {
+    cudaEventRecord(sc->ev[3], sc->low);
+  }
   return 0;
 }
 
@@ -519,8 +531,9 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   ColsumArgs db2_reduce{};
   const bool join_late = o->gemm_mode == BIGCN_GEMM_SPARSE && phase == 0;
   SideCtx* sc = side_ctx();
-  cudaStream_t ss = sc ? (debug_knob(7) ? sc->s.side : sc->bw[0]) : st;
-  cudaStream_t s2 = sc ? (debug_knob(7) ? sc->side2 : sc->bw[1]) : st;
+  const bool bw_lo = debug_knob(12) & 1;
+  cudaStream_t ss = sc ? (debug_knob(7) ? sc->s.side : bw_lo ? sc->bwlo[0] : sc->bw[0]) : st;
+  cudaStream_t s2 = sc ? (debug_knob(7) ? sc->side2 : bw_lo ? sc->bwlo[1] : sc->bw[1]) : st;
   if (phase == 2) goto dw1_only;
   // 1. per-tree scaled gradient gs = grad_feat / n_b and db2 (from the readout's positive counts)
   {
@@ -723,6 +736,10 @@ static void knob_defaults() {
   // 0 = backward on the tensor cores (k_h64_tc<bwd>); 2 = forward and backward; 3 = forward only.  Measured at the
   // bench configuration (tools/stepbench.py 8:0,1,2,3): 0.3706 / 0.3697 / 0.3744 / 0.3719 ms per step.
   g_knob[8] = 1;
+  // knob 12: bit 0 = the backward's dW2 / db chains run at the prep streams' priority (below this step's column sort,
+  // which then no longer queues behind them); bit 1 = the sort's last two launches at the step stream's priority.
+  // tools/stepbench.py 12:0,1,2,3 -> 0.3347 / 0.3319 / 0.3347 / 0.3328 ms per step.
+  g_knob[12] = 1;
   if (const char* e = getenv("BIGCN_MIX_TC")) {
     if (e[0] == 'b' && e[1] == 'w') g_knob[8] = 0;        // "bwd"
     else if (e[0] == 'b') g_knob[8] = 2;                  // "both"
@@ -749,8 +766,8 @@ extern "C" int bigcn_join_internal_streams(bigcn_stream_t stream) {
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[2], 0);
   cudaEventRecord(sc->ev[6], sc->side2);
   cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[6], 0);
-  for (int i = 0; i < 2; ++i) {
-    cudaEventRecord(sc->ev[11], sc->bw[i]);
+  for (cudaStream_t s : {sc->bw[0], sc->bw[1], sc->bwlo[0], sc->bwlo[1], sc->tail}) {
+    cudaEventRecord(sc->ev[11], s);
     cudaStreamWaitEvent((cudaStream_t)stream, sc->ev[11], 0);
   }
   return batch_prepare_join((cudaStream_t)stream);

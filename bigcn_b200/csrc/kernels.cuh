@@ -152,9 +152,11 @@ struct XSparse {
 int debug_knob(int key);
 int64_t xs_capacity(int64_t N, int64_t K);
 XSparse xs_carve(Carver& c, int64_t N, int64_t K);
-int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st);
+// st_tail: leave the last two launches (xs_sort_finish) to the caller
+int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st, bool st_tail = false);
 int xs_build_csr(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st);
-int xs_sort_csc(const XSparse& x, cudaStream_t st);
+int xs_sort_csc(const XSparse& x, cudaStream_t st, bool st_tail = false);
+int xs_sort_finish(const XSparse& x, cudaStream_t st);
 int dw_sparse(const XSparse& x, const float* t, int64_t ldt, int n_out, float* dw_a, float* dw_b, int64_t ldw,
               cudaStream_t st);
 int xw_fp32_capture(const float*, int64_t, int64_t, const float*, int, float*, int64_t, const XSparse&, cudaStream_t);

@@ -372,9 +372,8 @@ int xs_build_csr(const XSparse& x, const float* x_dense, bool from_capture, cuda
 }
 
 // CSR -> column-sorted CSC (stable LSD radix sort of the column keys) + hub-column lists
-int xs_sort_csc(const XSparse& x, cudaStream_t st) {
+int xs_sort_csc(const XSparse& x, cudaStream_t st, bool st_tail) {
   const int nblk = (int)xs_nblk(x.cap);
-  const int cap_ctas = num_sms() * 4;
   const int passes = radix_passes_for(x.K);
   cudaMemsetAsync(x.hist + (int64_t)256 * nblk, 0, 4 * 256 * sizeof(int32_t), st);   // digit totals
   int grid_keys = nblk;   // blocks past the live keys return at once
@@ -386,6 +385,13 @@ int xs_sort_csc(const XSparse& x, cudaStream_t st) {
     k_xs_scatter<<<grid_keys, RSX_THREADS, 0, st>>>(x, p & 1, 8 * p, nblk);
     BIGCN_CHECK_LAUNCH("k_xs_scatter");
   }
+  return st_tail ? 0 : xs_sort_finish(x, st);
+}
+
+// the last two launches of the column sort (on their own so that a caller can give them a more urgent stream)
+int xs_sort_finish(const XSparse& x, cudaStream_t st) {
+  const int cap_ctas = num_sms() * 4;
+  const int passes = radix_passes_for(x.K);
   int gf = (int)ceil_div(x.cap, 256);
   if (gf > cap_ctas) gf = cap_ctas;
   k_xs_finish<<<gf, 256, 0, st>>>(x, passes & 1);
@@ -397,9 +403,9 @@ int xs_sort_csc(const XSparse& x, cudaStream_t st) {
 }
 
 // everything between the row capture / a caller's CSR and the column-sorted copy
-int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st) {
+int xs_build_csc(const XSparse& x, const float* x_dense, bool from_capture, cudaStream_t st, bool st_tail) {
   if (int rc = xs_build_csr(x, x_dense, from_capture, st)) return rc;
-  return xs_sort_csc(x, st);
+  return xs_sort_csc(x, st, st_tail);
 }
 
 // ---- dW1[o, k] = sum_{(i,v) in column k} v * T[i, o]: CSR sweep over the columns ------------

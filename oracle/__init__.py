@@ -22,6 +22,16 @@ instead: the hand-checkable 5-node vector below, torch's own CPU ops wherever th
 and an independent dense-matrix derivation of the published formula D^-1/2 (A + I) D^-1/2 X W in fp64
 (tests/test_oracle.py::test_gcnconv_matches_dense_normalised_adjacency).
 
+Pinned this round -- everything the reference's OWN files decide: tests/golden/ref_wiring.npz holds outputs of
+model/Twitter/BiGCN_Twitter.py:19-131 (imported unmodified) and of the classes of model/Weibo/BiGCN_Weibo.py:16-89,
+run in the build container over dense stand-ins of the two absent wheels (an explicit [N, N] normalised adjacency
+for GCNConv, index_add_ / count for scatter_mean -- independent of this package; tests/golden/
+make_ref_wiring_golden.py).  tests/test_oracle.py::test_oracle_matches_reference_model_code holds the restated
+modules to them in eval AND training mode (same torch generator state -> same F.dropout masks), log-probs <= 2e-6,
+loss, all ten gradients (so the autograd effect of ``copy.copy`` at :44 is the reference's, not an assumption);
+tests/test_gpu_parity.py::test_reference_model_code_fixture holds the CUDA path to them directly.  What remains
+unpinned is only the inside of the two library calls (gcn_norm's conventions, summation order).
+
 Pinned exception: ``evaluate_oracle`` (tools/evaluate.py) is checked against
 outputs of the reference's own file (tests/golden/make_evaluate_golden.py).
 For the GCN path the only pin available is the hand-checkable 5-node known-answer vector of

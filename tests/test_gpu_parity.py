@@ -366,6 +366,32 @@ def test_golden_small_batch(dev):
                            batch=b.batch.cpu(), rootindex=b.rootindex.cpu()), dev)
 
 
+def test_reference_model_code_fixture(dev):
+    """tests/golden/ref_wiring.npz: outputs of the reference's own BiGCN_Twitter.py:19-131 (run over dense stand-ins of
+    the two absent wheels, tests/golden/make_ref_wiring_golden.py) -- eval-mode log-probs, nll loss and all ten
+    gradients -- against the CUDA path directly, no oracle in between."""
+    import bigcn_b200
+    ref = np.load(os.path.join(GOLD, "ref_wiring.npz"))
+    gold = json.load(open(os.path.join(GOLD, "bigcn_small.json")))
+    b = Batch(x=torch.from_numpy(unhex(gold["x"]).reshape(gold["N"], gold["K"])),
+              edge_index=torch.tensor(gold["edge_index"]).reshape(2, -1),
+              BU_edge_index=torch.tensor(gold["BU_edge_index"]).reshape(2, -1),
+              batch=torch.tensor(gold["batch"]), rootindex=torch.tensor(gold["rootindex"]),
+              y=torch.from_numpy(ref["twitter/y"])).to(dev)
+    for mode in ("fp32", "auto"):
+        m = bigcn_b200.BiGCN(gold["K"], 64, 64, dev, num_classes=4, gemm_mode=mode).to(dev).eval()
+        m.load_state_dict({k[14:]: torch.from_numpy(ref[k]) for k in ref.files if k.startswith("twitter/state/")})
+        got = m(b)
+        loss = torch.nn.functional.nll_loss(got, b.y)
+        loss.backward()
+        m.check_inputs()
+        assert rel_err(got, torch.from_numpy(ref["twitter/eval/logp"])) < LOGP_TOL, mode
+        assert abs(float(loss.detach()) - float(ref["twitter/eval/loss"].item())) < 1e-5
+        for k, p in m.named_parameters():
+            e = rel_err(p.grad, torch.from_numpy(ref[f"twitter/eval/grad/{k}"]))
+            assert e < GRAD_TOL, f"{mode} {k}: {e:.3e}"
+
+
 @pytest.mark.parametrize("deg_by", ["target", "source"])
 def test_eval_logits_and_grads_edge_cases(dev, deg_by):
     K, cases = edge_cases()

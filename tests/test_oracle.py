@@ -114,6 +114,44 @@ def test_golden_small_batch_reproduces():
     assert g["deg"].tolist() == gold["graph_td"]["deg"]
 
 
+def _wiring_case(name):
+    """tests/golden/ref_wiring.npz: the reference's own model files run over dense stand-ins of the two absent wheels
+    (tests/golden/make_ref_wiring_golden.py) on the bigcn_small.json batch."""
+    ref = np.load(os.path.join(GOLD, "ref_wiring.npz"))
+    gold = json.load(open(os.path.join(GOLD, "bigcn_small.json")))
+    b = Data(x=torch.from_numpy(unhex(gold["x"]).reshape(gold["N"], gold["K"])),
+             edge_index=torch.tensor(gold["edge_index"]).reshape(2, -1),
+             BU_edge_index=torch.tensor(gold["BU_edge_index"]).reshape(2, -1),
+             batch=torch.tensor(gold["batch"]), rootindex=torch.tensor(gold["rootindex"]),
+             y=torch.from_numpy(ref[f"{name}/y"]))
+    state = {k[len(name) + 7:]: torch.from_numpy(ref[k]) for k in ref.files if k.startswith(f"{name}/state/")}
+    return ref, gold, b, state
+
+
+@pytest.mark.parametrize("name,hid,cls", [("twitter", 64, bigcn_oracle.BiGCN), ("weibo", 16, bigcn_oracle.Net)])
+@pytest.mark.parametrize("loops", [False, True])
+def test_oracle_matches_reference_model_code(name, hid, cls, loops):
+    """The restated modules against the outputs of BiGCN_Twitter.py:19-131 / BiGCN_Weibo.py:16-89 themselves: eval and
+    training mode (the same torch generator state feeds F.dropout: TD's mask is drawn first, then BU's), loss and all
+    ten gradients.  Differences left: summation order inside GCNConv (dense matrix there, index_add_ here)."""
+    ref, gold, b, state = _wiring_case(name)
+    m = cls(gold["K"], hid, hid, reference_loops=loops)
+    m.load_state_dict(state)
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        m.zero_grad()
+        torch.manual_seed(int(ref[f"{name}/{mode}/dropout_seed"].item()))
+        logp = m(b)
+        loss = torch.nn.functional.nll_loss(logp, b.y)
+        loss.backward()
+        np.testing.assert_allclose(logp.detach().numpy(), ref[f"{name}/{mode}/logp"], rtol=0, atol=2e-6)
+        assert abs(float(loss.detach()) - float(ref[f"{name}/{mode}/loss"].item())) <= 2e-6
+        for k, p in m.named_parameters():
+            want = ref[f"{name}/{mode}/grad/{k}"]
+            np.testing.assert_allclose(p.grad.numpy(), want, rtol=0, atol=1e-6 + 1e-5 * float(np.abs(want).max()),
+                                       err_msg=f"{name} {mode} {k}")
+
+
 def test_reference_loops_equal_vectorised_form():
     b = make_batch("twitter15", 3, seed=3, train=True, in_feats=64)
     torch.manual_seed(0)
