@@ -151,7 +151,7 @@ constexpr int CAP_CHUNK = 1024;   // floats per chunk
 template <int CAPW, int CAPS>
 __global__ void __launch_bounds__(32 * CAPW) k_x_capture_tma(const float* __restrict__ x, int64_t N, int64_t K,
                                                              int32_t* __restrict__ xs_cnt, int32_t* __restrict__ xs_col,
-                                                             float* __restrict__ xs_val) {
+                                                             float* __restrict__ xs_val, int no_fence, int row_mod) {
   extern __shared__ __align__(128) float cap_smem[];
   float (*buf)[CAPS][CAP_CHUNK] = reinterpret_cast<float (*)[CAPS][CAP_CHUNK]>(cap_smem);
   __shared__ __align__(8) uint64_t full[CAPW][CAPS];
@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(32 * CAPW) k_x_capture_tma(const float* __rest
     const int nfl = (int)min((int64_t)CAP_CHUNK, K - (int64_t)pc * CAP_CHUNK);
     const uint32_t fb = smem_u32(&full[warp][s]);
     mbar_expect_tx(fb, (uint32_t)nfl * 4);
-    bulk_g2s_hint(smem_u32(&buf[warp][s][0]), x + prow * K + (int64_t)pc * CAP_CHUNK, (uint32_t)nfl * 4, fb, pol);
+    // row_mod: timing experiment only (tools/stepbench.py set:14=64): every row reads one of the first row_mod rows, i.e.
+    // the pass runs out of L2 -- same footprint and instruction stream, no HBM traffic
+    const int64_t srow = row_mod > 0 ? prow % row_mod : prow;
+    bulk_g2s_hint(smem_u32(&buf[warp][s][0]), x + srow * K + (int64_t)pc * CAP_CHUNK, (uint32_t)nfl * 4, fb, pol);
     if (++pc == nchunk) { pc = 0; prow += stride; }
   };
   if (lane == 0)
@@ -187,33 +190,62 @@ __global__ void __launch_bounds__(32 * CAPW) k_x_capture_tma(const float* __rest
     for (int c = 0; c < nchunk; ++c) {
       const int nfl = (int)min((int64_t)CAP_CHUNK, K - (int64_t)c * CAP_CHUNK);
       mbar_wait(smem_u32(&full[warp][s]), ph);
-      const float* b = &buf[warp][s][0];
+      // lane l owns floats [32 l, 32 l + 32) of the chunk: eight 16-byte reads, rotated by the lane so that the eight
+      // lanes of a quarter-warp hit eight different bank groups; one bit per non-zero
+      const float* seg = &buf[warp][s][0] + lane * 32;
+      unsigned mask = 0;
 #pragma unroll
-      for (int u = 0; u < CAP_CHUNK / 128; ++u) {
-        const int f0 = u * 128 + lane * 4;
-        const float4 v = f0 < nfl ? *reinterpret_cast<const float4*>(b + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool any = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
-        if (__ballot_sync(FULL_MASK, any) == 0u) continue;
+      for (int u = 0; u < 8; ++u) {
+        const int pu = (u + lane) & 7;
+        const float4 v = *reinterpret_cast<const float4*>(seg + 4 * pu);
+        const unsigned m4 = (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
+        mask |= m4 << (4 * pu);
+      }
+      const int valid = nfl - lane * 32;   // the last chunk of a row is short: what lies behind it is a previous chunk
+      if (valid < 32) mask = valid <= 0 ? 0u : (mask & ((1u << valid) - 1u));
+      if (__ballot_sync(FULL_MASK, mask != 0u)) {
+        // The slots of a row follow the order of the fused scan (k_xw_scan: per block of 128 floats, component q of the
+        // float4s first, then the lane), because the product sums in slot order and must not depend on which pass
+        // captured the row.  Four lanes own one block of 128: lane l holds float4s 8 (l & 3) .. + 8 of block l >> 2.
+        // Counts per component, one byte each (<= 8 per lane, <= 32 per block and component, <= 128 per block):
+        unsigned cq = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float comp = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
-          unsigned m = __ballot_sync(FULL_MASK, comp != 0.f);
-          while (m) {
-            const int sl = __ffs(m) - 1;
-            m &= m - 1;
-            const float val = __shfl_sync(FULL_MASK, comp, sl);
-            if (lane == 0 && nz < XS_ELL) {
-              xs_col[row * XS_ELL + nz] = (int32_t)((int64_t)c * CAP_CHUNK + u * 128 + sl * 4 + q);
-              xs_val[row * XS_ELL + nz] = val;
-            }
-            ++nz;
+        for (int q = 0; q < 4; ++q) cq |= (unsigned)__popc(mask & (0x11111111u << q)) << (8 * q);
+        unsigned gincl = cq;   // inclusive scan over the four lanes of the block
+#pragma unroll
+        for (int d = 1; d < 4; d <<= 1) {
+          const unsigned t = __shfl_up_sync(FULL_MASK, gincl, d, 4);
+          if ((lane & 3) >= d) gincl += t;
+        }
+        const unsigned gt = __shfl_sync(FULL_MASK, gincl, 3, 4);            // the block's counts per component
+        const unsigned qbase = (gt << 8) + (gt << 16) + (gt << 24);         // byte q: entries of components < q (< 128)
+        const int bt = (int)((gt & 0xff) + ((gt >> 8) & 0xff) + ((gt >> 16) & 0xff) + (gt >> 24));
+        int binc = bt;         // inclusive scan of the block totals over the eight blocks (every lane of a block holds bt)
+#pragma unroll
+        for (int d = 4; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FULL_MASK, binc, d);
+          if (lane >= d) binc += t;
+        }
+        const int base = nz + binc - bt;
+        unsigned next = qbase + (gincl - cq);   // byte q: this lane's next slot of component q inside the block
+        const int col0 = c * CAP_CHUNK + lane * 32;
+        while (mask) {
+          const int p = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int sh = 8 * (p & 3);
+          const int slot = base + (int)((next >> sh) & 0xffu);
+          next += 1u << sh;
+          if (slot < XS_ELL) {
+            xs_col[row * XS_ELL + slot] = col0 + p;
+            xs_val[row * XS_ELL + slot] = seg[p];
           }
         }
+        nz += __shfl_sync(FULL_MASK, binc, 31);
       }
       // the stage is read: hand it back to the TMA engine (generic-proxy reads before the async-proxy write)
       __syncwarp();
       if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!no_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(s);
       }
       if (++s == CAPS) { s = 0; ph ^= 1; }
@@ -238,16 +270,22 @@ int x_capture(const float* x, int64_t N, int64_t K, const XSparse& xs, cudaStrea
       cudaFuncSetAttribute(k_x_capture_tma<W_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);              \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    k_x_capture_tma<W_, S_><<<grid, 32 * W_, smem, st>>>(x, N, K, xs.cnt, xs.ell_col, xs.ell_val);                     \
+    k_x_capture_tma<W_, S_><<<grid, 32 * W_, smem, st>>>(x, N, K, xs.cnt, xs.ell_col, xs.ell_val, debug_knob(13), debug_knob(14)); \
   } while (0)
     switch (debug_knob(10)) {
       case 1: CAP_LAUNCH(4, 2); break;
-      case 2: CAP_LAUNCH(4, 3); break;
+      case 2: CAP_LAUNCH(6, 2); break;
       case 3: CAP_LAUNCH(8, 2); break;
       case 4: CAP_LAUNCH(4, 4); break;
       case 5: CAP_LAUNCH(6, 3); break;
       case 6: CAP_LAUNCH(8, 3); break;
-      default: CAP_LAUNCH(6, 2); break;
+      case 7: CAP_LAUNCH(7, 2); break;
+      case 8: CAP_LAUNCH(2, 6); break;
+      case 10: CAP_LAUNCH(3, 4); break;
+      case 11: CAP_LAUNCH(2, 4); break;
+      case 12: CAP_LAUNCH(2, 8); break;
+      case 13: CAP_LAUNCH(1, 12); break;
+      default: CAP_LAUNCH(4, 3); break;
     }
 #undef CAP_LAUNCH
     BIGCN_CHECK_LAUNCH("k_x_capture_tma");

@@ -41,7 +41,10 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
-    spec = [a for a in sys.argv[1:]] or ["1:0,1,2,3,4,5,6", "2:0,1,2,3,4,5", "3:0,1,2,3,4"]
+    for a in [a for a in sys.argv[1:] if a.startswith("set:")]:      # "set:13=1": holds for the whole run (combinations)
+        key, v = a[4:].split("=")
+        lib.bigcn_debug_set(int(key), int(v))
+    spec = [a for a in sys.argv[1:] if not a.startswith("set:")] or ["1:0,1,2,3,4,5,6", "2:0,1,2,3,4,5", "3:0,1,2,3,4"]
     print(f"baseline {run():.4f} ms/step", flush=True)
     for s in spec:
         key, vals = s.split(":")
