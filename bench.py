@@ -614,16 +614,17 @@ def run_ours(args):
         unp_ms = time_kernel(cap_fn, 12, torch)
         lib.bigcn_debug_set(10, 0)
         unp_gbs = cap_bytes / (unp_ms * 1e-3) / 1e9
-        roof_cap = {"kernel": "k_x_capture_tma<6,2> (bigcn_batch_prepare: the one pass over the dense x of a step, run a step ahead "
+        roof_cap = {"kernel": "k_x_capture_tma<4,3> (bigcn_batch_prepare: the one pass over the dense x of a step, run a step ahead "
                               "beside the current step's chain; TMA-fed, persistent, PACED: at most 48 KB in flight per SM)",
                     "bound": "hbm", "achieved": cap_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": cap_gbs / hbm_peak,
                     "traffic": None, "peak_source": peak_src, "ms": cap_ms, "algorithmic_bytes": cap_bytes,
                     "frac_of_8TBs_nominal": cap_gbs / 8000.0,
-                    "paced_by_design": "the pass has a whole step (~0.33 ms) to read 625 MB, i.e. needs ~1.9 TB/s; it keeps 6 warps x 2 x 4 KB "
-                                       "of bulk copies in flight per SM (192 threads, 48 KB of shared memory) so that the step's "
-                                       "latency-bound kernels do not queue behind a saturated memory system.  `unpaced` below is the same "
-                                       "pass as a kernel that takes the whole machine: faster alone, but the step is 7 % slower with it "
-                                       "(tools/stepbench.py 10:0,9: 0.337 vs 0.362 ms)",
+                    "paced_by_design": "the pass has a whole step (~0.33 ms) to read 625 MB, i.e. needs ~1.9 TB/s; it keeps 4 warps x 3 x 4 KB "
+                                       "of bulk copies in flight per SM (128 threads, 48 KB of shared memory): what it must not take from "
+                                       "the step's latency-bound kernels is SM slots, registers and shared memory (the same pass fed from "
+                                       "L2-resident rows leaves the step time unchanged, so HBM contention is not what the chain feels).  "
+                                       "`unpaced` below is the same pass as a kernel that takes the whole machine: faster alone, but the "
+                                       "step is 10 % slower with it (tools/stepbench.py 10:0,9: 0.326 vs 0.362 ms)",
                     "unpaced": {"kernel": "k_xw_scan<64, capture, no product> (LDG form, 3.9 k short CTAs)", "ms": unp_ms,
                                 "achieved": unp_gbs, "frac": unp_gbs / hbm_peak, "frac_of_8TBs_nominal": unp_gbs / 8000.0,
                                 "note": "a read-only stream: `peak` is the measured COPY bandwidth (read + write traffic), which a "

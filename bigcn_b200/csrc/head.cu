@@ -272,6 +272,19 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
                        const float* __restrict__ seg_lr, int n_seg, double beta1d, double beta2d,
                        float eps, float wd, float gscale, int64_t* step_count) {
   __shared__ float s_bc[2];
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  // the first quad of every thread is on its way while thread 0 works out the bias corrections
+  float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), gv0 = pv0, mv0 = pv0, vv0 = pv0;
+  if (tid < n4) {
+    pv0 = reinterpret_cast<float4*>(p)[tid];
+    gv0 = reinterpret_cast<const float4*>(g)[tid];
+    mv0 = reinterpret_cast<float4*>(m)[tid];
+    vv0 = reinterpret_cast<float4*>(v)[tid];
+  }
   if (threadIdx.x == 0) {   // the double-precision pow() runs once per block, not per thread
     const double step = (double)(*(volatile int64_t*)step_count + 1);
     s_bc[0] = (float)(1.0 - pow(beta1d, step));
@@ -297,16 +310,14 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     const float denom = sqrtf(vi) / bc2s + eps;
     return pv - (lr / bc1) * (mi / denom);
   };
-  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
-                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
-  const int64_t n4 = vec ? n / 4 : 0;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = tid; q < n4; q += nth) {
-    float4 pv = reinterpret_cast<float4*>(p)[q];
-    const float4 gv = reinterpret_cast<const float4*>(g)[q];
-    float4 mv = reinterpret_cast<float4*>(m)[q];
-    float4 vv = reinterpret_cast<float4*>(v)[q];
+    float4 pv = pv0, gv = gv0, mv = mv0, vv = vv0;
+    if (q != tid) {
+      pv = reinterpret_cast<float4*>(p)[q];
+      gv = reinterpret_cast<const float4*>(g)[q];
+      mv = reinterpret_cast<float4*>(m)[q];
+      vv = reinterpret_cast<float4*>(v)[q];
+    }
     // lr groups may change inside a quad only if a segment end is not a multiple of 4
     const float lr0 = lr_of(4 * q + 0), lr3 = lr_of(4 * q + 3);
     const bool same = lr0 == lr3;

@@ -142,11 +142,12 @@ int xw_fp32_capture(const float* x, int64_t N, int64_t K, const float* wt, int n
 
 // ---- the background pass over x (bigcn_batch_prepare): capture only, fed by the TMA engine -----------------------------
 // One small persistent CTA per SM, CAPW warps, one ROW each: lane 0 of a warp streams its row into the warp's ring in shared
-// memory with cp.async.bulk (4 KB chunks = the 1024-column blocks of the fused scan, L2 evict-first), the warp ballots the
-// chunks and record the non-zeros in exactly the order of k_xw_scan (same ELL contents).  The point is the footprint:
-// 160 threads, ~40 registers, 32 KB of shared memory per SM and at most CAPW * CAPS * 4 KB in flight per SM, so the pass
-// runs the whole length of a step at a third of the HBM bandwidth without taking slots or registers from, or queueing the
-// memory system ahead of, the step's own latency-bound kernels.
+// memory with cp.async.bulk (4 KB chunks = the 1024-column blocks of the fused scan, L2 evict-first); every lane owns 32
+// consecutive floats of a chunk, builds a bit mask of its non-zeros, and two warp scans place them in the row's ELL slots in
+// exactly the slot order of k_xw_scan (same ELL contents; tools/capture_check.py).  The point is the footprint: 4 warps x 3
+// stages by default -- 128 threads, 42 registers, 48 KB of shared memory per SM and at most CAPW * CAPS * 4 KB in flight per
+// SM -- so the pass runs the whole length of a step without taking slots or registers from the step's own latency-bound
+// kernels (the chain feels the footprint of the pass, not its HBM traffic).
 constexpr int CAP_CHUNK = 1024;   // floats per chunk
 template <int CAPW, int CAPS>
 __global__ void __launch_bounds__(32 * CAPW) k_x_capture_tma(const float* __restrict__ x, int64_t N, int64_t K,
