@@ -83,6 +83,28 @@ class DeviceForest:
         return DeviceForest(node_ptr, edge_ptr, cat(es, np.int32), cat(ed, np.int32), x_ptr, cat(xc, np.int32),
                             cat(xv, np.float32), roots, ys, k, device)
 
+    @staticmethod
+    def from_npz_dir(fold_x, data_path, device, treeDic=None, lower=2, upper=100000):
+        """Pack the reference's preprocessed dataset: one ``<id>.npz`` per tree under ``data_path`` with ``x`` [n, K],
+        ``edgeindex`` [2, e] = [parent; child], ``rootindex`` and ``y`` (written by Process/getTwittergraph.py:67-72,
+        read per item and per epoch by ``BiGraphDataset.__getitem__``, Process/dataset.py:64-99 -- here once).  The id
+        filter is ``BiGraphDataset.__init__``'s (dataset.py:48-59): PHEME paths take ``fold_x`` as is, the others keep
+        the ids found in ``treeDic`` whose tree has ``lower .. upper`` nodes.  ``self.ids`` holds the kept ids in
+        order: tree t of the forest is ``ids[t]``."""
+        import os
+        from .data import Data
+        if str(data_path).find("PHEME") == -1 and treeDic is not None:
+            fold_x = [i for i in fold_x if i in treeDic and lower <= len(treeDic[i]) <= upper]
+        trees = []
+        for i in fold_x:
+            z = np.load(os.path.join(data_path, str(i) + ".npz"), allow_pickle=True)
+            ei = np.asarray(z["edgeindex"], np.int64).reshape(2, -1)
+            trees.append(Data(x=torch.tensor(np.asarray(z["x"]), dtype=torch.float32), edge_index=torch.from_numpy(ei),
+                              rootindex=torch.tensor([int(z["rootindex"])]), y=torch.tensor([int(z["y"])])))
+        forest = DeviceForest.from_data_list(trees, device)
+        forest.ids = list(fold_x)
+        return forest
+
     def batch(self, tree_ids, td_droprate=0.0, bu_droprate=0.0, seed=0) -> Batch:
         """The collated batch of ``tree_ids`` (host sequence, in batch order) with DropEdge at the
         given rates, on the device; ``data.x`` is a SparseX."""

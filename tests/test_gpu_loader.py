@@ -220,3 +220,58 @@ def test_synthetic_forest_generator_is_a_valid_dataset(dev):
     f = synth_forest_device("pheme", 200, dev, seed=5)
     b = forest_slice_batch(f, 17, 60)
     assert b.x.shape[1] == 768 and int(b.rootindex.numel()) == 43 and bool((b.batch[b.rootindex] == torch.arange(43, device=dev)).all())
+
+
+def _ref_dataset():
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    return os.path.join(gold, "ref_dataset"), np.load(os.path.join(gold, "ref_dataset.npz"))
+
+
+def _ref_items(ref, tag, n):
+    from bigcn_b200.data import Data
+    return [Data(**{k: torch.from_numpy(ref[f"{tag}/{j}/{k}"]) for k in ("x", "edge_index", "BU_edge_index", "rootindex", "y")})
+            for j in range(n)]
+
+
+def test_npz_dataset_against_the_reference_dataset_class(dev):
+    """tests/golden/ref_dataset.npz: what the reference's own ``BiGraphDataset.__getitem__`` (Process/dataset.py:64-99)
+    returned for the ``.npz`` trees under tests/golden/ref_dataset/ (tests/golden/make_ref_dataset_golden.py).
+    ``DeviceForest.from_npz_dir`` reads the same files: same id filter, and without DropEdge the assembled batch is the
+    PyG collate of the reference's items, bit for bit; with DropEdge 0.2 / 0.3 every tree keeps exactly as many edges
+    as the reference kept, as an order-preserving subset, BU drawn from the flipped list independently of TD."""
+    import bigcn_b200
+    d, ref = _ref_dataset()
+    fold_x = [str(i) for i in ref["fold_x"]]
+    sizes = {"1001": 9, "1002": 1, "1003": 14, "1004": 5, "1005": 2, "1006": 23, "1007": 7}
+    treeDic = {i: {j: {} for j in range(n)} for i, n in sizes.items()}
+    forest = bigcn_b200.DeviceForest.from_npz_dir(fold_x, d, dev, treeDic=treeDic, lower=2)
+    assert forest.ids == [str(i) for i in ref["nodrop/kept_ids"]] and forest.in_feats == int(ref["K"])
+    nt = len(forest.ids)
+    items = _ref_items(ref, "nodrop", nt)
+    for order in (list(range(nt)), [4, 0, 5, 2]):
+        got, want = forest.batch(order), collate([items[i] for i in order])
+        for k in ("edge_index", "BU_edge_index", "batch", "rootindex", "y"):
+            assert torch.equal(getattr(got, k).cpu(), getattr(want, k)), k
+        assert torch.equal(got.x.to_dense().cpu(), want.x)
+    dropped = _ref_items(ref, "drop", nt)
+    got = forest.batch(list(range(nt)), 0.2, 0.3, seed=11)
+    node_off = np.concatenate([[0], np.cumsum([int(t.x.shape[0]) for t in items])])
+    for name, flip in (("edge_index", False), ("BU_edge_index", True)):
+        e = getattr(got, name).cpu().numpy()
+        tree_of_edge = np.searchsorted(node_off, e[0], side="right") - 1
+        for t in range(nt):
+            mine = e[:, tree_of_edge == t] - node_off[t]
+            assert mine.shape[1] == getattr(dropped[t], name).shape[1], (name, t)      # the reference's count
+            full = items[t].edge_index.numpy()[::-1] if flip else items[t].edge_index.numpy()
+            pos, j = [], 0
+            for c in range(mine.shape[1]):      # an order-preserving subset of the tree's own list
+                while j < full.shape[1] and not (full[:, j] == mine[:, c]).all():
+                    j += 1
+                assert j < full.shape[1], (name, t)
+                pos.append(j)
+                j += 1
+    # the reference's own dropped lists are such subsets too (the fixture is what it claims to be)
+    for t in range(nt):
+        assert dropped[t].edge_index.shape[1] == int(items[t].edge_index.shape[1] * (1 - 0.2))
+        assert dropped[t].BU_edge_index.shape[1] == int(items[t].edge_index.shape[1] * (1 - 0.3))

@@ -267,3 +267,32 @@ def test_gcnconv_matches_dense_normalised_adjacency():
     cnt = np.maximum(m.sum(1, keepdims=True), 1.0)
     got = gcn_oracle.scatter_mean(torch.from_numpy(src), torch.from_numpy(batch), 5).numpy()
     assert np.abs(got - (m / cnt) @ src).max() <= 1e-14
+
+
+def test_reference_dataset_fixture_contract():
+    """tests/golden/ref_dataset.npz (outputs of the reference's BiGraphDataset, Process/dataset.py:45-99): the input
+    contract bigcn_b200.data restates -- BU = flipped TD list, DropEdge keeps int(e * (1 - rate)) positions as an
+    order-preserving subset per direction, the id filter drops single-post trees and unknown ids -- and the host-side
+    ``drop_edge`` follows the same count rule."""
+    ref = np.load(os.path.join(GOLD, "ref_dataset.npz"))
+    kept = [str(i) for i in ref["nodrop/kept_ids"]]
+    assert kept == ["1001", "1003", "1004", "1005", "1006", "1007"]
+    rng = np.random.default_rng(0)
+    for j in range(len(kept)):
+        ei, bu = ref[f"nodrop/{j}/edge_index"], ref[f"nodrop/{j}/BU_edge_index"]
+        assert (bu == ei[::-1]).all() and ref[f"nodrop/{j}/x"].dtype == np.float32
+        z = np.load(os.path.join(GOLD, "ref_dataset", kept[j] + ".npz"))
+        assert (z["edgeindex"] == ei).all() and int(z["rootindex"]) == int(ref[f"nodrop/{j}/rootindex"][0])
+        d_td, d_bu = ref[f"drop/{j}/edge_index"], ref[f"drop/{j}/BU_edge_index"]
+        e = ei.shape[1]
+        assert d_td.shape[1] == int(e * (1 - 0.2)) and d_bu.shape[1] == int(e * (1 - 0.3))
+        for sub, full in ((d_td, ei), (d_bu, bu)):
+            pos = 0
+            for c in range(sub.shape[1]):
+                while not (full[:, pos] == sub[:, c]).all():
+                    pos += 1
+                pos += 1
+        mine = drop_edge(Data(x=torch.from_numpy(ref[f"nodrop/{j}/x"]), edge_index=torch.from_numpy(ei.copy()),
+                              BU_edge_index=torch.from_numpy(bu.copy()), rootindex=torch.tensor([0]), y=torch.tensor([0])),
+                         0.2, 0.3, rng)
+        assert mine.edge_index.shape[1] == d_td.shape[1] and mine.BU_edge_index.shape[1] == d_bu.shape[1]
