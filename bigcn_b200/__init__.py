@@ -14,10 +14,12 @@ from .trainer import FusedTrainer  # noqa: E402,F401
 from . import data, ops, torch_ops  # noqa: E402,F401  (torch_ops registers torch.ops.bigcn_b200.*)
 from .ops import SparseX, host_dense_to_csr  # noqa: E402,F401
 from .loader import DeviceForest  # noqa: E402,F401
+from . import ingest  # noqa: E402,F401
+from .ingest import forest_from_raw  # noqa: E402,F401
 from .metrics import EvalCounts  # noqa: E402,F401
 from .feeder import HostFeeder  # noqa: E402,F401
 from .training import train_GCN  # noqa: E402,F401
 from .checkpoint import EarlyStopping, EarlyStopping2class, make_checkpoint  # noqa: E402,F401
 
 __all__ = ["GCNConv", "TDrumorGCN", "BUrumorGCN", "BiGCN", "Net", "FusedTrainer", "BigcnError",
-           "SparseX", "host_dense_to_csr", "DeviceForest", "EvalCounts", "HostFeeder", "train_GCN", "EarlyStopping", "EarlyStopping2class", "make_checkpoint", "data", "ops", "torch_ops"]
+           "SparseX", "host_dense_to_csr", "DeviceForest", "forest_from_raw", "ingest", "EvalCounts", "HostFeeder", "train_GCN", "EarlyStopping", "EarlyStopping2class", "make_checkpoint", "data", "ops", "torch_ops"]
