@@ -487,10 +487,15 @@ def run_ours(args):
         """A loader loop over the device-resident dataset: every step assembles its batch on the device (collate + a
         fresh DropEdge) and enqueues the step; the loss read back every step is the PREVIOUS step's, so the host
         enqueues step i while the device still runs step i-1 (these batches are new objects every step: no CUDA-graph
-        replay, the host's enqueue rate is what this route measures)."""
+        replay; batch i+1 is assembled before step i is enqueued and handed to it as next_data, so its graph prep,
+        root columns and CSR build run underneath step i)."""
         j = i % N_ROTATE
-        bd = forest.batch(ids_of[j], 0.2, 0.2, seed=i)
-        return late_forest(tr.step(bd, b_global=b_global, node_id_base=id_base[j]))
+        if forest_it["i"] != i:             # (re)start the loader at step i
+            forest_it["gen"] = forest.batches([ids_of[k % N_ROTATE] for k in range(i, i + 4096)], 0.2, 0.2, seeds=range(i, i + 4096))
+        bd, nxt = next(forest_it["gen"])
+        forest_it["i"] = i + 1
+        return late_forest(tr.step(bd, b_global=b_global, node_id_base=id_base[j], next_data=nxt))
+    forest_it = {"i": -1, "gen": None}
 
     small_bytes = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in small_keys)
     routes = {}

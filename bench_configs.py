@@ -50,9 +50,9 @@ def c2_epoch(torch, bigcn_b200, dev, epochs=4, warm=2):
         model.train()
         tev.reset()
         order = rng.permutation(train_ids)
-        for bi, lo in enumerate(range(0, len(order), 128)):
-            data = forest.batch(order[lo:lo + 128], 0.2, 0.2, seed=ep * 4096 + bi)
-            tr.step(data)
+        lists = [order[lo:lo + 128] for lo in range(0, len(order), 128)]
+        for data, nxt in forest.batches(lists, 0.2, 0.2, seeds=[ep * 4096 + bi for bi in range(len(lists))]):
+            tr.step(data, next_data=nxt)
             tev.update(tr.last_logp, data.y)
         state["train_loss"], _, _ = tev.epoch_means()            # host read (BiGCN_Twitter.py:199-200)
         model.eval()
@@ -158,7 +158,7 @@ def c5_powerlaw(torch, bigcn_b200, dev, rank, world, pg, max_over_ranks, total_t
     f = synth_forest_device("powerlaw", per_rank, dev, seed=50 + rank)
     forest = bigcn_b200.DeviceForest.from_device_arrays(f)
     out = {"workload": f"{total_trees} power-law reply trees (Pareto(2) sizes, 2..10000 nodes), K=5000 BoW kept as CSR in HBM, "
-                       f"one pass: DeviceForest.batch (collate + DropEdge 0.2/0.2 on the device) + FusedTrainer.step; the trees "
+                       f"one pass: DeviceForest.batches (collate + DropEdge 0.2/0.2 on the device) + FusedTrainer.step(batch, next_data=next batch); the trees "
                        f"are split over the {world} rank(s) (strong scaling), gradients reduced every step",
            "trees_per_rank": per_rank, "nodes_per_rank": int(f["node_ptr"][-1]), "by_batch": {}}
     for bsz in (128, 4096):
@@ -173,8 +173,9 @@ def c5_powerlaw(torch, bigcn_b200, dev, rank, world, pg, max_over_ranks, total_t
         ids = np.arange(per_rank, dtype=np.int64)
 
         def run(n0, n1):
-            for s in range(n0, n1):
-                tr.step(forest.batch(ids[s * bsz:(s + 1) * bsz], 0.2, 0.2, seed=s), b_global=bsz * world)
+            lists = [ids[s * bsz:(s + 1) * bsz] for s in range(n0, n1)]
+            for data, nxt in forest.batches(lists, 0.2, 0.2, seeds=range(n0, n1)):
+                tr.step(data, b_global=bsz * world, next_data=nxt)
         run(0, min(20, nsteps))                   # warm-up on the first batches (they are streamed again below)
         tr.check_inputs()
         if world > 1:

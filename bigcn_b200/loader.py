@@ -34,6 +34,12 @@ class DeviceForest:
         self.root_local, self.y = t(root_local, torch.int32), t(y, torch.int64)
         self.num_trees = len(self.h_node_ptr) - 1
         self._stage, self._turn = None, 0
+        self._cache_ptrs()
+
+    def _cache_ptrs(self):
+        # the dataset arrays never move: their addresses are looked up once, not on every batch
+        for k in ("node_ptr", "edge_ptr", "edge_src", "edge_dst", "x_ptr", "x_col", "x_val", "root_local", "y"):
+            setattr(self, "_p_" + k, _p(getattr(self, k)))
 
     @staticmethod
     def from_device_arrays(f):
@@ -52,6 +58,7 @@ class DeviceForest:
         self.root_local, self.y = f["root_local"], f["y"].to(torch.int64)
         self.num_trees = len(self.h_node_ptr) - 1
         self._stage, self._turn = None, 0
+        self._cache_ptrs()
         return self
 
     @staticmethod
@@ -105,45 +112,56 @@ class DeviceForest:
         forest.ids = list(fold_x)
         return forest
 
+    def batches(self, id_lists, td_droprate=0.0, bu_droprate=0.0, seeds=None):
+        """The loader loop (the reference's ``DataLoader`` over ``BiGraphDataset``, BiGCN_Twitter.py:168): yields
+        ``(batch_i, batch_i+1)`` -- the second one already assembled (None after the last) so that
+        ``FusedTrainer.step(batch_i, next_data=batch_i+1)`` can run batch i+1's weight-independent half (graph prep,
+        root columns, CSR of x) underneath step i.  ``seeds[i]``: DropEdge seed of batch i (default i)."""
+        id_lists = list(id_lists)
+        seeds = list(range(len(id_lists))) if seeds is None else list(seeds)
+        nxt = self.batch(id_lists[0], td_droprate, bu_droprate, seed=seeds[0]) if id_lists else None
+        for i in range(len(id_lists)):
+            cur = nxt
+            nxt = self.batch(id_lists[i + 1], td_droprate, bu_droprate, seed=seeds[i + 1]) if i + 1 < len(id_lists) else None
+            yield cur, nxt
+
     def batch(self, tree_ids, td_droprate=0.0, bu_droprate=0.0, seed=0) -> Batch:
         """The collated batch of ``tree_ids`` (host sequence, in batch order) with DropEdge at the
         given rates, on the device; ``data.x`` is a SparseX."""
         L.require_device()
         ids = np.asarray(tree_ids, np.int64)
         b = len(ids)
-        n_t = self.h_node_ptr[ids + 1] - self.h_node_ptr[ids]
-        e_t = self.h_edge_ptr[ids + 1] - self.h_edge_ptr[ids]
-        z_t = self.h_x_ptr_at_tree[ids + 1] - self.h_x_ptr_at_tree[ids]
-        # int(length * (1 - droprate)), dataset.py:72,84 (Python float arithmetic = IEEE double)
-        keep = lambda rate: e_t if rate <= 0 else np.floor(e_t.astype(np.float64) * (1.0 - rate)).astype(np.int64)  # noqa: E731
-        offs = np.zeros((5, b + 1), np.int64)
-        offs[0, :b] = ids
-        for row, v in zip(range(1, 5), (n_t, keep(td_droprate), keep(bu_droprate), z_t)):
-            offs[row, 1:] = np.cumsum(v)
-        n, e_td, e_bu, nnz = (int(offs[r, -1]) for r in range(1, 5))
         dev = self.device
-        # offsets through a ring of pinned staging buffers; a slot is rewritten only after the H2D copy that last
-        # read it has completed (the epoch loop never synchronises the host, so the device may lag many batches)
+        # The per-tree offsets live in a ring of pinned staging buffers which the assembly kernels read IN PLACE
+        # (pinned memory is device-addressable: 5 (b + 1) int64 cross PCIe inside the kernels, no copy, no device
+        # buffer).  A slot is rewritten only after the kernels that last read it have completed: the epoch loop never
+        # synchronises the host, so the device may lag many batches.
         need = 5 * (b + 1)
         if self._stage is None or self._stage[0][0].numel() < need:
             if self._stage is not None:
-                for _, ev in self._stage:
+                for _, ev, _ in self._stage:
                     if ev is not None:
                         ev.synchronize()
-            self._stage = [[torch.empty(max(need, 4096), dtype=torch.int64).pin_memory(), None] for _ in range(4)]
+            self._stage = []
+            for _ in range(4):
+                t = torch.empty(max(need, 4096), dtype=torch.int64).pin_memory()
+                self._stage.append([t, None, t.numpy()])
         self._turn = (self._turn + 1) % len(self._stage)
         slot = self._stage[self._turn]
         if slot[1] is not None:
             slot[1].synchronize()
-        hbuf = slot[0]
-        hbuf[:need].copy_(torch.from_numpy(offs.reshape(-1)))
-        d_offs = torch.empty(need, dtype=torch.int64, device=dev)
-        d_offs.copy_(hbuf[:need], non_blocking=True)
-        if slot[1] is None:
-            slot[1] = torch.cuda.Event()
-        slot[1].record()
-        d_offs = d_offs.view(5, b + 1)
-        # one int64 block [edge_index | BU_edge_index | batch | rootindex | y], one int32 block [x ptr | x col]
+        offs = slot[2][:need].reshape(5, b + 1)
+        ids1 = ids + 1
+        e_t = self.h_edge_ptr[ids1] - self.h_edge_ptr[ids]
+        offs[0, :b] = ids
+        offs[1:, 0] = 0
+        np.cumsum(self.h_node_ptr[ids1] - self.h_node_ptr[ids], out=offs[1, 1:])
+        # int(length * (1 - droprate)), dataset.py:72,84 (Python float arithmetic = IEEE double)
+        for row, rate in ((2, td_droprate), (3, bu_droprate)):
+            np.cumsum(e_t if rate <= 0 else np.floor(e_t.astype(np.float64) * (1.0 - rate)).astype(np.int64), out=offs[row, 1:])
+        np.cumsum(self.h_x_ptr_at_tree[ids1] - self.h_x_ptr_at_tree[ids], out=offs[4, 1:])
+        n, e_td, e_bu, nnz = (int(v) for v in offs[1:, b])
+        # one int64 block [edge_index | BU_edge_index | batch | rootindex | y], one 32-bit block [x ptr | x col | x val]
         blk = torch.empty(2 * e_td + 2 * e_bu + n + 2 * b, dtype=torch.int64, device=dev)
         o = 0
         ei = blk[o:o + 2 * e_td].view(2, e_td); o += 2 * e_td
@@ -151,18 +169,20 @@ class DeviceForest:
         batch = blk[o:o + n]; o += n
         root = blk[o:o + b]; o += b
         y = blk[o:o + b]
-        iblk = torch.empty(n + 1 + nnz, dtype=torch.int32, device=dev)
+        iblk = torch.empty(n + 1 + 2 * nnz, dtype=torch.int32, device=dev)
         if b == 0:
             iblk.zero_()
-        ox_ptr, ox_col = iblk[:n + 1], iblk[n + 1:]
-        ox_val = torch.empty(nnz, dtype=torch.float32, device=dev)
-        row = lambda r: d_offs[r].data_ptr()  # noqa: E731
-        check(lib().bigcn_assemble_batch(_p(self.node_ptr), _p(self.edge_ptr), _p(self.edge_src), _p(self.edge_dst),
-                                         _p(self.x_ptr), _p(self.x_col), _p(self.x_val), _p(self.root_local), _p(self.y),
-                                         row(0), row(1), row(2), row(3), row(4), b, e_td, e_bu,
-                                         int(seed) & ((1 << 64) - 1), _p(ei), _p(bu), _p(batch), _p(root), _p(y),
-                                         _p(ox_ptr), _p(ox_col), _p(ox_val), _stream()), "assemble_batch")
-        out = Batch(x=SparseX(ox_ptr, ox_col, ox_val, (n, self.in_feats)), edge_index=ei, BU_edge_index=bu,
-                    batch=batch, rootindex=root, y=y)
-        out._keep = d_offs
-        return out
+        ox_ptr, ox_col = iblk[:n + 1], iblk[n + 1:n + 1 + nnz]
+        ox_val = iblk[n + 1 + nnz:].view(torch.float32)
+        cur = torch.cuda.current_stream(dev)
+        base, pitch = slot[0].data_ptr(), 8 * (b + 1)
+        check(lib().bigcn_assemble_batch(self._p_node_ptr, self._p_edge_ptr, self._p_edge_src, self._p_edge_dst,
+                                         self._p_x_ptr, self._p_x_col, self._p_x_val, self._p_root_local, self._p_y,
+                                         base, base + pitch, base + 2 * pitch, base + 3 * pitch, base + 4 * pitch,
+                                         b, e_td, e_bu, int(seed) & ((1 << 64) - 1), _p(ei), _p(bu), _p(batch), _p(root),
+                                         _p(y), _p(ox_ptr), _p(ox_col), _p(ox_val), cur.cuda_stream), "assemble_batch")
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record(cur)
+        return Batch(x=SparseX(ox_ptr, ox_col, ox_val, (n, self.in_feats)), edge_index=ei, BU_edge_index=bu,
+                     batch=batch, rootindex=root, y=y)

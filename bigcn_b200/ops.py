@@ -11,7 +11,9 @@ from ._lib import H, Dims, BatchPtrs, Params, Graph, Opts, check, lib
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # the raw handle of torch's current stream on the current device (what torch.cuda.current_stream().cuda_stream
+    # returns, without building a Stream object: this runs on every library call)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _p(t):

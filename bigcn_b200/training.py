@@ -2,7 +2,7 @@
 with this library's pieces in place of the host-side ones -- same structure, same bookkeeping,
 no per-batch host synchronisation:
 
-  loadBiData + DataLoader(shuffle=True) per epoch (:160-169)  -> DeviceForest.batch(ids, droprates, seed)
+  loadBiData + DataLoader(shuffle=True) per epoch (:160-169)  -> DeviceForest.batches(id lists, droprates, seeds)
   forward / nll_loss / backward / optimizer.step (:183-189)    -> FusedTrainer.step
   loss.item(), pred.eq(y).sum().item() per batch (:188-191)    -> EvalCounts.update (device), read once per epoch
   evaluation4class per validation batch + np.mean (:217-246)   -> EvalCounts.epoch_means
@@ -57,9 +57,10 @@ def train_GCN(model, forest, train_ids, test_ids, TDdroprate, BUdroprate, lr, we
             model.train()
             train_ev.reset()
             order = rng.permutation(train_ids)                        # DataLoader(shuffle=True), :168
-            for bi, lo in enumerate(range(0, len(order), batchsize)):
-                data = forest.batch(order[lo:lo + batchsize], TDdroprate, BUdroprate, seed=(seed << 20) + epoch * 4096 + bi)
-                tr.step(data)                                          # :183-189
+            lists = [order[lo:lo + batchsize] for lo in range(0, len(order), batchsize)]
+            seeds = [(seed << 20) + epoch * 4096 + bi for bi in range(len(lists))]
+            for data, nxt in forest.batches(lists, TDdroprate, BUdroprate, seeds):   # batch i+1 is prepared under step i
+                tr.step(data, next_data=nxt)                           # :183-189
                 train_ev.update(tr.last_logp, data.y)                  # :188-191, no .item()
             # np.mean over batches of the per-batch loss / accuracy (:199-200): one read per epoch
             tl, ta, _ = train_ev.epoch_means()

@@ -413,7 +413,9 @@ int bigcn_dense_rows_to_csr(const float* x, int64_t N, int64_t K, const int32_t*
  * the TD and, independently, of the BU list, order preserved) and PyG's collate
  * (BiGCN_Twitter.py:168: concatenate, offset the *index keys by the node count, batch vector) do on
  * the host.  The caller computes the four offset arrays on the host from the tree sizes
- * (td_off/bu_off: kept edges per tree) -- no synchronisation.  Outputs: the five attributes
+ * (td_off/bu_off: kept edges per tree) -- no synchronisation; tree_id and the four offset arrays [B+1]
+ * may be device memory or PINNED HOST memory the kernels read in place (then the caller must not rewrite
+ * them before the launches have completed).  Outputs: the five attributes
  * forward(data) reads, with data.x as CSR (ox_ptr/ox_col/ox_val), and y. */
 int bigcn_assemble_batch(const int64_t* node_ptr, const int64_t* edge_ptr, const int32_t* edge_src,
                          const int32_t* edge_dst, const int64_t* x_ptr, const int32_t* x_col,

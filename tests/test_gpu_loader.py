@@ -275,3 +275,34 @@ def test_npz_dataset_against_the_reference_dataset_class(dev):
     for t in range(nt):
         assert dropped[t].edge_index.shape[1] == int(items[t].edge_index.shape[1] * (1 - 0.2))
         assert dropped[t].BU_edge_index.shape[1] == int(items[t].edge_index.shape[1] * (1 - 0.3))
+
+
+def test_batches_lookahead_loop_equals_plain_loop(dev):
+    """DeviceForest.batches hands every step its successor (next_data): the successor's weight-independent half runs
+    underneath the step -- same parameters, moments and losses, bit for bit, as assembling and stepping one by one."""
+    import bigcn_b200
+    trees = trees_for(k=5000, sizes=(30, 1, 200, 17, 90, 5, 2, 350, 44, 8, 120, 60))
+    forest = bigcn_b200.DeviceForest.from_data_list(trees, dev)
+    rng = np.random.default_rng(2)
+    lists = [rng.choice(len(trees), 6, replace=False) for _ in range(7)]
+    seeds = list(range(50, 57))
+    res = []
+    for look in (False, True):
+        torch.manual_seed(3)
+        m = bigcn_b200.BiGCN(5000, 64, 64, dev, gemm_mode="sparse", validate="off").to(dev).train()
+        tr = bigcn_b200.FusedTrainer(m)
+        losses = []
+        if look:
+            seen = 0
+            for b, nxt in forest.batches(lists, 0.2, 0.2, seeds):
+                losses.append(tr.step(b, next_data=nxt).clone())
+                seen += 1
+                assert (nxt is None) == (seen == len(lists))
+        else:
+            for ids, sd in zip(lists, seeds):
+                losses.append(tr.step(forest.batch(ids, 0.2, 0.2, seed=sd)).clone())
+        tr.check_inputs()
+        res.append((tr.flat.clone(), tr.exp_avg.clone(), torch.cat(losses)))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    assert list(forest.batches([])) == []
