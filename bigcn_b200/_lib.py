@@ -49,7 +49,7 @@ class Opts(C.Structure):
     _fields_ = [("training", C.c_int32), ("p_drop", C.c_float), ("seed", C.c_uint64),
                 ("deg_by", C.c_int32), ("gemm_mode", C.c_int32), ("dir_mask", C.c_int32),
                 ("bwd_phase", C.c_int32), ("skip_wgrad_prep", C.c_int32), ("fused_tail", C.c_int32),
-                ("seed_dev", c_ptr)]
+                ("seed_dev", c_ptr), ("dense_roots", C.c_int32)]
 
 
 class BigcnError(RuntimeError):

@@ -139,6 +139,7 @@ struct FeatWs {
   float* gs[2];             // [B][64] grad_feat / n_b
   unsigned long long* keep[2];  // [N] bit t: root slot t of the node's tree survived dropout (train mode)
   float* S[2];              // [(blocks + B)][DW2B_CAP][64] masked T2 sums per (row block, tree, slot)
+  float* rootR[2];          // [splits][N][64] column-split partials of the dense-root product (rootdense.cu), small batches
   float* ro_part;           // readout slice partials
   XSparse xs;               // row-sparse view of X (gemm_mode SPARSE)
   void* prep_ws; size_t prep_bytes;
@@ -216,8 +217,15 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes, voi
   for (int d = 0; d < 2; ++d) w.dP[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.pos[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   for (int d = 0; d < 2; ++d) w.gs[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
-  for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>((size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H);
+  {   // sparse roots: masked T2 sums per (row block, tree, slot); dense roots (rootdense.cu): [segments][K][64] partials
+    const size_t s_sparse = (size_t)(dw2b_blocks(N) + B) * DW2B_CAP * H, s_dense = (size_t)K * H;
+    for (int d = 0; d < 2; ++d) w.S[d] = c.take<float>(s_sparse > s_dense ? s_sparse : s_dense);
+  }
   for (int d = 0; d < 2; ++d) w.keep[d] = c.take<unsigned long long>((size_t)(N > 0 ? N : 1));
+  {
+    const int64_t rows = 8 * (N > 0 ? N : 1);
+    for (int d = 0; d < 2; ++d) w.rootR[d] = c.take<float>((size_t)(rows < RD_CAP_ROWS ? rows : RD_CAP_ROWS) * H);
+  }
   w.ro_part = c.take<float>(readout_scratch_floats(N, B, 2));
   // the weight-independent part: the caller's prepared buffer, or the tail of this workspace
   const size_t step_bytes = align_up(c.off, 256);
@@ -316,6 +324,21 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
   //    second side stream: the root rows' positive columns and, without dropout, the per-tree root
   //    projection (needs the transposed W2b) -- a short chain of its own, not behind the graph prep
   if (sc) stream_after(sc, 6, st, s2);
+  // training on DENSE root features (opts.dense_roots; PHEME): the root half of conv2.lin as a tiled product into z, beside
+  // the X * W product; the mix kernel then adds it instead of walking K-long column lists per node
+  const bool dense_roots = dropping && o->dense_roots != 0 && bt->x != nullptr && N > 0;
+  const int root_splits = dense_roots ? (debug_knob(15) == 1 ? 1 : root_dense_splits(N, K)) : 0;   // knob 15 = 1: one split (tests)
+  if (dense_roots) {
+    RootDenseArgs a{};
+    a.x = bt->x; a.rootindex = bt->rootindex; a.batch = bt->batch;
+    a.N = N; a.B = B; a.K = K; a.node_id_base = bt->node_id_base;
+    a.ksplit = root_splits;
+    for (int q = 0; q < dirs.n; ++q) {
+      const int d = dirs.id[q];   // one split: straight into z (the mix kernel reads a node's R before it writes the node's z)
+      a.w2bT[q] = w.w2bT[d]; a.r[q] = root_splits > 1 ? w.rootR[d] : w.z[d]; a.drop[q] = make_drop(o, d);
+    }
+    if (int rc = root_dense_forward(a, dirs.n, s2)) return rc;
+  }
   {
     RootNzArgs a{bt->x, bt->rootindex, N, B, K, w.rnz_cnt, w.rnz_col, w.rnz_val, flags,
                  w.slot, w.overflow, DW2B_CAP};
@@ -326,7 +349,7 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
     } else {
       if (int rc = root_nz_launch(a, s2)) return rc;
     }
-    if (mix_tc_available() && !o->skip_wgrad_prep) {   // hi / lo split of W2a, W2a^T for the tensor-core 64 x 64 products
+    if (mix_tc_available() && !o->skip_wgrad_prep && debug_knob(8) != 1) {   // hi / lo split of W2a, W2a^T for the tensor-core 64 x 64 products (knob 8 = 1, the default: FFMA forms, no split needed)
       const float* w2[2] = {dir_w2(pr, dirs.id[0]), dirs.n == 2 ? dir_w2(pr, dirs.id[1]) : nullptr};
       if (int rc = mix_tc_split_weights(w2, dirs.n, H + K, w.w2a_split, s2)) return rc;
     }
@@ -395,11 +418,13 @@ int features_forward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const bigc
       m.w2aT = w.w2aT[d]; m.w2bT = w.w2bT[d]; m.P = w.P[d];
       m.h1 = w.h1[d]; m.a1 = w.a1[d]; m.z = w.z[d];
       m.drop = make_drop(o, d);
-      m.keep = w.keep[d];
+      m.keep = dense_roots ? nullptr : w.keep[d];
     }
+    a.root_splits = root_splits;
+    for (int q = 0; q < dirs.n; ++q) a.root_r[q] = root_splits > 1 ? w.rootR[dirs.id[q]] : w.z[dirs.id[q]];
     // the tcgen05 form of the forward product (sweep + activate, then k_h64_tc) is measured slower than the fused
     // sweep at these sizes: kept behind a knob for the A/B
-    if (mix_tc_available() && (debug_knob(8) == 2 || debug_knob(8) == 3)) {
+    if (mix_tc_available() && !dense_roots && (debug_knob(8) == 2 || debug_knob(8) == 3)) {
       if (int rc = mix_tc_forward(a, dirs.n, w.w2a_split, st)) return rc;
     } else {
       if (int rc = prop1_mix_launch(a, dirs.n, st)) return rc;
@@ -589,6 +614,17 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       }
       if (int rc = segsum_launch(sg, B, dirs.n, s2)) return rc;
     }
+    if (dropping && o->dense_roots != 0 && bt->x != nullptr && N > 0) {   // dense roots: tiled masked product (rootdense.cu)
+      Dw2bDenseArgs a{};
+      a.x = bt->x; a.rootindex = bt->rootindex; a.batch = bt->batch;
+      a.N = N; a.B = B; a.K = K; a.ld = H + K; a.node_id_base = bt->node_id_base;
+      a.nseg = dw2b_dense_segments(N, B, K);
+      for (int q = 0; q < dirs.n; ++q) {
+        const int d = dirs.id[q];
+        a.t2[q] = t2[d]; a.part[q] = w.S[d]; a.dw2[q] = gdir_w2(gr, d); a.drop[q] = make_drop(o, d);
+      }
+      if (int rc = dw2b_dense_backward(a, dirs.n, s2)) return rc;
+    } else {
     Dw2bArgs a{};
     a.x = bt->x; a.rootindex = bt->rootindex; a.node_ptr = w.node_ptr; a.batch = bt->batch;
     a.rnz_cnt = w.rnz_cnt; a.rnz_col = w.rnz_col; a.rnz_val = w.rnz_val; a.slot = w.slot;
@@ -599,6 +635,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
       a.d[q] = Dw2bDir{t2[d], w.dP[d], gdir_w2(gr, d), w.S[d], make_drop(o, d), w.keep[d]};
     }
     if (int rc = dw2b_launch(a, dirs.n, dropping, s2)) return rc;
+    }
   }
   // 5. G1 = (T2 W2a) * mask * [H1 > 0]; db1
   {

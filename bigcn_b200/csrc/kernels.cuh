@@ -42,7 +42,10 @@ int root_nz_csr_launch(const RootNzArgs&, const int32_t*, const int32_t*, const 
 struct RootProjArgs { const int32_t* cnt; const int32_t* col; const float* val; const float* w2bT[2]; float* P[2]; int64_t B, K; };
 int root_proj_launch(const RootProjArgs&, int, cudaStream_t);
 struct MixDir { const int32_t* ptr; const int32_t* idx; const float* dis; const float* xw; const float* b1; const float* w2aT; const float* w2bT; const float* P; float* h1; float* a1; float* z; DropSpec drop; int32_t* lng; int64_t E; unsigned long long* keep; };
-struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; };
+struct MixArgs { MixDir d[2]; int64_t N, K, ldxw; int32_t cb; int64_t node_id_base; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val;
+                 int32_t root_splits;    /* training, dense roots (rootdense.cu): > 0 = the root half comes as this many
+                                            partial sums root_r[d] + s * N * 64, added in order; the list walk is skipped */
+                 const float* root_r[2]; };
 int prop1_mix_launch(const MixArgs&, int, cudaStream_t);
 // tcgen05 form (mix_tc.cu): sweep + activate, then the 64 x 64 product on the tensor cores with the root part in the epilogue
 bool mix_tc_available();
@@ -115,6 +118,30 @@ int segsum_launch(const SegSumArgs&, int64_t, int, cudaStream_t);
 struct Dw2bDir { const float* t2; const float* dP; float* dw2; float* S; DropSpec drop; const unsigned long long* keep; };
 struct Dw2bArgs { Dw2bDir d[2]; const float* x; const int64_t* rootindex; const int32_t* node_ptr; const int64_t* batch; const int32_t* rnz_cnt; const int32_t* rnz_col; const float* rnz_val; const int32_t* slot; const int32_t* overflow; int64_t N, B, K, ld, node_id_base; };
 int dw2b_launch(const Dw2bArgs&, int, bool, cudaStream_t);
+// dense root features in training mode (rootdense.cu): the root half of conv2.lin and its weight gradient as tiled products
+struct RootDenseArgs {
+  const float* x; const int64_t* rootindex; const int64_t* batch;
+  int64_t N, B, K, node_id_base;
+  const float* w2bT[2];   // [K][64]
+  float* r[2];            // [ksplit][N][64]: sum over the split's columns of keep * relu(x_root) * W2b^T (unscaled)
+  int32_t ksplit;         // column ranges summed by different CTAs (small batches: a CTA's chain of K / 32 chunks is the
+                          // latency of the whole pass); the consumer adds the partials in split order
+  DropSpec drop[2];
+};
+constexpr int64_t RD_CAP_ROWS = 32768;   // rows of split partials per direction the workspace holds
+int root_dense_splits(int64_t N, int64_t K);
+struct Dw2bDenseArgs {
+  const float* x; const int64_t* rootindex; const int64_t* batch;
+  int64_t N, B, K, ld, node_id_base, seg_rows;
+  int nseg;
+  const float* t2[2];     // [N][64]
+  float* part[2];         // [nseg][K][64]
+  float* dw2[2];          // conv2.lin.weight gradient [64][64 + K]
+  DropSpec drop[2];
+};
+int root_dense_forward(const RootDenseArgs&, int ndir, cudaStream_t);
+int dw2b_dense_segments(int64_t N, int64_t B, int64_t K);
+int dw2b_dense_backward(const Dw2bDenseArgs&, int ndir, cudaStream_t);
 int dw2b_blocks(int64_t N);
 int dropout_mask_launch(const DropSpec&, int64_t, int64_t, int64_t, uint8_t*, cudaStream_t);
 int cs_chunks(int64_t N);

@@ -270,6 +270,9 @@ struct PostMix {
   const float* rnz_val;
   int64_t K, node_id_base;
   float4 b1;
+  int root_splits;
+  const float* root_r;
+  int64_t root_stride;
   // bias, H1, relu, dropout, A1 of one row -> the conv2.lin input of its 64 hidden columns
   __device__ __forceinline__ float4 activate(int i, float4 h1, int sub) const {
     h1.x = __fadd_rn(h1.x, b1.x);
@@ -286,7 +289,20 @@ struct PostMix {
   __device__ __forceinline__ void finish(int i, float4 z, int sub, unsigned hm, float* scratch) const {
     const int64_t node = node_id_base + i;
     const int64_t b = batch[i];
-    if (p.drop.on) {
+    if (p.drop.on && root_splits > 0) {   // dense roots: k_root_dense left R[i] (one split: the sums of the walk below, in its order)
+      float4 rv = ld4(root_r + (int64_t)i * H + 4 * sub);
+      for (int s = 1; s < root_splits; ++s) {
+        const float4 t = ld4(root_r + s * root_stride + (int64_t)i * H + 4 * sub);
+        rv.x += t.x;
+        rv.y += t.y;
+        rv.z += t.z;
+        rv.w += t.w;
+      }
+      z.x = fmaf(p.drop.scale, rv.x, z.x);
+      z.y = fmaf(p.drop.scale, rv.y, z.y);
+      z.z = fmaf(p.drop.scale, rv.z, z.z);
+      z.w = fmaf(p.drop.scale, rv.w, z.w);
+    } else if (p.drop.on) {
       const int n = rnz_cnt[b];
       float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
       unsigned long long kept = 0ull;   // bit t = root slot t survived for this node (slots 0..63)
@@ -372,7 +388,8 @@ __global__ void __launch_bounds__(256, MINB) k_prop1_mix(MixArgs a) {
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) sW[i] = p.w2aT[i];
   // csr_sweep starts with a __syncthreads()
   const int sub = threadIdx.x & 15;
-  PostMix post{p, sW, a.batch, a.rnz_cnt, a.rnz_col, a.rnz_val, a.K, a.node_id_base, ld4(p.b1 + 4 * sub)};
+  PostMix post{p, sW, a.batch, a.rnz_cnt, a.rnz_col, a.rnz_val, a.K, a.node_id_base, ld4(p.b1 + 4 * sub), a.root_splits,
+               a.root_r[blockIdx.y], a.N * H};
   csr_sweep<R, Q, true>(Csr{p.ptr, p.idx, p.lng, p.E}, WtGcn{p.dis}, (int)a.N, a.cb, sweep_smem,
                         ValRow{p.xw, a.ldxw}, post);
 }

@@ -91,6 +91,7 @@ class _RumorGCN(torch.nn.Module):
         self.node_id_base = 0
         self.last_flags = None
         self._auto_mode = None
+        self.dense_roots = "auto"           # see resolved_dense_roots
 
     def resolved_gemm_mode(self, x):
         """``gemm_mode`` with 'auto' resolved: a sparse ``data.x`` -> 'sparse'; a dense one -> 'sparse' for
@@ -104,6 +105,15 @@ class _RumorGCN(torch.nn.Module):
             self._auto_mode = pick_gemm_mode(x.detach())
         return self._auto_mode
 
+    def resolved_dense_roots(self, x):
+        """``opts.dense_roots`` (training only): the root half of conv2.lin as a tiled masked product instead of a walk
+        over each tree's positive root columns.  ``self.dense_roots`` = True / False forces it; 'auto' (default) turns
+        it on when ``gemm_mode='auto'`` measured DENSE features (PHEME's sentence embeddings) -- bag-of-words roots
+        (~20 columns) keep the list walk.  Same forward sums in the same order either way."""
+        if self.dense_roots != "auto":
+            return bool(self.dense_roots) and isinstance(x, torch.Tensor) and x.layout == torch.strided
+        return self.gemm_mode == "auto" and self.resolved_gemm_mode(x) != "sparse"
+
     def _conv_params(self):
         return (self.conv1.lin.weight, self.conv1.bias, self.conv2.lin.weight, self.conv2.bias)
 
@@ -115,7 +125,8 @@ class _RumorGCN(torch.nn.Module):
         # want_grad: autograd.Function.forward cannot see torch.no_grad() (needs_input_grad is True for
         # parameters either way); inference then skips the capture / column sort of x that only dW1 needs
         return dict(training=self.training, p=self.p, seed=seed, deg_by=self.deg_by,
-                    gemm_mode=self.resolved_gemm_mode(x), dir_mask=dir_mask, node_id_base=self.node_id_base,
+                    gemm_mode=self.resolved_gemm_mode(x), dense_roots=self.resolved_dense_roots(x),
+                    dir_mask=dir_mask, node_id_base=self.node_id_base,
                     want_grad=torch.is_grad_enabled())
 
     def forward(self, data):

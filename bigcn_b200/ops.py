@@ -518,7 +518,7 @@ class FeaturesFunction(torch.autograd.Function):
         dims, bt, pr = _make_structs(x, ei, bu_ei, batch, rootindex, params, 0, opts["node_id_base"], xs)
         o = Opts(training=int(opts["training"]), p_drop=float(opts["p"]), seed=int(opts["seed"]),
                  deg_by=L.DEG_BY[opts["deg_by"]], gemm_mode=L.GEMM_MODE[opts["gemm_mode"]],
-                 dir_mask=int(opts["dir_mask"]),
+                 dir_mask=int(opts["dir_mask"]), dense_roots=int(bool(opts.get("dense_roots", False))),
                  # inference (torch.no_grad() or no parameter wants a gradient): no column sort of x
                  skip_wgrad_prep=int(not (opts.get("want_grad", True) and any(ctx.needs_input_grad))))
         ws_bytes = lib().bigcn_features_workspace_bytes(C.byref(dims))

@@ -175,7 +175,8 @@ class FusedTrainer:
         # optimiser kernel) -- the same value whether the step is enqueued or replayed from a CUDA graph
         o = Opts(training=int(m.training), p_drop=float(td.p), seed=int(td.seed if seed is None else seed) & ((1 << 64) - 1),
                  deg_by=L.DEG_BY[td.deg_by], gemm_mode=L.GEMM_MODE[td.resolved_gemm_mode(data.x)], dir_mask=L.DIR_TD | L.DIR_BU,
-                 fused_tail=1, seed_dev=self.step_count[2:].data_ptr() if seed is None else None)
+                 fused_tail=1, seed_dev=self.step_count[2:].data_ptr() if seed is None else None,
+                 dense_roots=int(td.resolved_dense_roots(data.x)))
         dev = xs.device if xs is not None else x.device
         b = dims.B
         p = {"dims": dims, "bt": bt, "o": o, "b": b, "c": c, "dev": dev, "y": y, "b_global": int(b_global or b),
@@ -322,7 +323,7 @@ class FusedTrainer:
             (x.data_ptr(), tuple(x.shape), x.dtype, x.layout)
         small = tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in
                       (data.edge_index, data.BU_edge_index, data.batch, data.rootindex, data.y))
-        return (id(data), xk, small, b_global, node_id_base, m.training, td.p, td.deg_by, td.gemm_mode, td.seed)
+        return (id(data), xk, small, b_global, node_id_base, m.training, td.p, td.deg_by, td.gemm_mode, td.dense_roots, td.seed)
 
     def step(self, data, b_global=None, node_id_base=0, seed=None, next_data=None):
         """One optimisation step on a device-resident batch; returns the loss (device scalar).
@@ -511,8 +512,9 @@ def launches_per_step(n_nodes: int, n_dirs: int = 2, training: bool = True, gemm
     if sparse:      # row scan x2 + compaction (or CSR ingest), radix passes over the column keys, finish, hub columns
         kbits = max(1, (in_feats - 1).bit_length())
         csc = (1 if sparse_input else 3) + 3 * ((kbits + 7) // 8) + 2
-    # transposes, W2a hi/lo split, prep, root_nz, [root_proj], xw, [csc build], mix, prop2, readout x2
-    fwd = 1 + 1 + prep + 1 + (0 if training else 1) + xw + csc + 1 + 1 + 2
+    # transposes, prep, root_nz, [root_proj], xw, [csc build], mix, prop2, readout x2  (the W2a hi/lo split is only launched
+    # when the tcgen05 forms of the 64 x 64 products are selected: BIGCN_MIX_TC)
+    fwd = 1 + prep + 1 + (0 if training else 1) + xw + csc + 1 + 1 + 2
     head = 1 + 1 + 3                           # head fwd, nll, head bwd (feat, w partial, w reduce)
     if sparse:
         dw = 1                                 # sweep over the column-sorted non-zeros

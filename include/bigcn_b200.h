@@ -145,6 +145,10 @@ typedef struct bigcn_opts {
   const uint64_t* seed_dev; /* NULL, or a device counter: the Philox key is seed + *seed_dev, read when the
                                kernels run.  bigcn_adam_step / bigcn_dp_reduce_adam advance step_count[2] once
                                per step, so a captured CUDA graph of the step draws fresh masks at every replay */
+  int32_t dense_roots; /* training only: 1 = the root rows of x are dense (PHEME's sentence embeddings): the root half of
+                          conv2.lin (BiGCN_Twitter.py:45-56) and its weight gradient run as tiled masked products
+                          instead of walks over each tree's list of positive root columns; needs a dense x.  Same
+                          forward sums in the same order either way; 0 suits bag-of-words roots */
 } bigcn_opts_t;
 
 const char* bigcn_last_error(void);

@@ -3,6 +3,7 @@ oracle on the same seeded inputs.  Bars: graph prep / propagate / dropout mask b
 fp32 log-probs max|d| <= 1e-5 * max|ref| (BASELINE.json north_star); gradients
 max|d| <= 1e-4 * max|ref| per tensor."""
 import copy
+import ctypes as C
 import json
 import os
 
@@ -593,3 +594,66 @@ def test_fused_trainer_matches_reference_adam(dev):
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         assert rel_err(p, q) < 2e-5, name
     assert int(tr.step_count[0].item()) == 3
+
+
+def test_dense_root_features_training(dev):
+    """PHEME-shaped batches (K = 768 dense features, 21 % single-node trees) in training mode: the tiled masked products
+    for the root half of conv2.lin and its weight gradient (csrc/rootdense.cu, opts.dense_roots -- what gemm_mode 'auto'
+    selects for dense features) against (a) the oracle with the kernel's Philox mask injected, (b) the list walk
+    (dense_roots off): the forward is the same sum in the same order, bit for bit; of the gradients only conv2's weight
+    may differ, by summation order."""
+    import bigcn_b200
+    K = 768
+    for seed, (shape, nt, kk) in enumerate((("pheme", 24, 768), ("pheme", 90, 768), ("twitter15", 3, 70))):   # K = 70: K % 4 != 0
+        b = make_batch(shape, nt, seed=70 + seed, train=True, in_feats=kk)
+        if kk != 768:
+            b.x = torch.tanh(torch.randn(b.x.shape[0], kk))           # dense, about half positive
+        ref, m = make_pair(kk, 4, dev, seed=20 + seed)
+        ref.train(); m.train()
+        bd = clone_batch(b, dev)
+        for mod in (m.TDrumorGCN, m.BUrumorGCN):
+            mod.gemm_mode, mod.dense_roots = "fp32", True               # exact products: isolates the root part
+        got = m(bd)
+        ktd, kbu = masks_for(m, b, kk)
+        want = ref(b, keep_td=ktd, keep_bu=kbu)
+        assert rel_err(got, want) < LOGP_TOL, (shape, nt, rel_err(got, want))
+        torch.nn.functional.nll_loss(want, b.y).backward()
+        torch.nn.functional.nll_loss(got, bd.y).backward()
+        compare_grads(m, ref)
+        m.check_inputs()
+        # the list walk with the same seed: identical forward, identical gradients except (by rounding) conv2.lin.weight
+        m2 = copy.deepcopy(m)
+        m2.zero_grad()
+        for mod in (m2.TDrumorGCN, m2.BUrumorGCN):
+            mod.dense_roots = False
+            mod.seed, mod._calls = m.TDrumorGCN.last_seed, 0
+        got2 = m2(bd)
+        assert m2.TDrumorGCN.last_seed == m.TDrumorGCN.last_seed
+        assert rel_err(got2, got) < 2e-6          # small batches split the columns over CTAs: partial sums, other rounding
+        torch.nn.functional.nll_loss(got2, bd.y).backward()
+        # ... and with ONE column split the tiled product is the list walk's sum, term by term: bit-identical forward,
+        # bit-identical gradients except (summation order) conv2.lin.weight
+        lib = bigcn_b200.lib()
+        lib.bigcn_debug_set.argtypes = [C.c_int, C.c_int]
+        lib.bigcn_debug_set.restype = None
+        lib.bigcn_debug_set(15, 1)
+        try:
+            m3 = copy.deepcopy(m)
+            m3.zero_grad()
+            for mod in (m3.TDrumorGCN, m3.BUrumorGCN):
+                mod.seed, mod._calls = m.TDrumorGCN.last_seed, 0
+            got3 = m3(bd)
+            torch.nn.functional.nll_loss(got3, bd.y).backward()
+        finally:
+            lib.bigcn_debug_set(15, 0)
+        assert torch.equal(got3, got2)
+        for (name, p), (_, q) in zip(m3.named_parameters(), m2.named_parameters()):
+            if name.endswith("conv2.lin.weight"):
+                assert rel_err(p.grad, q.grad) < 1e-5, name
+            else:
+                assert torch.equal(p.grad, q.grad), name
+    # gemm_mode 'auto' on dense features turns it on by itself; bag-of-words features keep the list walk
+    m = bigcn_b200.BiGCN(768, 64, 64, dev).to(dev).train()
+    assert m.TDrumorGCN.resolved_dense_roots(clone_batch(make_batch("pheme", 24, seed=1, train=True), dev).x) is True
+    m = bigcn_b200.BiGCN(5000, 64, 64, dev).to(dev).train()
+    assert m.TDrumorGCN.resolved_dense_roots(clone_batch(make_batch("twitter15", 3, seed=1, train=True), dev).x) is False
