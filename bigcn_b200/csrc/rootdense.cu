@@ -43,58 +43,73 @@ __device__ __forceinline__ void masked_root_quad(const float* __restrict__ x, in
   }
 }
 
-// ---- forward: R[i, 0:64] for 64 nodes per CTA ---------------------------------------------------
-// 256 threads: thread t owns outputs 8 (t & 7) .. + 7 of nodes (t >> 3) and (t >> 3) + 32.
+// ---- forward: R[i, 0:64] for 32 * NPT nodes per CTA ----------------------------------------------
+// 256 threads; thread t owns outputs 4 q .. + 3 and 32 + 4 q .. + 3 (q = t & 7: the eight lanes of a quarter-warp read
+// 128 contiguous bytes of a W row, conflict-free) of the NPT consecutive nodes NPT * (t >> 3) ...  The operand tile is
+// stored [column][node], so a thread's nodes come as one vector load that its quarter-warp shares.  Shared-memory
+// wavefronts per column and warp: NPT = 2: 2 + 8 for 8 packed fmas per thread; NPT = 4: 4 + 8 for 16 (the first
+// version -- outputs 8 q .. + 7, a two-way bank conflict on every W load -- ran at 44 % conflicted wavefronts and was
+// bound by them: profiles/r02e_prof_rootdense_*).
+template <int NPT>
 __global__ void __launch_bounds__(256) k_root_dense(RootDenseArgs a) {
+  constexpr int TN = 32 * NPT;
   __shared__ __align__(16) float sW[RD_KC][H];
-  __shared__ float sA[64][RD_KC + 1];
-  __shared__ int64_t sRoot[64];
+  __shared__ __align__(16) float sA[RD_KC][TN + 4];
+  __shared__ int64_t sRoot[TN];
   const int d = blockIdx.y, split = blockIdx.z;
   // this CTA's column range: whole chunks, split evenly
   const int64_t nchunk = (a.K + RD_KC - 1) / RD_KC;
   const int64_t kbeg = nchunk * split / a.ksplit * RD_KC, kend = min(a.K, nchunk * (split + 1) / a.ksplit * RD_KC);
-  const int64_t i0 = (int64_t)blockIdx.x * 64;
-  const int t = threadIdx.x, oq = t & 7, r0 = t >> 3, r1 = r0 + 32;
+  const int64_t i0 = (int64_t)blockIdx.x * TN;
+  const int t = threadIdx.x, oq = t & 7, n0 = NPT * (t >> 3);
   const DropSpec ds = a.drop[d];
-  if (t < 64) sRoot[t] = i0 + t < a.N ? a.rootindex[a.batch[i0 + t]] : -1;
-  float4 acc[2][2];
+  if (t < TN) sRoot[t] = i0 + t < a.N ? a.rootindex[a.batch[i0 + t]] : -1;
+  float4 acc[NPT][2];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) acc[r][0] = acc[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < NPT; ++r) acc[r][0] = acc[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   for (int64_t k0 = kbeg; k0 < kend; k0 += RD_KC) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {   // the W2b^T chunk: 32 x 64 floats
-      const int f = (t * 2 + u) * 4, kk = f >> 6, o = f & 63;
+      const int f = (t + 256 * u) * 4, kk = f >> 6, o = f & 63;
       const float4 w = k0 + kk < kend ? ld4(a.w2bT[d] + (k0 + kk) * H + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       st4(&sW[kk][o], w);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {   // the masked root operand: 64 nodes x 8 quads
-      const int q = t + 256 * u, node = q >> 3, kq = q & 7;
+    for (int u = 0; u < NPT; ++u) {   // the masked root operand: TN nodes x 8 quads, consecutive lanes = consecutive nodes
+      const int q = t + 256 * u, node = q % TN, kq = q / TN;
       float m[4];
       masked_root_quad(a.x, sRoot[node], a.K, k0 + 4 * kq, ds, a.node_id_base + i0 + node, m);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sA[node][4 * kq + j] = m[j];
+      for (int j = 0; j < 4; ++j) sA[4 * kq + j][node] = k0 + 4 * kq + j < kend ? m[j] : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < RD_KC; ++kk) {
-      const float a0 = sA[r0][kk], a1 = sA[r1][kk];
-      const float4 w0 = ld4(&sW[kk][8 * oq]), w1 = ld4(&sW[kk][8 * oq + 4]);
-      fma4(acc[0][0], a0, w0);
-      fma4(acc[0][1], a0, w1);
-      fma4(acc[1][0], a1, w0);
-      fma4(acc[1][1], a1, w1);
+      float av[NPT];
+      if constexpr (NPT == 4) {
+        const float4 v = ld4(&sA[kk][n0]);
+        av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(&sA[kk][n0]);
+        av[0] = v.x; av[1] = v.y;
+      }
+      const float4 w0 = ld4(&sW[kk][4 * oq]), w1 = ld4(&sW[kk][32 + 4 * oq]);
+#pragma unroll
+      for (int r = 0; r < NPT; ++r) {
+        fma4(acc[r][0], av[r], w0);
+        fma4(acc[r][1], av[r], w1);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int64_t i = i0 + (r == 0 ? r0 : r1);
+  for (int r = 0; r < NPT; ++r) {
+    const int64_t i = i0 + n0 + r;
     if (i < a.N) {
-      float* out = a.r[d] + ((int64_t)split * a.N + i) * H + 8 * oq;
-      st4(out, acc[r][0]);
-      st4(out + 4, acc[r][1]);
+      float* out = a.r[d] + ((int64_t)split * a.N + i) * H;
+      st4(out + 4 * oq, acc[r][0]);
+      st4(out + 32 + 4 * oq, acc[r][1]);
     }
   }
 }
@@ -111,50 +126,65 @@ int root_dense_splits(int64_t N, int64_t K) {
 
 int root_dense_forward(const RootDenseArgs& a, int ndir, cudaStream_t st) {
   if (a.N == 0) return 0;
-  k_root_dense<<<dim3((unsigned)ceil_div(a.N, 64), ndir, a.ksplit), 256, 0, st>>>(a);
+  if (a.N * ndir * a.ksplit >= (int64_t)128 * 2 * num_sms())   // enough 128-node tiles for two waves: the leaner inner loop
+    k_root_dense<4><<<dim3((unsigned)ceil_div(a.N, 128), ndir, a.ksplit), 256, 0, st>>>(a);
+  else
+    k_root_dense<2><<<dim3((unsigned)ceil_div(a.N, 64), ndir, a.ksplit), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_root_dense");
   return 0;
 }
 
-// ---- backward: dW2b partials, CTA = 32 columns x one node segment --------------------------------
-// thread t owns outputs 8 (t & 7) .. + 7 of column k0 + (t >> 3); nodes of the segment in tiles of 32, ascending.
+// ---- backward: dW2b partials, CTA = 128 columns x one node segment -------------------------------
+// thread t owns outputs 4 q .. + 3 and 32 + 4 q .. + 3 (q = t & 7) of the four columns k0 + 4 (t >> 3) .. + 3; nodes of
+// the segment in tiles of 32, ascending.  The operand tile is stored [node][column]: a thread's four columns are one
+// vector load.  Per node and warp: 4 + 8 shared-memory wavefronts for 16 packed fmas per thread.
+constexpr int RD_BK = 128;   // columns per CTA
 __global__ void __launch_bounds__(256) k_dw2b_dense_part(Dw2bDenseArgs a) {
   __shared__ __align__(16) float sT[32][H];
-  __shared__ float sA[32][RD_KC + 1];
+  __shared__ __align__(16) float sA[32][RD_BK + 4];
   const int d = blockIdx.z, seg = blockIdx.y;
-  const int64_t k0 = (int64_t)blockIdx.x * RD_KC;
-  const int t = threadIdx.x, oq = t & 7, kk = t >> 3;
+  const int64_t k0 = (int64_t)blockIdx.x * RD_BK;
+  const int t = threadIdx.x, oq = t & 7, kq = t >> 3;   // columns k0 + 4 kq .. + 3
   const DropSpec ds = a.drop[d];
   const int64_t s0 = (int64_t)seg * a.seg_rows, s1 = min(a.N, s0 + a.seg_rows);
-  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  float4 acc[4][2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i0 = s0; i0 < s1; i0 += 32) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {   // T2 rows of the tile
-      const int f = (t * 2 + u) * 4, nn = f >> 6, o = f & 63;
+      const int f = (t + 256 * u) * 4, nn = f >> 6, o = f & 63;
       const float4 v = i0 + nn < s1 ? ld4(a.t2[d] + (i0 + nn) * H + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       st4(&sT[nn][o], v);
     }
-    {                               // the masked root operand: 32 nodes x 8 quads
-      const int node = t >> 3, kq = t & 7;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {   // the masked root operand: 32 nodes x 32 quads, consecutive lanes = consecutive quads
+      const int q = t + 256 * u, node = q >> 5, cq = q & 31;
       const int64_t i = i0 + node;
       float m[4];
-      masked_root_quad(a.x, i < s1 ? a.rootindex[a.batch[i]] : -1, a.K, k0 + 4 * kq, ds, a.node_id_base + i, m);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sA[node][4 * kq + j] = m[j];
+      masked_root_quad(a.x, i < s1 ? a.rootindex[a.batch[i]] : -1, a.K, k0 + 4 * cq, ds, a.node_id_base + i, m);
+      st4(&sA[node][4 * cq], make_float4(m[0], m[1], m[2], m[3]));
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
     for (int nn = 0; nn < 32; ++nn) {
-      const float av = sA[nn][kk];
-      fma4(acc0, av, ld4(&sT[nn][8 * oq]));
-      fma4(acc1, av, ld4(&sT[nn][8 * oq + 4]));
+      const float4 av = ld4(&sA[nn][4 * kq]);
+      const float4 t0 = ld4(&sT[nn][4 * oq]), t1 = ld4(&sT[nn][32 + 4 * oq]);
+      fma4(acc[0][0], av.x, t0); fma4(acc[0][1], av.x, t1);
+      fma4(acc[1][0], av.y, t0); fma4(acc[1][1], av.y, t1);
+      fma4(acc[2][0], av.z, t0); fma4(acc[2][1], av.z, t1);
+      fma4(acc[3][0], av.w, t0); fma4(acc[3][1], av.w, t1);
     }
     __syncthreads();
   }
-  if (k0 + kk < a.K) {
-    float* p = a.part[d] + ((int64_t)seg * a.K + k0 + kk) * H + 8 * oq;
-    st4(p, acc0);
-    st4(p + 4, acc1);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int64_t k = k0 + 4 * kq + c;
+    if (k < a.K) {
+      float* p = a.part[d] + ((int64_t)seg * a.K + k) * H;
+      st4(p + 4 * oq, acc[c][0]);
+      st4(p + 32 + 4 * oq, acc[c][1]);
+    }
   }
 }
 
@@ -173,8 +203,8 @@ int dw2b_dense_segments(int64_t N, int64_t B, int64_t K) {
   // the partials live in the S buffer of the sparse-root path: (dw2b_blocks(N) + B) * DW2B_CAP * 64 floats per direction,
   // never less than one segment (carve_features)
   int64_t fit = ((int64_t)dw2b_blocks(N) + B) * DW2B_CAP / (K > 0 ? K : 1);
-  int64_t want = ceil_div(N > 0 ? N : 1, 2048);
-  if (want > 16) want = 16;
+  int64_t want = ceil_div(N > 0 ? N : 1, 512);
+  if (want > 64) want = 64;
   if (want > fit) want = fit;
   return (int)(want < 1 ? 1 : want);
 }
@@ -183,7 +213,7 @@ int dw2b_dense_backward(const Dw2bDenseArgs& a0, int ndir, cudaStream_t st) {
   if (a0.K == 0) return 0;
   Dw2bDenseArgs a = a0;
   a.seg_rows = ceil_div(ceil_div(a.N > 0 ? a.N : 1, a.nseg), 32) * 32;
-  k_dw2b_dense_part<<<dim3((unsigned)ceil_div(a.K, RD_KC), a.nseg, ndir), 256, 0, st>>>(a);
+  k_dw2b_dense_part<<<dim3((unsigned)ceil_div(a.K, RD_BK), a.nseg, ndir), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_dw2b_dense_part");
   k_dw2b_dense_reduce<<<dim3((unsigned)ceil_div(a.K * H, 256), ndir), 256, 0, st>>>(a);
   BIGCN_CHECK_LAUNCH("k_dw2b_dense_reduce");
