@@ -202,7 +202,8 @@ static FeatWs carve_features(const bigcn_dims_t* dm, void* ws, size_t bytes, voi
   const size_t nh = (size_t)(N > 0 ? N : 1) * H;
   for (int d = 0; d < 2; ++d) w.P[d] = c.take<float>((size_t)(B > 0 ? B : 1) * H);
   w.xw = c.take<float>(2 * nh);
-  for (int d = 0; d < 2; ++d) w.h1[d] = c.take<float>(nh);
+  w.h1[0] = c.take<float>(2 * nh);   // one block: the backward's dW1 GEMM keeps the lo half of T1's TF32 split here
+  w.h1[1] = w.h1[0] + nh;
   for (int d = 0; d < 2; ++d) w.a1[d] = c.take<float>(nh);
   w.z[0] = c.take<float>(2 * nh);
   w.z[1] = w.z[0] + nh;
@@ -554,7 +555,9 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
   // other gradients while the second X stream runs)
   const int phase = o->bwd_phase;
   ColsumArgs db2_reduce{};
-  const bool join_late = o->gemm_mode == BIGCN_GEMM_SPARSE && phase == 0;
+  // the dW2 / db chains on the side streams are joined AFTER the dW1 product (nothing it writes is read by them: its
+  // scratch is Z (G1, consumed by the propagate before it) and H1 (dead since the forward), not T2)
+  const bool join_late = phase == 0;
   SideCtx* sc = side_ctx();
   const bool bw_lo = debug_knob(12) & 1;
   cudaStream_t ss = sc ? (debug_knob(7) ? sc->s.side : bw_lo ? sc->bwlo[0] : sc->bw[0]) : st;
@@ -667,8 +670,7 @@ int features_backward(const bigcn_dims_t* dm, const bigcn_batch_t* bt, const big
     }
     if (int rc = propagate_launch(a, dirs.n, st)) return rc;
   }
-  // the dense dW1 paths reuse T2's buffer, which the side stream reads: join first.  The sparse
-  // sweep touches none of the side stream's buffers and joins after it.
+  // bwd_phase 1 (the caller reduces these gradients while dW1 runs): everything but dW1 is complete at return
   if (sc && !join_late) {
     stream_after(sc, 1, ss, st);
     stream_after(sc, 7, s2, st);
@@ -683,16 +685,16 @@ dw1_only:
       // column-sorted X: built by this step's forward on the low-priority stream (a prepared batch brought it along)
       if (sc) cudaStreamWaitEvent(st, sc->ev[3], 0);
       if (int rc = dw_sparse(w.xs, t1cat, n_out, n_out, da, db, K, st)) return rc;
-      if (sc && join_late) {
-        stream_after(sc, 1, ss, st);
-        stream_after(sc, 7, s2, st);
-      }
     } else if (o->gemm_mode == BIGCN_GEMM_FP32) {
       if (int rc = dw_fp32(bt->x, N, K, t1cat, n_out, n_out, w.dw_part, da, K, 0, db, K, 0, st)) return rc;
-    } else {   // G1 (w.z) and T2 (w.xw) are dead here: they hold the TF32 hi / lo split of T1
-      if (int rc = dw_tc(bt->x, N, K, t1cat, n_out, n_out, w.z[0], w.xw, w.dw_part, da, K, 0, db, K, 0,
+    } else {   // G1 (w.z) and H1 are dead here: they hold the TF32 hi / lo split of T1 (T2 is still being read by the dW2 chains)
+      if (int rc = dw_tc(bt->x, N, K, t1cat, n_out, n_out, w.z[0], w.h1[0], w.dw_part, da, K, 0, db, K, 0,
                          o->gemm_mode, st))
         return rc;
+    }
+    if (sc && join_late) {
+      stream_after(sc, 1, ss, st);
+      stream_after(sc, 7, s2, st);
     }
   }
   return 0;
