@@ -1,5 +1,6 @@
 import sys, time, cProfile, pstats, io
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bigcn_b200
 from bigcn_b200.data import Batch, make_batch_shard
 dev = torch.device("cuda", 0)

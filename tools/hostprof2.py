@@ -1,5 +1,6 @@
 import sys, time, cProfile, pstats, io
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, bigcn_b200
 from bigcn_b200.data import synth_forest_device
 dev = torch.device("cuda", 0)
